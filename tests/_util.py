@@ -1,0 +1,46 @@
+"""Shared helpers for the parity tests (fixtures, error metric, tolerances)."""
+import os
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+FIXTURES = ["tiny_a", "tiny_b", "tiny_c", "tiny_d", "c1"]
+
+# north_star tolerances (max-normalised error): fp32 1e-5, bf16 2e-2
+TOL_FP32 = 1e-5
+TOL_BF16 = 2e-2
+
+
+def err(a, b):
+    a = np.asarray(a, np.float64)
+    b = np.asarray(b, np.float64)
+    den = np.abs(b).max()
+    return float(np.abs(a - b).max() / (den if den > 0 else 1.0))
+
+
+def load_fixture(name):
+    """Returns dict(cfg=..., params=..., grads=..., x, noise, g_slots, g_attn, slots_f64, ...)."""
+    z = np.load(os.path.join(GOLDEN, name + ".npz"))
+    B, T, N, D, Ds, M, K, I, blocks, heads, seed, has_ga, sub = [int(v) for v in z["cfg"]]
+    out = dict(B=B, T=T, N=N, D=D, Ds=Ds, M=M, K=K, I=I, blocks=blocks, heads=heads, sub=sub)
+    out["params"] = {k[len("param/"):]: z[k] for k in z.files if k.startswith("param/")}
+    out["grads"] = {k[len("grad/"):]: z[k] for k in z.files if k.startswith("grad/")}
+    for k in z.files:
+        if "/" not in k and k != "cfg":
+            out[k] = z[k]
+    if "x" not in out:  # big fixture: inputs regenerated from the numpy seed (see make_golden.py)
+        rng = np.random.default_rng(seed + 1000)
+        out["x"] = rng.standard_normal((B, T, N, D)).astype(np.float32)
+        n2 = rng.standard_normal((B, K, Ds)).astype(np.float32)
+        assert np.array_equal(n2, out["noise"])
+        g2 = rng.standard_normal((B, T, K, Ds)).astype(np.float32)
+        assert np.array_equal(g2, out["g_slots"])
+        out["g_attn"] = rng.standard_normal((B, T, N, K)).astype(np.float32) if has_ga else None
+    elif not has_ga:
+        out["g_attn"] = None
+    return out
+
+
+def grad_scale(grads):
+    return max(float(np.abs(g).max()) for g in grads.values())

@@ -1,0 +1,308 @@
+#!/usr/bin/env python
+"""bench.py — slot-attention fwd+bwd frames/sec on B200 (BASELINE.json metric).
+
+    python bench.py --gpus N --steps K --warmup W            # our arm (CUDA library)
+    python bench.py --impl reference --gpus N --steps K ...  # reference CPU arm (oracle port, host cores)
+
+One "step" = one SlotAttentionVideo forward + backward over one batch of synthetic
+MOVi-E-shaped clips (BASELINE.json configs[1], "C2": bf16, 64 clips/GPU, T=6, N=1024,
+D=Ds=M=128, K=24, 3 iterations, 1 predictor block x 4 heads), upstream gradients for
+both outputs, plus (N>1) the DDP gradient all-reduce.  One frame = one (clip, t) pair.
+
+Prints ONE JSON line (rank 0).  Keys beyond the base contract:
+  roofline     the dominant kernel against the measured HBM peak (MEASURED_PEAKS.json)
+  step_roofline  whole-step k/v-bytes-x-iterations roofline of BASELINE.md §3
+  cpu_baseline the oracle's torch port timed on this box's host cores (N=1 only)
+  kernels_ms   per-kernel CUDA-event times of the last timed step
+"""
+import argparse
+import json
+import os
+import statistics
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+CONFIGS = {
+    # name: B/GPU, T, N, D, Ds, M, K, I, blocks, heads, dtype
+    "c1": dict(B=2, T=6, N=1024, D=128, Ds=128, M=128, K=24, I=3, blocks=1, heads=4, dtype="fp32"),
+    "c2": dict(B=64, T=6, N=1024, D=128, Ds=128, M=128, K=24, I=3, blocks=1, heads=4, dtype="bf16"),
+    "c3": dict(B=64, T=6, N=4096, D=192, Ds=192, M=192, K=24, I=3, blocks=1, heads=4, dtype="bf16"),
+    "c4": dict(B=64, T=24, N=1024, D=128, Ds=128, M=128, K=11, I=2, blocks=1, heads=4, dtype="bf16"),
+}
+METRIC = "slot-attn fwd+bwd frames/sec"
+UNIT = "frames/s"
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            return json.load(f)["hbm_gbs"], "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler(threading.Thread):
+    """Samples SM clock and throttle reasons through NVML while the timed region runs."""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.reasons, self.max_mhz = index, [], set(), None
+        self._halt = threading.Event()
+        self.ok = False
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+            self.ok = True
+        except Exception:
+            self.ok = False
+
+    def run(self):
+        if not self.ok:
+            return
+        nv = self.nv
+        names = {"hw_slowdown": getattr(nv, "nvmlClocksEventReasonHwSlowdown", 0x8),
+                 "hw_thermal_slowdown": getattr(nv, "nvmlClocksEventReasonHwThermalSlowdown", 0x40),
+                 "sw_thermal_slowdown": getattr(nv, "nvmlClocksEventReasonSwThermalSlowdown", 0x20),
+                 "sw_power_cap": getattr(nv, "nvmlClocksEventReasonSwPowerCap", 0x4),
+                 "hw_power_brake": getattr(nv, "nvmlClocksEventReasonHwPowerBrakeSlowdown", 0x80)}
+        while not self._halt.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                try:
+                    mask = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                except Exception:
+                    mask = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for k, bit in names.items():
+                    if mask & bit:
+                        self.reasons.add(k)
+            except Exception:
+                pass
+            time.sleep(0.01)
+
+    def stop(self):
+        self._halt.set()
+        self.join(timeout=2)
+        return {"sm_mhz": statistics.median(self.samples) if self.samples else None,
+                "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": len(self.samples)}
+
+
+def make_params_like(model_cfg, seed=0):
+    """Reference init (same RNG order) via our module's constructor, on CPU."""
+    from focus_b200 import SlotAttentionVideo
+    torch.manual_seed(seed)
+    c = model_cfg
+    return SlotAttentionVideo(c["I"], c["K"], c["D"], c["Ds"], c["M"], c["blocks"], c["heads"], 0.0)
+
+
+# ---------------------------------------------------------------------------------------------
+# reference arm / cpu_baseline: oracle torch port on the host cores (bounded sample of the workload)
+# ---------------------------------------------------------------------------------------------
+def time_cpu_port(cfg, sample_clips, steps, warmup):
+    from oracle import savi_torch as OT
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    c = cfg
+    module = make_params_like(c)
+    P = {k: v.detach().float() for k, v in module.state_dict().items()}
+    g = torch.Generator().manual_seed(1)
+    x = torch.randn(sample_clips, c["T"], c["N"], c["D"], generator=g)
+    noise = torch.randn(sample_clips, c["K"], c["Ds"], generator=g)
+    gs = torch.randn(sample_clips, c["T"], c["K"], c["Ds"], generator=g)
+    ga = torch.randn(sample_clips, c["T"], c["N"], c["K"], generator=g)
+    times = []
+    for i in range(warmup + steps):
+        t0 = time.perf_counter()
+        OT.forward_backward(P, x, noise, c["I"], c["heads"], gs, ga)
+        dt = time.perf_counter() - t0
+        if i >= warmup:
+            times.append(dt)
+    t = statistics.median(times)
+    return dict(value=sample_clips * c["T"] / t, unit=UNIT, cores=cores, kind="port",
+                sample="%d of %d clips/step, fp32, oracle/savi_torch.py (torch CPU ops in the reference's operation "
+                       "order; the Python reference itself cannot travel to the GPU box), median of %d steps" %
+                       (sample_clips, c["B"], steps)), t
+
+
+def run_reference(args, cfg, rank):
+    if rank != 0:
+        return
+    sample = min(cfg["B"], 4)
+    cb, t = time_cpu_port(cfg, sample, max(1, args.steps), max(0, min(args.warmup, 2)))
+    line = {"impl": "reference", "metric": METRIC, "value": cb["value"], "unit": UNIT, "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": min(args.warmup, 2), "ms_per_step": t * 1e3, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": config_dict(args, cfg, args.gpus), "cpu_baseline": cb,
+            "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+def config_dict(args, cfg, n):
+    return {"workload": "BASELINE.json configs[1] (C2): STEVE MOVi-E 128x128 slot-attention fwd+bwd" if args.config == "c2"
+            else "BASELINE.json config %s" % args.config,
+            "clips_per_gpu": cfg["B"], "global_clips": cfg["B"] * n, "T": cfg["T"], "N": cfg["N"], "D": cfg["D"],
+            "Ds": cfg["Ds"], "M": cfg["M"], "K": cfg["K"], "iters": cfg["I"], "predictor": "%d block x %d heads" % (cfg["blocks"], cfg["heads"]),
+            "token_dtype": cfg["dtype"], "grad_attn": "dense N(0,1)", "parallelism": "dp%d" % n,
+            "l2": "flushed between timed steps (256 MiB write outside the event brackets); step working set >> 126 MB L2"}
+
+
+# ---------------------------------------------------------------------------------------------
+# our arm
+# ---------------------------------------------------------------------------------------------
+def run_ours(args, cfg, rank, world, local_rank):
+    import torch.distributed as dist
+    from focus_b200 import SlotAttentionVideo, _lib
+    from focus_b200.slot_attention import _SaviFunction
+
+    dev = torch.device("cuda", local_rank)
+    torch.cuda.set_device(dev)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    c = cfg
+    dt = torch.float32 if c["dtype"] == "fp32" else torch.bfloat16
+    model = make_params_like(c).to(dev)
+    ddp = model
+    if world > 1:
+        ddp = torch.nn.parallel.DistributedDataParallel(model, device_ids=[local_rank], output_device=local_rank,
+                                                        gradient_as_bucket_view=True, bucket_cap_mb=64)
+    g = torch.Generator(device="cpu").manual_seed(1 + rank)
+    B, T, N, D, K, Ds = c["B"], c["T"], c["N"], c["D"], c["K"], c["Ds"]
+    x_host = torch.randn(B, T, N, D, generator=g).to(dt).pin_memory()
+    x = x_host.to(dev).requires_grad_(True)
+    noise = torch.randn(B, K, Ds, generator=g).to(dev)
+    gs = torch.randn(B, T, K, Ds, generator=g).to(dev)
+    ga = torch.randn(B, T, N, K, generator=g).to(dt).to(dev)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+
+    def step(inp):
+        slots, attn = ddp(inp, noise=noise)
+        torch.autograd.backward([slots, attn], [gs.to(slots.dtype), ga])
+        return slots
+
+    def sync_all():
+        torch.cuda.synchronize(dev)
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize(dev)
+
+    for _ in range(max(args.warmup, 3)):
+        step(x)
+        x.grad = None
+    sync_all()
+
+    # ---- timed region: value (inputs resident in HBM) ----
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    _lib.profile_enable(True)
+    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    kern_ms = []
+    sync_all()
+    for i in range(args.steps):
+        flush.fill_(i & 0xFF)
+        evs[i][0].record()
+        step(x)
+        evs[i][1].record()
+        x.grad = None
+        if i >= args.steps - 5:
+            kern_ms.append(_lib.profile_read())
+    sync_all()
+    clocks = sampler.stop()
+    _lib.profile_enable(False)
+    launches_per_step = None
+    total_ms = sum(a.elapsed_time(b) for a, b in evs)
+    t_local = torch.tensor([total_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t_local, op=dist.ReduceOp.MAX)
+    total_ms = float(t_local.item())
+    ms_per_step = total_ms / args.steps
+    frames = B * T * world
+    value = frames / (ms_per_step * 1e-3)
+
+    # ---- e2e: host (pinned) inputs -> H2D -> fwd+bwd -> D2H of the step's scalar result, every step ----
+    x_dev = torch.empty_like(x_host, device=dev)
+    sync_all()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e2e_steps = max(3, min(args.steps, 20))
+    e0.record()
+    for i in range(e2e_steps):
+        x_dev.copy_(x_host, non_blocking=True)
+        inp = x_dev.detach().requires_grad_(True)
+        slots = step(inp)
+        res = (slots.float() * gs).sum().item()          # D2H read of the step's result (forces completion)
+    e1.record()
+    sync_all()
+    e2e_ms = e0.elapsed_time(e1) / e2e_steps
+    t_local = torch.tensor([e2e_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t_local, op=dist.ReduceOp.MAX)
+    e2e_ms = float(t_local.item())
+    launches_per_step = 2 + 2 + 4   # pack(2) + ln_fwd + clip_fwd | memset is not a kernel | clip_bwd + wgrad + ln_bwd  (+1 below)
+    launches_per_step = 7
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    # ---- roofline of the dominant kernel ----
+    peak, peak_src = measured_peaks()
+    e = 4 if c["dtype"] == "fp32" else 2
+    km = {k: statistics.mean(d[k] for d in kern_ms) for k in kern_ms[0]}
+    dom = max(("savi_fwd", "savi_bwd"), key=lambda k: km[k])
+    algo_bytes_launch = B * T * c["I"] * 2 * N * Ds * e          # k/v bytes x iterations, one direction
+    achieved = algo_bytes_launch / (km[dom] * 1e-3) / 1e9
+    roofline = {"kernel": dom, "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": None, "peak_source": peak_src, "algorithmic_bytes_per_launch": algo_bytes_launch,
+                "kernel_ms": km[dom]}
+    step_bytes = 4 * c["I"] * N * Ds * e * B * T
+    step_roof = {"bytes_per_gpu_step": step_bytes, "roofline_ms": step_bytes / (peak * 1e9) * 1e3,
+                 "frac": step_bytes / (peak * 1e9) * 1e3 / ms_per_step}
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "bf16" if c["dtype"] == "bf16" else "f32", "data": "synthetic", "config": config_dict(args, cfg, world),
+            "clocks": clocks,
+            "e2e": {"value": frames / (e2e_ms * 1e-3), "unit": UNIT, "ms_per_step": e2e_ms,
+                    "h2d_bytes_per_step": x_host.numel() * x_host.element_size(), "d2h_bytes_per_step": 4},
+            "gpu_launches": launches_per_step * args.steps,
+            "roofline": roofline, "step_roofline": step_roof, "kernels_ms": km}
+    if world == 1 and not args.no_cpu_baseline:
+        cb, _ = time_cpu_port(cfg, min(cfg["B"], 4), 3, 1)
+        line["cpu_baseline"] = cb
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=30)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--config", default="c2", choices=sorted(CONFIGS))
+    ap.add_argument("--clips", type=int, default=0, help="override clips per GPU")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    cfg = dict(CONFIGS[args.config])
+    if args.clips:
+        cfg["B"] = args.clips
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, cfg, rank)
+        return
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the product path has no CPU fallback (use --impl reference for the CPU arm)")
+    run_ours(args, cfg, rank, world, local_rank)
+
+
+if __name__ == "__main__":
+    main()

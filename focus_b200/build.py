@@ -1,0 +1,60 @@
+"""Builds focus_b200/libfocus_savi.so in-tree with nvcc for sm_100a (no torch headers)."""
+import os
+import subprocess
+import sys
+from concurrent.futures import ThreadPoolExecutor
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+CSRC = os.path.join(HERE, "csrc")
+OUT = os.path.join(HERE, "libfocus_savi.so")
+# (source, object name, extra defines): the clip kernels are compiled once per token dtype
+UNITS = [("savi_api.cu", "savi_api.o", []),
+         ("savi_wgrad.cu", "savi_wgrad.o", []),
+         ("savi_fwd.cu", "savi_fwd_f32.o", ["-DSAVI_TOK=float", "-DSAVI_SUFFIX=f32"]),
+         ("savi_fwd.cu", "savi_fwd_bf16.o", ["-DSAVI_TOK=__nv_bfloat16", "-DSAVI_SUFFIX=bf16"]),
+         ("savi_bwd.cu", "savi_bwd_f32.o", ["-DSAVI_TOK=float", "-DSAVI_SUFFIX=f32"]),
+         ("savi_bwd.cu", "savi_bwd_bf16.o", ["-DSAVI_TOK=__nv_bfloat16", "-DSAVI_SUFFIX=bf16"])]
+NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
+              "-Xcompiler", "-fPIC", "-I" + os.path.join(ROOT, "include"), "-I" + CSRC]
+
+
+def _newest_source_mtime():
+    m = 0.0
+    for d in (CSRC, os.path.join(ROOT, "include")):
+        for f in os.listdir(d):
+            m = max(m, os.path.getmtime(os.path.join(d, f)))
+    return m
+
+
+def build(force=False, verbose=False):
+    """Compile the CUDA library if it is missing or older than its sources. Returns the .so path."""
+    if not force and os.path.exists(OUT) and os.path.getmtime(OUT) >= _newest_source_mtime():
+        return OUT
+    nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+    objdir = os.path.join(HERE, "build")
+    os.makedirs(objdir, exist_ok=True)
+    extra = ["-Xptxas", "-v"] if verbose else []
+
+    def cc(unit):
+        src, oname, defs = unit
+        obj = os.path.join(objdir, oname)
+        cmd = [nvcc] + NVCC_FLAGS + extra + defs + ["-c", os.path.join(CSRC, src), "-o", obj]
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        if r.returncode != 0:
+            raise RuntimeError("nvcc failed for %s:\n%s\n%s" % (oname, r.stdout, r.stderr))
+        if verbose:
+            sys.stderr.write(r.stderr)
+        return obj
+
+    with ThreadPoolExecutor(len(UNITS)) as ex:
+        objs = list(ex.map(cc, UNITS))
+    cmd = [nvcc, "-shared", "-o", OUT] + objs + ["-lcudart"]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError("link failed:\n%s\n%s" % (r.stdout, r.stderr))
+    return OUT
+
+
+if __name__ == "__main__":
+    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))

@@ -1,0 +1,63 @@
+// Kernel argument blocks (passed by value as __grid_constant__) and the
+// launcher prototypes shared by savi_api.cu / savi_fwd.cu / savi_bwd.cu.
+#pragma once
+#include <cuda_runtime.h>
+#include "savi_layout.h"
+
+struct FwdArgs {
+    Dims d;
+    ParamOff po;
+    SavedLayout sl;
+    FwdWsLayout wl;
+    const float* packed;
+    const float* noise;
+    float* slots_out;
+    void* attn_out;
+    unsigned char* saved;
+    float* ws;
+    int TN;               // tokens per shared-memory tile
+    int arena_floats;     // floats of dynamic shared memory usable as the linear-layer staging arena
+    int smem_bytes;
+};
+
+struct BwdArgs {
+    Dims d;
+    ParamOff po;
+    SavedLayout sl;
+    BwdWsLayout wl;
+    const float* packed;
+    const float* noise;
+    const unsigned char* saved;
+    const float* grad_slots;
+    const void* grad_attn;      // nullable
+    float* grad_params;         // flat, zeroed before the clip kernel
+    float* grad_noise;          // nullable
+    float* ws;
+    int TN;
+    int arena_floats;
+    int smem_bytes;
+};
+
+struct WgradJob {               // dW[o][c] (+)= alpha * sum_r dY[r][o] * X[r][c]
+    const float* dY; const float* X; float* dW;
+    int R, O, C, ldy, ldx;
+    float alpha;
+};
+constexpr int WGRAD_MAX_JOBS = 7 + 6 * SAVI_MAX_BLOCKS;
+struct WgradArgs { WgradJob job[WGRAD_MAX_JOBS]; int njobs; int rows_per_split; };
+
+// per-kernel timing hooks (savi_api.cu); no-ops unless savi_profile_enable(1)
+void savi_prof_begin(int slot, cudaStream_t st);
+void savi_prof_end(int slot, cudaStream_t st);
+
+cudaError_t savi_launch_forward(const FwdArgs& a, const void* inputs, cudaStream_t st, int* launches);
+cudaError_t savi_launch_backward(const BwdArgs& a, const void* inputs, void* grad_inputs, cudaStream_t st, int* launches);
+cudaError_t savi_launch_forward_f32(const FwdArgs& a, const void* inputs, cudaStream_t st, int* launches);
+cudaError_t savi_launch_forward_bf16(const FwdArgs& a, const void* inputs, cudaStream_t st, int* launches);
+cudaError_t savi_launch_bwd_clip_f32(const BwdArgs& a, cudaStream_t st);
+cudaError_t savi_launch_bwd_clip_bf16(const BwdArgs& a, cudaStream_t st);
+cudaError_t savi_launch_ln_bwd_f32(const BwdArgs& a, const void* inputs, void* grad_inputs, cudaStream_t st);
+cudaError_t savi_launch_ln_bwd_bf16(const BwdArgs& a, const void* inputs, void* grad_inputs, cudaStream_t st);
+static inline int savi_fwd_kmax(int K) { return K <= 8 ? 8 : K <= 16 ? 16 : K <= 24 ? 24 : K <= 32 ? 32 : 64; }
+size_t savi_fwd_smem_bytes(const Dims& d, int TN);
+size_t savi_bwd_smem_bytes(const Dims& d, int TN);

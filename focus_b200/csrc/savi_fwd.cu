@@ -1,0 +1,387 @@
+// Forward kernels: token LayerNorm prologue and the per-clip recurrence kernel.
+//
+// Reference semantics: /root/reference/slowfast/models/STEVE/steve.py:52-105
+// (SlotAttentionVideo.forward) and transformer.py:22-49, 70-86, 106-114.
+#include "savi_dev.cuh"
+#include "savi_args.h"
+
+// ---------------------------------------------------------------------------
+// K1: xhat = LayerNorm_D(inputs) (steve.py:60), one warp per token.
+// Streams `inputs` once from HBM with 16-byte accesses, writes xhat in the token
+// dtype plus (mean, rstd) per token for the backward.
+// ---------------------------------------------------------------------------
+template <typename TokT>
+__global__ void __launch_bounds__(NT) ln_tokens_fwd_kernel(const TokT* __restrict__ x, TokT* __restrict__ xhat,
+                                                           float2* __restrict__ stats, const float* __restrict__ g,
+                                                           const float* __restrict__ b, int64_t rows, int D, float eps) {
+    constexpr int VEC = Tok<TokT>::VEC;
+    const int lane = threadIdx.x & 31;
+    const int chunks = D / VEC;                       // 16-byte chunks per row (<= 64 for D <= 512)
+    const int64_t warp0 = (int64_t)blockIdx.x * NW + (threadIdx.x >> 5);
+    const int64_t nwarps = (int64_t)gridDim.x * NW;
+    for (int64_t row = warp0; row < rows; row += nwarps) {
+        const TokT* xr = x + row * D;
+        float v[2][VEC];
+        float s = 0.f;
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+            const int c = lane + 32 * j;
+            if (c < chunks) {
+                Tok<TokT>::load(xr + c * VEC, v[j]);
+#pragma unroll
+                for (int e = 0; e < VEC; ++e) s += v[j][e];
+            }
+        }
+        const float mean = warp_sum(s) / (float)D;
+        float q = 0.f;
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+            const int c = lane + 32 * j;
+            if (c < chunks) {
+#pragma unroll
+                for (int e = 0; e < VEC; ++e) { float t = v[j][e] - mean; q = fmaf(t, t, q); }
+            }
+        }
+        const float rstd = 1.0f / sqrtf(warp_sum(q) / (float)D + eps);
+        if (lane == 0) stats[row] = make_float2(mean, rstd);
+        TokT* yr = xhat + row * D;
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+            const int c = lane + 32 * j;
+            if (c < chunks) {
+#pragma unroll
+                for (int e = 0; e < VEC; e += 4) {
+                    const int d = c * VEC + e;
+                    const float4 gg = __ldg(reinterpret_cast<const float4*>(g + d));
+                    const float4 bb = __ldg(reinterpret_cast<const float4*>(b + d));
+                    float4 o;
+                    o.x = (v[j][e + 0] - mean) * rstd * gg.x + bb.x;
+                    o.y = (v[j][e + 1] - mean) * rstd * gg.y + bb.y;
+                    o.z = (v[j][e + 2] - mean) * rstd * gg.z + bb.z;
+                    o.w = (v[j][e + 3] - mean) * rstd * gg.w + bb.w;
+                    Tok<TokT>::store4(yr + d, o);
+                }
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------
+// Attention step over this CTA's share of the tokens of frame (b,t)
+// (steve.py:76-83 in the folded form):
+//   L = xhat qk^T ; P = softmax_K(L) ; A = P + eps ; part = [sum_n A x , sum_n A]
+// One thread per token for the logits/softmax (all K logits in registers), then a
+// register-tiled outer-product accumulation over the tile.
+// ---------------------------------------------------------------------------
+template <typename TokT, int KMAX>
+__device__ void token_pass_fwd(const Dims& d, const TokT* __restrict__ xh, int n_lo, int n_hi,
+                               const float* qk_g, float* part_g, TokT* attn_g, unsigned char* smem, int TN) {
+    const int tid = threadIdx.x, K = d.K, KP = d.KP, D = d.D;
+    const int cst = coef_stride(KP), xst = tile_stride_bytes(D, sizeof(TokT));
+    float* qk_s = reinterpret_cast<float*>(smem);                  // [KMAX][D], rows >= K are zero
+    float* acc_s = qk_s + (size_t)KMAX * D;                        // [KP][D]
+    float* ssum_s = acc_s + (size_t)KP * D;                        // [KP]
+    float* coef = ssum_s + KP;                                     // [TN][cst]
+    unsigned char* xs = reinterpret_cast<unsigned char*>(coef + (size_t)TN * cst);
+
+    __syncthreads();
+    for (int i = tid * 4; i < KMAX * D; i += NT * 4)
+        st4(qk_s + i, (i < K * D) ? ld4(qk_g + i) : make_float4(0.f, 0.f, 0.f, 0.f));
+    for (int i = tid; i < KP * D + KP; i += NT) acc_s[i] = 0.f;    // acc_s and ssum_s are contiguous
+
+    for (int n0 = n_lo; n0 < n_hi; n0 += TN) {
+        const int tn = min(TN, n_hi - n0);
+        __syncthreads();
+        load_token_tile<TokT>(xs, xst, xh, n0, tn, D);
+        __syncthreads();
+        for (int n = tid; n < tn; n += NT) {
+            float acc[KMAX];
+#pragma unroll
+            for (int k = 0; k < KMAX; ++k) acc[k] = 0.f;
+            const TokT* xr = reinterpret_cast<const TokT*>(xs + (size_t)n * xst);
+            constexpr int VEC = Tok<TokT>::VEC;
+            for (int c = 0; c < D; c += VEC) {
+                float xv[VEC];
+                Tok<TokT>::load(xr + c, xv);
+#pragma unroll
+                for (int k = 0; k < KMAX; ++k) {
+#pragma unroll
+                    for (int e = 0; e < VEC; e += 4) {
+                        const float4 w = ld4(qk_s + (size_t)k * D + c + e);
+                        acc[k] = fmaf(xv[e], w.x, acc[k]); acc[k] = fmaf(xv[e + 1], w.y, acc[k]);
+                        acc[k] = fmaf(xv[e + 2], w.z, acc[k]); acc[k] = fmaf(xv[e + 3], w.w, acc[k]);
+                    }
+                }
+            }
+            float mx = -INFINITY;
+#pragma unroll
+            for (int k = 0; k < KMAX; ++k) if (k < K) mx = fmaxf(mx, acc[k]);
+            float sum = 0.f;
+#pragma unroll
+            for (int k = 0; k < KMAX; ++k) { acc[k] = (k < K) ? expf(acc[k] - mx) : 0.f; sum += acc[k]; }
+            const float inv = 1.0f / sum;
+#pragma unroll
+            for (int k = 0; k < KMAX; ++k) acc[k] *= inv;          // P (softmax over slots, steve.py:77)
+            if (attn_g) {
+                TokT* ar = attn_g + (size_t)(n0 + n) * K;
+#pragma unroll
+                for (int k = 0; k < KMAX; ++k) if (k < K) ar[k] = Tok<TokT>::from_f(acc[k]);
+            }
+            float* cr = coef + (size_t)n * cst;
+#pragma unroll
+            for (int k = 0; k < KMAX; k += 4) {
+                if (k < KP) {
+                    float4 a;
+                    a.x = (k + 0 < K) ? acc[k + 0] + d.eps : 0.f;   // A = P + eps (steve.py:81)
+                    a.y = (k + 1 < K) ? acc[k + 1] + d.eps : 0.f;
+                    a.z = (k + 2 < K) ? acc[k + 2] + d.eps : 0.f;
+                    a.w = (k + 3 < K) ? acc[k + 3] + d.eps : 0.f;
+                    st4(cr + k, a);
+                }
+            }
+        }
+        __syncthreads();
+        tile_outer_accum<TokT>(acc_s, ssum_s, coef, cst, xs, xst, tn, KP, D);
+    }
+    __syncthreads();
+    for (int i = tid; i < K * D; i += NT) part_g[i] = acc_s[i];
+    for (int i = tid; i < KP; i += NT) part_g[(size_t)K * D + i] = ssum_s[i];
+}
+
+// Multi-head self-attention core of the predictor on one clip (transformer.py:34-47).
+// Q is already scaled by dh^-1/2.  att: [H][K][K] (global), O: [K][Ds].
+static __device__ void mha_core_fwd(const float* Q, const float* Kk, const float* V, float* att, float* O,
+                             int K, int Ds, int H) {
+    const int dh = Ds / H, tid = threadIdx.x;
+    for (int idx = tid; idx < H * K * K; idx += NT) {
+        const int j = idx % K, i = (idx / K) % K, h = idx / (K * K);
+        const float* q = Q + (size_t)i * Ds + h * dh;
+        const float* k = Kk + (size_t)j * Ds + h * dh;
+        float s = 0.f;
+        for (int c = 0; c < dh; ++c) s = fmaf(q[c], k[c], s);
+        att[idx] = s;
+    }
+    __syncthreads();
+    for (int row = tid; row < H * K; row += NT) {
+        float* a = att + (size_t)row * K;
+        float mx = -INFINITY;
+        for (int j = 0; j < K; ++j) mx = fmaxf(mx, a[j]);
+        float sum = 0.f;
+        for (int j = 0; j < K; ++j) { float e = expf(a[j] - mx); a[j] = e; sum += e; }
+        const float inv = 1.0f / sum;
+        for (int j = 0; j < K; ++j) a[j] *= inv;
+    }
+    __syncthreads();
+    for (int idx = tid; idx < K * Ds; idx += NT) {
+        const int c = idx % Ds, i = idx / Ds, h = c / dh;
+        const float* a = att + ((size_t)h * K + i) * K;
+        float s = 0.f;
+        for (int j = 0; j < K; ++j) s = fmaf(a[j], V[(size_t)j * Ds + c], s);
+        O[idx] = s;
+    }
+    __syncthreads();
+}
+
+// ---------------------------------------------------------------------------
+// K2: the whole T x I recurrence of one clip.  grid = B * CN CTAs, cluster CN.
+// ---------------------------------------------------------------------------
+template <typename TokT, int KMAX>
+__global__ void __launch_bounds__(NT, 1) savi_fwd_kernel(const __grid_constant__ FwdArgs a) {
+    extern __shared__ float4 smem4[];
+    unsigned char* smem = reinterpret_cast<unsigned char*>(smem4);
+    float* arena = reinterpret_cast<float*>(smem4);
+    const Dims& d = a.d;
+    const ParamOff& po = a.po;
+    const int tid = threadIdx.x;
+    const int CN = d.CN, b = blockIdx.x / CN, rank = blockIdx.x % CN;
+    const int K = d.K, Ds = d.Ds, D = d.D, M = d.M, B = d.B, KP = d.KP;
+    const int per = ((d.N + CN - 1) / CN + 3) & ~3;
+    const int n_lo = min(d.N, rank * per), n_hi = min(d.N, n_lo + per);
+    const float* P = a.packed;
+    float* fb = reinterpret_cast<float*>(a.saved + a.sl.fbase);
+    const TokT* xhat = reinterpret_cast<const TokT*>(a.saved + a.sl.xhat);
+    float* cs = a.ws + a.wl.cta + (size_t)blockIdx.x * a.wl.cta_floats;    // this CTA's scratch
+    float* h = cs + a.wl.h;
+    float* st = cs + a.wl.st;
+    float* gi = cs + a.wl.gi;
+    float* gh = cs + a.wl.gh;
+    const bool lead = (rank == 0);
+    const int AF = a.arena_floats;
+#define LIN(Y, ldy, X, ldx, W, ldw, bias, Res, ldr, R_, C_, O_, alpha, fl) \
+    cta_linear(Y, ldy, X, ldx, W, ldw, bias, Res, ldr, nullptr, 0, R_, C_, O_, alpha, fl, arena, AF)
+
+    // slots0 = mu + exp(log_sigma) * noise   (steve.py:56-57)
+    for (int i = tid; i < K * Ds; i += NT) {
+        const int c = i % Ds;
+        h[i] = P[po.slot_mu + c] + expf(P[po.slot_log_sigma + c]) * a.noise[(size_t)b * K * Ds + i];
+    }
+    __syncthreads();
+
+    for (int t = 0; t < d.T; ++t) {
+        const TokT* xh_t = xhat + ((size_t)b * d.T + t) * d.N * D;
+        for (int it = 0; it < d.I; ++it) {
+            const int64_t s = (int64_t)t * d.I + it;
+            // step record: the saved arrays for the cluster leader, a private shadow for the other ranks
+            float* r_hp = lead ? frow(fb, a.sl.hp, s, b, B, K, Ds) : cs + a.wl.sh_hp;
+            float* r_q = lead ? frow(fb, a.sl.q, s, b, B, K, Ds) : cs + a.wl.sh_q;
+            float* r_qk = lead ? frow(fb, a.sl.qk, s, b, B, K, D) : cs + a.wl.sh_qk;
+            float* r_ux = lead ? frow(fb, a.sl.ux, s, b, B, K, D) : cs + a.wl.sh_ux;
+            float* r_u = lead ? frow(fb, a.sl.u, s, b, B, K, Ds) : cs + a.wl.sh_u;
+            float* r_r = lead ? frow(fb, a.sl.r, s, b, B, K, Ds) : cs + a.wl.sh_r;
+            float* r_z = lead ? frow(fb, a.sl.z, s, b, B, K, Ds) : cs + a.wl.sh_z;
+            float* r_n = lead ? frow(fb, a.sl.n, s, b, B, K, Ds) : cs + a.wl.sh_n;
+            float* r_ghn = lead ? frow(fb, a.sl.ghn, s, b, B, K, Ds) : cs + a.wl.sh_ghn;
+            float* r_ss = lead ? fb + a.sl.ssum + (s * B + b) * KP : cs + a.wl.sh_ssum;
+
+            cta_copy(r_hp, h, K * Ds);                                                   // slots_prev (steve.py:71)
+            cta_ln(st, Ds, h, Ds, P + po.ln_s_w, P + po.ln_s_b, K, Ds, d.ln_eps);      // :72
+            LIN(r_q, Ds, st, Ds, P + po.wq_t, Ds, nullptr, nullptr, 0, K, Ds, Ds, 1.0f, 0);            // :75
+            LIN(r_qk, D, r_q, Ds, P + po.wk, D, nullptr, nullptr, 0, K, Ds, D, d.qscale, 0);           // fold Wk and Ds^-1/2 (:61,63)
+
+            float* part = a.ws + a.wl.part + (((size_t)b * 2 + (s & 1)) * CN + rank) * ((size_t)K * D + KP);
+            TokT* attn_t = (it == d.I - 1) ? reinterpret_cast<TokT*>(a.attn_out) + ((size_t)b * d.T + t) * d.N * K : nullptr;
+            token_pass_fwd<TokT, KMAX>(d, xh_t, n_lo, n_hi, r_qk, part, attn_t, smem, a.TN);
+            __threadfence();
+            sync_clip(CN);
+            // combine the ranks' partial sums in a fixed order: Ux = (sum A x) / (sum A)   (:82-83)
+            {
+                const float* pb = a.ws + a.wl.part + (((size_t)b * 2 + (s & 1)) * CN) * ((size_t)K * D + KP);
+                const size_t pstride = (size_t)K * D + KP;
+                for (int i = tid; i < K * D; i += NT) {
+                    const int k = i / D;
+                    float num = 0.f, den = 0.f;
+                    for (int r = 0; r < CN; ++r) { num += __ldcg(pb + r * pstride + i); den += __ldcg(pb + r * pstride + (size_t)K * D + k); }
+                    r_ux[i] = num / den;
+                    if (i % D == 0) r_ss[k] = den;
+                }
+                __syncthreads();
+            }
+            LIN(r_u, Ds, r_ux, D, P + po.wv_t, Ds, nullptr, nullptr, 0, K, D, Ds, 1.0f, 0);              // updates (:83)
+            LIN(gi, 3 * Ds, r_u, Ds, P + po.wih_t, 3 * Ds, P + po.bih, nullptr, 0, K, Ds, 3 * Ds, 1.0f, 0);   // GRUCell (:87)
+            LIN(gh, 3 * Ds, r_hp, Ds, P + po.whh_t, 3 * Ds, P + po.bhh, nullptr, 0, K, Ds, 3 * Ds, 1.0f, 0);
+            const bool mlp = (it < d.I - 1);
+            float* r_hg = nullptr; float* r_a = nullptr;
+            if (mlp) {
+                const int64_t sm = (int64_t)t * (d.I - 1) + it;
+                r_hg = lead ? frow(fb, a.sl.hg, sm, b, B, K, Ds) : cs + a.wl.sh_hg;
+                r_a = lead ? frow(fb, a.sl.a, sm, b, B, K, M) : cs + a.wl.sh_a;
+            }
+            for (int i = tid; i < K * Ds; i += NT) {
+                const int k = i / Ds, c = i - k * Ds;
+                const float* gik = gi + (size_t)k * 3 * Ds; const float* ghk = gh + (size_t)k * 3 * Ds;
+                const float r = sigmoidf_(gik[c] + ghk[c]);
+                const float z = sigmoidf_(gik[Ds + c] + ghk[Ds + c]);
+                const float ghn = ghk[2 * Ds + c];
+                const float n = tanhf(gik[2 * Ds + c] + r * ghn);
+                const float hn = (1.0f - z) * n + z * r_hp[i];
+                r_r[i] = r; r_z[i] = z; r_n[i] = n; r_ghn[i] = ghn;
+                h[i] = hn;
+                if (mlp) r_hg[i] = hn;
+            }
+            __syncthreads();
+            if (mlp) {                                                                    // residual MLP (:92-93)
+                cta_ln(st, Ds, h, Ds, P + po.ln_m_w, P + po.ln_m_b, K, Ds, d.ln_eps);
+                LIN(r_a, M, st, Ds, P + po.w1_t, M, P + po.b1, nullptr, 0, K, Ds, M, 1.0f, LIN_RELU);
+                LIN(h, Ds, r_a, M, P + po.w2_t, Ds, P + po.b2, r_hg, Ds, K, M, Ds, 1.0f, 0);
+            }
+        }
+        if (lead) cta_copy(a.slots_out + ((size_t)b * d.T + t) * K * Ds, h, K * Ds);     // collect (:96-97)
+        if (t < d.T - 1) {
+            // predictor (:100).  The reference also evaluates it after the last frame and discards the result.
+            if (lead) cta_copy(fb + a.sl.px0 + ((size_t)t * B + b) * K * Ds, h, K * Ds);
+            __syncthreads();
+            const float hscale = 1.0f / sqrtf((float)(Ds / d.heads));
+            const float* x = h;
+            for (int j = 0; j < d.blocks; ++j) {
+                const int64_t f = (int64_t)j * (d.T - 1) + t;        // block j's rows are contiguous
+                const BlockOff& bo = po.blk[j];
+                const BlockOffT& bt = po.blkt[j];
+                float* p_y = lead ? frow(fb, a.sl.py, f, b, B, K, Ds) : cs + a.wl.sh_py;
+                float* p_q = lead ? frow(fb, a.sl.pq, f, b, B, K, Ds) : cs + a.wl.sh_pq;
+                float* p_k = lead ? frow(fb, a.sl.pk, f, b, B, K, Ds) : cs + a.wl.sh_pk;
+                float* p_v = lead ? frow(fb, a.sl.pv, f, b, B, K, Ds) : cs + a.wl.sh_pv;
+                float* p_o = lead ? frow(fb, a.sl.po, f, b, B, K, Ds) : cs + a.wl.sh_po;
+                float* p_x1 = lead ? frow(fb, a.sl.px1, f, b, B, K, Ds) : cs + a.wl.sh_px1;
+                float* p_l2 = lead ? frow(fb, a.sl.pl2, f, b, B, K, Ds) : cs + a.wl.sh_pl2;
+                float* p_f = lead ? frow(fb, a.sl.pf, f, b, B, K, 4 * Ds) : cs + a.wl.sh_pf;
+                float* p_x2 = lead ? frow(fb, a.sl.px2, f, b, B, K, Ds) : cs + a.wl.sh_px2;
+                float* p_att = lead ? fb + a.sl.patt + (f * B + b) * ((int64_t)d.heads * K * K) : cs + a.wl.sh_patt;
+                cta_ln(p_y, Ds, x, Ds, P + bo.ln1_w, P + bo.ln1_b, K, Ds, d.ln_eps);
+                LIN(p_q, Ds, p_y, Ds, P + bt.pq_t, Ds, nullptr, nullptr, 0, K, Ds, Ds, hscale, 0);
+                LIN(p_k, Ds, p_y, Ds, P + bt.pk_t, Ds, nullptr, nullptr, 0, K, Ds, Ds, 1.0f, 0);
+                LIN(p_v, Ds, p_y, Ds, P + bt.pv_t, Ds, nullptr, nullptr, 0, K, Ds, Ds, 1.0f, 0);
+                mha_core_fwd(p_q, p_k, p_v, p_att, p_o, K, Ds, d.heads);
+                // first block adds the residual to the NORMALISED input (transformer.py:75-78)
+                LIN(p_x1, Ds, p_o, Ds, P + bt.po_t, Ds, nullptr, (j == 0) ? p_y : x, Ds, K, Ds, Ds, 1.0f, 0);
+                cta_ln(p_l2, Ds, p_x1, Ds, P + bo.ln2_w, P + bo.ln2_b, K, Ds, d.ln_eps);
+                LIN(p_f, 4 * Ds, p_l2, Ds, P + bt.f1_t, 4 * Ds, P + bo.f1b, nullptr, 0, K, Ds, 4 * Ds, 1.0f, LIN_RELU);
+                LIN(p_x2, Ds, p_f, 4 * Ds, P + bt.f2_t, Ds, P + bo.f2b, p_x1, Ds, K, 4 * Ds, Ds, 1.0f, 0);
+                x = p_x2;
+            }
+            cta_ln(st, Ds, x, Ds, P + po.lnf_w, P + po.lnf_b, K, Ds, d.ln_eps);
+            cta_copy(h, st, K * Ds);
+            __syncthreads();
+        }
+    }
+#undef LIN
+}
+
+// ---------------------------------------------------------------------------
+// host-side launchers
+// ---------------------------------------------------------------------------
+template <typename TokT>
+static cudaError_t launch_ln_fwd(const FwdArgs& a, const void* inputs, cudaStream_t st) {
+    const int64_t rows = (int64_t)a.d.B * a.d.T * a.d.N;
+    int grid = (int)((rows + NW - 1) / NW);
+    if (grid > 148 * 16) grid = 148 * 16;
+    ln_tokens_fwd_kernel<TokT><<<grid, NT, 0, st>>>(
+        reinterpret_cast<const TokT*>(inputs), reinterpret_cast<TokT*>(a.saved + a.sl.xhat),
+        reinterpret_cast<float2*>(a.saved + a.sl.stats), a.packed + a.po.ln_in_w, a.packed + a.po.ln_in_b, rows, a.d.D,
+        a.d.ln_eps);
+    return cudaGetLastError();
+}
+
+template <typename TokT, int KMAX>
+static cudaError_t launch_fwd_t(const FwdArgs& a, cudaStream_t st) {
+    auto kern = savi_fwd_kernel<TokT, KMAX>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, a.smem_bytes);
+    if (e != cudaSuccess) return e;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(a.d.B * a.d.CN);
+    cfg.blockDim = dim3(NT);
+    cfg.dynamicSmemBytes = a.smem_bytes;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = a.d.CN; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kern, a);
+}
+
+template <typename TokT>
+static cudaError_t launch_fwd_k(const FwdArgs& a, cudaStream_t st) {
+    const int K = a.d.K;
+    if (K <= 8) return launch_fwd_t<TokT, 8>(a, st);
+    if (K <= 16) return launch_fwd_t<TokT, 16>(a, st);
+    if (K <= 24) return launch_fwd_t<TokT, 24>(a, st);
+    if (K <= 32) return launch_fwd_t<TokT, 32>(a, st);
+    return launch_fwd_t<TokT, 64>(a, st);
+}
+
+#ifndef SAVI_TOK
+#error "compile with -DSAVI_TOK=float -DSAVI_SUFFIX=f32 (or __nv_bfloat16 / bf16)"
+#endif
+#define SAVI_CAT2(a, b) a##b
+#define SAVI_CAT(a, b) SAVI_CAT2(a, b)
+
+cudaError_t SAVI_CAT(savi_launch_forward_, SAVI_SUFFIX)(const FwdArgs& a, const void* inputs, cudaStream_t st, int* launches) {
+    savi_prof_begin(1, st);
+    cudaError_t e = launch_ln_fwd<SAVI_TOK>(a, inputs, st);
+    savi_prof_end(1, st);
+    if (e != cudaSuccess) return e;
+    savi_prof_begin(2, st);
+    e = launch_fwd_k<SAVI_TOK>(a, st);
+    savi_prof_end(2, st);
+    *launches += 2;
+    return e;
+}

@@ -1,0 +1,134 @@
+// Weight-gradient GEMM and the backward launch sequence.
+#include "savi_dev.cuh"
+#include "savi_args.h"
+
+// ---------------------------------------------------------------------------
+// K4: weight gradients.  dW[o][c] += alpha * sum_r dY[r][o] X[r][c] for every weight
+// matrix in one launch; r runs over all steps and clips (tall-skinny TN GEMM,
+// split along r, fp32 atomics into the zeroed flat gradient buffer).
+// ---------------------------------------------------------------------------
+constexpr int WG_T = 64, WG_R = 16;
+__global__ void __launch_bounds__(256) wgrad_kernel(const __grid_constant__ WgradArgs wa) {
+    const WgradJob& jb = wa.job[blockIdx.z];
+    const int to = (jb.O + WG_T - 1) / WG_T, tc = (jb.C + WG_T - 1) / WG_T;
+    if ((int)blockIdx.x >= to * tc) return;
+    const int o0 = (blockIdx.x / tc) * WG_T, c0 = (blockIdx.x % tc) * WG_T;
+    const int r_begin = blockIdx.y * wa.rows_per_split;
+    if (r_begin >= jb.R) return;
+    const int r_end = min(jb.R, r_begin + wa.rows_per_split);
+    __shared__ __align__(16) float ys[WG_R][WG_T];
+    __shared__ __align__(16) float xs[WG_R][WG_T];
+    const int tid = threadIdx.x, ty = tid >> 4, tx = tid & 15;
+    const int lr = tid >> 4, lc = (tid & 15) * 4;        // loader: row lr, 4 columns at lc
+    float acc[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+    for (int r0 = r_begin; r0 < r_end; r0 += WG_R) {
+        const int r = r0 + lr;
+        float4 yv = make_float4(0.f, 0.f, 0.f, 0.f), xv = yv;
+        if (r < r_end) {
+            const float* yp = jb.dY + (size_t)r * jb.ldy + o0 + lc;
+            const float* xp = jb.X + (size_t)r * jb.ldx + c0 + lc;
+            if (o0 + lc + 3 < jb.O) yv = ld4(yp);
+            else { if (o0 + lc < jb.O) yv.x = yp[0]; if (o0 + lc + 1 < jb.O) yv.y = yp[1]; if (o0 + lc + 2 < jb.O) yv.z = yp[2]; }
+            if (c0 + lc + 3 < jb.C) xv = ld4(xp);
+            else { if (c0 + lc < jb.C) xv.x = xp[0]; if (c0 + lc + 1 < jb.C) xv.y = xp[1]; if (c0 + lc + 2 < jb.C) xv.z = xp[2]; }
+        }
+        __syncthreads();
+        st4(&ys[lr][lc], yv);
+        st4(&xs[lr][lc], xv);
+        __syncthreads();
+#pragma unroll
+        for (int rr = 0; rr < WG_R; ++rr) {
+            const float4 y = ld4(&ys[rr][ty * 4]);
+            const float4 x = ld4(&xs[rr][tx * 4]);
+            const float yy[4] = {y.x, y.y, y.z, y.w};
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                acc[i][0] = fmaf(yy[i], x.x, acc[i][0]); acc[i][1] = fmaf(yy[i], x.y, acc[i][1]);
+                acc[i][2] = fmaf(yy[i], x.z, acc[i][2]); acc[i][3] = fmaf(yy[i], x.w, acc[i][3]);
+            }
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int o = o0 + ty * 4 + i;
+        if (o < jb.O) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int c = c0 + tx * 4 + j;
+                if (c < jb.C) atomicAdd(jb.dW + (size_t)o * jb.C + c, jb.alpha * acc[i][j]);
+            }
+        }
+    }
+}
+
+
+cudaError_t savi_launch_forward(const FwdArgs& a, const void* inputs, cudaStream_t st, int* launches) {
+    return a.d.tok_bytes == 4 ? savi_launch_forward_f32(a, inputs, st, launches) : savi_launch_forward_bf16(a, inputs, st, launches);
+}
+
+static void add_job(WgradArgs& wa, const float* dY, int ldy, const float* X, int ldx, float* dW, int64_t R, int O, int C, float alpha) {
+    if (R <= 0) return;
+    WgradJob& j = wa.job[wa.njobs++];
+    j.dY = dY; j.X = X; j.dW = dW; j.R = (int)R; j.O = O; j.C = C; j.ldy = ldy; j.ldx = ldx; j.alpha = alpha;
+}
+
+cudaError_t savi_launch_backward(const BwdArgs& a, const void* inputs, void* grad_inputs, cudaStream_t st, int* launches) {
+    const Dims& d = a.d;
+    cudaError_t e = cudaMemsetAsync(a.grad_params, 0, (size_t)a.po.total * sizeof(float), st);
+    if (e != cudaSuccess) return e;
+    savi_prof_begin(3, st);
+    if (d.tok_bytes == 4) e = savi_launch_bwd_clip_f32(a, st); else e = savi_launch_bwd_clip_bf16(a, st);
+    savi_prof_end(3, st);
+    if (e != cudaSuccess) return e;
+    *launches += 1;
+
+    const float* fb = reinterpret_cast<const float*>(a.saved + a.sl.fbase);
+    const float* W = a.ws;
+    float* G = a.grad_params;
+    const int Ds = d.Ds, D = d.D, M = d.M;
+    const int64_t R = (int64_t)d.S * d.B * d.K, Rm = (int64_t)d.Sm * d.B * d.K, Rb = (int64_t)(d.T - 1) * d.B * d.K;
+    WgradArgs wa; wa.njobs = 0;
+    add_job(wa, W + a.wl.dq, Ds, W + a.wl.st, Ds, G + a.po.wq, R, Ds, Ds, 1.0f);
+    add_job(wa, fb + a.sl.q, Ds, W + a.wl.dqk, D, G + a.po.wk, R, Ds, D, d.qscale);
+    add_job(wa, W + a.wl.du, Ds, fb + a.sl.ux, D, G + a.po.wv, R, Ds, D, 1.0f);
+    add_job(wa, W + a.wl.dgi, 3 * Ds, fb + a.sl.u, Ds, G + a.po.wih, R, 3 * Ds, Ds, 1.0f);
+    add_job(wa, W + a.wl.dgh, 3 * Ds, fb + a.sl.hp, Ds, G + a.po.whh, R, 3 * Ds, Ds, 1.0f);
+    add_job(wa, W + a.wl.da, M, W + a.wl.m, Ds, G + a.po.w1, Rm, M, Ds, 1.0f);
+    add_job(wa, W + a.wl.dhm, Ds, fb + a.sl.a, M, G + a.po.w2, Rm, Ds, M, 1.0f);
+    for (int j = 0; j < d.blocks; ++j) {
+        const int64_t ro = (int64_t)j * Rb;      // block j's rows are contiguous: f = j*(T-1)+t
+        const BlockOff& bo = a.po.blk[j];
+        add_job(wa, W + a.wl.pdq + ro * Ds, Ds, fb + a.sl.py + ro * Ds, Ds, G + bo.pq, Rb, Ds, Ds, 1.0f);
+        add_job(wa, W + a.wl.pdk + ro * Ds, Ds, fb + a.sl.py + ro * Ds, Ds, G + bo.pk, Rb, Ds, Ds, 1.0f);
+        add_job(wa, W + a.wl.pdv + ro * Ds, Ds, fb + a.sl.py + ro * Ds, Ds, G + bo.pv, Rb, Ds, Ds, 1.0f);
+        add_job(wa, W + a.wl.pdx1 + ro * Ds, Ds, fb + a.sl.po + ro * Ds, Ds, G + bo.po, Rb, Ds, Ds, 1.0f);
+        add_job(wa, W + a.wl.pdf + ro * 4 * Ds, 4 * Ds, fb + a.sl.pl2 + ro * Ds, Ds, G + bo.f1, Rb, 4 * Ds, Ds, 1.0f);
+        add_job(wa, W + a.wl.pdx2 + ro * Ds, Ds, fb + a.sl.pf + ro * 4 * Ds, 4 * Ds, G + bo.f2, Rb, Ds, 4 * Ds, 1.0f);
+    }
+    if (wa.njobs > 0) {
+        int maxR = 0, maxTiles = 0;
+        for (int j = 0; j < wa.njobs; ++j) {
+            maxR = wa.job[j].R > maxR ? wa.job[j].R : maxR;
+            int tl = ((wa.job[j].O + WG_T - 1) / WG_T) * ((wa.job[j].C + WG_T - 1) / WG_T);
+            maxTiles = tl > maxTiles ? tl : maxTiles;
+        }
+        wa.rows_per_split = 512;
+        int splits = (maxR + wa.rows_per_split - 1) / wa.rows_per_split;
+        if (splits > 256) { wa.rows_per_split = ((maxR + 255) / 256 + WG_R - 1) / WG_R * WG_R; splits = (maxR + wa.rows_per_split - 1) / wa.rows_per_split; }
+        savi_prof_begin(4, st);
+        wgrad_kernel<<<dim3(maxTiles, splits, wa.njobs), 256, 0, st>>>(wa);
+        savi_prof_end(4, st);
+        e = cudaGetLastError();
+        if (e != cudaSuccess) return e;
+        *launches += 1;
+    }
+    savi_prof_begin(5, st);
+    if (d.tok_bytes == 4) e = savi_launch_ln_bwd_f32(a, inputs, grad_inputs, st); else e = savi_launch_ln_bwd_bf16(a, inputs, grad_inputs, st);
+    savi_prof_end(5, st);
+    *launches += 1;
+    return e;
+}

@@ -115,6 +115,14 @@ def _softmax(x):
     return e / e.sum(-1, keepdims=True)
 
 
+def round_bf16(a):
+    """Round-to-nearest-even to bfloat16 precision (returned in a's dtype)."""
+    f = np.ascontiguousarray(a, dtype=np.float32)
+    u = f.view(np.uint32).astype(np.uint64)
+    u = ((u + 0x7FFF + ((u >> 16) & 1)) >> 16) << 16
+    return u.astype(np.uint32).view(np.float32).astype(a.dtype).reshape(a.shape)
+
+
 def _acc(d, k, v):
     d[k] = d.get(k, 0) + v
 
@@ -193,11 +201,15 @@ def _predictor_bwd(P, sv, dout, blocks, heads, G):
 # ----------------------------------------------------------------------------
 # forward
 # ----------------------------------------------------------------------------
-def forward(P, x, noise, num_iterations, heads, eps=1e-8, folded=True, keep=False):
+def forward(P, x, noise, num_iterations, heads, eps=1e-8, folded=True, keep=False, token_dtype=None):
     """x [B,T,N,D], noise [B,K,Ds] -> slots [B,T,K,Ds], attn [B,T,N,K] (pre-eps softmax).
 
     dtype follows x (run float64 for the oracle, float32 to measure rounding).
     keep=True also returns everything backward() needs.
+    token_dtype="bf16" models the ONE quantisation point of the CUDA bf16 mode: the
+    LayerNorm'd token stream xhat is stored in bfloat16 (everything on the slot side
+    stays fp32 there, fp64 here); backward() then differentiates that same function
+    (rounding treated as identity), which is what the kernels compute.
     """
     dt = x.dtype
     P = {k: np.asarray(v, dtype=dt) for k, v in P.items()}
@@ -210,6 +222,8 @@ def forward(P, x, noise, num_iterations, heads, eps=1e-8, folded=True, keep=Fals
 
     h = P["slot_mu"] + np.exp(P["slot_log_sigma"]) * noise.astype(dt)       # steve.py:56-57
     xhat, zx, rx = _ln(x, P["norm_inputs.weight"], P["norm_inputs.bias"])   # steve.py:60
+    if token_dtype == "bf16":
+        xhat = round_bf16(xhat)
     if not folded:
         k = (xhat @ P["project_k.weight"].T) * sc                           # steve.py:61,63
         v = xhat @ P["project_v.weight"].T                                  # steve.py:62

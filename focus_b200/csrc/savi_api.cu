@@ -3,7 +3,8 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
-#include "savi_dev.cuh"
+#include <cstdlib>
+#include "savi_dx_mma.cuh"
 #include "savi_args.h"
 
 static thread_local char g_err[512] = "";
@@ -89,6 +90,14 @@ static int validate(const SaviShape* s, Dims& d) {
     d.S = s->T * s->I; d.Sm = s->T * (s->I - 1); d.Sp = (s->T - 1) * s->blocks;
     d.tok_bytes = s->dtype == SAVI_DTYPE_F32 ? 4 : 2;
     d.eps = s->eps; d.ln_eps = s->ln_eps; d.qscale = 1.0f / sqrtf((float)s->Ds);
+    d.KC = ((s->K + 15) / 16) * 16;
+    // tensor-core path: bf16 token stream and shapes the mma.sync tiles cover; everything else takes the SIMT path
+    const int MT = d.KC / 16 == 3 ? 4 : d.KC / 16;
+    d.mma = (s->dtype == SAVI_DTYPE_BF16 && s->D % 16 == 0 && s->D <= 256 && s->Ds % 8 == 0 && s->M % 8 == 0 &&
+             s->N % 8 == 0 && !getenv("SAVI_DISABLE_MMA") &&
+             dx_smem_bytes(s->I, d.KC, s->D) <= (size_t)kMaxSmem &&
+             tmma_smem_bytes(MT, s->D, s->K, 1, true) <= (size_t)kMaxSmem) ? 1 : 0;
+    if (d.mma) d.KC = MT * 16;
     return SAVI_OK;
 }
 
@@ -104,7 +113,21 @@ size_t savi_bwd_smem_bytes(const Dims& d, int TN) {
 }
 
 // tokens per tile: the largest of 256..16 that fits; the same dynamic smem doubles as the linear-layer arena
-static int plan_smem(const Dims& d, bool bwd, int* TN, int* arena_floats, int* smem_bytes) {
+static int plan_smem(const Dims& d, bool bwd, int* TN, int* arena_floats, int* smem_bytes, int* stages) {
+    *stages = 1;
+    if (d.mma) {
+        const int MT = d.KC / 16;
+        int cmax = 4 * d.Ds; if (d.M > cmax) cmax = d.M; if (d.D > cmax) cmax = d.D;
+        size_t tok = tmma_smem_bytes(MT, d.D, d.K, 2, bwd);
+        *stages = 2;
+        if (tok > (size_t)kMaxSmem) { tok = tmma_smem_bytes(MT, d.D, d.K, 1, bwd); *stages = 1; }
+        size_t want = lin_mma_smem(MT, cmax);
+        if (want > (size_t)kMaxSmem) want = (size_t)160 * 1024;     // such layers fall back to the SIMT linear inside the kernel
+        size_t bytes = tok > want ? tok : want;
+        bytes = (bytes + 15) / 16 * 16;
+        *TN = TMMA_TN; *smem_bytes = (int)bytes; *arena_floats = (int)(bytes / 4);
+        return SAVI_OK;
+    }
     int per = ((d.N + d.CN - 1) / d.CN + 3) & ~3;
     int tn = 256;
     while (tn > 16 && (tn / 2 >= per || (bwd ? savi_bwd_smem_bytes(d, tn) : savi_fwd_smem_bytes(d, tn)) > (size_t)kMaxSmem - 1024)) tn /= 2;
@@ -130,11 +153,12 @@ extern "C" int savi_query(const SaviShape* shape, SaviSizes* sizes) {
     FwdWsLayout fl; savi_fwd_ws_layout(d, fl);
     BwdWsLayout bl; savi_bwd_ws_layout(d, bl);
     int tn, af, sb;
-    if ((rc = plan_smem(d, false, &tn, &af, &sb))) return rc;
-    if ((rc = plan_smem(d, true, &tn, &af, &sb))) return rc;
+    int stg;
+    if ((rc = plan_smem(d, false, &tn, &af, &sb, &stg))) return rc;
+    if ((rc = plan_smem(d, true, &tn, &af, &sb, &stg))) return rc;
     sizes->n_params = 21 + 12 * shape->blocks;
     sizes->param_floats = po.total;
-    sizes->packed_bytes = (int64_t)po.packed_total * 4;
+    sizes->packed_bytes = (int64_t)po.packed_total * 8;      // fp32 + bf16 hi + bf16 lo images
     sizes->saved_bytes = sl.total_bytes;
     sizes->fwd_ws_bytes = fl.total_bytes;
     sizes->bwd_ws_bytes = bl.total_bytes;
@@ -201,6 +225,15 @@ __global__ void pack_transpose_kernel(const __grid_constant__ TrArgs ta, float* 
     }
 }
 
+// packed fp32 -> bf16 hi / lo images (x = hi + lo up to 2^-17 |x|)
+__global__ void pack_split_kernel(const float* __restrict__ packed, bf16* __restrict__ hi, bf16* __restrict__ lo, int n) {
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        bf16 h, l;
+        split_bf16(packed[i], h, l);
+        hi[i] = h; lo[i] = l;
+    }
+}
+
 static int check_device() {
     int dev = 0;
     cudaError_t e = cudaGetDevice(&dev);
@@ -248,9 +281,15 @@ extern "C" int savi_pack_params(const SaviShape* shape, const void* const* param
     }
     pack_transpose_kernel<<<dim3(64, ta.count), 256, 0, st>>>(ta, reinterpret_cast<float*>(packed));
     e = cudaGetLastError();
-    savi_prof_end(0, st);
     if (e != cudaSuccess) return cuda_fail(e, "pack_transpose_kernel");
-    g_launches = 2;
+    {
+        bf16* hi = reinterpret_cast<bf16*>(reinterpret_cast<float*>(packed) + po.packed_total);
+        pack_split_kernel<<<148, 512, 0, st>>>(reinterpret_cast<const float*>(packed), hi, hi + po.packed_total, po.packed_total);
+        e = cudaGetLastError();
+        if (e != cudaSuccess) return cuda_fail(e, "pack_split_kernel");
+    }
+    savi_prof_end(0, st);
+    g_launches = 3;
     return SAVI_OK;
 }
 
@@ -264,7 +303,7 @@ extern "C" int savi_forward(const SaviShape* shape, const void* packed, const vo
     savi_param_offsets(*shape, a.po);
     savi_saved_layout(a.d, a.sl);
     savi_fwd_ws_layout(a.d, a.wl);
-    if ((rc = plan_smem(a.d, false, &a.TN, &a.arena_floats, &a.smem_bytes))) return rc;
+    if ((rc = plan_smem(a.d, false, &a.TN, &a.arena_floats, &a.smem_bytes, &a.stages))) return rc;
     a.packed = reinterpret_cast<const float*>(packed);
     a.noise = reinterpret_cast<const float*>(noise);
     a.slots_out = reinterpret_cast<float*>(slots_out);
@@ -289,7 +328,7 @@ extern "C" int savi_backward(const SaviShape* shape, const void* packed, const v
     savi_param_offsets(*shape, a.po);
     savi_saved_layout(a.d, a.sl);
     savi_bwd_ws_layout(a.d, a.wl);
-    if ((rc = plan_smem(a.d, true, &a.TN, &a.arena_floats, &a.smem_bytes))) return rc;
+    if ((rc = plan_smem(a.d, true, &a.TN, &a.arena_floats, &a.smem_bytes, &a.stages))) return rc;
     a.packed = reinterpret_cast<const float*>(packed);
     a.noise = reinterpret_cast<const float*>(noise);
     a.saved = reinterpret_cast<const unsigned char*>(saved);

@@ -15,6 +15,7 @@ struct FwdArgs {
     void* attn_out;
     unsigned char* saved;
     float* ws;
+    int stages;           // token-tile pipeline depth of the tensor-core path
     int TN;               // tokens per shared-memory tile
     int arena_floats;     // floats of dynamic shared memory usable as the linear-layer staging arena
     int smem_bytes;
@@ -33,6 +34,7 @@ struct BwdArgs {
     float* grad_params;         // flat, zeroed before the clip kernel
     float* grad_noise;          // nullable
     float* ws;
+    int stages;
     int TN;
     int arena_floats;
     int smem_bytes;
@@ -58,6 +60,8 @@ cudaError_t savi_launch_bwd_clip_f32(const BwdArgs& a, cudaStream_t st);
 cudaError_t savi_launch_bwd_clip_bf16(const BwdArgs& a, cudaStream_t st);
 cudaError_t savi_launch_ln_bwd_f32(const BwdArgs& a, const void* inputs, void* grad_inputs, cudaStream_t st);
 cudaError_t savi_launch_ln_bwd_bf16(const BwdArgs& a, const void* inputs, void* grad_inputs, cudaStream_t st);
+cudaError_t savi_launch_dx_mma(const BwdArgs& a, const void* inputs, void* grad_inputs, cudaStream_t st);
+size_t savi_dx_smem_bytes(const Dims& d);
 static inline int savi_fwd_kmax(int K) { return K <= 8 ? 8 : K <= 16 ? 16 : K <= 24 ? 24 : K <= 32 ? 32 : 64; }
 size_t savi_fwd_smem_bytes(const Dims& d, int TN);
 size_t savi_bwd_smem_bytes(const Dims& d, int TN);

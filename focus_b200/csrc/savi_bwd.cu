@@ -3,7 +3,7 @@
 // The reference has no explicit backward (autograd through steve.py:52-105); the
 // closed form implemented here is SURVEY.md Appendix A.2 in the folded form and is
 // restated and validated against the reference's autograd in oracle/savi_numpy.py.
-#include "savi_dev.cuh"
+#include "savi_dx_mma.cuh"
 #include "savi_args.h"
 
 // ---------------------------------------------------------------------------
@@ -201,7 +201,7 @@ static __device__ void mha_core_bwd(const float* dO, const float* Q, const float
 // Writes: dxhat accumulator, the staged (dY, X) operands of the weight-gradient
 // GEMMs, vector-parameter gradients (atomics into the flat gradient buffer).
 // ---------------------------------------------------------------------------
-template <typename TokT, int KMAX>
+template <typename TokT, int KMAX, bool MMA>
 __global__ void __launch_bounds__(NT, 1) savi_bwd_kernel(const __grid_constant__ BwdArgs a) {
     extern __shared__ float4 smem4[];
     unsigned char* smem = reinterpret_cast<unsigned char*>(smem4);
@@ -211,7 +211,7 @@ __global__ void __launch_bounds__(NT, 1) savi_bwd_kernel(const __grid_constant__
     const int tid = threadIdx.x;
     const int CN = d.CN, b = blockIdx.x / CN, rank = blockIdx.x % CN;
     const int K = d.K, Ds = d.Ds, D = d.D, M = d.M, B = d.B, KP = d.KP;
-    const int per = ((d.N + CN - 1) / CN + 3) & ~3;
+    const int per = ((d.N + CN - 1) / CN + 15) & ~15;
     const int n_lo = min(d.N, rank * per), n_hi = min(d.N, n_lo + per);
     const float* P = a.packed;
     float* G = a.grad_params;
@@ -224,13 +224,18 @@ __global__ void __launch_bounds__(NT, 1) savi_bwd_kernel(const __grid_constant__
     float* t0 = cs + a.wl.t0;
     float* t1 = cs + a.wl.t1;
     float* t2 = cs + a.wl.t2;
-    float* dux = cs + a.wl.dux;
+    float* dux = cs + a.wl.dux;     // mma mode: redirected per step into the staged field array
     float* cvec = cs + a.wl.cvec;
     const bool lead = (rank == 0);
     const int AF = a.arena_floats;
     const float hscale = 1.0f / sqrtf((float)(Ds / d.heads));
-#define LIN(Y, ldy, X, ldx, Wp, ldw, Res, ldr, Mask, ldm, R_, C_, O_, alpha) \
-    cta_linear(Y, ldy, X, ldx, Wp, ldw, nullptr, Res, ldr, Mask, ldm, R_, C_, O_, alpha, 0, arena, AF)
+    constexpr int MT = (KMAX + 15) / 16;
+    const bf16* Phi = reinterpret_cast<const bf16*>(P + po.packed_total);
+    const bf16* Plo = Phi + po.packed_total;
+    // backward linears dX = dY . W contract over the OUT index: SIMT uses the original [out][in] copy as its
+    // "[C][O]" operand, the tensor-core path uses the transposed copy ([in][out] = "[O'][C']" with C' = out)
+#define LIN(Y, ldy, X, ldx, W_io, W_oi, Res, ldr, Mask, ldm, R_, C_, O_, alpha) \
+    lin<MMA, MT>(P, Phi, Plo, Y, ldy, X, ldx, W_io, W_oi, nullptr, Res, ldr, Mask, ldm, R_, C_, O_, alpha, 0, arena, AF)
 
     for (int i = tid; i < K * Ds; i += NT) dh[i] = 0.f;
     __syncthreads();
@@ -246,6 +251,7 @@ __global__ void __launch_bounds__(NT, 1) savi_bwd_kernel(const __grid_constant__
             for (int j = d.blocks - 1; j >= 0; --j) {
                 const int64_t f = (int64_t)j * (d.T - 1) + t;
                 const BlockOff& bo = po.blk[j];
+                const BlockOffT& bt = po.blkt[j];
                 const float* p_y = frow(fb, a.sl.py, f, b, B, K, Ds);
                 const float* p_q = frow(fb, a.sl.pq, f, b, B, K, Ds);
                 const float* p_k = frow(fb, a.sl.pk, f, b, B, K, Ds);
@@ -262,15 +268,15 @@ __global__ void __launch_bounds__(NT, 1) savi_bwd_kernel(const __grid_constant__
                 (void)p_y;
                 cta_copy(s_dx2, t0, K * Ds);
                 if (lead) cta_colsum_atomic(G + bo.f2b, t0, Ds, K, Ds);
-                LIN(s_df, 4 * Ds, t0, Ds, P + bo.f2, 4 * Ds, nullptr, 0, p_f, 4 * Ds, K, Ds, 4 * Ds, 1.0f);      // d relu-out, masked
+                LIN(s_df, 4 * Ds, t0, Ds, bo.f2, bt.f2_t, nullptr, 0, p_f, 4 * Ds, K, Ds, 4 * Ds, 1.0f);      // d relu-out, masked
                 if (lead) cta_colsum_atomic(G + bo.f1b, s_df, 4 * Ds, K, 4 * Ds);
-                LIN(t1, Ds, s_df, 4 * Ds, P + bo.f1, Ds, nullptr, 0, nullptr, 0, K, 4 * Ds, Ds, 1.0f);
+                LIN(t1, Ds, s_df, 4 * Ds, bo.f1, bt.f1_t, nullptr, 0, nullptr, 0, K, 4 * Ds, Ds, 1.0f);
                 cta_ln_bwd(s_dx1, Ds, t0, Ds, t1, Ds, p_x1, Ds, P + bo.ln2_w, G + bo.ln2_w, G + bo.ln2_b, K, Ds, d.ln_eps, lead);
-                LIN(t1, Ds, s_dx1, Ds, P + bo.po, Ds, nullptr, 0, nullptr, 0, K, Ds, Ds, 1.0f);                  // dO
+                LIN(t1, Ds, s_dx1, Ds, bo.po, bt.po_t, nullptr, 0, nullptr, 0, K, Ds, Ds, 1.0f);                  // dO
                 mha_core_bwd(t1, p_q, p_k, p_v, p_att, t2, s_dq, s_dk, s_dv, K, Ds, d.heads, hscale);
-                LIN(t1, Ds, s_dq, Ds, P + bo.pq, Ds, (j == 0) ? s_dx1 : nullptr, Ds, nullptr, 0, K, Ds, Ds, 1.0f);
-                LIN(t1, Ds, s_dk, Ds, P + bo.pk, Ds, t1, Ds, nullptr, 0, K, Ds, Ds, 1.0f);
-                LIN(t1, Ds, s_dv, Ds, P + bo.pv, Ds, t1, Ds, nullptr, 0, K, Ds, Ds, 1.0f);                      // dy
+                LIN(t1, Ds, s_dq, Ds, bo.pq, bt.pq_t, (j == 0) ? s_dx1 : nullptr, Ds, nullptr, 0, K, Ds, Ds, 1.0f);
+                LIN(t1, Ds, s_dk, Ds, bo.pk, bt.pk_t, t1, Ds, nullptr, 0, K, Ds, Ds, 1.0f);
+                LIN(t1, Ds, s_dv, Ds, bo.pv, bt.pv_t, t1, Ds, nullptr, 0, K, Ds, Ds, 1.0f);                      // dy
                 const float* x_in = (j == 0) ? px0 : frow(fb, a.sl.px2, (int64_t)(j - 1) * (d.T - 1) + t, b, B, K, Ds);
                 cta_ln_bwd(t0, Ds, (j == 0) ? nullptr : s_dx1, Ds, t1, Ds, x_in, Ds, P + bo.ln1_w, G + bo.ln1_w, G + bo.ln1_b,
                            K, Ds, d.ln_eps, lead);
@@ -310,10 +316,10 @@ __global__ void __launch_bounds__(NT, 1) savi_bwd_kernel(const __grid_constant__
                 float* s_m = lead ? frow(W, a.wl.m, sm, b, B, K, Ds) : cs + a.wl.sh_m;
                 cta_copy(s_dhm, dh, K * Ds);
                 if (lead) cta_colsum_atomic(G + po.b2, dh, Ds, K, Ds);
-                LIN(s_da, M, dh, Ds, P + po.w2, M, nullptr, 0, r_a, M, K, Ds, M, 1.0f);
+                LIN(s_da, M, dh, Ds, po.w2, po.w2_t, nullptr, 0, r_a, M, K, Ds, M, 1.0f);
                 if (lead) cta_colsum_atomic(G + po.b1, s_da, M, K, M);
                 cta_ln(s_m, Ds, r_hg, Ds, P + po.ln_m_w, P + po.ln_m_b, K, Ds, d.ln_eps);
-                LIN(t0, Ds, s_da, M, P + po.w1, Ds, nullptr, 0, nullptr, 0, K, M, Ds, 1.0f);
+                LIN(t0, Ds, s_da, M, po.w1, po.w1_t, nullptr, 0, nullptr, 0, K, M, Ds, 1.0f);
                 cta_ln_bwd(dhg, Ds, dh, Ds, t0, Ds, r_hg, Ds, P + po.ln_m_w, G + po.ln_m_w, G + po.ln_m_b, K, Ds, d.ln_eps, lead);
                 cur = dhg;
             }
@@ -331,10 +337,11 @@ __global__ void __launch_bounds__(NT, 1) savi_bwd_kernel(const __grid_constant__
             }
             __syncthreads();
             if (lead) { cta_colsum_atomic(G + po.bih, s_dgi, 3 * Ds, K, 3 * Ds); cta_colsum_atomic(G + po.bhh, s_dgh, 3 * Ds, K, 3 * Ds); }
-            LIN(dh, Ds, s_dgh, 3 * Ds, P + po.whh, Ds, dh, Ds, nullptr, 0, K, 3 * Ds, Ds, 1.0f);
-            LIN(s_du, Ds, s_dgi, 3 * Ds, P + po.wih, Ds, nullptr, 0, nullptr, 0, K, 3 * Ds, Ds, 1.0f);
+            LIN(dh, Ds, s_dgh, 3 * Ds, po.whh, po.whh_t, dh, Ds, nullptr, 0, K, 3 * Ds, Ds, 1.0f);
+            LIN(s_du, Ds, s_dgi, 3 * Ds, po.wih, po.wih_t, nullptr, 0, nullptr, 0, K, 3 * Ds, Ds, 1.0f);
             // ---- attention step backward ----
-            LIN(dux, D, s_du, Ds, P + po.wv, D, nullptr, 0, nullptr, 0, K, Ds, D, 1.0f);
+            if (MMA) dux = lead ? frow(W, a.wl.duxs, s, b, B, K, D) : cs + a.wl.dux;
+            LIN(dux, D, s_du, Ds, po.wv, po.wv_t, nullptr, 0, nullptr, 0, K, Ds, D, 1.0f);
             {
                 const int warp = tid >> 5, lane = tid & 31;
                 for (int k = warp; k < KP; k += NW) {
@@ -348,7 +355,13 @@ __global__ void __launch_bounds__(NT, 1) savi_bwd_kernel(const __grid_constant__
             float* part = W + a.wl.part + (((size_t)b * 2 + (s & 1)) * CN + rank) * ((size_t)K * D);
             const TokT* ga = (a.grad_attn && it == d.I - 1)
                                  ? reinterpret_cast<const TokT*>(a.grad_attn) + ((size_t)b * d.T + t) * d.N * K : nullptr;
-            token_pass_bwd<TokT, KMAX>(d, xh_t, n_lo, n_hi, r_qk, dux, cvec, ga, dxh_t, it != d.I - 1, part, smem, a.TN);
+            if constexpr (MMA) {
+                bf16* coef = reinterpret_cast<bf16*>(reinterpret_cast<unsigned char*>(W) + a.wl.coef) +
+                             ((((size_t)b * d.T + t) * d.I + it) * 2 * d.KC) * d.N;
+                token_pass_bwd_mma<MT>(d, xh_t, n_lo, n_hi, r_qk, dux, cvec, ga, coef, part, smem, a.stages);
+            } else {
+                token_pass_bwd<TokT, KMAX>(d, xh_t, n_lo, n_hi, r_qk, dux, cvec, ga, dxh_t, it != d.I - 1, part, smem, a.TN);
+            }
             __threadfence();
             sync_clip(CN);
             {
@@ -360,9 +373,9 @@ __global__ void __launch_bounds__(NT, 1) savi_bwd_kernel(const __grid_constant__
                 }
                 __syncthreads();
             }
-            LIN(s_dq, Ds, s_dqk, D, P + po.wk_t, Ds, nullptr, 0, nullptr, 0, K, D, Ds, d.qscale);
+            LIN(s_dq, Ds, s_dqk, D, po.wk_t, po.wk, nullptr, 0, nullptr, 0, K, D, Ds, d.qscale);
             cta_ln(s_st, Ds, r_hp, Ds, P + po.ln_s_w, P + po.ln_s_b, K, Ds, d.ln_eps);
-            LIN(t0, Ds, s_dq, Ds, P + po.wq, Ds, nullptr, 0, nullptr, 0, K, Ds, Ds, 1.0f);
+            LIN(t0, Ds, s_dq, Ds, po.wq, po.wq_t, nullptr, 0, nullptr, 0, K, Ds, Ds, 1.0f);
             cta_ln_bwd(dh, Ds, dh, Ds, t0, Ds, r_hp, Ds, P + po.ln_s_w, G + po.ln_s_w, G + po.ln_s_b, K, Ds, d.ln_eps, lead);
         }
     }
@@ -453,9 +466,9 @@ __global__ void __launch_bounds__(NT) ln_tokens_bwd_kernel(const TokT* __restric
 // ---------------------------------------------------------------------------
 // host-side launchers
 // ---------------------------------------------------------------------------
-template <typename TokT, int KMAX>
+template <typename TokT, int KMAX, bool MMA>
 static cudaError_t launch_bwd_t(const BwdArgs& a, cudaStream_t st) {
-    auto kern = savi_bwd_kernel<TokT, KMAX>;
+    auto kern = savi_bwd_kernel<TokT, KMAX, MMA>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, a.smem_bytes);
     if (e != cudaSuccess) return e;
     cudaLaunchConfig_t cfg = {};
@@ -473,11 +486,18 @@ static cudaError_t launch_bwd_t(const BwdArgs& a, cudaStream_t st) {
 template <typename TokT>
 static cudaError_t launch_bwd_k(const BwdArgs& a, cudaStream_t st) {
     const int K = a.d.K;
-    if (K <= 8) return launch_bwd_t<TokT, 8>(a, st);
-    if (K <= 16) return launch_bwd_t<TokT, 16>(a, st);
-    if (K <= 24) return launch_bwd_t<TokT, 24>(a, st);
-    if (K <= 32) return launch_bwd_t<TokT, 32>(a, st);
-    return launch_bwd_t<TokT, 64>(a, st);
+    if constexpr (sizeof(TokT) == 2) {
+        if (a.d.mma) {
+            if (K <= 16) return launch_bwd_t<TokT, 16, true>(a, st);
+            if (K <= 32) return launch_bwd_t<TokT, 32, true>(a, st);
+            return launch_bwd_t<TokT, 64, true>(a, st);
+        }
+    }
+    if (K <= 8) return launch_bwd_t<TokT, 8, false>(a, st);
+    if (K <= 16) return launch_bwd_t<TokT, 16, false>(a, st);
+    if (K <= 24) return launch_bwd_t<TokT, 24, false>(a, st);
+    if (K <= 32) return launch_bwd_t<TokT, 32, false>(a, st);
+    return launch_bwd_t<TokT, 64, false>(a, st);
 }
 
 #ifndef SAVI_TOK
@@ -500,3 +520,32 @@ cudaError_t SAVI_CAT(savi_launch_ln_bwd_, SAVI_SUFFIX)(const BwdArgs& a, const v
                                                        a.grad_params + a.po.ln_in_w, a.grad_params + a.po.ln_in_b, rows, d.D);
     return cudaGetLastError();
 }
+
+#if defined(SAVI_IS_BF16)
+size_t savi_dx_smem_bytes(const Dims& d) { return dx_smem_bytes(d.I, d.KC, d.D); }
+
+cudaError_t savi_launch_dx_mma(const BwdArgs& a, const void* inputs, void* grad_inputs, cudaStream_t st) {
+    const Dims& d = a.d;
+    DxArgs x;
+    x.x = reinterpret_cast<const bf16*>(inputs);
+    x.stats = reinterpret_cast<const float2*>(a.saved + a.sl.stats);
+    x.coef = reinterpret_cast<const bf16*>(reinterpret_cast<const unsigned char*>(a.ws) + a.wl.coef);
+    x.qk = reinterpret_cast<const float*>(a.saved + a.sl.fbase) + a.sl.qk;
+    x.dux = a.ws + a.wl.duxs;
+    x.gamma = a.packed + a.po.ln_in_w;
+    x.dx = reinterpret_cast<bf16*>(grad_inputs);
+    x.dgamma = a.grad_params + a.po.ln_in_w; x.dbeta = a.grad_params + a.po.ln_in_b;
+    x.B = d.B; x.T = d.T; x.N = d.N; x.D = d.D; x.K = d.K; x.I = d.I; x.KC = d.KC; x.tiles_per_cta = 4;
+    const int tiles = (d.N + TMMA_TN - 1) / TMMA_TN;
+    dim3 grid((tiles + x.tiles_per_cta - 1) / x.tiles_per_cta, d.B * d.T);
+    const int smem = (int)dx_smem_bytes(d.I, d.KC, d.D);
+    cudaError_t e;
+#define DX_LAUNCH(ND_) \
+    e = cudaFuncSetAttribute(dx_finalize_kernel<ND_>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); \
+    if (e != cudaSuccess) return e; \
+    dx_finalize_kernel<ND_><<<grid, NT, smem, st>>>(x);
+    if (d.D <= 64) { DX_LAUNCH(8) } else if (d.D <= 128) { DX_LAUNCH(16) } else if (d.D <= 192) { DX_LAUNCH(24) } else { DX_LAUNCH(32) }
+#undef DX_LAUNCH
+    return cudaGetLastError();
+}
+#endif

@@ -2,7 +2,7 @@
 //
 // Reference semantics: /root/reference/slowfast/models/STEVE/steve.py:52-105
 // (SlotAttentionVideo.forward) and transformer.py:22-49, 70-86, 106-114.
-#include "savi_dev.cuh"
+#include "savi_token_mma.cuh"
 #include "savi_args.h"
 
 // ---------------------------------------------------------------------------
@@ -185,7 +185,7 @@ static __device__ void mha_core_fwd(const float* Q, const float* Kk, const float
 // ---------------------------------------------------------------------------
 // K2: the whole T x I recurrence of one clip.  grid = B * CN CTAs, cluster CN.
 // ---------------------------------------------------------------------------
-template <typename TokT, int KMAX>
+template <typename TokT, int KMAX, bool MMA>
 __global__ void __launch_bounds__(NT, 1) savi_fwd_kernel(const __grid_constant__ FwdArgs a) {
     extern __shared__ float4 smem4[];
     unsigned char* smem = reinterpret_cast<unsigned char*>(smem4);
@@ -195,7 +195,7 @@ __global__ void __launch_bounds__(NT, 1) savi_fwd_kernel(const __grid_constant__
     const int tid = threadIdx.x;
     const int CN = d.CN, b = blockIdx.x / CN, rank = blockIdx.x % CN;
     const int K = d.K, Ds = d.Ds, D = d.D, M = d.M, B = d.B, KP = d.KP;
-    const int per = ((d.N + CN - 1) / CN + 3) & ~3;
+    const int per = ((d.N + CN - 1) / CN + 15) & ~15;
     const int n_lo = min(d.N, rank * per), n_hi = min(d.N, n_lo + per);
     const float* P = a.packed;
     float* fb = reinterpret_cast<float*>(a.saved + a.sl.fbase);
@@ -207,8 +207,12 @@ __global__ void __launch_bounds__(NT, 1) savi_fwd_kernel(const __grid_constant__
     float* gh = cs + a.wl.gh;
     const bool lead = (rank == 0);
     const int AF = a.arena_floats;
-#define LIN(Y, ldy, X, ldx, W, ldw, bias, Res, ldr, R_, C_, O_, alpha, fl) \
-    cta_linear(Y, ldy, X, ldx, W, ldw, bias, Res, ldr, nullptr, 0, R_, C_, O_, alpha, fl, arena, AF)
+    constexpr int MT = (KMAX + 15) / 16;
+    const bf16* Phi = reinterpret_cast<const bf16*>(P + po.packed_total);      // bf16 hi / lo images of the packed buffer
+    const bf16* Plo = Phi + po.packed_total;
+    // W_io: offset of the [in][out] fp32 copy (SIMT path), W_oi: offset of the [out][in] copy (tensor-core path)
+#define LIN(Y, ldy, X, ldx, W_io, W_oi, bias, Res, ldr, R_, C_, O_, alpha, fl) \
+    lin<MMA, MT>(P, Phi, Plo, Y, ldy, X, ldx, W_io, W_oi, bias, Res, ldr, nullptr, 0, R_, C_, O_, alpha, fl, arena, AF)
 
     // slots0 = mu + exp(log_sigma) * noise   (steve.py:56-57)
     for (int i = tid; i < K * Ds; i += NT) {
@@ -235,12 +239,13 @@ __global__ void __launch_bounds__(NT, 1) savi_fwd_kernel(const __grid_constant__
 
             cta_copy(r_hp, h, K * Ds);                                                   // slots_prev (steve.py:71)
             cta_ln(st, Ds, h, Ds, P + po.ln_s_w, P + po.ln_s_b, K, Ds, d.ln_eps);      // :72
-            LIN(r_q, Ds, st, Ds, P + po.wq_t, Ds, nullptr, nullptr, 0, K, Ds, Ds, 1.0f, 0);            // :75
-            LIN(r_qk, D, r_q, Ds, P + po.wk, D, nullptr, nullptr, 0, K, Ds, D, d.qscale, 0);           // fold Wk and Ds^-1/2 (:61,63)
+            LIN(r_q, Ds, st, Ds, po.wq_t, po.wq, nullptr, nullptr, 0, K, Ds, Ds, 1.0f, 0);            // :75
+            LIN(r_qk, D, r_q, Ds, po.wk, po.wk_t, nullptr, nullptr, 0, K, Ds, D, d.qscale, 0);           // fold Wk and Ds^-1/2 (:61,63)
 
             float* part = a.ws + a.wl.part + (((size_t)b * 2 + (s & 1)) * CN + rank) * ((size_t)K * D + KP);
             TokT* attn_t = (it == d.I - 1) ? reinterpret_cast<TokT*>(a.attn_out) + ((size_t)b * d.T + t) * d.N * K : nullptr;
-            token_pass_fwd<TokT, KMAX>(d, xh_t, n_lo, n_hi, r_qk, part, attn_t, smem, a.TN);
+            if constexpr (MMA) token_pass_fwd_mma<MT>(d, xh_t, n_lo, n_hi, r_qk, part, attn_t, smem, a.stages);
+            else token_pass_fwd<TokT, KMAX>(d, xh_t, n_lo, n_hi, r_qk, part, attn_t, smem, a.TN);
             __threadfence();
             sync_clip(CN);
             // combine the ranks' partial sums in a fixed order: Ux = (sum A x) / (sum A)   (:82-83)
@@ -256,9 +261,9 @@ __global__ void __launch_bounds__(NT, 1) savi_fwd_kernel(const __grid_constant__
                 }
                 __syncthreads();
             }
-            LIN(r_u, Ds, r_ux, D, P + po.wv_t, Ds, nullptr, nullptr, 0, K, D, Ds, 1.0f, 0);              // updates (:83)
-            LIN(gi, 3 * Ds, r_u, Ds, P + po.wih_t, 3 * Ds, P + po.bih, nullptr, 0, K, Ds, 3 * Ds, 1.0f, 0);   // GRUCell (:87)
-            LIN(gh, 3 * Ds, r_hp, Ds, P + po.whh_t, 3 * Ds, P + po.bhh, nullptr, 0, K, Ds, 3 * Ds, 1.0f, 0);
+            LIN(r_u, Ds, r_ux, D, po.wv_t, po.wv, nullptr, nullptr, 0, K, D, Ds, 1.0f, 0);              // updates (:83)
+            LIN(gi, 3 * Ds, r_u, Ds, po.wih_t, po.wih, P + po.bih, nullptr, 0, K, Ds, 3 * Ds, 1.0f, 0);   // GRUCell (:87)
+            LIN(gh, 3 * Ds, r_hp, Ds, po.whh_t, po.whh, P + po.bhh, nullptr, 0, K, Ds, 3 * Ds, 1.0f, 0);
             const bool mlp = (it < d.I - 1);
             float* r_hg = nullptr; float* r_a = nullptr;
             if (mlp) {
@@ -281,8 +286,8 @@ __global__ void __launch_bounds__(NT, 1) savi_fwd_kernel(const __grid_constant__
             __syncthreads();
             if (mlp) {                                                                    // residual MLP (:92-93)
                 cta_ln(st, Ds, h, Ds, P + po.ln_m_w, P + po.ln_m_b, K, Ds, d.ln_eps);
-                LIN(r_a, M, st, Ds, P + po.w1_t, M, P + po.b1, nullptr, 0, K, Ds, M, 1.0f, LIN_RELU);
-                LIN(h, Ds, r_a, M, P + po.w2_t, Ds, P + po.b2, r_hg, Ds, K, M, Ds, 1.0f, 0);
+                LIN(r_a, M, st, Ds, po.w1_t, po.w1, P + po.b1, nullptr, 0, K, Ds, M, 1.0f, LIN_RELU);
+                LIN(h, Ds, r_a, M, po.w2_t, po.w2, P + po.b2, r_hg, Ds, K, M, Ds, 1.0f, 0);
             }
         }
         if (lead) cta_copy(a.slots_out + ((size_t)b * d.T + t) * K * Ds, h, K * Ds);     // collect (:96-97)
@@ -307,15 +312,15 @@ __global__ void __launch_bounds__(NT, 1) savi_fwd_kernel(const __grid_constant__
                 float* p_x2 = lead ? frow(fb, a.sl.px2, f, b, B, K, Ds) : cs + a.wl.sh_px2;
                 float* p_att = lead ? fb + a.sl.patt + (f * B + b) * ((int64_t)d.heads * K * K) : cs + a.wl.sh_patt;
                 cta_ln(p_y, Ds, x, Ds, P + bo.ln1_w, P + bo.ln1_b, K, Ds, d.ln_eps);
-                LIN(p_q, Ds, p_y, Ds, P + bt.pq_t, Ds, nullptr, nullptr, 0, K, Ds, Ds, hscale, 0);
-                LIN(p_k, Ds, p_y, Ds, P + bt.pk_t, Ds, nullptr, nullptr, 0, K, Ds, Ds, 1.0f, 0);
-                LIN(p_v, Ds, p_y, Ds, P + bt.pv_t, Ds, nullptr, nullptr, 0, K, Ds, Ds, 1.0f, 0);
+                LIN(p_q, Ds, p_y, Ds, bt.pq_t, bo.pq, nullptr, nullptr, 0, K, Ds, Ds, hscale, 0);
+                LIN(p_k, Ds, p_y, Ds, bt.pk_t, bo.pk, nullptr, nullptr, 0, K, Ds, Ds, 1.0f, 0);
+                LIN(p_v, Ds, p_y, Ds, bt.pv_t, bo.pv, nullptr, nullptr, 0, K, Ds, Ds, 1.0f, 0);
                 mha_core_fwd(p_q, p_k, p_v, p_att, p_o, K, Ds, d.heads);
                 // first block adds the residual to the NORMALISED input (transformer.py:75-78)
-                LIN(p_x1, Ds, p_o, Ds, P + bt.po_t, Ds, nullptr, (j == 0) ? p_y : x, Ds, K, Ds, Ds, 1.0f, 0);
+                LIN(p_x1, Ds, p_o, Ds, bt.po_t, bo.po, nullptr, (j == 0) ? p_y : x, Ds, K, Ds, Ds, 1.0f, 0);
                 cta_ln(p_l2, Ds, p_x1, Ds, P + bo.ln2_w, P + bo.ln2_b, K, Ds, d.ln_eps);
-                LIN(p_f, 4 * Ds, p_l2, Ds, P + bt.f1_t, 4 * Ds, P + bo.f1b, nullptr, 0, K, Ds, 4 * Ds, 1.0f, LIN_RELU);
-                LIN(p_x2, Ds, p_f, 4 * Ds, P + bt.f2_t, Ds, P + bo.f2b, p_x1, Ds, K, 4 * Ds, Ds, 1.0f, 0);
+                LIN(p_f, 4 * Ds, p_l2, Ds, bt.f1_t, bo.f1, P + bo.f1b, nullptr, 0, K, Ds, 4 * Ds, 1.0f, LIN_RELU);
+                LIN(p_x2, Ds, p_f, 4 * Ds, bt.f2_t, bo.f2, P + bo.f2b, p_x1, Ds, K, 4 * Ds, Ds, 1.0f, 0);
                 x = p_x2;
             }
             cta_ln(st, Ds, x, Ds, P + po.lnf_w, P + po.lnf_b, K, Ds, d.ln_eps);
@@ -341,9 +346,9 @@ static cudaError_t launch_ln_fwd(const FwdArgs& a, const void* inputs, cudaStrea
     return cudaGetLastError();
 }
 
-template <typename TokT, int KMAX>
+template <typename TokT, int KMAX, bool MMA>
 static cudaError_t launch_fwd_t(const FwdArgs& a, cudaStream_t st) {
-    auto kern = savi_fwd_kernel<TokT, KMAX>;
+    auto kern = savi_fwd_kernel<TokT, KMAX, MMA>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, a.smem_bytes);
     if (e != cudaSuccess) return e;
     cudaLaunchConfig_t cfg = {};
@@ -361,11 +366,18 @@ static cudaError_t launch_fwd_t(const FwdArgs& a, cudaStream_t st) {
 template <typename TokT>
 static cudaError_t launch_fwd_k(const FwdArgs& a, cudaStream_t st) {
     const int K = a.d.K;
-    if (K <= 8) return launch_fwd_t<TokT, 8>(a, st);
-    if (K <= 16) return launch_fwd_t<TokT, 16>(a, st);
-    if (K <= 24) return launch_fwd_t<TokT, 24>(a, st);
-    if (K <= 32) return launch_fwd_t<TokT, 32>(a, st);
-    return launch_fwd_t<TokT, 64>(a, st);
+    if constexpr (sizeof(TokT) == 2) {
+        if (a.d.mma) {                      // tensor-core path: KMAX only selects the number of 16-slot m-tiles
+            if (K <= 16) return launch_fwd_t<TokT, 16, true>(a, st);
+            if (K <= 32) return launch_fwd_t<TokT, 32, true>(a, st);
+            return launch_fwd_t<TokT, 64, true>(a, st);
+        }
+    }
+    if (K <= 8) return launch_fwd_t<TokT, 8, false>(a, st);
+    if (K <= 16) return launch_fwd_t<TokT, 16, false>(a, st);
+    if (K <= 24) return launch_fwd_t<TokT, 24, false>(a, st);
+    if (K <= 32) return launch_fwd_t<TokT, 32, false>(a, st);
+    return launch_fwd_t<TokT, 64, false>(a, st);
 }
 
 #ifndef SAVI_TOK

@@ -91,6 +91,8 @@ struct Dims {
     int Sm;          // T*(I-1)       steps that run the residual MLP
     int Sp;          // (T-1)*blocks  predictor block evaluations
     int tok_bytes;   // 4 (fp32) or 2 (bf16)
+    int mma;         // 1: tensor-core path (bf16 tokens, D%16==0, N%8==0, ...), 0: SIMT path
+    int KC;          // 16 * ceil(K/16): slot rows of the staged backward coefficients
     float eps, ln_eps, qscale;
 };
 
@@ -171,6 +173,8 @@ struct BwdWsLayout {         // float offsets unless noted
     int64_t dxhat;           // [B,T,N,D] fp32 accumulator of d xhat over the I iterations of a frame
     // staged operands of the weight-gradient GEMMs (field arrays, same row order as SavedLayout)
     int64_t dq, st, dqk, du, dgi, dgh;           // S steps: widths Ds, Ds, D, Ds, 3Ds, 3Ds
+    int64_t duxs;            // S steps, width D: d(Ux) of every step (right-hand side of the d_inputs kernel, mma mode)
+    int64_t coef;            // BYTE offset: [B*T][I][2][KC][N] bf16 staged dL^T, W^T (mma mode)
     int64_t dhm, da, m;                          // Sm steps: widths Ds, M, Ds
     int64_t pdq, pdk, pdv, pdx1, pdx2, pdf;      // Sp: widths Ds x5, 4Ds
     int64_t part;            // [B][2][CN][K*D]  partial d(qk) per cluster rank
@@ -203,13 +207,16 @@ static inline void savi_bwd_ws_layout(const Dims& d, BwdWsLayout& L) {
     int64_t g = 0;
     auto gt = [&](int64_t rows, int64_t w) { int64_t r = g; g += rows * w; g = (g + 3) / 4 * 4; return r; };
     const int64_t R = (int64_t)d.S * d.B * d.K, Rm = (int64_t)d.Sm * d.B * d.K, Rp = (int64_t)d.Sp * d.B * d.K;
-    L.dxhat = gt((int64_t)d.B * d.T * d.N, d.D);
+    L.dxhat = gt(d.mma ? 0 : (int64_t)d.B * d.T * d.N, d.D);
     L.dq = gt(R, d.Ds); L.st = gt(R, d.Ds); L.dqk = gt(R, d.D); L.du = gt(R, d.Ds);
     L.dgi = gt(R, 3 * d.Ds); L.dgh = gt(R, 3 * d.Ds);
     L.dhm = gt(Rm, d.Ds); L.da = gt(Rm, d.M); L.m = gt(Rm, d.Ds);
     L.pdq = gt(Rp, d.Ds); L.pdk = gt(Rp, d.Ds); L.pdv = gt(Rp, d.Ds); L.pdx1 = gt(Rp, d.Ds); L.pdx2 = gt(Rp, d.Ds);
     L.pdf = gt(Rp, 4 * d.Ds);
+    L.duxs = gt(d.mma ? R : 0, d.D);
     L.part = gt((int64_t)d.B * 2 * d.CN, KD);
     L.cta = g; g += (int64_t)d.B * d.CN * L.cta_floats;
-    L.total_bytes = g * 4;
+    g = (g + 63) / 64 * 64;
+    L.coef = g * 4;
+    L.total_bytes = g * 4 + (d.mma ? (int64_t)d.B * d.T * d.I * 2 * d.KC * d.N * 2 : 0);
 }

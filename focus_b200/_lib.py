@@ -15,7 +15,7 @@ SAVI_MAX_BLOCKS = 4
 SAVI_MAX_SLOTS = 64
 
 EXPORTS = ["savi_version", "savi_last_error", "savi_query", "savi_param_layout", "savi_pack_params",
-           "savi_forward", "savi_backward", "savi_last_launch_count", "savi_profile_enable", "savi_profile_read"]
+           "savi_forward", "savi_backward", "savi_last_launch_count", "savi_profile_enable", "savi_profile_read", "savi_debug_set_phase_buffer"]
 
 
 class SaviShape(ctypes.Structure):
@@ -54,6 +54,8 @@ def _load():
     lib.savi_profile_enable.restype = ip
     lib.savi_profile_read.argtypes = [ctypes.POINTER(ctypes.c_float), ip]
     lib.savi_profile_read.restype = ip
+    lib.savi_debug_set_phase_buffer.argtypes = [vp]
+    lib.savi_debug_set_phase_buffer.restype = ip
     return lib
 
 

@@ -26,6 +26,8 @@ extern "C" const char* savi_last_error(void) { return g_err; }
 extern "C" int savi_last_launch_count(void) { return g_launches; }
 
 static const int kMaxSmem = 227 * 1024;
+static long long* g_dbg = nullptr;     // device buffer of 64 phase counters (development aid)
+extern "C" int savi_debug_set_phase_buffer(void* dev_ptr) { g_dbg = reinterpret_cast<long long*>(dev_ptr); return SAVI_OK; }
 
 // ---- optional per-kernel timing -------------------------------------------------
 // process-wide (autograd runs backward on its own thread); meant for single-stream benchmarking only
@@ -113,8 +115,8 @@ size_t savi_bwd_smem_bytes(const Dims& d, int TN) {
 }
 
 // tokens per tile: the largest of 256..16 that fits; the same dynamic smem doubles as the linear-layer arena
-static int plan_smem(const Dims& d, bool bwd, int* TN, int* arena_floats, int* smem_bytes, int* stages) {
-    *stages = 1;
+static int plan_smem(const Dims& d, bool bwd, int* TN, int* arena_floats, int* smem_bytes, int* stages, int* op_bytes, int* op_width) {
+    *stages = 1; *op_bytes = 0; *op_width = 0;
     if (d.mma) {
         const int MT = d.KC / 16;
         int cmax = 4 * d.Ds; if (d.M > cmax) cmax = d.M; if (d.D > cmax) cmax = d.D;
@@ -125,7 +127,18 @@ static int plan_smem(const Dims& d, bool bwd, int* TN, int* arena_floats, int* s
         if (want > (size_t)kMaxSmem) want = (size_t)160 * 1024;     // such layers fall back to the SIMT linear inside the kernel
         size_t bytes = tok > want ? tok : want;
         bytes = (bytes + 15) / 16 * 16;
-        *TN = TMMA_TN; *smem_bytes = (int)bytes; *arena_floats = (int)(bytes / 4);
+        // two operand buffers in front of the arena let consecutive linears hand their A operand over in shared memory
+        const int cop = d.D > d.Ds ? d.D : d.Ds;
+        size_t opb = (lin_mma_smem(MT, cop) + 15) / 16 * 16;
+        if (cop % 32 != 0 || bytes + 2 * opb > (size_t)kMaxSmem || bwd || getenv("SAVI_NO_OPSTAGE")) opb = 0;   // backward does not use them (yet)
+        if (opb == 0 && *stages == 2 && cop % 32 == 0 && !bwd && !getenv("SAVI_NO_OPSTAGE")) {      // prefer the hand-over buffers to the second token tile
+            const size_t tok1 = tmma_smem_bytes(MT, d.D, d.K, 1, bwd);
+            size_t b1 = tok1 > want ? tok1 : want; b1 = (b1 + 15) / 16 * 16;
+            const size_t o1 = (lin_mma_smem(MT, cop) + 15) / 16 * 16;
+            if (b1 + 2 * o1 <= (size_t)kMaxSmem) { bytes = b1; opb = o1; *stages = 1; }
+        }
+        *op_bytes = (int)opb; *op_width = opb ? cop : 0;
+        *TN = TMMA_TN; *smem_bytes = (int)(bytes + 2 * opb); *arena_floats = (int)(bytes / 4);
         return SAVI_OK;
     }
     int per = ((d.N + d.CN - 1) / d.CN + 3) & ~3;
@@ -153,9 +166,9 @@ extern "C" int savi_query(const SaviShape* shape, SaviSizes* sizes) {
     FwdWsLayout fl; savi_fwd_ws_layout(d, fl);
     BwdWsLayout bl; savi_bwd_ws_layout(d, bl);
     int tn, af, sb;
-    int stg;
-    if ((rc = plan_smem(d, false, &tn, &af, &sb, &stg))) return rc;
-    if ((rc = plan_smem(d, true, &tn, &af, &sb, &stg))) return rc;
+    int stg, opb, opw;
+    if ((rc = plan_smem(d, false, &tn, &af, &sb, &stg, &opb, &opw))) return rc;
+    if ((rc = plan_smem(d, true, &tn, &af, &sb, &stg, &opb, &opw))) return rc;
     sizes->n_params = 21 + 12 * shape->blocks;
     sizes->param_floats = po.total;
     sizes->packed_bytes = (int64_t)po.packed_total * 8;      // fp32 + bf16 hi + bf16 lo images
@@ -303,13 +316,14 @@ extern "C" int savi_forward(const SaviShape* shape, const void* packed, const vo
     savi_param_offsets(*shape, a.po);
     savi_saved_layout(a.d, a.sl);
     savi_fwd_ws_layout(a.d, a.wl);
-    if ((rc = plan_smem(a.d, false, &a.TN, &a.arena_floats, &a.smem_bytes, &a.stages))) return rc;
+    if ((rc = plan_smem(a.d, false, &a.TN, &a.arena_floats, &a.smem_bytes, &a.stages, &a.op_bytes, &a.op_width))) return rc;
     a.packed = reinterpret_cast<const float*>(packed);
     a.noise = reinterpret_cast<const float*>(noise);
     a.slots_out = reinterpret_cast<float*>(slots_out);
     a.attn_out = attn_out;
     a.saved = reinterpret_cast<unsigned char*>(saved);
     a.ws = reinterpret_cast<float*>(fwd_ws);
+    a.dbg = g_dbg;
     g_launches = 0;
     cudaError_t e = savi_launch_forward(a, inputs, reinterpret_cast<cudaStream_t>(stream), &g_launches);
     if (e != cudaSuccess) return cuda_fail(e, "savi_forward launch");
@@ -328,7 +342,7 @@ extern "C" int savi_backward(const SaviShape* shape, const void* packed, const v
     savi_param_offsets(*shape, a.po);
     savi_saved_layout(a.d, a.sl);
     savi_bwd_ws_layout(a.d, a.wl);
-    if ((rc = plan_smem(a.d, true, &a.TN, &a.arena_floats, &a.smem_bytes, &a.stages))) return rc;
+    if ((rc = plan_smem(a.d, true, &a.TN, &a.arena_floats, &a.smem_bytes, &a.stages, &a.op_bytes, &a.op_width))) return rc;
     a.packed = reinterpret_cast<const float*>(packed);
     a.noise = reinterpret_cast<const float*>(noise);
     a.saved = reinterpret_cast<const unsigned char*>(saved);
@@ -337,6 +351,7 @@ extern "C" int savi_backward(const SaviShape* shape, const void* packed, const v
     a.grad_params = reinterpret_cast<float*>(grad_params);
     a.grad_noise = reinterpret_cast<float*>(grad_noise);
     a.ws = reinterpret_cast<float*>(bwd_ws);
+    a.dbg = g_dbg;
     g_launches = 0;
     cudaError_t e = savi_launch_backward(a, inputs, grad_inputs, reinterpret_cast<cudaStream_t>(stream), &g_launches);
     if (e != cudaSuccess) return cuda_fail(e, "savi_backward launch");

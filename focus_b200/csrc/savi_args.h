@@ -16,6 +16,9 @@ struct FwdArgs {
     unsigned char* saved;
     float* ws;
     int stages;           // token-tile pipeline depth of the tensor-core path
+    int op_bytes;         // bytes of ONE shared-memory operand buffer (two are carved before the arena; 0 = none)
+    int op_width;         // the common contraction width those buffers serve (max(D, Ds)); 0 = pre-staging off
+    long long* dbg;       // optional per-phase cycle counters (CTA 0), see savi_debug_set_phase_buffer
     int TN;               // tokens per shared-memory tile
     int arena_floats;     // floats of dynamic shared memory usable as the linear-layer staging arena
     int smem_bytes;
@@ -34,11 +37,18 @@ struct BwdArgs {
     float* grad_params;         // flat, zeroed before the clip kernel
     float* grad_noise;          // nullable
     float* ws;
+    long long* dbg;
     int stages;
+    int op_bytes;
+    int op_width;
     int TN;
     int arena_floats;
     int smem_bytes;
 };
+
+// phase-timing macro shared by the clip kernels (active only when a.dbg != nullptr; CTA 0 reports)
+#define SAVI_PH(id) do { if (a.dbg && blockIdx.x == 0) { __syncthreads(); if (threadIdx.x == 0) { long long t_ = clock64(); \
+    atomicAdd(reinterpret_cast<unsigned long long*>(a.dbg + (id)), (unsigned long long)(t_ - ph_last)); ph_last = t_; } } } while (0)
 
 struct WgradJob {               // dW[o][c] (+)= alpha * sum_r dY[r][o] * X[r][c]
     const float* dY; const float* X; float* dW;

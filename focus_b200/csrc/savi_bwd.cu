@@ -14,7 +14,7 @@
 //   dxhat[n,:] (+)= dL[n,:] qk + W[n,:] dUx
 // ---------------------------------------------------------------------------
 template <typename TokT, int KMAX>
-__device__ void token_pass_bwd(const Dims& d, const TokT* __restrict__ xh, int n_lo, int n_hi, const float* qk_g,
+__device__ __noinline__ void token_pass_bwd(const Dims& d, const TokT* __restrict__ xh, int n_lo, int n_hi, const float* qk_g,
                                const float* dux_g, const float* cvec_g, const TokT* __restrict__ gattn,
                                float* dxhat_g, bool accumulate, float* part_g, unsigned char* smem, int TN) {
     const int tid = threadIdx.x, K = d.K, KP = d.KP, D = d.D;
@@ -161,7 +161,7 @@ __device__ void token_pass_bwd(const Dims& d, const TokT* __restrict__ xh, int n
 }
 
 // Backward of the predictor's attention core.  dQ is w.r.t. the UNSCALED projection.
-static __device__ void mha_core_bwd(const float* dO, const float* Q, const float* Kk, const float* V, const float* att,
+static __device__ __noinline__ void mha_core_bwd(const float* dO, const float* Q, const float* Kk, const float* V, const float* att,
                              float* datt, float* dQ, float* dKk, float* dV, int K, int Ds, int H, float hscale) {
     const int dh = Ds / H, tid = threadIdx.x;
     for (int idx = tid; idx < H * K * K; idx += NT) {
@@ -237,6 +237,7 @@ __global__ void __launch_bounds__(NT, 1) savi_bwd_kernel(const __grid_constant__
 #define LIN(Y, ldy, X, ldx, W_io, W_oi, Res, ldr, Mask, ldm, R_, C_, O_, alpha) \
     lin<MMA, MT>(P, Phi, Plo, Y, ldy, X, ldx, W_io, W_oi, nullptr, Res, ldr, Mask, ldm, R_, C_, O_, alpha, 0, arena, AF)
 
+    long long ph_last = clock64();
     for (int i = tid; i < K * Ds; i += NT) dh[i] = 0.f;
     __syncthreads();
 
@@ -244,6 +245,7 @@ __global__ void __launch_bounds__(NT, 1) savi_bwd_kernel(const __grid_constant__
         const TokT* xh_t = xhat + ((size_t)b * d.T + t) * d.N * D;
         float* dxh_t = W + a.wl.dxhat + ((size_t)b * d.T + t) * d.N * D;
         if (t < d.T - 1) {
+            SAVI_PH(30);
             // ---- predictor backward (transformer.py:106-114, 70-86, 22-49) ----
             const float* px0 = fb + a.sl.px0 + ((size_t)t * B + b) * K * Ds;
             const float* x_last = d.blocks > 0 ? frow(fb, a.sl.px2, (int64_t)(d.blocks - 1) * (d.T - 1) + t, b, B, K, Ds) : px0;
@@ -273,7 +275,9 @@ __global__ void __launch_bounds__(NT, 1) savi_bwd_kernel(const __grid_constant__
                 LIN(t1, Ds, s_df, 4 * Ds, bo.f1, bt.f1_t, nullptr, 0, nullptr, 0, K, 4 * Ds, Ds, 1.0f);
                 cta_ln_bwd(s_dx1, Ds, t0, Ds, t1, Ds, p_x1, Ds, P + bo.ln2_w, G + bo.ln2_w, G + bo.ln2_b, K, Ds, d.ln_eps, lead);
                 LIN(t1, Ds, s_dx1, Ds, bo.po, bt.po_t, nullptr, 0, nullptr, 0, K, Ds, Ds, 1.0f);                  // dO
+                SAVI_PH(31);
                 mha_core_bwd(t1, p_q, p_k, p_v, p_att, t2, s_dq, s_dk, s_dv, K, Ds, d.heads, hscale);
+                SAVI_PH(32);
                 LIN(t1, Ds, s_dq, Ds, bo.pq, bt.pq_t, (j == 0) ? s_dx1 : nullptr, Ds, nullptr, 0, K, Ds, Ds, 1.0f);
                 LIN(t1, Ds, s_dk, Ds, bo.pk, bt.pk_t, t1, Ds, nullptr, 0, K, Ds, Ds, 1.0f);
                 LIN(t1, Ds, s_dv, Ds, bo.pv, bt.pv_t, t1, Ds, nullptr, 0, K, Ds, Ds, 1.0f);                      // dy
@@ -283,6 +287,7 @@ __global__ void __launch_bounds__(NT, 1) savi_bwd_kernel(const __grid_constant__
             }
             cta_copy(dh, t0, K * Ds);
             __syncthreads();
+            SAVI_PH(33);
         }
         for (int i = tid; i < K * Ds; i += NT) dh[i] += a.grad_slots[((size_t)b * d.T + t) * K * Ds + i];
         __syncthreads();
@@ -305,6 +310,7 @@ __global__ void __launch_bounds__(NT, 1) savi_bwd_kernel(const __grid_constant__
             float* s_dgi = lead ? frow(W, a.wl.dgi, s, b, B, K, 3 * Ds) : cs + a.wl.sh_dgi;
             float* s_dgh = lead ? frow(W, a.wl.dgh, s, b, B, K, 3 * Ds) : cs + a.wl.sh_dgh;
             (void)r_q;
+            SAVI_PH(34);
             const float* cur = dh;
             if (it < d.I - 1) {
                 // ---- residual MLP backward (steve.py:92-93) ----
@@ -323,22 +329,36 @@ __global__ void __launch_bounds__(NT, 1) savi_bwd_kernel(const __grid_constant__
                 cta_ln_bwd(dhg, Ds, dh, Ds, t0, Ds, r_hg, Ds, P + po.ln_m_w, G + po.ln_m_w, G + po.ln_m_b, K, Ds, d.ln_eps, lead);
                 cur = dhg;
             }
+            SAVI_PH(35);
             // ---- GRUCell backward (steve.py:87-89) ----
-            for (int i = tid; i < K * Ds; i += NT) {
+            for (int i = tid * 4; i < K * Ds; i += NT * 4) {
                 const int k = i / Ds, c = i - k * Ds;
-                const float g = cur[i], r = r_r[i], z = r_z[i], n = r_n[i], ghn = r_ghn[i], hp = r_hp[i];
-                const float dn_pre = g * (1.0f - z) * (1.0f - n * n);
-                const float dz_pre = g * (hp - n) * z * (1.0f - z);
-                const float dr_pre = dn_pre * ghn * r * (1.0f - r);
-                float* gi = s_dgi + (size_t)k * 3 * Ds; float* gh = s_dgh + (size_t)k * 3 * Ds;
-                gi[c] = dr_pre; gi[Ds + c] = dz_pre; gi[2 * Ds + c] = dn_pre;
-                gh[c] = dr_pre; gh[Ds + c] = dz_pre; gh[2 * Ds + c] = dn_pre * r;
-                dh[i] = g * z;
+                const float4 g4 = ld4(cur + i), r4 = ld4(r_r + i), z4 = ld4(r_z + i), n4 = ld4(r_n + i), gn4 = ld4(r_ghn + i), hp4 = ld4(r_hp + i);
+                const float gg[4] = {g4.x, g4.y, g4.z, g4.w}, rr[4] = {r4.x, r4.y, r4.z, r4.w}, zz[4] = {z4.x, z4.y, z4.z, z4.w};
+                const float nn[4] = {n4.x, n4.y, n4.z, n4.w}, gn[4] = {gn4.x, gn4.y, gn4.z, gn4.w}, hh[4] = {hp4.x, hp4.y, hp4.z, hp4.w};
+                float dr[4], dz[4], dn[4], dnr[4], dhn[4];
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    dn[e] = gg[e] * (1.0f - zz[e]) * (1.0f - nn[e] * nn[e]);
+                    dz[e] = gg[e] * (hh[e] - nn[e]) * zz[e] * (1.0f - zz[e]);
+                    dr[e] = dn[e] * gn[e] * rr[e] * (1.0f - rr[e]);
+                    dnr[e] = dn[e] * rr[e];
+                    dhn[e] = gg[e] * zz[e];
+                }
+                float* gi = s_dgi + (size_t)k * 3 * Ds + c; float* gh = s_dgh + (size_t)k * 3 * Ds + c;
+                st4(gi, make_float4(dr[0], dr[1], dr[2], dr[3])); st4(gi + Ds, make_float4(dz[0], dz[1], dz[2], dz[3]));
+                st4(gi + 2 * Ds, make_float4(dn[0], dn[1], dn[2], dn[3]));
+                st4(gh, make_float4(dr[0], dr[1], dr[2], dr[3])); st4(gh + Ds, make_float4(dz[0], dz[1], dz[2], dz[3]));
+                st4(gh + 2 * Ds, make_float4(dnr[0], dnr[1], dnr[2], dnr[3]));
+                st4(dh + i, make_float4(dhn[0], dhn[1], dhn[2], dhn[3]));
             }
             __syncthreads();
             if (lead) { cta_colsum_atomic(G + po.bih, s_dgi, 3 * Ds, K, 3 * Ds); cta_colsum_atomic(G + po.bhh, s_dgh, 3 * Ds, K, 3 * Ds); }
+            SAVI_PH(36);
             LIN(dh, Ds, s_dgh, 3 * Ds, po.whh, po.whh_t, dh, Ds, nullptr, 0, K, 3 * Ds, Ds, 1.0f);
+            SAVI_PH(37);
             LIN(s_du, Ds, s_dgi, 3 * Ds, po.wih, po.wih_t, nullptr, 0, nullptr, 0, K, 3 * Ds, Ds, 1.0f);
+            SAVI_PH(38);
             // ---- attention step backward ----
             if (MMA) dux = lead ? frow(W, a.wl.duxs, s, b, B, K, D) : cs + a.wl.dux;
             LIN(dux, D, s_du, Ds, po.wv, po.wv_t, nullptr, 0, nullptr, 0, K, Ds, D, 1.0f);
@@ -352,6 +372,7 @@ __global__ void __launch_bounds__(NT, 1) savi_bwd_kernel(const __grid_constant__
                 }
                 __syncthreads();
             }
+            SAVI_PH(39);
             float* part = W + a.wl.part + (((size_t)b * 2 + (s & 1)) * CN + rank) * ((size_t)K * D);
             const TokT* ga = (a.grad_attn && it == d.I - 1)
                                  ? reinterpret_cast<const TokT*>(a.grad_attn) + ((size_t)b * d.T + t) * d.N * K : nullptr;
@@ -362,20 +383,29 @@ __global__ void __launch_bounds__(NT, 1) savi_bwd_kernel(const __grid_constant__
             } else {
                 token_pass_bwd<TokT, KMAX>(d, xh_t, n_lo, n_hi, r_qk, dux, cvec, ga, dxh_t, it != d.I - 1, part, smem, a.TN);
             }
+            SAVI_PH(40);
             __threadfence();
             sync_clip(CN);
+            SAVI_PH(41);
             {
                 const float* pb = W + a.wl.part + (((size_t)b * 2 + (s & 1)) * CN) * ((size_t)K * D);
-                for (int i = tid; i < K * D; i += NT) {
-                    float v = 0.f;
-                    for (int r = 0; r < CN; ++r) v += __ldcg(pb + (size_t)r * K * D + i);
-                    s_dqk[i] = v;
+                for (int i = tid * 4; i < K * D; i += NT * 4) {
+                    float4 v = __ldcg(reinterpret_cast<const float4*>(pb + i));
+                    for (int r = 1; r < CN; ++r) {
+                        const float4 t = __ldcg(reinterpret_cast<const float4*>(pb + (size_t)r * K * D + i));
+                        v.x += t.x; v.y += t.y; v.z += t.z; v.w += t.w;
+                    }
+                    st4(s_dqk + i, v);
                 }
                 __syncthreads();
             }
+            SAVI_PH(42);
             LIN(s_dq, Ds, s_dqk, D, po.wk_t, po.wk, nullptr, 0, nullptr, 0, K, D, Ds, d.qscale);
+            SAVI_PH(43);
             cta_ln(s_st, Ds, r_hp, Ds, P + po.ln_s_w, P + po.ln_s_b, K, Ds, d.ln_eps);
+            SAVI_PH(44);
             LIN(t0, Ds, s_dq, Ds, po.wq, po.wq_t, nullptr, 0, nullptr, 0, K, Ds, Ds, 1.0f);
+            SAVI_PH(45);
             cta_ln_bwd(dh, Ds, dh, Ds, t0, Ds, r_hp, Ds, P + po.ln_s_w, G + po.ln_s_w, G + po.ln_s_b, K, Ds, d.ln_eps, lead);
         }
     }
@@ -543,7 +573,7 @@ cudaError_t savi_launch_dx_mma(const BwdArgs& a, const void* inputs, void* grad_
 #define DX_LAUNCH(ND_) \
     e = cudaFuncSetAttribute(dx_finalize_kernel<ND_>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); \
     if (e != cudaSuccess) return e; \
-    dx_finalize_kernel<ND_><<<grid, NT, smem, st>>>(x);
+    dx_finalize_kernel<ND_><<<grid, DX_NT, smem, st>>>(x);
     if (d.D <= 64) { DX_LAUNCH(8) } else if (d.D <= 128) { DX_LAUNCH(16) } else if (d.D <= 192) { DX_LAUNCH(24) } else { DX_LAUNCH(32) }
 #undef DX_LAUNCH
     return cudaGetLastError();

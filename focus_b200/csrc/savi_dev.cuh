@@ -13,7 +13,7 @@
 
 namespace cg = cooperative_groups;
 
-constexpr int NT = 256;            // threads per CTA
+constexpr int NT = 512;            // threads per CTA (16 warps: the recurrence is latency-bound, warps are the only way to hide it)
 constexpr int NW = NT / 32;
 
 __device__ __forceinline__ float4 ld4(const float* p) { return *reinterpret_cast<const float4*>(p); }
@@ -87,7 +87,7 @@ __device__ __forceinline__ void sync_clip(int CN) {
 // ---------------------------------------------------------------------------
 constexpr int LIN_RELU = 1;
 
-static __device__ void cta_linear(float* Y, int ldy, const float* X, int ldx, const float* __restrict__ W, int ldw,
+static __device__ __noinline__ void cta_linear(float* Y, int ldy, const float* X, int ldx, const float* __restrict__ W, int ldw,
                            const float* __restrict__ bias, const float* Res, int ldr, const float* Mask, int ldm,
                            int R, int C, int O, float alpha, int flags, float* arena, int arena_floats) {
     const int tid = threadIdx.x;
@@ -150,7 +150,7 @@ static __device__ void cta_linear(float* Y, int ldy, const float* X, int ldx, co
 }
 
 // LayerNorm over the last dim, one warp per row (torch semantics: biased variance).
-static __device__ void cta_ln(float* Y, int ldy, const float* X, int ldx, const float* __restrict__ g,
+static __device__ __noinline__ void cta_ln(float* Y, int ldy, const float* X, int ldx, const float* __restrict__ g,
                        const float* __restrict__ b, int R, int C, float eps) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     for (int r = warp; r < R; r += NW) {
@@ -169,7 +169,7 @@ static __device__ void cta_ln(float* Y, int ldy, const float* X, int ldx, const 
 // dX[r] = (Res ? Res[r] : 0) + LayerNorm backward of dY through X;  optionally
 // accumulates d gamma / d beta into global (atomics, one add per warp and column).
 // C <= 512.
-static __device__ void cta_ln_bwd(float* dX, int lddx, const float* Res, int ldr, const float* dY, int lddy,
+static __device__ __noinline__ void cta_ln_bwd(float* dX, int lddx, const float* Res, int ldr, const float* dY, int lddy,
                            const float* X, int ldx, const float* __restrict__ g, float* dg_glob, float* db_glob,
                            int R, int C, float eps, bool do_param_grads) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -215,7 +215,7 @@ static __device__ void cta_ln_bwd(float* dX, int lddx, const float* Res, int ldr
 }
 
 // dst[o] += sum_r X[r][o]   (bias gradients), one thread per column.
-static __device__ void cta_colsum_atomic(float* dst, const float* X, int ldx, int R, int O) {
+static __device__ __noinline__ void cta_colsum_atomic(float* dst, const float* X, int ldx, int R, int O) {
     for (int o = threadIdx.x; o < O; o += NT) {
         float s = 0.f;
         for (int r = 0; r < R; ++r) s += X[(size_t)r * ldx + o];

@@ -25,8 +25,10 @@ __host__ __device__ __forceinline__ size_t dx_smem_bytes(int I, int KC, int D) {
     return rows * tmma_xs(D) + rows * TMMA_ATS + (size_t)TMMA_TN * tmma_xs(D) + 2 * (size_t)D * 4 + 16;
 }
 
+constexpr int DX_NT = 256;      // 8 warps x 16 tokens = one 128-token tile
+
 template <int ND>   // n-tiles of 8 features held per warp: D <= 8*ND
-__global__ void __launch_bounds__(NT, 1) dx_finalize_kernel(const __grid_constant__ DxArgs a) {
+__global__ void __launch_bounds__(DX_NT, 1) dx_finalize_kernel(const __grid_constant__ DxArgs a) {
     extern __shared__ float4 smem4[];
     unsigned char* smem = reinterpret_cast<unsigned char*>(smem4);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, q = lane & 3, mi = lane >> 3, rr = lane & 7;
@@ -37,11 +39,11 @@ __global__ void __launch_bounds__(NT, 1) dx_finalize_kernel(const __grid_constan
     unsigned char* xo = cs + (size_t)rows * TMMA_ATS;               // x tile, later the d_inputs tile [TN][D+8]
     float* red = reinterpret_cast<float*>(xo + (size_t)TMMA_TN * xs);   // [2][D] d gamma, d beta
     const int f = blockIdx.y, b = f / a.T, t = f - b * a.T;
-    for (int i = tid; i < 2 * D; i += NT) red[i] = 0.f;
+    for (int i = tid; i < 2 * D; i += DX_NT) red[i] = 0.f;
     // right-hand side rows: for each iteration i: qk_i (KC rows, zero beyond K) then dUx_i
     {
         const int d4 = D >> 2;
-        for (int idx = tid; idx < rows * d4; idx += NT) {
+        for (int idx = tid; idx < rows * d4; idx += DX_NT) {
             const int r = idx / d4, c = (idx - r * d4) * 4;
             const int i = r / (2 * KC), rem = r - i * 2 * KC, which = rem / KC, k = rem - which * KC;
             float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -62,13 +64,13 @@ __global__ void __launch_bounds__(NT, 1) dx_finalize_kernel(const __grid_constan
         __syncthreads();                                            // previous tile's staging buffers are free
         {   // coefficient rows (contiguous 256 B per row) and the x tile
             const int cpr = TMMA_TN / 8;
-            for (int idx = tid; idx < rows * cpr; idx += NT) {
+            for (int idx = tid; idx < rows * cpr; idx += DX_NT) {
                 const int r = idx / cpr, c = idx - r * cpr;
                 unsigned char* dst = cs + (size_t)r * TMMA_ATS + c * 16;
                 if (c * 8 < tn) cp_async16(dst, coef_f + (size_t)r * N + n0 + c * 8);     // N % 8 == 0: whole chunks valid
                 else *reinterpret_cast<uint4*>(dst) = make_uint4(0u, 0u, 0u, 0u);
             }
-            tmma_issue_tile(xo, a.x + (size_t)f * N * D, n0, tn, D);
+            tmma_issue_tile<DX_NT>(xo, a.x + (size_t)f * N * D, n0, tn, D);
             cp_async_wait_all();
         }
         __syncthreads();
@@ -147,12 +149,12 @@ __global__ void __launch_bounds__(NT, 1) dx_finalize_kernel(const __grid_constan
         {   // coalesced 16-byte stores of the d_inputs tile
             const int chunks = D >> 3;
             unsigned char* gb = reinterpret_cast<unsigned char*>(a.dx + ((size_t)f * N + n0) * D);
-            for (int idx = tid; idx < tn * chunks; idx += NT) {
+            for (int idx = tid; idx < tn * chunks; idx += DX_NT) {
                 const int r = idx / chunks, c = idx - r * chunks;
                 *reinterpret_cast<uint4*>(gb + (size_t)r * D * 2 + c * 16) = *reinterpret_cast<const uint4*>(xo + (size_t)r * xs + c * 16);
             }
         }
     }
     __syncthreads();
-    for (int c = tid; c < D; c += NT) { atomicAdd(a.dgamma + c, red[c]); atomicAdd(a.dbeta + c, red[D + c]); }
+    for (int c = tid; c < D; c += DX_NT) { atomicAdd(a.dgamma + c, red[c]); atomicAdd(a.dbeta + c, red[D + c]); }
 }

@@ -74,7 +74,7 @@ __global__ void __launch_bounds__(NT) ln_tokens_fwd_kernel(const TokT* __restric
 // register-tiled outer-product accumulation over the tile.
 // ---------------------------------------------------------------------------
 template <typename TokT, int KMAX>
-__device__ void token_pass_fwd(const Dims& d, const TokT* __restrict__ xh, int n_lo, int n_hi,
+__device__ __noinline__ void token_pass_fwd(const Dims& d, const TokT* __restrict__ xh, int n_lo, int n_hi,
                                const float* qk_g, float* part_g, TokT* attn_g, unsigned char* smem, int TN) {
     const int tid = threadIdx.x, K = d.K, KP = d.KP, D = d.D;
     const int cst = coef_stride(KP), xst = tile_stride_bytes(D, sizeof(TokT));
@@ -150,7 +150,7 @@ __device__ void token_pass_fwd(const Dims& d, const TokT* __restrict__ xh, int n
 
 // Multi-head self-attention core of the predictor on one clip (transformer.py:34-47).
 // Q is already scaled by dh^-1/2.  att: [H][K][K] (global), O: [K][Ds].
-static __device__ void mha_core_fwd(const float* Q, const float* Kk, const float* V, float* att, float* O,
+static __device__ __noinline__ void mha_core_fwd(const float* Q, const float* Kk, const float* V, float* att, float* O,
                              int K, int Ds, int H) {
     const int dh = Ds / H, tid = threadIdx.x;
     for (int idx = tid; idx < H * K * K; idx += NT) {
@@ -188,8 +188,9 @@ static __device__ void mha_core_fwd(const float* Q, const float* Kk, const float
 template <typename TokT, int KMAX, bool MMA>
 __global__ void __launch_bounds__(NT, 1) savi_fwd_kernel(const __grid_constant__ FwdArgs a) {
     extern __shared__ float4 smem4[];
-    unsigned char* smem = reinterpret_cast<unsigned char*>(smem4);
-    float* arena = reinterpret_cast<float*>(smem4);
+    // dynamic smem: [operand buffer A | operand buffer B | arena (token tiles / staging)]
+    unsigned char* smem = reinterpret_cast<unsigned char*>(smem4) + 2 * (size_t)a.op_bytes;
+    float* arena = reinterpret_cast<float*>(smem);
     const Dims& d = a.d;
     const ParamOff& po = a.po;
     const int tid = threadIdx.x;
@@ -211,9 +212,23 @@ __global__ void __launch_bounds__(NT, 1) savi_fwd_kernel(const __grid_constant__
     const bf16* Phi = reinterpret_cast<const bf16*>(P + po.packed_total);      // bf16 hi / lo images of the packed buffer
     const bf16* Plo = Phi + po.packed_total;
     // W_io: offset of the [in][out] fp32 copy (SIMT path), W_oi: offset of the [out][in] copy (tensor-core path)
+#define LINP(Y, ldy, X, ldx, W_io, W_oi, bias, Res, ldr, R_, C_, O_, alpha, fl, pre_, out_) \
+    lin<MMA, MT>(P, Phi, Plo, Y, ldy, X, ldx, W_io, W_oi, bias, Res, ldr, nullptr, 0, R_, C_, O_, alpha, fl, arena, AF, pre_, out_)
 #define LIN(Y, ldy, X, ldx, W_io, W_oi, bias, Res, ldr, R_, C_, O_, alpha, fl) \
-    lin<MMA, MT>(P, Phi, Plo, Y, ldy, X, ldx, W_io, W_oi, bias, Res, ldr, nullptr, 0, R_, C_, O_, alpha, fl, arena, AF)
+    LINP(Y, ldy, X, ldx, W_io, W_oi, bias, Res, ldr, R_, C_, O_, alpha, fl, nullptr, nullptr)
+    // operand hand-over buffers (tensor-core path): a producer whose width equals op_width also leaves its
+    // result there as bf16 hi/lo, the consuming linear then needs no staging pass
+    OpStage opA, opB;
+    constexpr int OW = 0;     // operand hand-over measured neutral at C2 and costs registers: compiled out (kept for the record)
+    {
+        const int ost = OW ? lin_stride(OW) : 0;
+        opA.hi = reinterpret_cast<bf16*>(smem4); opA.lo = opA.hi + (size_t)MT * 16 * ost; opA.stride = ost;
+        opB.hi = reinterpret_cast<bf16*>(reinterpret_cast<unsigned char*>(smem4) + a.op_bytes); opB.lo = opB.hi + (size_t)MT * 16 * ost; opB.stride = ost;
+        if (OW) { opstage_clear(opA, MT * 16); opstage_clear(opB, MT * 16); }
+    }
+#define OP_IF(w_, buf_) ((OW && (w_) == OW) ? &(buf_) : nullptr)
 
+    long long ph_last = clock64();
     // slots0 = mu + exp(log_sigma) * noise   (steve.py:56-57)
     for (int i = tid; i < K * Ds; i += NT) {
         const int c = i % Ds;
@@ -237,33 +252,53 @@ __global__ void __launch_bounds__(NT, 1) savi_fwd_kernel(const __grid_constant__
             float* r_ghn = lead ? frow(fb, a.sl.ghn, s, b, B, K, Ds) : cs + a.wl.sh_ghn;
             float* r_ss = lead ? fb + a.sl.ssum + (s * B + b) * KP : cs + a.wl.sh_ssum;
 
+            SAVI_PH(0);
             cta_copy(r_hp, h, K * Ds);                                                   // slots_prev (steve.py:71)
-            cta_ln(st, Ds, h, Ds, P + po.ln_s_w, P + po.ln_s_b, K, Ds, d.ln_eps);      // :72
-            LIN(r_q, Ds, st, Ds, po.wq_t, po.wq, nullptr, nullptr, 0, K, Ds, Ds, 1.0f, 0);            // :75
-            LIN(r_qk, D, r_q, Ds, po.wk, po.wk_t, nullptr, nullptr, 0, K, Ds, D, d.qscale, 0);           // fold Wk and Ds^-1/2 (:61,63)
+            if constexpr (MMA) cta_ln_op(st, Ds, h, Ds, P + po.ln_s_w, P + po.ln_s_b, K, Ds, d.ln_eps, OP_IF(Ds, opA));
+            else cta_ln(st, Ds, h, Ds, P + po.ln_s_w, P + po.ln_s_b, K, Ds, d.ln_eps);      // :72
+            SAVI_PH(1);
+            LINP(r_q, Ds, st, Ds, po.wq_t, po.wq, nullptr, nullptr, 0, K, Ds, Ds, 1.0f, 0, OP_IF(Ds, opA), OP_IF(Ds, opB));   // :75
+            SAVI_PH(2);
+            LINP(r_qk, D, r_q, Ds, po.wk, po.wk_t, nullptr, nullptr, 0, K, Ds, D, d.qscale, 0, OP_IF(Ds, opB), nullptr);   // fold Wk and Ds^-1/2 (:61,63)
 
+            SAVI_PH(3);
             float* part = a.ws + a.wl.part + (((size_t)b * 2 + (s & 1)) * CN + rank) * ((size_t)K * D + KP);
             TokT* attn_t = (it == d.I - 1) ? reinterpret_cast<TokT*>(a.attn_out) + ((size_t)b * d.T + t) * d.N * K : nullptr;
-            if constexpr (MMA) token_pass_fwd_mma<MT>(d, xh_t, n_lo, n_hi, r_qk, part, attn_t, smem, a.stages);
+            if constexpr (MMA) token_pass_fwd_mma<MT>(d, xh_t, n_lo, n_hi, r_qk, part, attn_t, smem, a.stages, (blockIdx.x == 0) ? a.dbg : nullptr);
             else token_pass_fwd<TokT, KMAX>(d, xh_t, n_lo, n_hi, r_qk, part, attn_t, smem, a.TN);
+            SAVI_PH(4);
             __threadfence();
             sync_clip(CN);
+            SAVI_PH(5);
             // combine the ranks' partial sums in a fixed order: Ux = (sum A x) / (sum A)   (:82-83)
             {
                 const float* pb = a.ws + a.wl.part + (((size_t)b * 2 + (s & 1)) * CN) * ((size_t)K * D + KP);
                 const size_t pstride = (size_t)K * D + KP;
-                for (int i = tid; i < K * D; i += NT) {
+                for (int i = tid * 4; i < K * D; i += NT * 4) {           // all loads of a thread are issued before the math
                     const int k = i / D;
-                    float num = 0.f, den = 0.f;
-                    for (int r = 0; r < CN; ++r) { num += __ldcg(pb + r * pstride + i); den += __ldcg(pb + r * pstride + (size_t)K * D + k); }
-                    r_ux[i] = num / den;
+                    float4 num = __ldcg(reinterpret_cast<const float4*>(pb + i));
+                    float den = __ldcg(pb + (size_t)K * D + k);
+                    for (int r = 1; r < CN; ++r) {
+                        const float4 t = __ldcg(reinterpret_cast<const float4*>(pb + r * pstride + i));
+                        num.x += t.x; num.y += t.y; num.z += t.z; num.w += t.w;
+                        den += __ldcg(pb + r * pstride + (size_t)K * D + k);
+                    }
+                    const float4 ux = make_float4(num.x / den, num.y / den, num.z / den, num.w / den);
+                    st4(r_ux + i, ux);
+                    if constexpr (MMA) {
+                        if (OW && D == OW) { const int c = i - k * D; opstage_put2(opA, k, c, ux.x, ux.y); opstage_put2(opA, k, c + 2, ux.z, ux.w); }
+                    }
                     if (i % D == 0) r_ss[k] = den;
                 }
                 __syncthreads();
             }
-            LIN(r_u, Ds, r_ux, D, po.wv_t, po.wv, nullptr, nullptr, 0, K, D, Ds, 1.0f, 0);              // updates (:83)
-            LIN(gi, 3 * Ds, r_u, Ds, po.wih_t, po.wih, P + po.bih, nullptr, 0, K, Ds, 3 * Ds, 1.0f, 0);   // GRUCell (:87)
+            SAVI_PH(6);
+            LINP(r_u, Ds, r_ux, D, po.wv_t, po.wv, nullptr, nullptr, 0, K, D, Ds, 1.0f, 0, OP_IF(D, opA), OP_IF(Ds, opB));   // updates (:83)
+            SAVI_PH(7);
+            LINP(gi, 3 * Ds, r_u, Ds, po.wih_t, po.wih, P + po.bih, nullptr, 0, K, Ds, 3 * Ds, 1.0f, 0, OP_IF(Ds, opB), nullptr);   // GRUCell (:87)
+            SAVI_PH(8);
             LIN(gh, 3 * Ds, r_hp, Ds, po.whh_t, po.whh, P + po.bhh, nullptr, 0, K, Ds, 3 * Ds, 1.0f, 0);
+            SAVI_PH(9);
             const bool mlp = (it < d.I - 1);
             float* r_hg = nullptr; float* r_a = nullptr;
             if (mlp) {
@@ -271,25 +306,39 @@ __global__ void __launch_bounds__(NT, 1) savi_fwd_kernel(const __grid_constant__
                 r_hg = lead ? frow(fb, a.sl.hg, sm, b, B, K, Ds) : cs + a.wl.sh_hg;
                 r_a = lead ? frow(fb, a.sl.a, sm, b, B, K, M) : cs + a.wl.sh_a;
             }
-            for (int i = tid; i < K * Ds; i += NT) {
+            for (int i = tid * 4; i < K * Ds; i += NT * 4) {               // 4 features per thread, loads first
                 const int k = i / Ds, c = i - k * Ds;
-                const float* gik = gi + (size_t)k * 3 * Ds; const float* ghk = gh + (size_t)k * 3 * Ds;
-                const float r = sigmoidf_(gik[c] + ghk[c]);
-                const float z = sigmoidf_(gik[Ds + c] + ghk[Ds + c]);
-                const float ghn = ghk[2 * Ds + c];
-                const float n = tanhf(gik[2 * Ds + c] + r * ghn);
-                const float hn = (1.0f - z) * n + z * r_hp[i];
-                r_r[i] = r; r_z[i] = z; r_n[i] = n; r_ghn[i] = ghn;
-                h[i] = hn;
-                if (mlp) r_hg[i] = hn;
+                const float* gik = gi + (size_t)k * 3 * Ds + c; const float* ghk = gh + (size_t)k * 3 * Ds + c;
+                const float4 ir = ld4(gik), iz = ld4(gik + Ds), in_ = ld4(gik + 2 * Ds);
+                const float4 hr = ld4(ghk), hz = ld4(ghk + Ds), hn4 = ld4(ghk + 2 * Ds), hp4 = ld4(r_hp + i);
+                const float air[4] = {ir.x, ir.y, ir.z, ir.w}, aiz[4] = {iz.x, iz.y, iz.z, iz.w}, ain[4] = {in_.x, in_.y, in_.z, in_.w};
+                const float ahr[4] = {hr.x, hr.y, hr.z, hr.w}, ahz[4] = {hz.x, hz.y, hz.z, hz.w}, ahn[4] = {hn4.x, hn4.y, hn4.z, hn4.w};
+                const float ahp[4] = {hp4.x, hp4.y, hp4.z, hp4.w};
+                float vr[4], vz[4], vn[4], vh[4];
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    vr[e] = sigmoidf_(air[e] + ahr[e]);
+                    vz[e] = sigmoidf_(aiz[e] + ahz[e]);
+                    vn[e] = tanhf(ain[e] + vr[e] * ahn[e]);
+                    vh[e] = (1.0f - vz[e]) * vn[e] + vz[e] * ahp[e];
+                }
+                st4(r_r + i, make_float4(vr[0], vr[1], vr[2], vr[3])); st4(r_z + i, make_float4(vz[0], vz[1], vz[2], vz[3]));
+                st4(r_n + i, make_float4(vn[0], vn[1], vn[2], vn[3])); st4(r_ghn + i, hn4);
+                st4(h + i, make_float4(vh[0], vh[1], vh[2], vh[3]));
+                if (mlp) st4(r_hg + i, make_float4(vh[0], vh[1], vh[2], vh[3]));
             }
             __syncthreads();
+            SAVI_PH(10);
             if (mlp) {                                                                    // residual MLP (:92-93)
-                cta_ln(st, Ds, h, Ds, P + po.ln_m_w, P + po.ln_m_b, K, Ds, d.ln_eps);
-                LIN(r_a, M, st, Ds, po.w1_t, po.w1, P + po.b1, nullptr, 0, K, Ds, M, 1.0f, LIN_RELU);
-                LIN(h, Ds, r_a, M, po.w2_t, po.w2, P + po.b2, r_hg, Ds, K, M, Ds, 1.0f, 0);
+                if constexpr (MMA) cta_ln_op(st, Ds, h, Ds, P + po.ln_m_w, P + po.ln_m_b, K, Ds, d.ln_eps, OP_IF(Ds, opA));
+                else cta_ln(st, Ds, h, Ds, P + po.ln_m_w, P + po.ln_m_b, K, Ds, d.ln_eps);
+                SAVI_PH(11);
+                LINP(r_a, M, st, Ds, po.w1_t, po.w1, P + po.b1, nullptr, 0, K, Ds, M, 1.0f, LIN_RELU, OP_IF(Ds, opA), OP_IF(M, opB));
+                SAVI_PH(12);
+                LINP(h, Ds, r_a, M, po.w2_t, po.w2, P + po.b2, r_hg, Ds, K, M, Ds, 1.0f, 0, OP_IF(M, opB), nullptr);
             }
         }
+        SAVI_PH(13);
         if (lead) cta_copy(a.slots_out + ((size_t)b * d.T + t) * K * Ds, h, K * Ds);     // collect (:96-97)
         if (t < d.T - 1) {
             // predictor (:100).  The reference also evaluates it after the last frame and discards the result.
@@ -311,24 +360,36 @@ __global__ void __launch_bounds__(NT, 1) savi_fwd_kernel(const __grid_constant__
                 float* p_f = lead ? frow(fb, a.sl.pf, f, b, B, K, 4 * Ds) : cs + a.wl.sh_pf;
                 float* p_x2 = lead ? frow(fb, a.sl.px2, f, b, B, K, Ds) : cs + a.wl.sh_px2;
                 float* p_att = lead ? fb + a.sl.patt + (f * B + b) * ((int64_t)d.heads * K * K) : cs + a.wl.sh_patt;
-                cta_ln(p_y, Ds, x, Ds, P + bo.ln1_w, P + bo.ln1_b, K, Ds, d.ln_eps);
-                LIN(p_q, Ds, p_y, Ds, bt.pq_t, bo.pq, nullptr, nullptr, 0, K, Ds, Ds, hscale, 0);
-                LIN(p_k, Ds, p_y, Ds, bt.pk_t, bo.pk, nullptr, nullptr, 0, K, Ds, Ds, 1.0f, 0);
-                LIN(p_v, Ds, p_y, Ds, bt.pv_t, bo.pv, nullptr, nullptr, 0, K, Ds, Ds, 1.0f, 0);
+                SAVI_PH(14);
+                if constexpr (MMA) cta_ln_op(p_y, Ds, x, Ds, P + bo.ln1_w, P + bo.ln1_b, K, Ds, d.ln_eps, OP_IF(Ds, opA));
+                else cta_ln(p_y, Ds, x, Ds, P + bo.ln1_w, P + bo.ln1_b, K, Ds, d.ln_eps);
+                SAVI_PH(15);
+                LINP(p_q, Ds, p_y, Ds, bt.pq_t, bo.pq, nullptr, nullptr, 0, K, Ds, Ds, hscale, 0, OP_IF(Ds, opA), nullptr);
+                LINP(p_k, Ds, p_y, Ds, bt.pk_t, bo.pk, nullptr, nullptr, 0, K, Ds, Ds, 1.0f, 0, OP_IF(Ds, opA), nullptr);
+                LINP(p_v, Ds, p_y, Ds, bt.pv_t, bo.pv, nullptr, nullptr, 0, K, Ds, Ds, 1.0f, 0, OP_IF(Ds, opA), nullptr);
+                SAVI_PH(16);
                 mha_core_fwd(p_q, p_k, p_v, p_att, p_o, K, Ds, d.heads);
+                SAVI_PH(17);
                 // first block adds the residual to the NORMALISED input (transformer.py:75-78)
                 LIN(p_x1, Ds, p_o, Ds, bt.po_t, bo.po, nullptr, (j == 0) ? p_y : x, Ds, K, Ds, Ds, 1.0f, 0);
-                cta_ln(p_l2, Ds, p_x1, Ds, P + bo.ln2_w, P + bo.ln2_b, K, Ds, d.ln_eps);
-                LIN(p_f, 4 * Ds, p_l2, Ds, bt.f1_t, bo.f1, P + bo.f1b, nullptr, 0, K, Ds, 4 * Ds, 1.0f, LIN_RELU);
+                SAVI_PH(18);
+                if constexpr (MMA) cta_ln_op(p_l2, Ds, p_x1, Ds, P + bo.ln2_w, P + bo.ln2_b, K, Ds, d.ln_eps, OP_IF(Ds, opA));
+                else cta_ln(p_l2, Ds, p_x1, Ds, P + bo.ln2_w, P + bo.ln2_b, K, Ds, d.ln_eps);
+                SAVI_PH(19);
+                LINP(p_f, 4 * Ds, p_l2, Ds, bt.f1_t, bo.f1, P + bo.f1b, nullptr, 0, K, Ds, 4 * Ds, 1.0f, LIN_RELU, OP_IF(Ds, opA), nullptr);
+                SAVI_PH(20);
                 LIN(p_x2, Ds, p_f, 4 * Ds, bt.f2_t, bo.f2, P + bo.f2b, p_x1, Ds, K, 4 * Ds, Ds, 1.0f, 0);
                 x = p_x2;
             }
+            SAVI_PH(21);
             cta_ln(st, Ds, x, Ds, P + po.lnf_w, P + po.lnf_b, K, Ds, d.ln_eps);
             cta_copy(h, st, K * Ds);
             __syncthreads();
         }
     }
 #undef LIN
+#undef LINP
+#undef OP_IF
 }
 
 // ---------------------------------------------------------------------------

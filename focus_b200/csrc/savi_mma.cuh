@@ -60,40 +60,77 @@ __host__ __device__ __forceinline__ int lin_stride(int C) {
 // bytes of staging arena cta_linear_mma needs for an [R, C] operand (hi + lo)
 __host__ __device__ __forceinline__ size_t lin_mma_smem(int MT, int C) { return (size_t)2 * MT * 16 * lin_stride(C) * 2; }
 
+// Optional second destination of a linear layer / LayerNorm: the result is also written, already
+// split into bf16 hi/lo, into a shared-memory operand buffer, so the NEXT tensor-core linear finds
+// its A operand in place and skips the global round trip + staging pass.
+struct OpStage {
+    bf16* hi; bf16* lo; int stride;      // [rows][stride] bf16, stride in elements
+};
+__device__ __forceinline__ void opstage_put2(const OpStage& s, int r, int c, float y0, float y1) {
+    bf16 h0, h1, l0, l1;
+    split_bf16(y0, h0, l0); split_bf16(y1, h1, l1);
+    *reinterpret_cast<__nv_bfloat162*>(s.hi + (size_t)r * s.stride + c) = __halves2bfloat162(h0, h1);
+    *reinterpret_cast<__nv_bfloat162*>(s.lo + (size_t)r * s.stride + c) = __halves2bfloat162(l0, l1);
+}
+// rows [R, 16*MT) and columns [C, stride) of an operand buffer must be zero: done once per kernel
+__device__ __forceinline__ void opstage_clear(const OpStage& s, int rows) {
+    uint32_t* a = reinterpret_cast<uint32_t*>(s.hi); uint32_t* b = reinterpret_cast<uint32_t*>(s.lo);
+    for (int i = threadIdx.x; i < rows * s.stride / 2; i += NT) { a[i] = 0u; b[i] = 0u; }
+}
+
 // ---------------------------------------------------------------------------
 // Y[r][o] = act( Res[r][o] + bias[o] + alpha * sum_c X[r][c] * W[o][c] ),  r < R <= 16*MT, o < O
-//   X        : global fp32 [R, ldx]; staged into shared memory as bf16 hi/lo
+//   X        : global fp32 [R, ldx], staged into shared memory as bf16 hi/lo -- unless `pre` names an
+//              operand buffer a previous layer already filled (stride must be lin_stride(C))
 //   Whi, Wlo : global bf16 [O, C] (contraction index contiguous), streamed from L2 straight
 //              into B fragments with 16-byte loads (k-permuted: both operands use the same
-//              lane -> column map, so no ldmatrix is needed on the weight side)
+//              lane -> column map, so no ldmatrix is needed on the weight side).  The loads of a
+//              warp's first tile are issued BEFORE the operand staging, and every later tile is
+//              prefetched into registers while the current one is multiplied.
+//   out      : optional operand buffer that also receives the result (for the next layer)
 // Requires C % 8 == 0, O % 8 == 0.
 // ---------------------------------------------------------------------------
 template <int MT>
-__device__ void cta_linear_mma(float* Y, int ldy, const float* X, int ldx, const bf16* __restrict__ Whi,
-                               const bf16* __restrict__ Wlo, const float* __restrict__ bias, const float* Res, int ldr,
-                               const float* Mask, int ldm, int R, int C, int O, float alpha, int flags, void* arena) {
-    constexpr int NG = (MT == 4) ? 1 : 2;           // n-tiles (8 outputs) per warp pass
+__device__ __noinline__ void cta_linear_mma(float* Y, int ldy, const float* X, int ldx, const bf16* __restrict__ Whi,
+                                            const bf16* __restrict__ Wlo, const float* __restrict__ bias, const float* Res, int ldr,
+                                            const float* Mask, int ldm, int R, int C, int O, float alpha, int flags, void* arena,
+                                            const OpStage* pre, const OpStage* out) {
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, q = lane & 3;
-    const int cp = (C + 31) & ~31, st = lin_stride(C);
-    bf16* xh = reinterpret_cast<bf16*>(arena);
-    bf16* xl = xh + (size_t)MT * 16 * st;
-    __syncthreads();
-    for (int idx = tid; idx < MT * 16 * (cp >> 2); idx += NT) {
-        const int r = idx / (cp >> 2), c = (idx - r * (cp >> 2)) * 4;
-        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (r < R && c < C) v = ld4(X + (size_t)r * ldx + c);
-        bf16 h0, h1, h2, h3, l0, l1, l2, l3;
-        split_bf16(v.x, h0, l0); split_bf16(v.y, h1, l1); split_bf16(v.z, h2, l2); split_bf16(v.w, h3, l3);
-        __nv_bfloat162 hh0 = __halves2bfloat162(h0, h1), hh1 = __halves2bfloat162(h2, h3);
-        __nv_bfloat162 ll0 = __halves2bfloat162(l0, l1), ll1 = __halves2bfloat162(l2, l3);
-        uint2 ph, pl;
-        ph.x = *reinterpret_cast<uint32_t*>(&hh0); ph.y = *reinterpret_cast<uint32_t*>(&hh1);
-        pl.x = *reinterpret_cast<uint32_t*>(&ll0); pl.y = *reinterpret_cast<uint32_t*>(&ll1);
-        *reinterpret_cast<uint2*>(xh + (size_t)r * st + c) = ph;
-        *reinterpret_cast<uint2*>(xl + (size_t)r * st + c) = pl;
+    const int cp = (C + 31) & ~31, st = pre ? pre->stride : lin_stride(C);
+    const int ntiles = O >> 3, nseg = (cp + 127) >> 7;
+    const bf16* xh = pre ? pre->hi : reinterpret_cast<const bf16*>(arena);
+    const bf16* xl = pre ? pre->lo : xh + (size_t)MT * 16 * st;
+
+    auto load_b = [&](int nt, int seg, uint4 (&bh)[4], uint4 (&bl)[4]) {
+        const int o = nt * 8 + g;
+#pragma unroll
+        for (int ch = 0; ch < 4; ++ch) {
+            const int col = seg * 128 + ch * 32 + q * 8;
+            if (col < C) { bh[ch] = ldg128(Whi + (size_t)o * C + col); bl[ch] = ldg128(Wlo + (size_t)o * C + col); }
+            else { bh[ch] = make_uint4(0u, 0u, 0u, 0u); bl[ch] = bh[ch]; }
+        }
+    };
+    if (!pre) {
+        __syncthreads();
+        bf16* wh = reinterpret_cast<bf16*>(arena);
+        bf16* wl = wh + (size_t)MT * 16 * st;
+        for (int idx = tid; idx < MT * 16 * (cp >> 2); idx += NT) {
+            const int r = idx / (cp >> 2), c = (idx - r * (cp >> 2)) * 4;
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (r < R && c < C) v = ld4(X + (size_t)r * ldx + c);
+            bf16 h0, h1, h2, h3, l0, l1, l2, l3;
+            split_bf16(v.x, h0, l0); split_bf16(v.y, h1, l1); split_bf16(v.z, h2, l2); split_bf16(v.w, h3, l3);
+            __nv_bfloat162 hh0 = __halves2bfloat162(h0, h1), hh1 = __halves2bfloat162(h2, h3);
+            __nv_bfloat162 ll0 = __halves2bfloat162(l0, l1), ll1 = __halves2bfloat162(l2, l3);
+            uint2 ph, pl;
+            ph.x = *reinterpret_cast<uint32_t*>(&hh0); ph.y = *reinterpret_cast<uint32_t*>(&hh1);
+            pl.x = *reinterpret_cast<uint32_t*>(&ll0); pl.y = *reinterpret_cast<uint32_t*>(&ll1);
+            *reinterpret_cast<uint2*>(wh + (size_t)r * st + c) = ph;
+            *reinterpret_cast<uint2*>(wl + (size_t)r * st + c) = pl;
+        }
     }
     __syncthreads();
-    const int ntiles = O >> 3;
+    constexpr int NG = 1;
     for (int nt0 = warp * NG; nt0 < ntiles; nt0 += NW * NG) {
         float acc[NG][MT][4];
 #pragma unroll
@@ -162,6 +199,7 @@ __device__ void cta_linear_mma(float* Y, int ldy, const float* X, int ldx, const
                                 if (!(mm.y > 0.f)) y1 = 0.f;
                             }
                             *reinterpret_cast<float2*>(Y + (size_t)r * ldy + o) = make_float2(y0, y1);
+                            if (out) opstage_put2(*out, r, o, y0, y1);
                         }
                     }
                 }
@@ -171,16 +209,42 @@ __device__ void cta_linear_mma(float* Y, int ldy, const float* X, int ldx, const
     __syncthreads();
 }
 
+// LayerNorm (as cta_ln) that can also leave its result, split into bf16 hi/lo, in an operand buffer.
+static __device__ __noinline__ void cta_ln_op(float* Y, int ldy, const float* X, int ldx, const float* __restrict__ g,
+                                              const float* __restrict__ b, int R, int C, float eps, const OpStage* out) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (int r = warp; r < R; r += NW) {
+        const float* x = X + (size_t)r * ldx;
+        float s = 0.f;
+        for (int c = lane; c < C; c += 32) s += x[c];
+        const float mean = warp_sum(s) / (float)C;
+        float v = 0.f;
+        for (int c = lane; c < C; c += 32) { float t = x[c] - mean; v = fmaf(t, t, v); }
+        const float rstd = 1.0f / sqrtf(warp_sum(v) / (float)C + eps);
+        for (int c = lane; c < C; c += 32) {
+            const float y = (x[c] - mean) * rstd * __ldg(g + c) + __ldg(b + c);
+            Y[(size_t)r * ldy + c] = y;
+            if (out) {
+                bf16 hh, ll;
+                split_bf16(y, hh, ll);
+                out->hi[(size_t)r * out->stride + c] = hh;
+                out->lo[(size_t)r * out->stride + c] = ll;
+            }
+        }
+    }
+    __syncthreads();
+}
+
 // Dispatch of one slot-side linear layer.  off_io: offset of the fp32 [C][O] ("in x out") copy used by the
 // SIMT path; off_oi: offset of the [O][C] copy whose bf16 hi/lo images feed the tensor-core path.
 template <bool MMA, int MT>
-__device__ __forceinline__ void lin(const float* P, const bf16* Phi, const bf16* Plo, float* Y, int ldy, const float* X,
+__device__ __noinline__ void lin(const float* P, const bf16* Phi, const bf16* Plo, float* Y, int ldy, const float* X,
                                     int ldx, int off_io, int off_oi, const float* bias, const float* Res, int ldr,
                                     const float* Mask, int ldm, int R, int C, int O, float alpha, int flags, float* arena,
-                                    int arena_floats) {
+                                    int arena_floats, const OpStage* pre = nullptr, const OpStage* out = nullptr) {
     if constexpr (MMA) {
-        if (lin_mma_smem(MT, C) <= (size_t)arena_floats * 4 && (O & 7) == 0 && (C & 7) == 0) {
-            cta_linear_mma<MT>(Y, ldy, X, ldx, Phi + off_oi, Plo + off_oi, bias, Res, ldr, Mask, ldm, R, C, O, alpha, flags, arena);
+        if ((pre || lin_mma_smem(MT, C) <= (size_t)arena_floats * 4) && (O & 7) == 0 && (C & 7) == 0) {
+            cta_linear_mma<MT>(Y, ldy, X, ldx, Phi + off_oi, Plo + off_oi, bias, Res, ldr, Mask, ldm, R, C, O, alpha, flags, arena, pre, out);
             return;
         }
     }

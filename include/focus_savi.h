@@ -127,6 +127,11 @@ int savi_last_launch_count(void);
 int savi_profile_enable(int on);
 int savi_profile_read(float* ms_host, int n);
 
+/* Development aid: when set to a device buffer of 64 int64 counters, CTA 0 of the clip kernels
+ * accumulates the SM cycles spent in each phase of the recurrence (tools/phase_times.py).
+ * Pass NULL to disable (default).  Adds barriers; never enable while benchmarking. */
+int savi_debug_set_phase_buffer(void* dev_ptr);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,40 @@
+"""Per-phase cycle breakdown of the clip kernels (CTA 0), via savi_debug_set_phase_buffer."""
+import os, sys
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import torch, bench
+from focus_b200 import _lib
+NAMES = {0: "top/pred-tail", 1: "copy+LN", 2: "lin q", 3: "lin qk", 4: "token pass", 5: "cluster sync", 6: "combine", 7: "lin U",
+         8: "lin gi", 9: "lin gh", 10: "gru pointwise", 11: "mlp LN", 12: "lin a", 13: "lin h(mlp2)", 14: "slots copy", 15: "pred LN1",
+         16: "pred QKV", 17: "pred mha core", 18: "pred Wo", 19: "pred LN2", 20: "pred F1", 21: "pred F2",
+         30: "B: top", 31: "B pred: LNf..dO", 32: "B pred mha core", 33: "B pred: dy..LN1", 34: "B step setup", 35: "B mlp bwd",
+         36: "B gru pointwise+colsum", 37: "B lin dh(whh)", 38: "B lin dU(wih)", 39: "B lin dUx + cvec", 40: "B token pass",
+         41: "B cluster sync", 42: "B combine", 43: "B lin dq", 44: "B LN st", 45: "B lin dst", 46: "B LN bwd", 50: "tp: stage qk + issue", 51: "tp: wait tile", 52: "tp: phase1 mma", 53: "tp: softmax", 54: "tp: stores+sync", 55: "tp: attn copy", 56: "tp: phase2", 57: "tp: epilogue"}
+cfg = sys.argv[1] if len(sys.argv) > 1 else "c2"
+c = dict(bench.CONFIGS[cfg])
+dt = torch.float32 if c["dtype"] == "fp32" else torch.bfloat16
+m = bench.make_params_like(c).cuda()
+g = torch.Generator().manual_seed(1)
+x = torch.randn(c["B"], c["T"], c["N"], c["D"], generator=g).to(dt).cuda().requires_grad_(True)
+noise = torch.randn(c["B"], c["K"], c["Ds"], generator=g).cuda()
+gs = torch.randn(c["B"], c["T"], c["K"], c["Ds"], generator=g).cuda()
+ga = torch.randn(c["B"], c["T"], c["N"], c["K"], generator=g).to(dt).cuda()
+def step():
+    s, at = m(x, noise=noise)
+    torch.autograd.backward([s, at], [gs.to(s.dtype), ga]); x.grad = None
+step(); torch.cuda.synchronize()
+buf = torch.zeros(64, dtype=torch.int64, device="cuda")
+_lib.lib.savi_debug_set_phase_buffer(buf.data_ptr())
+step(); torch.cuda.synchronize()
+_lib.lib.savi_debug_set_phase_buffer(None)
+v = buf.cpu().tolist()
+tot_f = sum(v[:30]); tot_b = sum(v[30:50])
+print("forward  total %.1f us (cycles @1.965GHz)" % (tot_f / 1965.0))
+for i in range(30):
+    if v[i]: print("  %-24s %8.1f us  %5.1f%%" % (NAMES.get(i, i), v[i] / 1965.0, 100.0 * v[i] / tot_f))
+print("backward total %.1f us" % (tot_b / 1965.0))
+for i in range(30, 50):
+    if v[i]: print("  %-24s %8.1f us  %5.1f%%" % (NAMES.get(i, i), v[i] / 1965.0, 100.0 * v[i] / tot_b))
+print('token pass fwd sub-phases (included in "token pass")')
+for i in range(50, 64):
+    if v[i]: print("  %-24s %8.1f us" % (NAMES.get(i, i), v[i] / 1965.0))

@@ -196,6 +196,56 @@ static __device__ __noinline__ void mha_core_bwd(const float* dO, const float* Q
     __syncthreads();
 }
 
+// Shared-memory version of mha_core_bwd (all five operands staged, odd row strides).
+static __device__ __noinline__ void mha_core_bwd_smem(const float* dO, const float* Q, const float* Kk, const float* V, const float* att,
+                                                      float* dQ, float* dKk, float* dV, int K, int Ds, int H, float hscale, float* arena) {
+    const int dh = Ds / H, tid = threadIdx.x, ld = Ds + 1, ka = K | 1;
+    float* sO = arena; float* sQ = sO + (size_t)K * ld; float* sK = sQ + (size_t)K * ld; float* sV = sK + (size_t)K * ld;
+    float* sA = sV + (size_t)K * ld; float* sD = sA + (size_t)H * K * ka;
+    __syncthreads();
+    for (int i = tid * 4; i < K * Ds; i += NT * 4) {
+        const int r = i / Ds, c = i - r * Ds;
+        const float4 o = ld4(dO + i), a = ld4(Q + i), b = ld4(Kk + i), v = ld4(V + i);
+        float* p0 = sO + (size_t)r * ld + c; float* p1 = sQ + (size_t)r * ld + c; float* p2 = sK + (size_t)r * ld + c; float* p3 = sV + (size_t)r * ld + c;
+        p0[0] = o.x; p0[1] = o.y; p0[2] = o.z; p0[3] = o.w;
+        p1[0] = a.x; p1[1] = a.y; p1[2] = a.z; p1[3] = a.w;
+        p2[0] = b.x; p2[1] = b.y; p2[2] = b.z; p2[3] = b.w;
+        p3[0] = v.x; p3[1] = v.y; p3[2] = v.z; p3[3] = v.w;
+    }
+    for (int idx = tid; idx < H * K * K; idx += NT) sA[(size_t)(idx / K) * ka + idx % K] = att[idx];
+    __syncthreads();
+    for (int idx = tid; idx < H * K * K; idx += NT) {
+        const int j = idx % K, i = (idx / K) % K, h = idx / (K * K);
+        const float* a = sO + (size_t)i * ld + h * dh;
+        const float* v = sV + (size_t)j * ld + h * dh;
+        float s = 0.f;
+        for (int c = 0; c < dh; ++c) s = fmaf(a[c], v[c], s);
+        sD[(size_t)(h * K + i) * ka + j] = s;
+    }
+    __syncthreads();
+    for (int row = tid; row < H * K; row += NT) {
+        const float* a = sA + (size_t)row * ka;
+        float* da = sD + (size_t)row * ka;
+        float dot = 0.f;
+        for (int j = 0; j < K; ++j) dot = fmaf(a[j], da[j], dot);
+        for (int j = 0; j < K; ++j) da[j] = a[j] * (da[j] - dot);
+    }
+    __syncthreads();
+    for (int idx = tid; idx < K * Ds; idx += NT) {
+        const int c = idx % Ds, i = idx / Ds, h = c / dh;
+        const float* dlg = sD + (size_t)h * K * ka;
+        const float* at = sA + (size_t)h * K * ka;
+        float sq = 0.f, sk = 0.f, sv = 0.f;
+        for (int j = 0; j < K; ++j) {
+            sq = fmaf(dlg[(size_t)i * ka + j], sK[(size_t)j * ld + c], sq);
+            sk = fmaf(dlg[(size_t)j * ka + i], sQ[(size_t)j * ld + c], sk);
+            sv = fmaf(at[(size_t)j * ka + i], sO[(size_t)j * ld + c], sv);
+        }
+        dQ[idx] = sq * hscale; dKk[idx] = sk; dV[idx] = sv;
+    }
+    __syncthreads();
+}
+
 // ---------------------------------------------------------------------------
 // K3: BPTT through the whole recurrence of one clip (frames T-1..0, iterations I-1..0).
 // Writes: dxhat accumulator, the staged (dY, X) operands of the weight-gradient
@@ -276,7 +326,8 @@ __global__ void __launch_bounds__(NT, 1) savi_bwd_kernel(const __grid_constant__
                 cta_ln_bwd(s_dx1, Ds, t0, Ds, t1, Ds, p_x1, Ds, P + bo.ln2_w, G + bo.ln2_w, G + bo.ln2_b, K, Ds, d.ln_eps, lead);
                 LIN(t1, Ds, s_dx1, Ds, bo.po, bt.po_t, nullptr, 0, nullptr, 0, K, Ds, Ds, 1.0f);                  // dO
                 SAVI_PH(31);
-                mha_core_bwd(t1, p_q, p_k, p_v, p_att, t2, s_dq, s_dk, s_dv, K, Ds, d.heads, hscale);
+                if (4 * K * (Ds + 1) + 2 * d.heads * K * (K | 1) <= AF) mha_core_bwd_smem(t1, p_q, p_k, p_v, p_att, s_dq, s_dk, s_dv, K, Ds, d.heads, hscale, arena);
+                else mha_core_bwd(t1, p_q, p_k, p_v, p_att, t2, s_dq, s_dk, s_dv, K, Ds, d.heads, hscale);
                 SAVI_PH(32);
                 LIN(t1, Ds, s_dq, Ds, bo.pq, bt.pq_t, (j == 0) ? s_dx1 : nullptr, Ds, nullptr, 0, K, Ds, Ds, 1.0f);
                 LIN(t1, Ds, s_dk, Ds, bo.pk, bt.pk_t, t1, Ds, nullptr, 0, K, Ds, Ds, 1.0f);

@@ -150,76 +150,112 @@ static __device__ __noinline__ void cta_linear(float* Y, int ldy, const float* X
 }
 
 // LayerNorm over the last dim, one warp per row (torch semantics: biased variance).
-static __device__ __noinline__ void cta_ln(float* Y, int ldy, const float* X, int ldx, const float* __restrict__ g,
-                       const float* __restrict__ b, int R, int C, float eps) {
+// Every element is loaded ONCE (all loads of a row are issued back to back, then reduced from
+// registers): the rows live in global memory and each dependent re-read would cost an L2 round trip.
+template <int VPT>   // values per lane: C <= 32 * VPT
+static __device__ __forceinline__ void cta_ln_t(float* Y, int ldy, const float* X, int ldx, const float* __restrict__ g,
+                                                 const float* __restrict__ b, int R, int C, float eps) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     for (int r = warp; r < R; r += NW) {
         const float* x = X + (size_t)r * ldx;
+        float v[VPT];
         float s = 0.f;
-        for (int c = lane; c < C; c += 32) s += x[c];
+#pragma unroll
+        for (int j = 0; j < VPT; ++j) { const int c = lane + 32 * j; v[j] = (c < C) ? x[c] : 0.f; s += v[j]; }
         const float mean = warp_sum(s) / (float)C;
-        float v = 0.f;
-        for (int c = lane; c < C; c += 32) { float t = x[c] - mean; v = fmaf(t, t, v); }
-        const float rstd = 1.0f / sqrtf(warp_sum(v) / (float)C + eps);
-        for (int c = lane; c < C; c += 32) Y[(size_t)r * ldy + c] = (x[c] - mean) * rstd * __ldg(g + c) + __ldg(b + c);
+        float q = 0.f;
+#pragma unroll
+        for (int j = 0; j < VPT; ++j) { const int c = lane + 32 * j; const float t = (c < C) ? v[j] - mean : 0.f; q = fmaf(t, t, q); }
+        const float rstd = 1.0f / sqrtf(warp_sum(q) / (float)C + eps);
+#pragma unroll
+        for (int j = 0; j < VPT; ++j) {
+            const int c = lane + 32 * j;
+            if (c < C) Y[(size_t)r * ldy + c] = (v[j] - mean) * rstd * __ldg(g + c) + __ldg(b + c);
+        }
     }
     __syncthreads();
 }
+static __device__ __noinline__ void cta_ln(float* Y, int ldy, const float* X, int ldx, const float* __restrict__ g,
+                                           const float* __restrict__ b, int R, int C, float eps) {
+    if (C <= 128) cta_ln_t<4>(Y, ldy, X, ldx, g, b, R, C, eps);
+    else if (C <= 256) cta_ln_t<8>(Y, ldy, X, ldx, g, b, R, C, eps);
+    else cta_ln_t<16>(Y, ldy, X, ldx, g, b, R, C, eps);
+}
 
 // dX[r] = (Res ? Res[r] : 0) + LayerNorm backward of dY through X;  optionally
-// accumulates d gamma / d beta into global (atomics, one add per warp and column).
-// C <= 512.
-static __device__ __noinline__ void cta_ln_bwd(float* dX, int lddx, const float* Res, int ldr, const float* dY, int lddy,
-                           const float* X, int ldx, const float* __restrict__ g, float* dg_glob, float* db_glob,
-                           int R, int C, float eps, bool do_param_grads) {
+// accumulates d gamma / d beta into global (atomics, one add per warp and column).  C <= 512.
+template <int VPT>
+static __device__ __forceinline__ void cta_ln_bwd_t(float* dX, int lddx, const float* Res, int ldr, const float* dY, int lddy,
+                                                     const float* X, int ldx, const float* __restrict__ g, float* dg_glob, float* db_glob,
+                                                     int R, int C, float eps, bool do_param_grads) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    float ag[16], ab[16];
+    float ag[VPT], ab[VPT], gm[VPT];
 #pragma unroll
-    for (int j = 0; j < 16; ++j) { ag[j] = 0.f; ab[j] = 0.f; }
+    for (int j = 0; j < VPT; ++j) { ag[j] = 0.f; ab[j] = 0.f; const int c = lane + 32 * j; gm[j] = (c < C) ? __ldg(g + c) : 0.f; }
     for (int r = warp; r < R; r += NW) {
         const float* x = X + (size_t)r * ldx;
         const float* dy = dY + (size_t)r * lddy;
+        float xv[VPT], dv[VPT], rv[VPT];
         float s = 0.f;
-        for (int c = lane; c < C; c += 32) s += x[c];
+#pragma unroll
+        for (int j = 0; j < VPT; ++j) {                      // all loads of the row first
+            const int c = lane + 32 * j;
+            xv[j] = (c < C) ? x[c] : 0.f;
+            dv[j] = (c < C) ? dy[c] : 0.f;
+            rv[j] = (Res && c < C) ? Res[(size_t)r * ldr + c] : 0.f;
+            s += xv[j];
+        }
         const float mean = warp_sum(s) / (float)C;
-        float v = 0.f;
-        for (int c = lane; c < C; c += 32) { float t = x[c] - mean; v = fmaf(t, t, v); }
-        const float rstd = 1.0f / sqrtf(warp_sum(v) / (float)C + eps);
+        float q = 0.f;
+#pragma unroll
+        for (int j = 0; j < VPT; ++j) { const int c = lane + 32 * j; const float t = (c < C) ? xv[j] - mean : 0.f; q = fmaf(t, t, q); }
+        const float rstd = 1.0f / sqrtf(warp_sum(q) / (float)C + eps);
         float s1 = 0.f, s2 = 0.f;
 #pragma unroll
-        for (int j = 0; j < 16; ++j) {
+        for (int j = 0; j < VPT; ++j) {
             const int c = lane + 32 * j;
-            if (c < C) {
-                const float z = (x[c] - mean) * rstd, d = dy[c];
-                const float dz = d * __ldg(g + c);
-                s1 += dz; s2 = fmaf(dz, z, s2);
-                ag[j] = fmaf(d, z, ag[j]); ab[j] += d;
-            }
+            const float z = (c < C) ? (xv[j] - mean) * rstd : 0.f;
+            const float dz = dv[j] * gm[j];
+            s1 += dz; s2 = fmaf(dz, z, s2);
+            ag[j] = fmaf(dv[j], z, ag[j]); ab[j] += dv[j];
+            xv[j] = z; dv[j] = dz;
         }
         s1 = warp_sum(s1) / (float)C; s2 = warp_sum(s2) / (float)C;
-        for (int c = lane; c < C; c += 32) {
-            const float z = (x[c] - mean) * rstd;
-            float o = rstd * (dy[c] * __ldg(g + c) - s1 - z * s2);
-            if (Res) o += Res[(size_t)r * ldr + c];
-            dX[(size_t)r * lddx + c] = o;
+#pragma unroll
+        for (int j = 0; j < VPT; ++j) {
+            const int c = lane + 32 * j;
+            if (c < C) dX[(size_t)r * lddx + c] = rstd * (dv[j] - s1 - xv[j] * s2) + rv[j];
         }
     }
     if (do_param_grads) {
 #pragma unroll
-        for (int j = 0; j < 16; ++j) {
+        for (int j = 0; j < VPT; ++j) {
             const int c = lane + 32 * j;
             if (c < C) { atomicAdd(dg_glob + c, ag[j]); atomicAdd(db_glob + c, ab[j]); }
         }
     }
     __syncthreads();
 }
+static __device__ __noinline__ void cta_ln_bwd(float* dX, int lddx, const float* Res, int ldr, const float* dY, int lddy,
+                                               const float* X, int ldx, const float* __restrict__ g, float* dg_glob, float* db_glob,
+                                               int R, int C, float eps, bool do_param_grads) {
+    if (C <= 128) cta_ln_bwd_t<4>(dX, lddx, Res, ldr, dY, lddy, X, ldx, g, dg_glob, db_glob, R, C, eps, do_param_grads);
+    else if (C <= 256) cta_ln_bwd_t<8>(dX, lddx, Res, ldr, dY, lddy, X, ldx, g, dg_glob, db_glob, R, C, eps, do_param_grads);
+    else cta_ln_bwd_t<16>(dX, lddx, Res, ldr, dY, lddy, X, ldx, g, dg_glob, db_glob, R, C, eps, do_param_grads);
+}
 
 // dst[o] += sum_r X[r][o]   (bias gradients), one thread per column.
 static __device__ __noinline__ void cta_colsum_atomic(float* dst, const float* X, int ldx, int R, int O) {
     for (int o = threadIdx.x; o < O; o += NT) {
-        float s = 0.f;
-        for (int r = 0; r < R; ++r) s += X[(size_t)r * ldx + o];
-        atomicAdd(dst + o, s);
+        float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+        int r = 0;
+        for (; r + 3 < R; r += 4) {
+            const float a0 = X[(size_t)r * ldx + o], a1 = X[(size_t)(r + 1) * ldx + o];
+            const float a2 = X[(size_t)(r + 2) * ldx + o], a3 = X[(size_t)(r + 3) * ldx + o];
+            s0 += a0; s1 += a1; s2 += a2; s3 += a3;
+        }
+        for (; r < R; ++r) s0 += X[(size_t)r * ldx + o];
+        atomicAdd(dst + o, (s0 + s1) + (s2 + s3));
     }
 }
 

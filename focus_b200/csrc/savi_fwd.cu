@@ -182,6 +182,52 @@ static __device__ __noinline__ void mha_core_fwd(const float* Q, const float* Kk
     __syncthreads();
 }
 
+// Same computation with Q, K, V and the attention matrix staged in shared memory (rows padded to an
+// odd stride: conflict-free for both the per-key and the per-feature access patterns).
+static __device__ __noinline__ void mha_core_fwd_smem(const float* Q, const float* Kk, const float* V, float* att, float* O,
+                                                      int K, int Ds, int H, float* arena) {
+    const int dh = Ds / H, tid = threadIdx.x, ld = Ds + 1, ka = K | 1;
+    float* sQ = arena; float* sK = sQ + (size_t)K * ld; float* sV = sK + (size_t)K * ld; float* sA = sV + (size_t)K * ld;
+    __syncthreads();
+    for (int i = tid * 4; i < K * Ds; i += NT * 4) {
+        const int r = i / Ds, c = i - r * Ds;
+        const float4 a = ld4(Q + i), b = ld4(Kk + i), v = ld4(V + i);
+        float* q = sQ + (size_t)r * ld + c; float* k = sK + (size_t)r * ld + c; float* w = sV + (size_t)r * ld + c;
+        q[0] = a.x; q[1] = a.y; q[2] = a.z; q[3] = a.w;
+        k[0] = b.x; k[1] = b.y; k[2] = b.z; k[3] = b.w;
+        w[0] = v.x; w[1] = v.y; w[2] = v.z; w[3] = v.w;
+    }
+    __syncthreads();
+    for (int idx = tid; idx < H * K * K; idx += NT) {
+        const int j = idx % K, i = (idx / K) % K, h = idx / (K * K);
+        const float* q = sQ + (size_t)i * ld + h * dh;
+        const float* k = sK + (size_t)j * ld + h * dh;
+        float s = 0.f;
+        for (int c = 0; c < dh; ++c) s = fmaf(q[c], k[c], s);
+        sA[(size_t)(h * K + i) * ka + j] = s;
+    }
+    __syncthreads();
+    for (int row = tid; row < H * K; row += NT) {
+        float* a = sA + (size_t)row * ka;
+        float mx = -INFINITY;
+        for (int j = 0; j < K; ++j) mx = fmaxf(mx, a[j]);
+        float sum = 0.f;
+        for (int j = 0; j < K; ++j) { float e = expf(a[j] - mx); a[j] = e; sum += e; }
+        const float inv = 1.0f / sum;
+        for (int j = 0; j < K; ++j) a[j] *= inv;
+    }
+    __syncthreads();
+    for (int idx = tid; idx < H * K * K; idx += NT) att[idx] = sA[(size_t)(idx / K) * ka + idx % K];     // saved for backward
+    for (int idx = tid; idx < K * Ds; idx += NT) {
+        const int c = idx % Ds, i = idx / Ds, h = c / dh;
+        const float* a = sA + (size_t)(h * K + i) * ka;
+        float s = 0.f;
+        for (int j = 0; j < K; ++j) s = fmaf(a[j], sV[(size_t)j * ld + c], s);
+        O[idx] = s;
+    }
+    __syncthreads();
+}
+
 // ---------------------------------------------------------------------------
 // K2: the whole T x I recurrence of one clip.  grid = B * CN CTAs, cluster CN.
 // ---------------------------------------------------------------------------
@@ -254,8 +300,7 @@ __global__ void __launch_bounds__(NT, 1) savi_fwd_kernel(const __grid_constant__
 
             SAVI_PH(0);
             cta_copy(r_hp, h, K * Ds);                                                   // slots_prev (steve.py:71)
-            if constexpr (MMA) cta_ln_op(st, Ds, h, Ds, P + po.ln_s_w, P + po.ln_s_b, K, Ds, d.ln_eps, OP_IF(Ds, opA));
-            else cta_ln(st, Ds, h, Ds, P + po.ln_s_w, P + po.ln_s_b, K, Ds, d.ln_eps);      // :72
+            cta_ln(st, Ds, h, Ds, P + po.ln_s_w, P + po.ln_s_b, K, Ds, d.ln_eps);      // :72
             SAVI_PH(1);
             LINP(r_q, Ds, st, Ds, po.wq_t, po.wq, nullptr, nullptr, 0, K, Ds, Ds, 1.0f, 0, OP_IF(Ds, opA), OP_IF(Ds, opB));   // :75
             SAVI_PH(2);
@@ -330,8 +375,7 @@ __global__ void __launch_bounds__(NT, 1) savi_fwd_kernel(const __grid_constant__
             __syncthreads();
             SAVI_PH(10);
             if (mlp) {                                                                    // residual MLP (:92-93)
-                if constexpr (MMA) cta_ln_op(st, Ds, h, Ds, P + po.ln_m_w, P + po.ln_m_b, K, Ds, d.ln_eps, OP_IF(Ds, opA));
-                else cta_ln(st, Ds, h, Ds, P + po.ln_m_w, P + po.ln_m_b, K, Ds, d.ln_eps);
+                cta_ln(st, Ds, h, Ds, P + po.ln_m_w, P + po.ln_m_b, K, Ds, d.ln_eps);
                 SAVI_PH(11);
                 LINP(r_a, M, st, Ds, po.w1_t, po.w1, P + po.b1, nullptr, 0, K, Ds, M, 1.0f, LIN_RELU, OP_IF(Ds, opA), OP_IF(M, opB));
                 SAVI_PH(12);
@@ -361,20 +405,19 @@ __global__ void __launch_bounds__(NT, 1) savi_fwd_kernel(const __grid_constant__
                 float* p_x2 = lead ? frow(fb, a.sl.px2, f, b, B, K, Ds) : cs + a.wl.sh_px2;
                 float* p_att = lead ? fb + a.sl.patt + (f * B + b) * ((int64_t)d.heads * K * K) : cs + a.wl.sh_patt;
                 SAVI_PH(14);
-                if constexpr (MMA) cta_ln_op(p_y, Ds, x, Ds, P + bo.ln1_w, P + bo.ln1_b, K, Ds, d.ln_eps, OP_IF(Ds, opA));
-                else cta_ln(p_y, Ds, x, Ds, P + bo.ln1_w, P + bo.ln1_b, K, Ds, d.ln_eps);
+                cta_ln(p_y, Ds, x, Ds, P + bo.ln1_w, P + bo.ln1_b, K, Ds, d.ln_eps);
                 SAVI_PH(15);
                 LINP(p_q, Ds, p_y, Ds, bt.pq_t, bo.pq, nullptr, nullptr, 0, K, Ds, Ds, hscale, 0, OP_IF(Ds, opA), nullptr);
                 LINP(p_k, Ds, p_y, Ds, bt.pk_t, bo.pk, nullptr, nullptr, 0, K, Ds, Ds, 1.0f, 0, OP_IF(Ds, opA), nullptr);
                 LINP(p_v, Ds, p_y, Ds, bt.pv_t, bo.pv, nullptr, nullptr, 0, K, Ds, Ds, 1.0f, 0, OP_IF(Ds, opA), nullptr);
                 SAVI_PH(16);
-                mha_core_fwd(p_q, p_k, p_v, p_att, p_o, K, Ds, d.heads);
+                if (3 * K * (Ds + 1) + d.heads * K * (K | 1) <= AF) mha_core_fwd_smem(p_q, p_k, p_v, p_att, p_o, K, Ds, d.heads, arena);
+                else mha_core_fwd(p_q, p_k, p_v, p_att, p_o, K, Ds, d.heads);
                 SAVI_PH(17);
                 // first block adds the residual to the NORMALISED input (transformer.py:75-78)
                 LIN(p_x1, Ds, p_o, Ds, bt.po_t, bo.po, nullptr, (j == 0) ? p_y : x, Ds, K, Ds, Ds, 1.0f, 0);
                 SAVI_PH(18);
-                if constexpr (MMA) cta_ln_op(p_l2, Ds, p_x1, Ds, P + bo.ln2_w, P + bo.ln2_b, K, Ds, d.ln_eps, OP_IF(Ds, opA));
-                else cta_ln(p_l2, Ds, p_x1, Ds, P + bo.ln2_w, P + bo.ln2_b, K, Ds, d.ln_eps);
+                cta_ln(p_l2, Ds, p_x1, Ds, P + bo.ln2_w, P + bo.ln2_b, K, Ds, d.ln_eps);
                 SAVI_PH(19);
                 LINP(p_f, 4 * Ds, p_l2, Ds, bt.f1_t, bo.f1, P + bo.f1b, nullptr, 0, K, Ds, 4 * Ds, 1.0f, LIN_RELU, OP_IF(Ds, opA), nullptr);
                 SAVI_PH(20);

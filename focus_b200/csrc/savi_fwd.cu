@@ -274,6 +274,7 @@ __global__ void __launch_bounds__(NT, 1) savi_fwd_kernel(const __grid_constant__
     }
 #define OP_IF(w_, buf_) ((OW && (w_) == OW) ? &(buf_) : nullptr)
 
+    if (blockIdx.x == 0 && tid == 0) g_lin_dbg = a.dbg;
     long long ph_last = clock64();
     // slots0 = mu + exp(log_sigma) * noise   (steve.py:56-57)
     for (int i = tid; i < K * Ds; i += NT) {

@@ -16,6 +16,11 @@
 
 typedef __nv_bfloat16 bf16;
 
+// development aid: sub-phase cycle counters of cta_linear_mma (slots 58..62 of the phase buffer), CTA 0 only
+__device__ long long* g_lin_dbg = nullptr;
+#define LIN_PH(id) do { if (ldbg) { if (threadIdx.x == 0) { long long t_ = clock64(); \
+    atomicAdd(reinterpret_cast<unsigned long long*>(ldbg + (id)), (unsigned long long)(t_ - lt_)); lt_ = t_; } } } while (0)
+
 __device__ __forceinline__ void mma16816(float (&c)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3,
                                          uint32_t b0, uint32_t b1) {
     asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};\n"
@@ -97,6 +102,8 @@ __device__ __noinline__ void cta_linear_mma(float* Y, int ldy, const float* X, i
                                             const OpStage* pre, const OpStage* out) {
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, q = lane & 3;
     const int cp = (C + 31) & ~31, st = pre ? pre->stride : lin_stride(C);
+    long long* ldbg = (blockIdx.x == 0) ? g_lin_dbg : nullptr;
+    long long lt_ = clock64();
     const int ntiles = O >> 3, nseg = (cp + 127) >> 7;
     const bf16* xh = pre ? pre->hi : reinterpret_cast<const bf16*>(arena);
     const bf16* xl = pre ? pre->lo : xh + (size_t)MT * 16 * st;
@@ -129,7 +136,9 @@ __device__ __noinline__ void cta_linear_mma(float* Y, int ldy, const float* X, i
             *reinterpret_cast<uint2*>(wl + (size_t)r * st + c) = pl;
         }
     }
+    LIN_PH(58);
     __syncthreads();
+    LIN_PH(59);
     constexpr int NG = 1;
     for (int nt0 = warp * NG; nt0 < ntiles; nt0 += NW * NG) {
         float acc[NG][MT][4];
@@ -155,6 +164,7 @@ __device__ __noinline__ void cta_linear_mma(float* Y, int ldy, const float* X, i
                     }
                 }
             }
+            LIN_PH(60);
 #pragma unroll
             for (int ch = 0; ch < 4; ++ch) {
                 const int col = cseg + ch * 32 + q * 8;
@@ -179,6 +189,7 @@ __device__ __noinline__ void cta_linear_mma(float* Y, int ldy, const float* X, i
                 }
             }
         }
+        LIN_PH(61);
 #pragma unroll
         for (int n = 0; n < NG; ++n) {
             if (nt0 + n < ntiles) {
@@ -206,7 +217,9 @@ __device__ __noinline__ void cta_linear_mma(float* Y, int ldy, const float* X, i
             }
         }
     }
+    LIN_PH(62);
     __syncthreads();
+    LIN_PH(63);
 }
 
 // LayerNorm (as cta_ln) that can also leave its result, split into bf16 hi/lo, in an operand buffer.

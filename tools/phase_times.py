@@ -9,7 +9,7 @@ NAMES = {0: "top/pred-tail", 1: "copy+LN", 2: "lin q", 3: "lin qk", 4: "token pa
          16: "pred QKV", 17: "pred mha core", 18: "pred Wo", 19: "pred LN2", 20: "pred F1", 21: "pred F2",
          30: "B: top", 31: "B pred: LNf..dO", 32: "B pred mha core", 33: "B pred: dy..LN1", 34: "B step setup", 35: "B mlp bwd",
          36: "B gru pointwise+colsum", 37: "B lin dh(whh)", 38: "B lin dU(wih)", 39: "B lin dUx + cvec", 40: "B token pass",
-         41: "B cluster sync", 42: "B combine", 43: "B lin dq", 44: "B LN st", 45: "B lin dst", 46: "B LN bwd", 50: "tp: stage qk + issue", 51: "tp: wait tile", 52: "tp: phase1 mma", 53: "tp: softmax", 54: "tp: stores+sync", 55: "tp: attn copy", 56: "tp: phase2", 57: "tp: epilogue"}
+         41: "B cluster sync", 42: "B combine", 43: "B lin dq", 44: "B LN st", 45: "B lin dst", 46: "B LN bwd", 50: "tp: stage qk + issue", 51: "tp: wait tile", 52: "tp: phase1 mma", 53: "tp: softmax", 54: "tp: stores+sync", 55: "tp: attn copy", 56: "tp: phase2", 57: "tp: epilogue", 58: "lin: entry+stage X", 59: "lin: sync", 60: "lin: issue B loads", 61: "lin: wait B + MMAs", 62: "lin: epilogue", 63: "lin: final sync"}
 cfg = sys.argv[1] if len(sys.argv) > 1 else "c2"
 c = dict(bench.CONFIGS[cfg])
 dt = torch.float32 if c["dtype"] == "fp32" else torch.bfloat16

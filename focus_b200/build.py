@@ -11,6 +11,7 @@ OUT = os.path.join(HERE, "libfocus_savi.so")
 # (source, object name, extra defines): the clip kernels are compiled once per token dtype
 UNITS = [("savi_api.cu", "savi_api.o", []),
          ("savi_wgrad.cu", "savi_wgrad.o", []),
+         ("savi_fwd_umma.cu", "savi_fwd_umma.o", []),
          ("savi_fwd.cu", "savi_fwd_f32.o", ["-DSAVI_TOK=float", "-DSAVI_SUFFIX=f32"]),
          ("savi_fwd.cu", "savi_fwd_bf16.o", ["-DSAVI_TOK=__nv_bfloat16", "-DSAVI_SUFFIX=bf16"]),
          ("savi_bwd.cu", "savi_bwd_f32.o", ["-DSAVI_TOK=float", "-DSAVI_SUFFIX=f32"]),
@@ -34,7 +35,7 @@ def build(force=False, verbose=False):
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
     objdir = os.path.join(HERE, "build")
     os.makedirs(objdir, exist_ok=True)
-    extra = ["-Xptxas", "-v"] if verbose else []
+    extra = (["-Xptxas", "-v"] if verbose else []) + os.environ.get("SAVI_NVCC_EXTRA", "").split()
 
     def cc(unit):
         src, oname, defs = unit

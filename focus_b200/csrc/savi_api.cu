@@ -100,6 +100,15 @@ static int validate(const SaviShape* s, Dims& d) {
              dx_smem_bytes(s->I, d.KC, s->D) <= (size_t)kMaxSmem &&
              tmma_smem_bytes(MT, s->D, s->K, 1, true) <= (size_t)kMaxSmem) ? 1 : 0;
     if (d.mma) d.KC = MT * 16;
+    // tcgen05 clip kernels: bf16 tokens, 128-wide features (one M tile per product), slots and scratch that fit shared memory
+    d.NTILE = (s->N + 127) / 128;
+    d.umma = 0;
+    if (d.mma && s->D == 128 && s->Ds == 128 && s->M == 128 && s->K <= 24 && (s->cluster == 0 || s->cluster <= 2) &&
+        (int64_t)s->heads * s->K * (s->K | 1) * 4 <= 16384 && !getenv("SAVI_DISABLE_UMMA")) {
+        d.umma = 1;
+        d.CN = s->cluster ? s->cluster : ((int64_t)s->B * 2 <= 148 ? 2 : 1);
+        if (d.NTILE < d.CN) d.CN = 1;
+    }
     return SAVI_OK;
 }
 
@@ -172,6 +181,10 @@ extern "C" int savi_query(const SaviShape* shape, SaviSizes* sizes) {
     sizes->n_params = 21 + 12 * shape->blocks;
     sizes->param_floats = po.total;
     sizes->packed_bytes = (int64_t)po.packed_total * 8;      // fp32 + bf16 hi + bf16 lo images
+    if (d.umma) {                                            // + the blocked SWIZZLE_128B operand images of the tcgen05 path
+        WImg wi; savi_wimg_layout(d.D, d.Ds, d.M, d.blocks, wi);
+        sizes->packed_bytes = savi_wimg_base(po.packed_total) + wi.total_bytes;
+    }
     sizes->saved_bytes = sl.total_bytes;
     sizes->fwd_ws_bytes = fl.total_bytes;
     sizes->bwd_ws_bytes = bl.total_bytes;
@@ -247,6 +260,28 @@ __global__ void pack_split_kernel(const float* __restrict__ packed, bf16* __rest
     }
 }
 
+// fp32 matrix A[R][C] (row-major at packed + src, leading dimension ld) -> blocked SWIZZLE_128B bf16 hi / lo image
+struct ImgJob { int src, R, C, ld; long long dst; };
+constexpr int MAXIMG = 2 * (7 + 6 * SAVI_MAX_BLOCKS);
+struct ImgArgs { ImgJob job[MAXIMG]; int count; };
+__global__ void pack_image_kernel(const __grid_constant__ ImgArgs ia, const float* __restrict__ packed, unsigned char* __restrict__ img) {
+    const ImgJob j = ia.job[blockIdx.y];
+    const int c8n = j.C >> 3;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < j.R * c8n; i += gridDim.x * blockDim.x) {
+        const int r = i / c8n, c0 = (i - r * c8n) * 8;
+        const float* src = packed + j.src + (size_t)r * j.ld + c0;
+        const float4 v0 = *reinterpret_cast<const float4*>(src), v1 = *reinterpret_cast<const float4*>(src + 4);
+        const float v[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
+        bf16 h[8], l[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) split_bf16(v[e], h[e], l[e]);
+        unsigned char* blk = img + j.dst + ((size_t)((r >> 7) * (j.C >> 6) + (c0 >> 6)) * 2) * UMMA_BLK;
+        const unsigned off = (unsigned)(r & 127) * 128u + (((unsigned)((c0 & 63) >> 3) ^ (unsigned)(r & 7)) << 4);
+        *reinterpret_cast<uint4*>(blk + off) = *reinterpret_cast<const uint4*>(h);
+        *reinterpret_cast<uint4*>(blk + UMMA_BLK + off) = *reinterpret_cast<const uint4*>(l);
+    }
+}
+
 static int check_device() {
     int dev = 0;
     cudaError_t e = cudaGetDevice(&dev);
@@ -301,8 +336,32 @@ extern "C" int savi_pack_params(const SaviShape* shape, const void* const* param
         e = cudaGetLastError();
         if (e != cudaSuccess) return cuda_fail(e, "pack_split_kernel");
     }
-    savi_prof_end(0, st);
     g_launches = 3;
+    if (d.umma) {
+        WImg wi; savi_wimg_layout(D, Ds, M, shape->blocks, wi);
+        ImgArgs ia; ia.count = 0;
+        auto im = [&](int src, int R, int C, int64_t dst) { ia.job[ia.count++] = ImgJob{src, R, C, C, (long long)dst}; };
+        // forward orientation: rows = output feature of the product (W itself; W_k enters transposed: qk = q W_k)
+        im(po.wq, Ds, Ds, wi.wq); im(po.wk_t, D, Ds, wi.wkT); im(po.wv, Ds, D, wi.wv);
+        im(po.wih, 3 * Ds, Ds, wi.wih); im(po.whh, 3 * Ds, Ds, wi.whh); im(po.w1, M, Ds, wi.w1); im(po.w2, Ds, M, wi.w2);
+        // backward orientation: rows = input feature (dX = dY W)
+        im(po.wq_t, Ds, Ds, wi.wqT); im(po.wk, Ds, D, wi.wk); im(po.wv_t, D, Ds, wi.wvT);
+        im(po.wih_t, Ds, 3 * Ds, wi.wihT); im(po.whh_t, Ds, 3 * Ds, wi.whhT); im(po.w1_t, Ds, M, wi.w1T); im(po.w2_t, M, Ds, wi.w2T);
+        for (int j = 0; j < shape->blocks; ++j) {
+            const BlockOff& b = po.blk[j]; const BlockOffT& t = po.blkt[j];
+            const WImgBlock& f = wi.blk[j]; const WImgBlock& r = wi.blkT[j];
+            im(b.pq, Ds, Ds, f.pq); im(b.pk, Ds, Ds, f.pk); im(b.pv, Ds, Ds, f.pv); im(b.po, Ds, Ds, f.po);
+            im(b.f1, 4 * Ds, Ds, f.f1); im(b.f2, Ds, 4 * Ds, f.f2);
+            im(t.pq_t, Ds, Ds, r.pq); im(t.pk_t, Ds, Ds, r.pk); im(t.pv_t, Ds, Ds, r.pv); im(t.po_t, Ds, Ds, r.po);
+            im(t.f1_t, Ds, 4 * Ds, r.f1); im(t.f2_t, 4 * Ds, Ds, r.f2);
+        }
+        pack_image_kernel<<<dim3(16, ia.count), 256, 0, st>>>(ia, reinterpret_cast<const float*>(packed),
+                                                              reinterpret_cast<unsigned char*>(packed) + savi_wimg_base(po.packed_total));
+        e = cudaGetLastError();
+        if (e != cudaSuccess) return cuda_fail(e, "pack_image_kernel");
+        g_launches = 4;
+    }
+    savi_prof_end(0, st);
     return SAVI_OK;
 }
 

@@ -10,10 +10,17 @@
 // Streams `inputs` once from HBM with 16-byte accesses, writes xhat in the token
 // dtype plus (mean, rstd) per token for the backward.
 // ---------------------------------------------------------------------------
+// tcgen05 path (ximg != nullptr): xhat is ALSO written as [frame][tile][D/64][128 rows][64] SWIZZLE_128B operand
+// blocks (savi_umma.cuh), rows past N zero-filled, so the clip kernels fetch a token tile with two 16 KB bulk copies.
+__device__ __forceinline__ unsigned char* ximg_chunk(unsigned char* ximg, int64_t frame, int n, int d, int NTILE, int D) {
+    const int tile = n >> 7, r = n & 127, db = d >> 6, dc = d & 63;
+    return ximg + ((frame * NTILE + tile) * (D >> 6) + db) * (int64_t)16384 + r * 128 + (((dc >> 3) ^ (r & 7)) << 4) + (dc & 7) * 2;
+}
 template <typename TokT>
 __global__ void __launch_bounds__(NT) ln_tokens_fwd_kernel(const TokT* __restrict__ x, TokT* __restrict__ xhat,
                                                            float2* __restrict__ stats, const float* __restrict__ g,
-                                                           const float* __restrict__ b, int64_t rows, int D, float eps) {
+                                                           const float* __restrict__ b, int64_t rows, int D, float eps,
+                                                           unsigned char* __restrict__ ximg, int N, int NTILE) {
     constexpr int VEC = Tok<TokT>::VEC;
     const int lane = threadIdx.x & 31;
     const int chunks = D / VEC;                       // 16-byte chunks per row (<= 64 for D <= 512)
@@ -60,8 +67,23 @@ __global__ void __launch_bounds__(NT) ln_tokens_fwd_kernel(const TokT* __restric
                     o.z = (v[j][e + 2] - mean) * rstd * gg.z + bb.z;
                     o.w = (v[j][e + 3] - mean) * rstd * gg.w + bb.w;
                     Tok<TokT>::store4(yr + d, o);
+                    if (ximg) {
+                        __nv_bfloat162 p0 = __floats2bfloat162_rn(o.x, o.y), p1 = __floats2bfloat162_rn(o.z, o.w);
+                        uint2 t; t.x = *reinterpret_cast<unsigned*>(&p0); t.y = *reinterpret_cast<unsigned*>(&p1);
+                        *reinterpret_cast<uint2*>(ximg_chunk(ximg, row / N, (int)(row % N), d, NTILE, D)) = t;
+                    }
                 }
             }
+        }
+    }
+    if (ximg && (N & 127)) {          // zero the padding rows of every frame's last tile
+        const int pad = NTILE * 128 - N, c16 = D >> 3;
+        const int64_t frames = rows / N, items = frames * pad * c16;
+        for (int64_t i = (int64_t)blockIdx.x * NT + threadIdx.x; i < items; i += (int64_t)gridDim.x * NT) {
+            const int c = (int)(i % c16);
+            const int64_t t = i / c16;
+            const int n = N + (int)(t % pad);
+            *reinterpret_cast<uint4*>(ximg_chunk(ximg, t / pad, n, c * 8, NTILE, D)) = make_uint4(0u, 0u, 0u, 0u);
         }
     }
 }
@@ -447,7 +469,7 @@ static cudaError_t launch_ln_fwd(const FwdArgs& a, const void* inputs, cudaStrea
     ln_tokens_fwd_kernel<TokT><<<grid, NT, 0, st>>>(
         reinterpret_cast<const TokT*>(inputs), reinterpret_cast<TokT*>(a.saved + a.sl.xhat),
         reinterpret_cast<float2*>(a.saved + a.sl.stats), a.packed + a.po.ln_in_w, a.packed + a.po.ln_in_b, rows, a.d.D,
-        a.d.ln_eps);
+        a.d.ln_eps, a.d.umma ? a.saved + a.sl.ximg : nullptr, a.d.N, a.d.NTILE);
     return cudaGetLastError();
 }
 
@@ -497,6 +519,11 @@ cudaError_t SAVI_CAT(savi_launch_forward_, SAVI_SUFFIX)(const FwdArgs& a, const 
     savi_prof_end(1, st);
     if (e != cudaSuccess) return e;
     savi_prof_begin(2, st);
+    if (a.d.umma) {
+        WImg wi;
+        savi_wimg_layout(a.d.D, a.d.Ds, a.d.M, a.d.blocks, wi);
+        e = savi_launch_fwd_umma(a, reinterpret_cast<const unsigned char*>(a.packed) + savi_wimg_base(a.po.packed_total), wi, st);
+    } else
     e = launch_fwd_k<SAVI_TOK>(a, st);
     savi_prof_end(2, st);
     *launches += 2;

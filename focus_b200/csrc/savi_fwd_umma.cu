@@ -1,0 +1,555 @@
+// tcgen05 forward clip kernel: the whole T x I recurrence (+ predictor) of one clip per CTA / CTA pair.
+//
+// Reference semantics: /root/reference/slowfast/models/STEVE/steve.py:52-105 (SlotAttentionVideo.forward),
+// transformer.py:22-49, 70-86, 106-114 (predictor).  Execution model: savi_umma_clip.cuh.
+// Writes exactly the saved-for-backward records of the mma.sync kernel (savi_layout.h: SavedLayout).
+#include "savi_umma_clip.cuh"
+
+using namespace uc;
+
+// TMEM columns (fp32 accumulators, 32 columns = 32 slots each)
+enum { TC_A = 0, TC_B = 32, TC_R = 64, TC_Z = 96, TC_HN = 128, TC_IN = 160, TC_S0 = 192, TC_S1 = 224, TC_NUMX = 256, TC_SSUM = 288,
+       TC_F0 = 320 /* predictor FFN hidden tiles: 4 x 32 */, TC_COLS = 512 };
+
+struct FwdUArgs {
+    FwdArgs a;
+    const unsigned char* wimg;     // blocked weight images (savi_layout.h: WImg)
+    WImg wi;
+};
+
+// ------------------------------------------------------------------------------------------------
+// issuer: attention step products of this CTA's token tiles
+//   P1(i): S[i&1]  = xhat_i . qk^T            (A = token tile, K-major;  B = qk hi / lo)
+//   P2(i): NUMX   += xhat_i^T . A_i           (A = token tile, MN-major; B = attention weights hi / lo)
+//          SSUM   += 1 . A_i
+// ------------------------------------------------------------------------------------------------
+struct TokState { uint32_t cnt_s[2], cnt_a[2]; };
+
+__device__ __forceinline__ void issue_token_pass(Ring& r, unsigned char* sm, const Smem& L, uint64_t* bars, uint32_t tb, int ntile,
+                                                 TokState& ts, uint32_t qk_op) {
+    int ts0[2] = {0, 0};
+    const uint32_t ones = smem_u32(sm + L.ones);
+    auto p2 = [&](int j) {
+        const int g = j & 1;
+        mbar_wait(&bars[B_AREADY + g], ts.cnt_a[g] & 1u);
+        fence_after_sync();
+        const uint32_t x0 = smem_u32(r.base + (size_t)ts0[g] * BLK);
+        const uint32_t aw = smem_u32(sm + (g ? L.aw1 : L.aw0));
+#pragma unroll 2
+        for (int kt = 0; kt < 8; ++kt) {
+            const uint32_t bh = aw + (kt >> 2) * OP_CB + (kt & 3) * 32, bl = bh + OP_LO;
+            const uint64_t ax = desc_mnmajor(x0 + kt * 2048, BLK);
+            const bool acc = j > 0 || kt > 0;
+            mma_ss(tb + TC_NUMX, ax, desc_kmajor(bh), IDESC_MK, acc);
+            mma_ss(tb + TC_NUMX, ax, desc_kmajor(bl), IDESC_MK, true);
+            mma_ss(tb + TC_SSUM, desc_mnmajor(ones, 2048), desc_kmajor(bh), IDESC_MK, acc);
+            mma_ss(tb + TC_SSUM, desc_mnmajor(ones, 2048), desc_kmajor(bl), IDESC_MK, true);
+        }
+        mma_commit(&r.empty[ts0[g]]);
+        mma_commit(&r.empty[ts0[g] + 1]);
+        mma_commit(&bars[B_AFREE + g]);
+        ++ts.cnt_a[g];
+    };
+    for (int i = 0; i < ntile; ++i) {
+        const int g = i & 1;
+        mbar_wait(&bars[B_SFREE + g], (ts.cnt_s[g] & 1u) ^ 1u);
+        fence_after_sync();
+        ts0[g] = r.stage;                                   // the ring has an even number of stages: the pair never wraps
+        const uint32_t acc_s = tb + (g ? TC_S1 : TC_S0);
+#pragma unroll
+        for (int db = 0; db < 2; ++db) {
+            mbar_wait(&r.full[r.stage], r.phase);
+            fence_after_sync();
+            const uint32_t a = smem_u32(r.base + (size_t)r.stage * BLK);
+            const uint32_t qh = qk_op + db * OP_CB, ql = qh + OP_LO;
+#pragma unroll
+            for (int k4 = 0; k4 < 4; ++k4) {
+                mma_ss(acc_s, desc_kmajor(a + k4 * 32), desc_kmajor(qh + k4 * 32), IDESC_KK, db > 0 || k4 > 0);
+                mma_ss(acc_s, desc_kmajor(a + k4 * 32), desc_kmajor(ql + k4 * 32), IDESC_KK, true);
+            }
+            r.advance();
+        }
+        mma_commit(&bars[B_SFULL + g]);
+        ++ts.cnt_s[g];
+        if (i >= 1) p2(i - 1);
+    }
+    p2(ntile - 1);
+    mma_commit(&bars[B_TOK]);
+}
+
+// ------------------------------------------------------------------------------------------------
+// compute threads: softmax over the slot axis of this group's token tiles (thread = token)
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void softmax_tiles(const Ctx& c, const Dims& d, int ntile, int tile0, bf16* attn_frame, TokState& ts) {
+    constexpr float LOG2E = 1.4426950408889634f;
+    const int g = c.g, K = c.K;
+    for (int i = g; i < ntile; i += 2) {
+        mbar_wait(&c.bars[B_SFULL + g], ts.cnt_s[g] & 1u);
+        fence_after_sync();
+        float l[32];
+        tmem_ld32(tmem_addr(c.tb, c.warp, g ? TC_S1 : TC_S0), l);
+        tmem_wait_ld();
+        fence_before_sync();
+        __syncwarp();
+        if (c.lane == 0) mbar_arrive(&c.bars[B_SFREE + g]);
+        ++ts.cnt_s[g];
+        float mx = -INFINITY;
+#pragma unroll
+        for (int s = 0; s < 32; ++s) if (s < K) mx = fmaxf(mx, l[s]);
+        mx *= LOG2E;
+        float sum = 0.f;
+#pragma unroll
+        for (int s = 0; s < 32; ++s) { l[s] = (s < K) ? exp2f(fmaf(l[s], LOG2E, -mx)) : 0.f; sum += l[s]; }
+        const float inv = 1.0f / sum;
+        const int n = (tile0 + i) * 128 + c.o;                  // token index inside the frame
+        const bool valid = n < d.N;
+        mbar_wait(&c.bars[B_AFREE + g], (ts.cnt_a[g] & 1u) ^ 1u);
+        unsigned char* aw = c.sm + (g ? c.L.aw1 : c.L.aw0) + (c.o >> 6) * OP_CB;
+        const int oc = c.o & 63;
+#pragma unroll
+        for (int s = 0; s < 32; ++s) {
+            if (s < K) {
+                l[s] *= inv;                                     // P (steve.py:77)
+                const float a = valid ? l[s] + d.eps : 0.f;      // A = P + eps (:81); padded tokens carry no weight
+                const bf16 hi = __float2bfloat16_rn(a);
+                const bf16 lo = __float2bfloat16_rn(a - __bfloat162float(hi));
+                const uint32_t off = sw128_off(s, oc);
+                *reinterpret_cast<bf16*>(aw + off) = hi;
+                *reinterpret_cast<bf16*>(aw + OP_LO + off) = lo;
+            }
+        }
+        fence_async_smem();
+        __syncwarp();
+        if (c.lane == 0) mbar_arrive(&c.bars[B_AREADY + g]);
+        ++ts.cnt_a[g];
+        if (attn_frame && valid) {                               // attns (:96): pre-epsilon softmax, [N][K]
+            bf16* row = attn_frame + (size_t)n * K;
+            if ((K & 7) == 0) {
+#pragma unroll
+                for (int s = 0; s < 32; s += 8) {
+                    if (s < K) {
+                        uint4 v;
+                        v.x = pack_bf16x2(l[s], l[s + 1]); v.y = pack_bf16x2(l[s + 2], l[s + 3]);
+                        v.z = pack_bf16x2(l[s + 4], l[s + 5]); v.w = pack_bf16x2(l[s + 6], l[s + 7]);
+                        *reinterpret_cast<uint4*>(row + s) = v;
+                    }
+                }
+            } else {
+#pragma unroll
+                for (int s = 0; s < 32; ++s) if (s < K) row[s] = __float2bfloat16_rn(l[s]);
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// predictor attention core on one clip, in shared memory (transformer.py:34-47).  Inputs: this thread's
+// q (scaled), k, v columns.  Output: its column of O = softmax(q k^T) v per head.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void mha_core(const Ctx& c, int H, const float (&q)[KHMAX], const float (&kx)[KHMAX], const float (&v)[KHMAX],
+                                         float (&out)[KHMAX], float* att_g /* nullable: [H][K][K] saved */) {
+    const int K = c.K, ld = F + 1, ka = K | 1, dh = F / H;
+    float* sQ = reinterpret_cast<float*>(c.sm + c.L.aw0);            // aw0 | aw1 | scratch are contiguous
+    float* sK = sQ + K * ld;
+    float* sV = sK + K * ld;
+    float* sA = reinterpret_cast<float*>(c.sm + c.L.opC);            // [H*K][ka]
+#pragma unroll
+    for (int kk = 0; kk < KHMAX; ++kk) {
+        const int k = c.g * c.KH + kk;
+        if (kk < c.KH && k < K) { sQ[k * ld + c.o] = q[kk]; sK[k * ld + c.o] = kx[kk]; sV[k * ld + c.o] = v[kk]; }
+    }
+    bar_sync_compute(1);
+    for (int idx = c.tid; idx < H * K * K; idx += NCT) {
+        const int j = idx % K, i = (idx / K) % K, h = idx / (K * K);
+        const float* a = sQ + i * ld + h * dh;
+        const float* b = sK + j * ld + h * dh;
+        float s = 0.f;
+        for (int e = 0; e < dh; ++e) s = fmaf(a[e], b[e], s);
+        sA[(h * K + i) * ka + j] = s;
+    }
+    bar_sync_compute(1);
+    for (int row = c.tid; row < H * K; row += NCT) {
+        float* a = sA + row * ka;
+        float mx = -INFINITY;
+        for (int j = 0; j < K; ++j) mx = fmaxf(mx, a[j]);
+        float sum = 0.f;
+        for (int j = 0; j < K; ++j) { const float e = expf(a[j] - mx); a[j] = e; sum += e; }
+        const float inv = 1.0f / sum;
+        for (int j = 0; j < K; ++j) a[j] *= inv;
+    }
+    bar_sync_compute(1);
+    if (att_g) for (int idx = c.tid; idx < H * K * K; idx += NCT) att_g[idx] = sA[(idx / K) * ka + idx % K];
+    const int h = c.o / dh;
+#pragma unroll
+    for (int kk = 0; kk < KHMAX; ++kk) {
+        const int i = c.g * c.KH + kk;
+        float s = 0.f;
+        if (kk < c.KH && i < K) {
+            const float* a = sA + (h * K + i) * ka;
+            for (int j = 0; j < K; ++j) s = fmaf(a[j], sV[j * ld + c.o], s);
+        }
+        out[kk] = s;
+    }
+    bar_sync_compute(1);                                             // sQ/sK/sV/sA are free again
+}
+
+// ------------------------------------------------------------------------------------------------
+// the kernel
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(NTHREADS, 1) savi_fwd_umma_kernel(const __grid_constant__ FwdUArgs ua) {
+    extern __shared__ unsigned char smem_raw[];
+    const FwdArgs& a = ua.a;
+    const Dims& d = a.d;
+    const ParamOff& po = a.po;
+    unsigned char* sm = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int CN = d.CN, b = blockIdx.x / CN, rank = blockIdx.x % CN;
+    const int K = d.K, B = d.B, KP = d.KP;
+    const Smem L = plan_smem(K, CN, 0, a.smem_bytes);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sm + L.bars);
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + NBAR);
+    const bool lead = (rank == 0);
+    // token tiles of this CTA
+    const int per = (d.NTILE + CN - 1) / CN;
+    const int tile0 = min(d.NTILE, rank * per), ntile = min(d.NTILE, tile0 + per) - tile0;
+    const float* P = a.packed;
+    float* fb = reinterpret_cast<float*>(a.saved + a.sl.fbase);
+    const unsigned char* ximg = a.saved + a.sl.ximg;
+
+    // ---- one-time setup ----
+    for (int i = tid * 16; i < L.bars; i += NTHREADS * 16) *reinterpret_cast<uint4*>(sm + i) = make_uint4(0u, 0u, 0u, 0u);   // operands: padded rows must be zero
+    __syncthreads();
+    for (int i = tid; i < 2048; i += NTHREADS) reinterpret_cast<uint16_t*>(sm + L.ones)[i] = 0x3F80;                     // bf16 1.0
+    if (tid == 0) {
+        for (int s = 0; s < L.nst; ++s) { mbar_init(&bars[B_FULL + s], 1); mbar_init(&bars[B_EMPTY + s], 1); }
+        mbar_init(&bars[B_OPND], NCW); mbar_init(&bars[B_ACC], 1); mbar_init(&bars[B_TOK], 1);
+        for (int g = 0; g < 2; ++g) {
+            mbar_init(&bars[B_SFULL + g], 1); mbar_init(&bars[B_SFREE + g], 4);
+            mbar_init(&bars[B_AREADY + g], 4); mbar_init(&bars[B_AFREE + g], 1);
+            mbar_init(&bars[B_INBOX + g], NCW);
+        }
+        for (int f = 0; f < 4; ++f) { mbar_init(&bars[B_FACC + f], 1); mbar_init(&bars[B_FOPND + f], NCW); }
+        mbar_init_fence();
+    }
+    if (warp == W_MMA) tmem_alloc(tmem_slot, TC_COLS);
+    fence_async_smem();
+    fence_before_sync();
+    __syncthreads();
+    fence_after_sync();
+    if (CN > 1) { cluster_arrive(); cluster_wait(); }          // the peer's barriers exist before anyone signals them
+    const uint32_t tb = *tmem_slot;
+
+    Ring ring;
+    ring.base = sm + L.ring; ring.full = &bars[B_FULL]; ring.empty = &bars[B_EMPTY]; ring.nst = L.nst; ring.stage = 0; ring.phase = 0;
+
+    if (warp == W_PROD) {
+        // =====================================================================================
+        // producer: the static block schedule (must mirror the issuer's consumption order)
+        // =====================================================================================
+        if (lane == 0) {
+            const unsigned char* W = ua.wimg;
+            const WImg& wi = ua.wi;
+            for (int t = 0; t < d.T; ++t) {
+                const unsigned char* xf = ximg + ((size_t)(b * d.T + t) * d.NTILE + tile0) * 2 * BLK;
+                for (int it = 0; it < d.I; ++it) {
+                    prod_blocks(ring, W + wi.wq, 4);
+                    prod_blocks(ring, W + wi.wkT, 4);
+                    prod_blocks(ring, xf, 2 * ntile);
+                    prod_blocks(ring, W + wi.whh, 12);
+                    prod_blocks(ring, W + wi.wv, 4);
+                    prod_blocks(ring, W + wi.wih, 12);
+                    if (it < d.I - 1) { prod_blocks(ring, W + wi.w1, 4); prod_blocks(ring, W + wi.w2, 4); }
+                }
+                if (t < d.T - 1) {
+                    for (int j = 0; j < d.blocks; ++j) {
+                        const WImgBlock& wb = wi.blk[j];
+                        prod_blocks(ring, W + wb.pq, 4); prod_blocks(ring, W + wb.pk, 4); prod_blocks(ring, W + wb.pv, 4);
+                        prod_blocks(ring, W + wb.po, 4);
+                        prod_blocks(ring, W + wb.f1, 16);
+                        prod_blocks(ring, W + wb.f2, 16);
+                    }
+                }
+            }
+        }
+    } else if (warp == W_MMA) {
+        // =====================================================================================
+        // tcgen05.mma issuer
+        // =====================================================================================
+        if (lane == 0) {
+            uint32_t ph_opnd = 0, pcall = 0;
+            TokState ts = {{0, 0}, {0, 0}};
+            const uint32_t opA = smem_u32(sm + L.opA), opB = smem_u32(sm + L.opB), opC = smem_u32(sm + L.opC);
+            const uint32_t aw0 = smem_u32(sm + L.aw0), aw1 = smem_u32(sm + L.aw1);
+            auto wait_opnd = [&]() { mbar_wait(&bars[B_OPND], ph_opnd); ph_opnd ^= 1u; fence_after_sync(); };
+            for (int t = 0; t < d.T; ++t) {
+                for (int it = 0; it < d.I; ++it) {
+                    wait_opnd();                                                          // s~ in opA, h_prev in opC
+                    issue_linear(ring, opA, tb + TC_A, 32, 1, 2, false); mma_commit(&bars[B_ACC]);      // q   (steve.py:75)
+                    wait_opnd();                                                          // q in opB
+                    issue_linear(ring, opB, tb + TC_B, 32, 1, 2, false); mma_commit(&bars[B_ACC]);      // qk  (fold of :61,63,76)
+                    wait_opnd();                                                          // qk in opA
+                    issue_token_pass(ring, sm, L, bars, tb, ntile, ts, opA);
+                    // GRU hidden-side product, off the critical path: runs while the compute threads combine the partial sums.
+                    // (It must not be streamed while token tiles are held in the ring: the ring is filled in order.)
+                    issue_linear(ring, opC, tb + TC_R, 32, 3, 2, false);                    // R, Z, HN = W_hh . h_prev
+                    wait_opnd();                                                          // Ux in opB
+                    issue_linear(ring, opB, tb + TC_A, 32, 1, 2, false); mma_commit(&bars[B_ACC]);      // updates (:83)
+                    wait_opnd();                                                          // U in opA
+                    issue_linear(ring, opA, tb + TC_R, 32, 2, 2, true);                                  // R, Z += W_i{r,z} . U
+                    issue_linear(ring, opA, tb + TC_IN, 32, 1, 2, false); mma_commit(&bars[B_ACC]);     // IN = W_in . U   (:87)
+                    if (it < d.I - 1) {
+                        wait_opnd();                                                      // LN_m(h') in opB
+                        issue_linear(ring, opB, tb + TC_A, 32, 1, 2, false); mma_commit(&bars[B_ACC]);  // mlp.0 (:92)
+                        wait_opnd();                                                      // a in opA
+                        issue_linear(ring, opA, tb + TC_B, 32, 1, 2, false); mma_commit(&bars[B_ACC]);  // mlp.2
+                    }
+                }
+                if (t < d.T - 1) {
+                    for (int j = 0; j < d.blocks; ++j) {
+                        wait_opnd();                                                      // y in opA
+                        issue_linear(ring, opA, tb + TC_R, 32, 3, 2, false); mma_commit(&bars[B_ACC]);  // q, k, v -> R, Z, HN columns
+                        wait_opnd();                                                      // attention output in opB
+                        issue_linear(ring, opB, tb + TC_A, 32, 1, 2, false); mma_commit(&bars[B_ACC]);  // proj_o
+                        wait_opnd();                                                      // LN2 in opA
+                        for (int f = 0; f < 4; ++f) { issue_linear(ring, opA, tb + TC_F0 + 32 * f, 32, 1, 2, false); mma_commit(&bars[B_FACC + f]); }   // ffn.0
+                        const uint32_t fop[4] = {opB, opC, aw0, aw1};
+                        for (int f = 0; f < 4; ++f) {                                     // ffn.2, contraction split in 4 chunks of 128
+                            mbar_wait(&bars[B_FOPND + f], pcall & 1u); fence_after_sync();
+                            issue_linear(ring, fop[f], tb + TC_B, 32, 1, 2, f > 0);
+                        }
+                        mma_commit(&bars[B_ACC]);
+                        ++pcall;
+                    }
+                }
+            }
+        }
+    } else {
+        // =====================================================================================
+        // compute threads
+        // =====================================================================================
+        Ctx c;
+        c.tid = tid; c.warp = warp; c.lane = lane; c.g = warp >> 2; c.o = (warp & 3) * 32 + lane;
+        c.KH = (K + 1) >> 1; c.K = K; c.sm = sm; c.L = L; c.tb = tb; c.bars = bars; c.ph_acc = 0; c.ph_opnd = 0;
+        const int o = c.o;
+        TokState ts = {{0, 0}, {0, 0}};
+        // per-feature parameters of this thread
+        const float g_s = P[po.ln_s_w + o], b_s = P[po.ln_s_b + o], g_m = P[po.ln_m_w + o], b_m = P[po.ln_m_b + o];
+        const float bir = P[po.bih + o], biz = P[po.bih + F + o], bin = P[po.bih + 2 * F + o];
+        const float bhr = P[po.bhh + o], bhz = P[po.bhh + F + o], bhn = P[po.bhh + 2 * F + o];
+        const float b1 = P[po.b1 + o], b2 = P[po.b2 + o];
+        float h[KHMAX], y[KHMAX];
+        {   // slots0 = mu + exp(log_sigma) * noise   (steve.py:56-57)
+            const float mu = P[po.slot_mu + o], sg = expf(P[po.slot_log_sigma + o]);
+            load_field(c, a.noise + (size_t)b * K * F, F, o, y);
+#pragma unroll
+            for (int kk = 0; kk < KHMAX; ++kk) h[kk] = mu + sg * y[kk];
+        }
+        uint32_t step = 0, pcall = 0;
+        for (int t = 0; t < d.T; ++t) {
+            for (int it = 0; it < d.I; ++it, ++step) {
+                const int64_t s = (int64_t)t * d.I + it;
+                // ---- slots_prev, LayerNorm, q ----
+                if (lead) save_field(c, frow(fb, a.sl.hp, s, b, B, K, F), F, o, h);
+                write_operand(c, L.opC, h);
+                layer_norm(c, h, y, g_s, b_s, d.ln_eps);                                   // :72
+                write_operand(c, L.opA, y);
+                signal_operand(c);
+                wait_acc(c); load_acc(c, TC_A, y); tmem_wait_ld();                         // q
+                if (lead) save_field(c, frow(fb, a.sl.q, s, b, B, K, F), F, o, y);
+                write_operand(c, L.opB, y);
+                signal_operand(c);
+                wait_acc(c); load_acc(c, TC_B, y); tmem_wait_ld();                         // qk = Ds^-1/2 q Wk
+#pragma unroll
+                for (int kk = 0; kk < KHMAX; ++kk) y[kk] *= d.qscale;
+                if (lead) save_field(c, frow(fb, a.sl.qk, s, b, B, K, F), F, o, y);
+                write_operand(c, L.opA, y);
+                signal_operand(c);
+                // ---- attention step over the token tiles ----
+                bf16* attn_frame = (it == d.I - 1) ? reinterpret_cast<bf16*>(a.attn_out) + ((size_t)b * d.T + t) * d.N * K : nullptr;
+                softmax_tiles(c, d, ntile, tile0, attn_frame, ts);
+                mbar_wait(&bars[B_TOK], step & 1u);
+                fence_after_sync();
+                float num[KHMAX], den[KHMAX];
+                load_acc(c, TC_NUMX, num); load_acc(c, TC_SSUM, den); tmem_wait_ld();
+                if (ntile == 0) {
+#pragma unroll
+                    for (int kk = 0; kk < KHMAX; ++kk) { num[kk] = 0.f; den[kk] = 0.f; }
+                }
+                if (CN > 1) {                                                              // exchange the partial sums with the peer CTA
+                    const int buf = step & 1;
+                    float* ib = reinterpret_cast<float*>(sm + L.inbox + buf * L.inbox_stride);
+                    const uint32_t peer = rank ^ 1u;
+                    const uint32_t rb = map_to_rank(ib, peer);
+#pragma unroll
+                    for (int kk = 0; kk < KHMAX; ++kk) {
+                        const int k = c.g * c.KH + kk;
+                        if (kk < c.KH && k < K) {
+                            st_cluster_f1(rb + (uint32_t)(k * F + o) * 4u, num[kk]);
+                            if (o == 0) st_cluster_f1(rb + (uint32_t)(KP * F + k) * 4u, den[kk]);
+                        }
+                    }
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive_remote(map_to_rank(&bars[B_INBOX + buf], peer));
+                    mbar_wait_cluster(&bars[B_INBOX + buf], (step >> 1) & 1u);
+#pragma unroll
+                    for (int kk = 0; kk < KHMAX; ++kk) {
+                        const int k = c.g * c.KH + kk;
+                        if (kk < c.KH && k < K) {
+                            const float pn = ib[k * F + o], pd = ib[KP * F + k];
+                            // fixed order rank 0 + rank 1 on both CTAs: their slot states stay bit-identical
+                            num[kk] = lead ? num[kk] + pn : pn + num[kk];
+                            den[kk] = lead ? den[kk] + pd : pd + den[kk];
+                        }
+                    }
+                }
+#pragma unroll
+                for (int kk = 0; kk < KHMAX; ++kk) y[kk] = (kk < c.KH && c.g * c.KH + kk < K) ? num[kk] / den[kk] : 0.f;      // Ux (:82-83)
+                if (lead) {
+                    save_field(c, frow(fb, a.sl.ux, s, b, B, K, F), F, o, y);
+                    if (o == 0) {
+                        float* r_ss = fb + a.sl.ssum + (s * B + b) * KP;
+#pragma unroll
+                        for (int kk = 0; kk < KHMAX; ++kk) { const int k = c.g * c.KH + kk; if (kk < c.KH && k < K) r_ss[k] = den[kk]; }
+                    }
+                }
+                write_operand(c, L.opB, y);
+                signal_operand(c);
+                wait_acc(c); load_acc(c, TC_A, y); tmem_wait_ld();                         // updates U (:83)
+                if (lead) save_field(c, frow(fb, a.sl.u, s, b, B, K, F), F, o, y);
+                write_operand(c, L.opA, y);
+                signal_operand(c);
+                // ---- GRUCell (:87-89) ----
+                wait_acc(c);
+                {
+                    float r_[KHMAX], z_[KHMAX], n_[KHMAX], hn[KHMAX];
+                    load_acc(c, TC_R, r_); load_acc(c, TC_Z, z_); load_acc(c, TC_IN, n_); load_acc(c, TC_HN, hn); tmem_wait_ld();
+                    const bool mlp = it < d.I - 1;
+#pragma unroll
+                    for (int kk = 0; kk < KHMAX; ++kk) {
+                        const float hnb = hn[kk] + bhn;
+                        const float vr = sigmoidf_(r_[kk] + bir + bhr);
+                        const float vz = sigmoidf_(z_[kk] + biz + bhz);
+                        const float vn = tanhf(n_[kk] + bin + vr * hnb);
+                        r_[kk] = vr; z_[kk] = vz; n_[kk] = vn; hn[kk] = hnb;
+                        h[kk] = (1.0f - vz) * vn + vz * h[kk];
+                    }
+                    if (lead) {
+                        save_field(c, frow(fb, a.sl.r, s, b, B, K, F), F, o, r_);
+                        save_field(c, frow(fb, a.sl.z, s, b, B, K, F), F, o, z_);
+                        save_field(c, frow(fb, a.sl.n, s, b, B, K, F), F, o, n_);
+                        save_field(c, frow(fb, a.sl.ghn, s, b, B, K, F), F, o, hn);
+                    }
+                    if (mlp) {                                                             // residual MLP (:92-93)
+                        const int64_t smi = (int64_t)t * (d.I - 1) + it;
+                        if (lead) save_field(c, frow(fb, a.sl.hg, smi, b, B, K, F), F, o, h);
+                        layer_norm(c, h, y, g_m, b_m, d.ln_eps);
+                        write_operand(c, L.opB, y);
+                        signal_operand(c);
+                        wait_acc(c); load_acc(c, TC_A, y); tmem_wait_ld();
+#pragma unroll
+                        for (int kk = 0; kk < KHMAX; ++kk) y[kk] = fmaxf(y[kk] + b1, 0.f);
+                        if (lead) save_field(c, frow(fb, a.sl.a, smi, b, B, K, F), F, o, y);
+                        write_operand(c, L.opA, y);
+                        signal_operand(c);
+                        wait_acc(c); load_acc(c, TC_B, y); tmem_wait_ld();
+#pragma unroll
+                        for (int kk = 0; kk < KHMAX; ++kk) h[kk] += y[kk] + b2;
+                    }
+                }
+            }
+            if (lead) save_field(c, a.slots_out + ((size_t)b * d.T + t) * K * F, F, o, h);      // collect (:96-97)
+            if (t < d.T - 1) {
+                // ---- predictor (:100; transformer.py:106-114) ----
+                if (lead) save_field(c, fb + a.sl.px0 + ((size_t)t * B + b) * K * F, F, o, h);
+                const float hscale = 1.0f / sqrtf((float)(F / d.heads));
+                float x[KHMAX];
+#pragma unroll
+                for (int kk = 0; kk < KHMAX; ++kk) x[kk] = h[kk];
+                for (int j = 0; j < d.blocks; ++j) {
+                    const int64_t f = (int64_t)j * (d.T - 1) + t;
+                    const BlockOff& bo = po.blk[j];
+                    float yv[KHMAX], q[KHMAX], kx[KHMAX], v[KHMAX], x1[KHMAX];
+                    layer_norm(c, x, yv, P[bo.ln1_w + o], P[bo.ln1_b + o], d.ln_eps);
+                    if (lead) save_field(c, frow(fb, a.sl.py, f, b, B, K, F), F, o, yv);
+                    write_operand(c, L.opA, yv);
+                    signal_operand(c);
+                    wait_acc(c);
+                    load_acc(c, TC_R, q); load_acc(c, TC_Z, kx); load_acc(c, TC_HN, v); tmem_wait_ld();
+#pragma unroll
+                    for (int kk = 0; kk < KHMAX; ++kk) q[kk] *= hscale;
+                    if (lead) {
+                        save_field(c, frow(fb, a.sl.pq, f, b, B, K, F), F, o, q);
+                        save_field(c, frow(fb, a.sl.pk, f, b, B, K, F), F, o, kx);
+                        save_field(c, frow(fb, a.sl.pv, f, b, B, K, F), F, o, v);
+                    }
+                    float ov[KHMAX];
+                    mha_core(c, d.heads, q, kx, v, ov, lead ? fb + a.sl.patt + (f * B + b) * ((int64_t)d.heads * K * K) : nullptr);
+                    if (lead) save_field(c, frow(fb, a.sl.po, f, b, B, K, F), F, o, ov);
+                    write_operand(c, L.opB, ov);
+                    signal_operand(c);
+                    wait_acc(c); load_acc(c, TC_A, x1); tmem_wait_ld();
+                    // the first block adds the residual to the NORMALISED input (transformer.py:75-78)
+#pragma unroll
+                    for (int kk = 0; kk < KHMAX; ++kk) x1[kk] += (j == 0) ? yv[kk] : x[kk];
+                    if (lead) save_field(c, frow(fb, a.sl.px1, f, b, B, K, F), F, o, x1);
+                    layer_norm(c, x1, yv, P[bo.ln2_w + o], P[bo.ln2_b + o], d.ln_eps);
+                    if (lead) save_field(c, frow(fb, a.sl.pl2, f, b, B, K, F), F, o, yv);
+                    write_operand(c, L.opA, yv);
+                    signal_operand(c);
+                    const int fop[4] = {L.opB, L.opC, L.aw0, L.aw1};
+                    // aw0 / aw1 hold attention-weight tiles between predictor calls: rows >= K are rewritten by nobody, and the
+                    // token pass only writes rows < K, so using them as slot-side operands (rows < K) keeps the zero padding intact
+                    for (int ff = 0; ff < 4; ++ff) {
+                        mbar_wait(&bars[B_FACC + ff], pcall & 1u); fence_after_sync();
+                        load_acc(c, TC_F0 + 32 * ff, yv); tmem_wait_ld();
+                        const float bb = P[bo.f1b + ff * F + o];
+#pragma unroll
+                        for (int kk = 0; kk < KHMAX; ++kk) yv[kk] = fmaxf(yv[kk] + bb, 0.f);
+                        if (lead) save_field(c, frow(fb, a.sl.pf, f, b, B, K, 4 * F), 4 * F, ff * F + o, yv);
+                        write_operand(c, fop[ff], yv);
+                        signal_operand(c, B_FOPND + ff);
+                    }
+                    ++pcall;
+                    wait_acc(c); load_acc(c, TC_B, yv); tmem_wait_ld();
+                    const float bb2 = P[bo.f2b + o];
+#pragma unroll
+                    for (int kk = 0; kk < KHMAX; ++kk) x[kk] = x1[kk] + yv[kk] + bb2;
+                    if (lead) save_field(c, frow(fb, a.sl.px2, f, b, B, K, F), F, o, x);
+                }
+                layer_norm(c, x, h, P[po.lnf_w + o], P[po.lnf_b + o], d.ln_eps);
+            }
+        }
+    }
+    // ---- teardown ----
+    __syncwarp();
+    fence_before_sync();
+    __syncthreads();
+    if (CN > 1) { cluster_arrive(); cluster_wait(); }          // nobody exits while its inbox may still be written
+    if (warp == W_MMA) tmem_dealloc(tb, TC_COLS);
+}
+
+// ------------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------------
+int savi_fwd_umma_smem_bytes(const Dims& d) {
+    const Smem L = plan_smem(d.K, d.CN, 0, 227 * 1024);
+    return L.ring + L.nst * BLK + 1024;
+}
+
+cudaError_t savi_launch_fwd_umma(const FwdArgs& a, const unsigned char* wimg, const WImg& wi, cudaStream_t st) {
+    FwdUArgs ua;
+    ua.a = a; ua.wimg = wimg; ua.wi = wi;
+    ua.a.smem_bytes = savi_fwd_umma_smem_bytes(a.d);
+    cudaError_t e = cudaFuncSetAttribute(savi_fwd_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ua.a.smem_bytes);
+    if (e != cudaSuccess) return e;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(a.d.B * a.d.CN);
+    cfg.blockDim = dim3(NTHREADS);
+    cfg.dynamicSmemBytes = ua.a.smem_bytes;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = a.d.CN; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, savi_fwd_umma_kernel, ua);
+}

@@ -38,6 +38,47 @@ struct ParamOff {
 
 static SAVI_HD int savi_align(int64_t x, int a) { return (int)((x + a - 1) / a * a); }
 
+// ---------------------------------------------------------------------------
+// tcgen05 path: every weight the clip kernels multiply by is also kept as a "blocked image": the
+// matrix A[R][C] (R = the 128-row M dimension of the MMA, C = contraction) is cut into [128 x 64]
+// blocks, each stored as a 16 KB SWIZZLE_128B K-major operand block, bf16 hi then bf16 lo, in the
+// order the kernels consume them: for rt in R/128: for cb in C/64: hi block, lo block.
+// One 1-D bulk copy moves a block from L2 into the shared-memory ring, ready for tcgen05.mma.
+// ---------------------------------------------------------------------------
+constexpr int64_t UMMA_BLK = 16384;
+static SAVI_HD int64_t wimg_bytes(int R, int C) { return (int64_t)(R / 128) * (C / 64) * 2 * UMMA_BLK; }
+struct WImgBlock { int64_t pq, pk, pv, po, f1, f2; };
+struct WImg {                // byte offsets from the image base
+    // forward orientation: rows = output feature
+    int64_t wq, wkT, wv, wih, whh, w1, w2;
+    WImgBlock blk[SAVI_MAX_BLOCKS];
+    // backward orientation: rows = input feature (dX = dY . W)
+    int64_t wqT, wk, wvT, wihT, whhT, w1T, w2T;
+    WImgBlock blkT[SAVI_MAX_BLOCKS];
+    int64_t total_bytes;
+};
+static inline void savi_wimg_layout(int D, int Ds, int M, int blocks, WImg& w) {
+    int64_t p = 0;
+    auto take = [&](int R, int C) { int64_t r = p; p += wimg_bytes(R, C); return r; };
+    w.wq = take(Ds, Ds); w.wkT = take(D, Ds); w.wv = take(Ds, D); w.wih = take(3 * Ds, Ds); w.whh = take(3 * Ds, Ds);
+    w.w1 = take(M, Ds); w.w2 = take(Ds, M);
+    for (int j = 0; j < SAVI_MAX_BLOCKS; ++j) {
+        WImgBlock& b = w.blk[j];
+        if (j < blocks) { b.pq = take(Ds, Ds); b.pk = take(Ds, Ds); b.pv = take(Ds, Ds); b.po = take(Ds, Ds); b.f1 = take(4 * Ds, Ds); b.f2 = take(Ds, 4 * Ds); }
+        else b = WImgBlock{0, 0, 0, 0, 0, 0};
+    }
+    w.wqT = take(Ds, Ds); w.wk = take(Ds, D); w.wvT = take(D, Ds); w.wihT = take(Ds, 3 * Ds); w.whhT = take(Ds, 3 * Ds);
+    w.w1T = take(Ds, M); w.w2T = take(M, Ds);
+    for (int j = 0; j < SAVI_MAX_BLOCKS; ++j) {
+        WImgBlock& b = w.blkT[j];
+        if (j < blocks) { b.pq = take(Ds, Ds); b.pk = take(Ds, Ds); b.pv = take(Ds, Ds); b.po = take(Ds, Ds); b.f1 = take(Ds, 4 * Ds); b.f2 = take(4 * Ds, Ds); }
+        else b = WImgBlock{0, 0, 0, 0, 0, 0};
+    }
+    w.total_bytes = p;
+}
+// the image region follows the fp32 / bf16-hi / bf16-lo copies in the packed buffer
+static SAVI_HD int64_t savi_wimg_base(int packed_total) { return ((int64_t)packed_total * 8 + 1023) / 1024 * 1024; }
+
 static inline void savi_param_offsets(const SaviShape& s, ParamOff& o) {
     const int D = s.D, Ds = s.Ds, M = s.M;
     int p = 0;
@@ -93,6 +134,8 @@ struct Dims {
     int tok_bytes;   // 4 (fp32) or 2 (bf16)
     int mma;         // 1: tensor-core path (bf16 tokens, D%16==0, N%8==0, ...), 0: SIMT path
     int KC;          // 16 * ceil(K/16): slot rows of the staged backward coefficients
+    int umma;        // 1: tcgen05 clip kernels (bf16 tokens, D = Ds = M = 128, K <= 24, CN <= 2)
+    int NTILE;       // ceil(N / 128): 128-token tiles per frame (tcgen05 path)
     float eps, ln_eps, qscale;
 };
 
@@ -109,6 +152,7 @@ struct SavedLayout {
     int64_t px0;                                 // [(T-1)*B*K, Ds] predictor input of each frame (= slots_out[:, t])
     int64_t py, pq, pk, pv, po, px1, pl2, pf, px2;   // widths Ds x7, 4Ds, Ds
     int64_t patt;                                // [Sp*B, heads*K*K]
+    int64_t ximg;        // bytes  [B*T][NTILE][D/64][128 rows][64] bf16, SWIZZLE_128B blocks of xhat (tcgen05 path only)
     int64_t total_bytes;
 };
 
@@ -128,7 +172,11 @@ static inline void savi_saved_layout(const Dims& d, SavedLayout& L) {
     L.py = take(Rp, d.Ds); L.pq = take(Rp, d.Ds); L.pk = take(Rp, d.Ds); L.pv = take(Rp, d.Ds); L.po = take(Rp, d.Ds);
     L.px1 = take(Rp, d.Ds); L.pl2 = take(Rp, d.Ds); L.pf = take(Rp, 4 * d.Ds); L.px2 = take(Rp, d.Ds);
     L.patt = take((int64_t)d.Sp * d.B, (int64_t)d.heads * d.K * d.K);
-    L.total_bytes = L.fbase + f * 4;
+    int64_t e = L.fbase + f * 4;
+    e = (e + 1023) / 1024 * 1024;
+    L.ximg = e;
+    if (d.umma) e += (int64_t)d.B * d.T * d.NTILE * (d.D / 64) * 16384;
+    L.total_bytes = e;
 }
 
 // ---------------------------------------------------------------------------

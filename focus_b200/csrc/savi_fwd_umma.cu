@@ -7,9 +7,14 @@
 
 using namespace uc;
 
-// TMEM columns (fp32 accumulators, 32 columns = 32 slots each)
-enum { TC_A = 0, TC_B = 32, TC_R = 64, TC_Z = 96, TC_HN = 128, TC_IN = 160, TC_S0 = 192, TC_S1 = 224, TC_NUMX = 256, TC_SSUM = 288,
-       TC_F0 = 320 /* predictor FFN hidden tiles: 4 x 32 */, TC_COLS = 512 };
+// development aid: cycle counters of compute thread 0 of CTA 0 (tools/phase_times.py); no barriers added
+#define UPH(id) do { if (dbg) { const long long t_ = clock64(); dbg[id] += t_ - ph_last; ph_last = t_; } } while (0)
+
+// TMEM columns: fp32 accumulators, 64 columns each (32 slots x {X_hi, X_lo} partial products)
+enum { TC_A = 0, TC_B = 64, TC_R = 128, TC_Z = 192, TC_HN = 256, TC_IN = 320, TC_S0 = 384, TC_S1 = 448,
+       TC_NUMX = TC_A, TC_SSUM = TC_B,        // live only during the token pass, when A and B are dead
+       TC_F0 = TC_R,                          // predictor FFN hidden tiles (4 x 64): the GRU accumulators are dead there
+       TC_COLS = 512 };
 
 struct FwdUArgs {
     FwdArgs a;
@@ -19,9 +24,9 @@ struct FwdUArgs {
 
 // ------------------------------------------------------------------------------------------------
 // issuer: attention step products of this CTA's token tiles
-//   P1(i): S[i&1]  = xhat_i . qk^T            (A = token tile, K-major;  B = qk hi / lo)
-//   P2(i): NUMX   += xhat_i^T . A_i           (A = token tile, MN-major; B = attention weights hi / lo)
-//          SSUM   += 1 . A_i
+//   P1(i): S[i&1]  = xhat_i . [qk_hi | qk_lo]       (A = token tile, K-major;  B = qk operand)
+//   P2(i): NUMX   += xhat_i^T . [A_hi | A_lo]       (A = token tile, MN-major; B = attention-weight tile)
+//          SSUM   += 1 . [A_hi | A_lo]
 // ------------------------------------------------------------------------------------------------
 struct TokState { uint32_t cnt_s[2], cnt_a[2]; };
 
@@ -36,14 +41,11 @@ __device__ __forceinline__ void issue_token_pass(Ring& r, unsigned char* sm, con
         const uint32_t x0 = smem_u32(r.base + (size_t)ts0[g] * BLK);
         const uint32_t aw = smem_u32(sm + (g ? L.aw1 : L.aw0));
 #pragma unroll 2
-        for (int kt = 0; kt < 8; ++kt) {
-            const uint32_t bh = aw + (kt >> 2) * OP_CB + (kt & 3) * 32, bl = bh + OP_LO;
-            const uint64_t ax = desc_mnmajor(x0 + kt * 2048, BLK);
+        for (int kt = 0; kt < 8; ++kt) {                              // 16 tokens per k-step
+            const uint64_t bw = desc_mnmajor(aw + kt * 2048, BLK);
             const bool acc = j > 0 || kt > 0;
-            mma_ss(tb + TC_NUMX, ax, desc_kmajor(bh), IDESC_MK, acc);
-            mma_ss(tb + TC_NUMX, ax, desc_kmajor(bl), IDESC_MK, true);
-            mma_ss(tb + TC_SSUM, desc_mnmajor(ones, 2048), desc_kmajor(bh), IDESC_MK, acc);
-            mma_ss(tb + TC_SSUM, desc_mnmajor(ones, 2048), desc_kmajor(bl), IDESC_MK, true);
+            mma_ss(tb + TC_NUMX, desc_mnmajor(x0 + kt * 2048, BLK), bw, IDESC_MN_MN64, acc);
+            mma_ss(tb + TC_SSUM, desc_mnmajor(ones, 2048), bw, IDESC_MN_MN64, acc);
         }
         mma_commit(&r.empty[ts0[g]]);
         mma_commit(&r.empty[ts0[g] + 1]);
@@ -61,12 +63,9 @@ __device__ __forceinline__ void issue_token_pass(Ring& r, unsigned char* sm, con
             mbar_wait(&r.full[r.stage], r.phase);
             fence_after_sync();
             const uint32_t a = smem_u32(r.base + (size_t)r.stage * BLK);
-            const uint32_t qh = qk_op + db * OP_CB, ql = qh + OP_LO;
 #pragma unroll
-            for (int k4 = 0; k4 < 4; ++k4) {
-                mma_ss(acc_s, desc_kmajor(a + k4 * 32), desc_kmajor(qh + k4 * 32), IDESC_KK, db > 0 || k4 > 0);
-                mma_ss(acc_s, desc_kmajor(a + k4 * 32), desc_kmajor(ql + k4 * 32), IDESC_KK, true);
-            }
+            for (int k4 = 0; k4 < 4; ++k4)
+                mma_ss(acc_s, desc_kmajor(a + k4 * 32), desc_mnmajor(qk_op + (db * 4 + k4) * 2048, BLK), IDESC_K_MN64, db > 0 || k4 > 0);
             r.advance();
         }
         mma_commit(&bars[B_SFULL + g]);
@@ -78,67 +77,84 @@ __device__ __forceinline__ void issue_token_pass(Ring& r, unsigned char* sm, con
 }
 
 // ------------------------------------------------------------------------------------------------
-// compute threads: softmax over the slot axis of this group's token tiles (thread = token)
+// compute threads: softmax over the slot axis (thread = token).  Warpgroups 2p and 2p + 1 share the tiles with
+// tile % 2 == p; each takes one half of the slots and they exchange (max, sum) through shared memory.
 // ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ void softmax_tiles(const Ctx& c, const Dims& d, int ntile, int tile0, bf16* attn_frame, TokState& ts) {
+__device__ __forceinline__ void softmax_tiles(const Ctx& c, const Dims& d, int ntile, int tile0, bf16* attn_frame, TokState& ts, long long* dbg) {
     constexpr float LOG2E = 1.4426950408889634f;
-    const int g = c.g, K = c.K;
-    for (int i = g; i < ntile; i += 2) {
-        mbar_wait(&c.bars[B_SFULL + g], ts.cnt_s[g] & 1u);
+    long long ph_last = clock64();
+    const int K = c.K, p = c.wg >> 1, h = c.wg & 1;
+    const int KHs = (((K + 1) >> 1) + 3) & ~3;                       // slots per half, a multiple of 4 (8-byte store granules)
+    const int s0 = h * KHs, ns = min(max(K - s0, 0), KHs);
+    const uint32_t scol = c.tb + c.tlane + (p ? TC_S1 : TC_S0) + s0;
+    unsigned char* awrow = c.sm + (p ? c.L.aw1 : c.L.aw0) + c.o * 128;
+    const uint32_t sw = (uint32_t)(c.o & 7);
+    for (int i = p; i < ntile; i += 2) {
+        mbar_wait(&c.bars[B_SFULL + p], ts.cnt_s[p] & 1u);
         fence_after_sync();
-        float l[32];
-        tmem_ld32(tmem_addr(c.tb, c.warp, g ? TC_S1 : TC_S0), l);
+        UPH(50);
+        float l[16], l2[16];
+        tmem_ld16(scol, l); tmem_ld16(scol + 32, l2);
         tmem_wait_ld();
         fence_before_sync();
         __syncwarp();
-        if (c.lane == 0) mbar_arrive(&c.bars[B_SFREE + g]);
-        ++ts.cnt_s[g];
+        if (c.lane == 0) mbar_arrive(&c.bars[B_SFREE + p]);
         float mx = -INFINITY;
 #pragma unroll
-        for (int s = 0; s < 32; ++s) if (s < K) mx = fmaxf(mx, l[s]);
+        for (int s = 0; s < 16; ++s) { l[s] += l2[s]; if (s < ns) mx = fmaxf(mx, l[s]); }
         mx *= LOG2E;
         float sum = 0.f;
 #pragma unroll
-        for (int s = 0; s < 32; ++s) { l[s] = (s < K) ? exp2f(fmaf(l[s], LOG2E, -mx)) : 0.f; sum += l[s]; }
-        const float inv = 1.0f / sum;
+        for (int s = 0; s < 16; ++s) { l[s] = (s < ns) ? exp2f(fmaf(l[s], LOG2E, -mx)) : 0.f; sum += l[s]; }
+        float2* xch = reinterpret_cast<float2*>(c.sm + c.L.xch) + ((p * 2 + (ts.cnt_s[p] & 1u)) * 2) * 128;
+        xch[h * 128 + c.o] = make_float2(mx, sum);
+        bar_sync_n(2 + p, 256);
+        const float2 other = xch[(h ^ 1) * 128 + c.o];
+        ++ts.cnt_s[p];
+        const float M = fmaxf(mx, other.x);
+        const float wme = exp2f(mx - M);
+        const float scale = wme / (sum * wme + other.y * exp2f(other.x - M));
         const int n = (tile0 + i) * 128 + c.o;                  // token index inside the frame
         const bool valid = n < d.N;
-        mbar_wait(&c.bars[B_AFREE + g], (ts.cnt_a[g] & 1u) ^ 1u);
-        unsigned char* aw = c.sm + (g ? c.L.aw1 : c.L.aw0) + (c.o >> 6) * OP_CB;
-        const int oc = c.o & 63;
+        UPH(51);
+        mbar_wait(&c.bars[B_AFREE + p], (ts.cnt_a[p] & 1u) ^ 1u);
+        UPH(52);
 #pragma unroll
-        for (int s = 0; s < 32; ++s) {
-            if (s < K) {
-                l[s] *= inv;                                     // P (steve.py:77)
-                const float a = valid ? l[s] + d.eps : 0.f;      // A = P + eps (:81); padded tokens carry no weight
-                const bf16 hi = __float2bfloat16_rn(a);
-                const bf16 lo = __float2bfloat16_rn(a - __bfloat162float(hi));
-                const uint32_t off = sw128_off(s, oc);
-                *reinterpret_cast<bf16*>(aw + off) = hi;
-                *reinterpret_cast<bf16*>(aw + OP_LO + off) = lo;
+        for (int s = 0; s < 16; s += 4) {
+            if (s < KHs) {
+                float a[4];
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    l[s + e] *= scale;                                   // P (steve.py:77)
+                    a[e] = (valid && s + e < ns) ? l[s + e] + d.eps : 0.f;   // A = P + eps (:81); padded tokens carry no weight
+                }
+                const __nv_bfloat162 h0 = __floats2bfloat162_rn(a[0], a[1]), h1 = __floats2bfloat162_rn(a[2], a[3]);
+                const float2 f0 = __bfloat1622float2(h0), f1 = __bfloat1622float2(h1);
+                uint2 hv, lv;
+                hv.x = *reinterpret_cast<const uint32_t*>(&h0); hv.y = *reinterpret_cast<const uint32_t*>(&h1);
+                lv.x = pack_bf16x2(a[0] - f0.x, a[1] - f0.y); lv.y = pack_bf16x2(a[2] - f1.x, a[3] - f1.y);
+                const uint32_t bo = (uint32_t)(s0 + s) * 2u;             // byte offset of slot s0 + s in the hi half of the row
+                *reinterpret_cast<uint2*>(awrow + ((((bo >> 4) ^ sw)) << 4) + (bo & 15u)) = hv;
+                *reinterpret_cast<uint2*>(awrow + (((((bo + 64u) >> 4) ^ sw)) << 4) + (bo & 15u)) = lv;
             }
         }
         fence_async_smem();
         __syncwarp();
-        if (c.lane == 0) mbar_arrive(&c.bars[B_AREADY + g]);
-        ++ts.cnt_a[g];
+        if (c.lane == 0) mbar_arrive(&c.bars[B_AREADY + p]);
+        ++ts.cnt_a[p];
+        UPH(53);
         if (attn_frame && valid) {                               // attns (:96): pre-epsilon softmax, [N][K]
-            bf16* row = attn_frame + (size_t)n * K;
-            if ((K & 7) == 0) {
+            bf16* row = attn_frame + (size_t)n * K + s0;
+            if ((K & 3) == 0) {
 #pragma unroll
-                for (int s = 0; s < 32; s += 8) {
-                    if (s < K) {
-                        uint4 v;
-                        v.x = pack_bf16x2(l[s], l[s + 1]); v.y = pack_bf16x2(l[s + 2], l[s + 3]);
-                        v.z = pack_bf16x2(l[s + 4], l[s + 5]); v.w = pack_bf16x2(l[s + 6], l[s + 7]);
-                        *reinterpret_cast<uint4*>(row + s) = v;
-                    }
-                }
+                for (int s = 0; s < 16; s += 4)
+                    if (s < ns) *reinterpret_cast<uint2*>(row + s) = make_uint2(pack_bf16x2(l[s], l[s + 1]), pack_bf16x2(l[s + 2], l[s + 3]));
             } else {
 #pragma unroll
-                for (int s = 0; s < 32; ++s) if (s < K) row[s] = __float2bfloat16_rn(l[s]);
+                for (int s = 0; s < 16; ++s) if (s < ns) row[s] = __float2bfloat16_rn(l[s]);
             }
         }
+        UPH(54);
     }
 }
 
@@ -146,19 +162,19 @@ __device__ __forceinline__ void softmax_tiles(const Ctx& c, const Dims& d, int n
 // predictor attention core on one clip, in shared memory (transformer.py:34-47).  Inputs: this thread's
 // q (scaled), k, v columns.  Output: its column of O = softmax(q k^T) v per head.
 // ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ void mha_core(const Ctx& c, int H, const float (&q)[KHMAX], const float (&kx)[KHMAX], const float (&v)[KHMAX],
-                                         float (&out)[KHMAX], float* att_g /* nullable: [H][K][K] saved */) {
+__device__ __forceinline__ void mha_core(const Ctx& c, int H, const float (&q)[KH], const float (&kx)[KH], const float (&v)[KH],
+                                         float (&out)[KH], float* att_g /* nullable: [H][K][K] saved */) {
     const int K = c.K, ld = F + 1, ka = K | 1, dh = F / H;
     float* sQ = reinterpret_cast<float*>(c.sm + c.L.aw0);            // aw0 | aw1 | scratch are contiguous
     float* sK = sQ + K * ld;
     float* sV = sK + K * ld;
     float* sA = reinterpret_cast<float*>(c.sm + c.L.opC);            // [H*K][ka]
 #pragma unroll
-    for (int kk = 0; kk < KHMAX; ++kk) {
-        const int k = c.g * c.KH + kk;
-        if (kk < c.KH && k < K) { sQ[k * ld + c.o] = q[kk]; sK[k * ld + c.o] = kx[kk]; sV[k * ld + c.o] = v[kk]; }
+    for (int kk = 0; kk < KH; ++kk) {
+        const int k = c.k0 + kk;
+        if (kk < c.nk) { sQ[k * ld + c.o] = q[kk]; sK[k * ld + c.o] = kx[kk]; sV[k * ld + c.o] = v[kk]; }
     }
-    bar_sync_compute(1);
+    bar_sync_compute();
     for (int idx = c.tid; idx < H * K * K; idx += NCT) {
         const int j = idx % K, i = (idx / K) % K, h = idx / (K * K);
         const float* a = sQ + i * ld + h * dh;
@@ -167,7 +183,7 @@ __device__ __forceinline__ void mha_core(const Ctx& c, int H, const float (&q)[K
         for (int e = 0; e < dh; ++e) s = fmaf(a[e], b[e], s);
         sA[(h * K + i) * ka + j] = s;
     }
-    bar_sync_compute(1);
+    bar_sync_compute();
     for (int row = c.tid; row < H * K; row += NCT) {
         float* a = sA + row * ka;
         float mx = -INFINITY;
@@ -177,20 +193,19 @@ __device__ __forceinline__ void mha_core(const Ctx& c, int H, const float (&q)[K
         const float inv = 1.0f / sum;
         for (int j = 0; j < K; ++j) a[j] *= inv;
     }
-    bar_sync_compute(1);
+    bar_sync_compute();
     if (att_g) for (int idx = c.tid; idx < H * K * K; idx += NCT) att_g[idx] = sA[(idx / K) * ka + idx % K];
     const int h = c.o / dh;
 #pragma unroll
-    for (int kk = 0; kk < KHMAX; ++kk) {
-        const int i = c.g * c.KH + kk;
+    for (int kk = 0; kk < KH; ++kk) {
         float s = 0.f;
-        if (kk < c.KH && i < K) {
-            const float* a = sA + (h * K + i) * ka;
+        if (kk < c.nk) {
+            const float* a = sA + (h * K + c.k0 + kk) * ka;
             for (int j = 0; j < K; ++j) s = fmaf(a[j], sV[j * ld + c.o], s);
         }
         out[kk] = s;
     }
-    bar_sync_compute(1);                                             // sQ/sK/sV/sA are free again
+    bar_sync_compute();                                              // sQ/sK/sV/sA are free again
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -217,15 +232,15 @@ __global__ void __launch_bounds__(NTHREADS, 1) savi_fwd_umma_kernel(const __grid
     const unsigned char* ximg = a.saved + a.sl.ximg;
 
     // ---- one-time setup ----
-    for (int i = tid * 16; i < L.bars; i += NTHREADS * 16) *reinterpret_cast<uint4*>(sm + i) = make_uint4(0u, 0u, 0u, 0u);   // operands: padded rows must be zero
+    for (int i = tid * 16; i < L.bars; i += NTHREADS * 16) *reinterpret_cast<uint4*>(sm + i) = make_uint4(0u, 0u, 0u, 0u);
     __syncthreads();
     for (int i = tid; i < 2048; i += NTHREADS) reinterpret_cast<uint16_t*>(sm + L.ones)[i] = 0x3F80;                     // bf16 1.0
     if (tid == 0) {
         for (int s = 0; s < L.nst; ++s) { mbar_init(&bars[B_FULL + s], 1); mbar_init(&bars[B_EMPTY + s], 1); }
         mbar_init(&bars[B_OPND], NCW); mbar_init(&bars[B_ACC], 1); mbar_init(&bars[B_TOK], 1);
         for (int g = 0; g < 2; ++g) {
-            mbar_init(&bars[B_SFULL + g], 1); mbar_init(&bars[B_SFREE + g], 4);
-            mbar_init(&bars[B_AREADY + g], 4); mbar_init(&bars[B_AFREE + g], 1);
+            mbar_init(&bars[B_SFULL + g], 1); mbar_init(&bars[B_SFREE + g], 8);
+            mbar_init(&bars[B_AREADY + g], 8); mbar_init(&bars[B_AFREE + g], 1);
             mbar_init(&bars[B_INBOX + g], NCW);
         }
         for (int f = 0; f < 4; ++f) { mbar_init(&bars[B_FACC + f], 1); mbar_init(&bars[B_FOPND + f], NCW); }
@@ -284,38 +299,37 @@ __global__ void __launch_bounds__(NTHREADS, 1) savi_fwd_umma_kernel(const __grid
             for (int t = 0; t < d.T; ++t) {
                 for (int it = 0; it < d.I; ++it) {
                     wait_opnd();                                                          // s~ in opA, h_prev in opC
-                    issue_linear(ring, opA, tb + TC_A, 32, 1, 2, false); mma_commit(&bars[B_ACC]);      // q   (steve.py:75)
+                    issue_linear(ring, opA, tb + TC_A, 1, 2, false); mma_commit(&bars[B_ACC]);          // q   (steve.py:75)
                     wait_opnd();                                                          // q in opB
-                    issue_linear(ring, opB, tb + TC_B, 32, 1, 2, false); mma_commit(&bars[B_ACC]);      // qk  (fold of :61,63,76)
+                    issue_linear(ring, opB, tb + TC_B, 1, 2, false); mma_commit(&bars[B_ACC]);          // qk  (fold of :61,63,76)
                     wait_opnd();                                                          // qk in opA
                     issue_token_pass(ring, sm, L, bars, tb, ntile, ts, opA);
                     // GRU hidden-side product, off the critical path: runs while the compute threads combine the partial sums.
                     // (It must not be streamed while token tiles are held in the ring: the ring is filled in order.)
-                    issue_linear(ring, opC, tb + TC_R, 32, 3, 2, false);                    // R, Z, HN = W_hh . h_prev
+                    issue_linear(ring, opC, tb + TC_R, 3, 2, false);                      // R, Z, HN = W_hh . h_prev
                     wait_opnd();                                                          // Ux in opB
-                    issue_linear(ring, opB, tb + TC_A, 32, 1, 2, false); mma_commit(&bars[B_ACC]);      // updates (:83)
+                    issue_linear(ring, opB, tb + TC_A, 1, 2, false); mma_commit(&bars[B_ACC]);          // updates (:83)
                     wait_opnd();                                                          // U in opA
-                    issue_linear(ring, opA, tb + TC_R, 32, 2, 2, true);                                  // R, Z += W_i{r,z} . U
-                    issue_linear(ring, opA, tb + TC_IN, 32, 1, 2, false); mma_commit(&bars[B_ACC]);     // IN = W_in . U   (:87)
+                    issue_linear(ring, opA, tb + TC_R, 2, 2, true);                                      // R, Z += W_i{r,z} . U
+                    issue_linear(ring, opA, tb + TC_IN, 1, 2, false); mma_commit(&bars[B_ACC]);         // IN = W_in . U   (:87)
                     if (it < d.I - 1) {
                         wait_opnd();                                                      // LN_m(h') in opB
-                        issue_linear(ring, opB, tb + TC_A, 32, 1, 2, false); mma_commit(&bars[B_ACC]);  // mlp.0 (:92)
+                        issue_linear(ring, opB, tb + TC_A, 1, 2, false); mma_commit(&bars[B_ACC]);      // mlp.0 (:92)
                         wait_opnd();                                                      // a in opA
-                        issue_linear(ring, opA, tb + TC_B, 32, 1, 2, false); mma_commit(&bars[B_ACC]);  // mlp.2
+                        issue_linear(ring, opA, tb + TC_B, 1, 2, false); mma_commit(&bars[B_ACC]);      // mlp.2
                     }
                 }
                 if (t < d.T - 1) {
                     for (int j = 0; j < d.blocks; ++j) {
                         wait_opnd();                                                      // y in opA
-                        issue_linear(ring, opA, tb + TC_R, 32, 3, 2, false); mma_commit(&bars[B_ACC]);  // q, k, v -> R, Z, HN columns
+                        issue_linear(ring, opA, tb + TC_R, 3, 2, false); mma_commit(&bars[B_ACC]);      // q, k, v -> R, Z, HN columns
                         wait_opnd();                                                      // attention output in opB
-                        issue_linear(ring, opB, tb + TC_A, 32, 1, 2, false); mma_commit(&bars[B_ACC]);  // proj_o
+                        issue_linear(ring, opB, tb + TC_A, 1, 2, false); mma_commit(&bars[B_ACC]);      // proj_o
                         wait_opnd();                                                      // LN2 in opA
-                        for (int f = 0; f < 4; ++f) { issue_linear(ring, opA, tb + TC_F0 + 32 * f, 32, 1, 2, false); mma_commit(&bars[B_FACC + f]); }   // ffn.0
-                        const uint32_t fop[4] = {opB, opC, aw0, aw1};
+                        for (int f = 0; f < 4; ++f) { issue_linear(ring, opA, tb + TC_F0 + 64 * f, 1, 2, false); mma_commit(&bars[B_FACC + f]); }   // ffn.0
                         for (int f = 0; f < 4; ++f) {                                     // ffn.2, contraction split in 4 chunks of 128
                             mbar_wait(&bars[B_FOPND + f], pcall & 1u); fence_after_sync();
-                            issue_linear(ring, fop[f], tb + TC_B, 32, 1, 2, f > 0);
+                            issue_linear(ring, f == 0 ? opB : f == 1 ? opC : f == 2 ? aw0 : aw1, tb + TC_B, 1, 2, f > 0);
                         }
                         mma_commit(&bars[B_ACC]);
                         ++pcall;
@@ -328,23 +342,26 @@ __global__ void __launch_bounds__(NTHREADS, 1) savi_fwd_umma_kernel(const __grid
         // compute threads
         // =====================================================================================
         Ctx c;
-        c.tid = tid; c.warp = warp; c.lane = lane; c.g = warp >> 2; c.o = (warp & 3) * 32 + lane;
-        c.KH = (K + 1) >> 1; c.K = K; c.sm = sm; c.L = L; c.tb = tb; c.bars = bars; c.ph_acc = 0; c.ph_opnd = 0;
+        ctx_init(c, tid, K, sm, L, tb, bars);
         const int o = c.o;
         TokState ts = {{0, 0}, {0, 0}};
         // per-feature parameters of this thread
         const float g_s = P[po.ln_s_w + o], b_s = P[po.ln_s_b + o], g_m = P[po.ln_m_w + o], b_m = P[po.ln_m_b + o];
-        const float bir = P[po.bih + o], biz = P[po.bih + F + o], bin = P[po.bih + 2 * F + o];
-        const float bhr = P[po.bhh + o], bhz = P[po.bhh + F + o], bhn = P[po.bhh + 2 * F + o];
+        const float b_r = P[po.bih + o] + P[po.bhh + o], b_z = P[po.bih + F + o] + P[po.bhh + F + o];
+        const float bin = P[po.bih + 2 * F + o], bhn = P[po.bhh + 2 * F + o];
         const float b1 = P[po.b1 + o], b2 = P[po.b2 + o];
-        float h[KHMAX], y[KHMAX];
+        float h[KH], y[KH];
         {   // slots0 = mu + exp(log_sigma) * noise   (steve.py:56-57)
             const float mu = P[po.slot_mu + o], sg = expf(P[po.slot_log_sigma + o]);
             load_field(c, a.noise + (size_t)b * K * F, F, o, y);
 #pragma unroll
-            for (int kk = 0; kk < KHMAX; ++kk) h[kk] = mu + sg * y[kk];
+            for (int kk = 0; kk < KH; ++kk) h[kk] = mu + sg * y[kk];
         }
         uint32_t step = 0, pcall = 0;
+        __shared__ long long sdbg[64];
+        if (a.dbg && blockIdx.x == 0 && tid == 0) for (int i = 0; i < 64; ++i) sdbg[i] = 0;
+        long long* dbg = (a.dbg && blockIdx.x == 0 && tid == 0) ? sdbg : nullptr;      // counters in shared memory: a global RMW per probe would stall the warp
+        long long ph_last = clock64();
         for (int t = 0; t < d.T; ++t) {
             for (int it = 0; it < d.I; ++it, ++step) {
                 const int64_t s = (int64_t)t * d.I + it;
@@ -354,81 +371,86 @@ __global__ void __launch_bounds__(NTHREADS, 1) savi_fwd_umma_kernel(const __grid
                 layer_norm(c, h, y, g_s, b_s, d.ln_eps);                                   // :72
                 write_operand(c, L.opA, y);
                 signal_operand(c);
-                wait_acc(c); load_acc(c, TC_A, y); tmem_wait_ld();                         // q
+                UPH(1);
+                wait_acc(c); UPH(2); load_acc(c, TC_A, y);                                  // q
                 if (lead) save_field(c, frow(fb, a.sl.q, s, b, B, K, F), F, o, y);
                 write_operand(c, L.opB, y);
                 signal_operand(c);
-                wait_acc(c); load_acc(c, TC_B, y); tmem_wait_ld();                         // qk = Ds^-1/2 q Wk
+                UPH(3);
+                wait_acc(c); UPH(4); load_acc(c, TC_B, y);                                  // qk = Ds^-1/2 q Wk
 #pragma unroll
-                for (int kk = 0; kk < KHMAX; ++kk) y[kk] *= d.qscale;
+                for (int kk = 0; kk < KH; ++kk) y[kk] *= d.qscale;
                 if (lead) save_field(c, frow(fb, a.sl.qk, s, b, B, K, F), F, o, y);
                 write_operand(c, L.opA, y);
                 signal_operand(c);
                 // ---- attention step over the token tiles ----
                 bf16* attn_frame = (it == d.I - 1) ? reinterpret_cast<bf16*>(a.attn_out) + ((size_t)b * d.T + t) * d.N * K : nullptr;
-                softmax_tiles(c, d, ntile, tile0, attn_frame, ts);
+                UPH(5);
+                softmax_tiles(c, d, ntile, tile0, attn_frame, ts, dbg);
+                UPH(6);
                 mbar_wait(&bars[B_TOK], step & 1u);
                 fence_after_sync();
-                float num[KHMAX], den[KHMAX];
-                load_acc(c, TC_NUMX, num); load_acc(c, TC_SSUM, den); tmem_wait_ld();
-                if (ntile == 0) {
-#pragma unroll
-                    for (int kk = 0; kk < KHMAX; ++kk) { num[kk] = 0.f; den[kk] = 0.f; }
-                }
+                UPH(7);
+                float num[KH], den[KH];
+                load_acc(c, TC_NUMX, num); load_acc(c, TC_SSUM, den);
                 if (CN > 1) {                                                              // exchange the partial sums with the peer CTA
                     const int buf = step & 1;
                     float* ib = reinterpret_cast<float*>(sm + L.inbox + buf * L.inbox_stride);
                     const uint32_t peer = rank ^ 1u;
-                    const uint32_t rb = map_to_rank(ib, peer);
+                    const uint32_t rb = map_to_rank(ib, peer) + (uint32_t)(c.k0 * F + o) * 4u;
 #pragma unroll
-                    for (int kk = 0; kk < KHMAX; ++kk) {
-                        const int k = c.g * c.KH + kk;
-                        if (kk < c.KH && k < K) {
-                            st_cluster_f1(rb + (uint32_t)(k * F + o) * 4u, num[kk]);
-                            if (o == 0) st_cluster_f1(rb + (uint32_t)(KP * F + k) * 4u, den[kk]);
-                        }
+                    for (int kk = 0; kk < KH; ++kk) if (kk < c.nk) st_cluster_f1(rb + (uint32_t)(kk * F) * 4u, num[kk]);
+                    if (o == 0) {
+                        const uint32_t rd = map_to_rank(ib + KP * F + c.k0, peer);
+#pragma unroll
+                        for (int kk = 0; kk < KH; ++kk) if (kk < c.nk) st_cluster_f1(rd + kk * 4u, den[kk]);
                     }
                     __syncwarp();
                     if (lane == 0) mbar_arrive_remote(map_to_rank(&bars[B_INBOX + buf], peer));
+                    UPH(8);
                     mbar_wait_cluster(&bars[B_INBOX + buf], (step >> 1) & 1u);
+                    UPH(9);
+                    const float* pn = ib + c.k0 * F + o;
+                    const float* pd = ib + KP * F + c.k0;
 #pragma unroll
-                    for (int kk = 0; kk < KHMAX; ++kk) {
-                        const int k = c.g * c.KH + kk;
-                        if (kk < c.KH && k < K) {
-                            const float pn = ib[k * F + o], pd = ib[KP * F + k];
+                    for (int kk = 0; kk < KH; ++kk) {
+                        if (kk < c.nk) {
                             // fixed order rank 0 + rank 1 on both CTAs: their slot states stay bit-identical
-                            num[kk] = lead ? num[kk] + pn : pn + num[kk];
-                            den[kk] = lead ? den[kk] + pd : pd + den[kk];
+                            num[kk] = lead ? num[kk] + pn[kk * F] : pn[kk * F] + num[kk];
+                            den[kk] = lead ? den[kk] + pd[kk] : pd[kk] + den[kk];
                         }
                     }
                 }
 #pragma unroll
-                for (int kk = 0; kk < KHMAX; ++kk) y[kk] = (kk < c.KH && c.g * c.KH + kk < K) ? num[kk] / den[kk] : 0.f;      // Ux (:82-83)
+                for (int kk = 0; kk < KH; ++kk) y[kk] = (kk < c.nk) ? num[kk] / den[kk] : 0.f;      // Ux (:82-83)
                 if (lead) {
                     save_field(c, frow(fb, a.sl.ux, s, b, B, K, F), F, o, y);
                     if (o == 0) {
-                        float* r_ss = fb + a.sl.ssum + (s * B + b) * KP;
+                        float* r_ss = fb + a.sl.ssum + (s * B + b) * KP + c.k0;
 #pragma unroll
-                        for (int kk = 0; kk < KHMAX; ++kk) { const int k = c.g * c.KH + kk; if (kk < c.KH && k < K) r_ss[k] = den[kk]; }
+                        for (int kk = 0; kk < KH; ++kk) if (kk < c.nk) r_ss[kk] = den[kk];
                     }
                 }
                 write_operand(c, L.opB, y);
                 signal_operand(c);
-                wait_acc(c); load_acc(c, TC_A, y); tmem_wait_ld();                         // updates U (:83)
+                UPH(10);
+                wait_acc(c); UPH(11); load_acc(c, TC_A, y);                                 // updates U (:83)
                 if (lead) save_field(c, frow(fb, a.sl.u, s, b, B, K, F), F, o, y);
                 write_operand(c, L.opA, y);
                 signal_operand(c);
                 // ---- GRUCell (:87-89) ----
+                UPH(12);
                 wait_acc(c);
+                UPH(13);
                 {
-                    float r_[KHMAX], z_[KHMAX], n_[KHMAX], hn[KHMAX];
-                    load_acc(c, TC_R, r_); load_acc(c, TC_Z, z_); load_acc(c, TC_IN, n_); load_acc(c, TC_HN, hn); tmem_wait_ld();
+                    float r_[KH], z_[KH], n_[KH], hn[KH];
+                    load_acc(c, TC_R, r_); load_acc(c, TC_Z, z_); load_acc(c, TC_IN, n_); load_acc(c, TC_HN, hn);
                     const bool mlp = it < d.I - 1;
 #pragma unroll
-                    for (int kk = 0; kk < KHMAX; ++kk) {
+                    for (int kk = 0; kk < KH; ++kk) {
                         const float hnb = hn[kk] + bhn;
-                        const float vr = sigmoidf_(r_[kk] + bir + bhr);
-                        const float vz = sigmoidf_(z_[kk] + biz + bhz);
+                        const float vr = sigmoidf_(r_[kk] + b_r);
+                        const float vz = sigmoidf_(z_[kk] + b_z);
                         const float vn = tanhf(n_[kk] + bin + vr * hnb);
                         r_[kk] = vr; z_[kk] = vz; n_[kk] = vn; hn[kk] = hnb;
                         h[kk] = (1.0f - vz) * vn + vz * h[kk];
@@ -442,19 +464,23 @@ __global__ void __launch_bounds__(NTHREADS, 1) savi_fwd_umma_kernel(const __grid
                     if (mlp) {                                                             // residual MLP (:92-93)
                         const int64_t smi = (int64_t)t * (d.I - 1) + it;
                         if (lead) save_field(c, frow(fb, a.sl.hg, smi, b, B, K, F), F, o, h);
+                        UPH(14);
                         layer_norm(c, h, y, g_m, b_m, d.ln_eps);
                         write_operand(c, L.opB, y);
                         signal_operand(c);
-                        wait_acc(c); load_acc(c, TC_A, y); tmem_wait_ld();
+                        UPH(15);
+                        wait_acc(c); UPH(16); load_acc(c, TC_A, y);
 #pragma unroll
-                        for (int kk = 0; kk < KHMAX; ++kk) y[kk] = fmaxf(y[kk] + b1, 0.f);
+                        for (int kk = 0; kk < KH; ++kk) y[kk] = fmaxf(y[kk] + b1, 0.f);
                         if (lead) save_field(c, frow(fb, a.sl.a, smi, b, B, K, F), F, o, y);
                         write_operand(c, L.opA, y);
                         signal_operand(c);
-                        wait_acc(c); load_acc(c, TC_B, y); tmem_wait_ld();
+                        UPH(17);
+                        wait_acc(c); UPH(18); load_acc(c, TC_B, y);
 #pragma unroll
-                        for (int kk = 0; kk < KHMAX; ++kk) h[kk] += y[kk] + b2;
+                        for (int kk = 0; kk < KH; ++kk) h[kk] += y[kk] + b2;
                     }
+                    UPH(19);
                 }
             }
             if (lead) save_field(c, a.slots_out + ((size_t)b * d.T + t) * K * F, F, o, h);      // collect (:96-97)
@@ -462,63 +488,63 @@ __global__ void __launch_bounds__(NTHREADS, 1) savi_fwd_umma_kernel(const __grid
                 // ---- predictor (:100; transformer.py:106-114) ----
                 if (lead) save_field(c, fb + a.sl.px0 + ((size_t)t * B + b) * K * F, F, o, h);
                 const float hscale = 1.0f / sqrtf((float)(F / d.heads));
-                float x[KHMAX];
+                float x[KH];
 #pragma unroll
-                for (int kk = 0; kk < KHMAX; ++kk) x[kk] = h[kk];
+                for (int kk = 0; kk < KH; ++kk) x[kk] = h[kk];
                 for (int j = 0; j < d.blocks; ++j) {
                     const int64_t f = (int64_t)j * (d.T - 1) + t;
                     const BlockOff& bo = po.blk[j];
-                    float yv[KHMAX], q[KHMAX], kx[KHMAX], v[KHMAX], x1[KHMAX];
+                    float yv[KH], q[KH], kx[KH], v[KH], x1[KH];
                     layer_norm(c, x, yv, P[bo.ln1_w + o], P[bo.ln1_b + o], d.ln_eps);
                     if (lead) save_field(c, frow(fb, a.sl.py, f, b, B, K, F), F, o, yv);
                     write_operand(c, L.opA, yv);
                     signal_operand(c);
                     wait_acc(c);
-                    load_acc(c, TC_R, q); load_acc(c, TC_Z, kx); load_acc(c, TC_HN, v); tmem_wait_ld();
+                    load_acc(c, TC_R, q); load_acc(c, TC_Z, kx); load_acc(c, TC_HN, v);
 #pragma unroll
-                    for (int kk = 0; kk < KHMAX; ++kk) q[kk] *= hscale;
+                    for (int kk = 0; kk < KH; ++kk) q[kk] *= hscale;
                     if (lead) {
                         save_field(c, frow(fb, a.sl.pq, f, b, B, K, F), F, o, q);
                         save_field(c, frow(fb, a.sl.pk, f, b, B, K, F), F, o, kx);
                         save_field(c, frow(fb, a.sl.pv, f, b, B, K, F), F, o, v);
                     }
-                    float ov[KHMAX];
+                    float ov[KH];
                     mha_core(c, d.heads, q, kx, v, ov, lead ? fb + a.sl.patt + (f * B + b) * ((int64_t)d.heads * K * K) : nullptr);
                     if (lead) save_field(c, frow(fb, a.sl.po, f, b, B, K, F), F, o, ov);
                     write_operand(c, L.opB, ov);
                     signal_operand(c);
-                    wait_acc(c); load_acc(c, TC_A, x1); tmem_wait_ld();
+                    wait_acc(c); load_acc(c, TC_A, x1);
                     // the first block adds the residual to the NORMALISED input (transformer.py:75-78)
 #pragma unroll
-                    for (int kk = 0; kk < KHMAX; ++kk) x1[kk] += (j == 0) ? yv[kk] : x[kk];
+                    for (int kk = 0; kk < KH; ++kk) x1[kk] += (j == 0) ? yv[kk] : x[kk];
                     if (lead) save_field(c, frow(fb, a.sl.px1, f, b, B, K, F), F, o, x1);
                     layer_norm(c, x1, yv, P[bo.ln2_w + o], P[bo.ln2_b + o], d.ln_eps);
                     if (lead) save_field(c, frow(fb, a.sl.pl2, f, b, B, K, F), F, o, yv);
                     write_operand(c, L.opA, yv);
                     signal_operand(c);
-                    const int fop[4] = {L.opB, L.opC, L.aw0, L.aw1};
-                    // aw0 / aw1 hold attention-weight tiles between predictor calls: rows >= K are rewritten by nobody, and the
-                    // token pass only writes rows < K, so using them as slot-side operands (rows < K) keeps the zero padding intact
+#pragma unroll
                     for (int ff = 0; ff < 4; ++ff) {
                         mbar_wait(&bars[B_FACC + ff], pcall & 1u); fence_after_sync();
-                        load_acc(c, TC_F0 + 32 * ff, yv); tmem_wait_ld();
+                        load_acc(c, TC_F0 + 64 * ff, yv);
                         const float bb = P[bo.f1b + ff * F + o];
 #pragma unroll
-                        for (int kk = 0; kk < KHMAX; ++kk) yv[kk] = fmaxf(yv[kk] + bb, 0.f);
+                        for (int kk = 0; kk < KH; ++kk) yv[kk] = fmaxf(yv[kk] + bb, 0.f);
                         if (lead) save_field(c, frow(fb, a.sl.pf, f, b, B, K, 4 * F), 4 * F, ff * F + o, yv);
-                        write_operand(c, fop[ff], yv);
+                        write_operand(c, ff == 0 ? L.opB : ff == 1 ? L.opC : ff == 2 ? L.aw0 : L.aw1, yv);
                         signal_operand(c, B_FOPND + ff);
                     }
                     ++pcall;
-                    wait_acc(c); load_acc(c, TC_B, yv); tmem_wait_ld();
+                    wait_acc(c); load_acc(c, TC_B, yv);
                     const float bb2 = P[bo.f2b + o];
 #pragma unroll
-                    for (int kk = 0; kk < KHMAX; ++kk) x[kk] = x1[kk] + yv[kk] + bb2;
+                    for (int kk = 0; kk < KH; ++kk) x[kk] = x1[kk] + yv[kk] + bb2;
                     if (lead) save_field(c, frow(fb, a.sl.px2, f, b, B, K, F), F, o, x);
                 }
                 layer_norm(c, x, h, P[po.lnf_w + o], P[po.lnf_b + o], d.ln_eps);
+                UPH(20);
             }
         }
+        if (dbg) for (int i = 0; i < 64; ++i) if (sdbg[i]) a.dbg[i] += sdbg[i];
     }
     // ---- teardown ----
     __syncwarp();
@@ -532,7 +558,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) savi_fwd_umma_kernel(const __grid
 // host side
 // ------------------------------------------------------------------------------------------------
 int savi_fwd_umma_smem_bytes(const Dims& d) {
-    const Smem L = plan_smem(d.K, d.CN, 0, 227 * 1024);
+    const Smem L = plan_smem(d.K, d.CN, 0, 227 * 1024 - 1024);      // 1 KB left for static shared memory
     return L.ring + L.nst * BLK + 1024;
 }
 

@@ -1,15 +1,21 @@
 // Shared pieces of the tcgen05 ("UMMA") clip kernels (forward: savi_fwd_umma.cu, backward: savi_bwd_umma.cu).
 //
 // Execution model.  One CTA (or a cluster of 2) owns one clip for the whole recurrence.
-//   * 8 compute warps (256 threads): thread (g, o), g = warp / 4, o = (warp % 4) * 32 + lane.  For slot-side
-//     tensors the thread owns FEATURE o of the slots [g*KH, g*KH + KH); the fp32 slot state lives in its
-//     registers for the whole kernel.  For the token pass it owns TOKEN o of the tiles with tile % 2 == g.
-//   * warp 8, one lane: producer.  Streams the static schedule of 16 KB operand blocks (weight images and
+//   * 16 compute warps (512 threads): thread (wg, o), wg = warp / 4, o = (warp % 4) * 32 + lane.  For slot-side
+//     tensors the thread owns FEATURE o of the 8 slots [8 wg, 8 wg + 8); the fp32 slot state lives in its
+//     registers for the whole kernel.  In the token pass it owns TOKEN o of a tile (two warpgroups share a
+//     tile, each takes half of the slot axis).
+//   * warp 16, one lane: producer.  Streams the static schedule of 16 KB operand blocks (weight images and
 //     token tiles, all pre-swizzled in global memory) into a shared-memory ring with 1-D bulk copies.
-//   * warp 9, one lane: tcgen05.mma issuer.  Every product is computed TRANSPOSED, Y^T = W . X^T, so the
+//   * warp 17, one lane: tcgen05.mma issuer.  Every product is computed TRANSPOSED, Y^T = W . X^T, so the
 //     128 output features are the M dimension of the tensor core and the (<= 32) slots are N: accumulator
 //     row = TMEM lane = feature = the compute thread that post-processes it (32x32b tcgen05.ld, no shuffles).
-// fp32 operands are split x = hi + lo (two bf16) and multiplied with three MMAs (hi.hi + hi.lo + lo.hi).
+//
+// fp32 operands are split x = hi + lo (two bf16).  An activation operand is ONE MN-major B matrix
+// [128 rows = contraction index][64 = 32 slots hi | 32 slots lo] (SWIZZLE_128B, 128 B per row): the thread that
+// owns feature / token `o` writes row `o` with two 16-byte stores.  Per 16-wide k-step a product is two MMAs,
+//     W_hi . [X_hi | X_lo]  (N = 64)   and   W_lo . X_hi  (N = 32),
+// and the epilogue adds accumulator columns s and 32 + s.
 #pragma once
 #include "savi_umma.cuh"
 #include "savi_dev.cuh"
@@ -19,23 +25,23 @@ namespace uc {
 using namespace umma;
 typedef __nv_bfloat16 bf16;
 
-constexpr int NCW = 8, NCT = NCW * 32;        // compute warps / threads
-constexpr int W_PROD = 8, W_MMA = 9;
-constexpr int NTHREADS = 320;
+constexpr int NCW = 16, NCT = NCW * 32;       // compute warps / threads
+constexpr int W_PROD = 16, W_MMA = 17;
+constexpr int NTHREADS = 576;
 constexpr int BLK = 16384;                    // ring block: [128 rows][64] bf16, SWIZZLE_128B
-constexpr int OPB = 16384;                    // operand buffer: hi [2 blocks of 32 x 64] 8 KB | lo 8 KB
-constexpr int OP_LO = 8192, OP_CB = 4096;     // byte offsets: lo half, second 64-column block
-constexpr int NS = 32;                        // MMA N (slots, zero-padded)
+constexpr int OPB = 16384;                    // activation operand: [128 rows][32 hi | 32 lo]
 constexpr int F = 128;                        // feature width handled by this path (D = Ds = M = 128)
-constexpr int KHMAX = 16;                     // slots per thread (register arrays)
-constexpr uint32_t IDESC_KK = idesc_bf16(128, NS, false, false);    // A K-major,  B K-major
-constexpr uint32_t IDESC_MK = idesc_bf16(128, NS, true, false);     // A MN-major, B K-major
+constexpr int KH = 8;                         // slots per compute thread
+constexpr uint32_t IDESC_K_MN64 = idesc_bf16(128, 64, false, true);    // A K-major,  B MN-major, N = 64
+constexpr uint32_t IDESC_K_MN32 = idesc_bf16(128, 32, false, true);    //                          N = 32 (hi half of B's rows)
+constexpr uint32_t IDESC_MN_MN64 = idesc_bf16(128, 64, true, true);    // A MN-major, B MN-major, N = 64
 
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
     __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
     return *reinterpret_cast<uint32_t*>(&v);
 }
-__device__ __forceinline__ void bar_sync_compute(int id) { asm volatile("bar.sync %0, %1;\n" :: "r"(id), "r"(NCT) : "memory"); }
+__device__ __forceinline__ void bar_sync_n(int id, int nthreads) { asm volatile("bar.sync %0, %1;\n" :: "r"(id), "r"(nthreads) : "memory"); }
+__device__ __forceinline__ void bar_sync_compute() { bar_sync_n(1, NCT); }
 
 __device__ __forceinline__ bool mbar_try_wait_cluster(uint64_t* bar, uint32_t parity) {
     uint32_t ok;
@@ -57,10 +63,11 @@ __device__ __forceinline__ void mbar_arrive_remote(uint32_t cluster_addr) {
 // ---- shared-memory plan -------------------------------------------------------------------------
 struct Smem {
     int ring, nst;                 // ring of nst blocks
-    int opA, opB, opC;             // slot-side B operands
-    int aw0, aw1;                  // token pass: attention-weight tiles [32 slots][128 tokens] hi | lo
+    int opA, opB, opC;             // slot-side activation operands
+    int aw0, aw1;                  // token pass: attention-weight tiles [128 tokens][32 hi | 32 lo]
     int scratch;                   // fp32 [KR][128] transposition scratch (LayerNorm statistics); follows aw1 (predictor q/k/v alias aw0..scratch)
     int stats;                     // float2 [32]
+    int xch;                       // token pass: softmax (max, sum) exchange between the two halves of the slot axis: float2 [2][2][2][128]
     int ones;                      // MN-major ones operand [16][128] bf16
     int inbox;                     // CN = 2: two buffers of [KR][128] + [32] fp32 written by the peer CTA
     int inbox_stride;
@@ -77,6 +84,7 @@ __host__ __device__ inline Smem plan_smem(int K, int CN, int aux_bytes, int max_
     s.aw0 = p; p += OPB; s.aw1 = p; p += OPB;
     s.scratch = p; p += KR * F * 4;
     s.stats = p; p += 32 * 8;
+    s.xch = p; p += 2 * 2 * 2 * 128 * 8;           // [pair][tile parity][half][token] float2
     p = (p + 1023) & ~1023;
     s.ones = p; p += 4096;
     s.inbox_stride = (KR * F * 4 + 32 * 4 + 127) & ~127;
@@ -117,28 +125,28 @@ __device__ __forceinline__ void prod_blocks(Ring& r, const unsigned char* src, i
 }
 
 // ---- issuer ------------------------------------------------------------------------------------
-// One linear layer, transposed: acc[rt] (+)= Wimg[rt] . X^T.  Blocks arrive through the ring in image order
-// (rt, cb, hi/lo).  xop: shared address of the operand buffer holding X hi | lo for columns [cb0*64, ...).
-__device__ __forceinline__ void issue_linear(Ring& r, uint32_t xop, uint32_t tacc, int col_stride, int ntile, int ncb, bool accumulate) {
+// One linear layer, transposed: acc[rt] (+)= Wimg[rt] . X^T.  Weight blocks arrive through the ring in image
+// order (rt, cb, hi, lo).  xop: shared address of the activation operand; its rows [cb*64, cb*64 + 64) are the
+// contraction range of block cb.  Accumulators are 64 columns wide (32 slots x {hi, lo} of X).
+__device__ __forceinline__ void issue_linear(Ring& r, uint32_t xop, uint32_t tacc, int ntile, int ncb, bool accumulate) {
     for (int rt = 0; rt < ntile; ++rt) {
-        const uint32_t d = tacc + rt * col_stride;
+        const uint32_t d = tacc + rt * 64;
         for (int cb = 0; cb < ncb; ++cb) {
-            const uint32_t xh = xop + cb * OP_CB, xl = xh + OP_LO;
+            const uint32_t xb = xop + cb * 8192;                         // 64 rows x 128 B
             mbar_wait(&r.full[r.stage], r.phase);
             fence_after_sync();
             uint32_t a = smem_u32(r.base + (size_t)r.stage * BLK);
 #pragma unroll
-            for (int k4 = 0; k4 < 4; ++k4) {
-                mma_ss(d, desc_kmajor(a + k4 * 32), desc_kmajor(xh + k4 * 32), IDESC_KK, accumulate || cb > 0 || k4 > 0);
-                mma_ss(d, desc_kmajor(a + k4 * 32), desc_kmajor(xl + k4 * 32), IDESC_KK, true);
-            }
+            for (int k4 = 0; k4 < 4; ++k4)
+                mma_ss(d, desc_kmajor(a + k4 * 32), desc_mnmajor(xb + k4 * 2048, BLK), IDESC_K_MN64, accumulate || cb > 0 || k4 > 0);
             mma_commit(&r.empty[r.stage]);
             r.advance();
             mbar_wait(&r.full[r.stage], r.phase);
             fence_after_sync();
             a = smem_u32(r.base + (size_t)r.stage * BLK);
 #pragma unroll
-            for (int k4 = 0; k4 < 4; ++k4) mma_ss(d, desc_kmajor(a + k4 * 32), desc_kmajor(xh + k4 * 32), IDESC_KK, true);
+            for (int k4 = 0; k4 < 4; ++k4)
+                mma_ss(d, desc_kmajor(a + k4 * 32), desc_mnmajor(xb + k4 * 2048, BLK), IDESC_K_MN32, true);
             mma_commit(&r.empty[r.stage]);
             r.advance();
         }
@@ -147,29 +155,41 @@ __device__ __forceinline__ void issue_linear(Ring& r, uint32_t xop, uint32_t tac
 
 // ---- compute-thread helpers ----------------------------------------------------------------------
 struct Ctx {
-    int tid, warp, lane, g, o, KH, K;
+    int tid, warp, lane, wg, o, K;
+    int nk;                      // valid slots of this thread: clamp(K - 8 wg, 0, 8)   (warp-uniform)
+    int k0;                      // first slot: 8 wg
     unsigned char* sm;
     Smem L;
     uint32_t tb;                 // TMEM base
+    uint32_t tlane;              // TMEM lane field of this warp's quadrant
+    uint32_t row_hi, row_lo;     // byte offsets of this thread's hi / lo 16-byte chunk inside an activation operand
     uint64_t* bars;
-    uint32_t ph_acc, ph_opnd;    // running phases of B_ACC (compute side) / B_OPND (issuer side)
+    uint32_t ph_acc;             // running phase of B_ACC (compute side)
 };
 
-// X^T operand: this thread's feature column o of its slots, split into bf16 hi / lo
-__device__ __forceinline__ void write_operand(const Ctx& c, int op_off, const float (&v)[KHMAX]) {
-    unsigned char* base = c.sm + op_off + (c.o >> 6) * OP_CB;
-    const int oc = c.o & 63;
+__device__ __forceinline__ void ctx_init(Ctx& c, int tid, int K, unsigned char* sm, const Smem& L, uint32_t tb, uint64_t* bars) {
+    c.tid = tid; c.warp = tid >> 5; c.lane = tid & 31; c.wg = c.warp >> 2; c.o = (c.warp & 3) * 32 + c.lane; c.K = K;
+    c.k0 = c.wg * KH;
+    c.nk = min(max(K - c.k0, 0), KH);
+    c.sm = sm; c.L = L; c.tb = tb; c.bars = bars; c.ph_acc = 0;
+    c.tlane = (uint32_t)((c.warp & 3) * 32) << 16;
+    c.row_hi = (uint32_t)c.o * 128u + ((uint32_t)(c.wg ^ (c.o & 7)) << 4);
+    c.row_lo = (uint32_t)c.o * 128u + ((uint32_t)((4 + c.wg) ^ (c.o & 7)) << 4);
+}
+
+// X^T operand row of this thread: its 8 slot values as bf16 hi (chunk wg) and lo (chunk 4 + wg); slots >= K are zero
+__device__ __forceinline__ void write_operand(const Ctx& c, int op_off, const float (&v)[KH]) {
+    uint32_t h[4], l[4];
 #pragma unroll
-    for (int kk = 0; kk < KHMAX; ++kk) {
-        const int k = c.g * c.KH + kk;
-        if (kk < c.KH && k < c.K) {
-            const bf16 hi = __float2bfloat16_rn(v[kk]);
-            const bf16 lo = __float2bfloat16_rn(v[kk] - __bfloat162float(hi));
-            const uint32_t off = sw128_off(k, oc);
-            *reinterpret_cast<bf16*>(base + off) = hi;
-            *reinterpret_cast<bf16*>(base + OP_LO + off) = lo;
-        }
+    for (int j = 0; j < 4; ++j) {
+        const float a = (2 * j < c.nk) ? v[2 * j] : 0.f, b = (2 * j + 1 < c.nk) ? v[2 * j + 1] : 0.f;
+        const __nv_bfloat162 hh = __floats2bfloat162_rn(a, b);
+        const float2 hf = __bfloat1622float2(hh);
+        h[j] = *reinterpret_cast<const uint32_t*>(&hh);
+        l[j] = pack_bf16x2(a - hf.x, b - hf.y);
     }
+    *reinterpret_cast<uint4*>(c.sm + op_off + c.row_hi) = make_uint4(h[0], h[1], h[2], h[3]);
+    *reinterpret_cast<uint4*>(c.sm + op_off + c.row_lo) = make_uint4(l[0], l[1], l[2], l[3]);
 }
 // operand complete: make the generic-proxy writes visible to the tensor core, one arrival per warp
 __device__ __forceinline__ void signal_operand(const Ctx& c, int bar = B_OPND) {
@@ -178,41 +198,40 @@ __device__ __forceinline__ void signal_operand(const Ctx& c, int bar = B_OPND) {
     __syncwarp();
     if (c.lane == 0) mbar_arrive(&c.bars[bar]);
 }
-// wait for the next accumulator commit, then load this thread's KH slot columns of accumulator `col`
 __device__ __forceinline__ void wait_acc(Ctx& c) {
     mbar_wait(&c.bars[B_ACC], c.ph_acc);
     c.ph_acc ^= 1u;
     fence_after_sync();
 }
-__device__ __forceinline__ void load_acc(const Ctx& c, int col, float (&v)[KHMAX]) {
-    tmem_ld16(tmem_addr(c.tb, c.warp, col + c.g * c.KH), v);
-}
-// store this thread's column of a [K][ld] fp32 field array row block
-__device__ __forceinline__ void save_field(const Ctx& c, float* dst, int ld, int col, const float (&v)[KHMAX]) {
+// this thread's 8 slot columns of a 64-column accumulator: (W_hi X_hi + W_lo X_hi) + W_hi X_lo
+__device__ __forceinline__ void load_acc(const Ctx& c, int col, float (&v)[KH]) {
+    float lo[KH];
+    tmem_ld8(c.tb + c.tlane + col + c.k0, v);
+    tmem_ld8(c.tb + c.tlane + col + 32 + c.k0, lo);
+    tmem_wait_ld();
 #pragma unroll
-    for (int kk = 0; kk < KHMAX; ++kk) {
-        const int k = c.g * c.KH + kk;
-        if (kk < c.KH && k < c.K) dst[(size_t)k * ld + col] = v[kk];
-    }
+    for (int kk = 0; kk < KH; ++kk) v[kk] += lo[kk];
 }
-__device__ __forceinline__ void load_field(const Ctx& c, const float* src, int ld, int col, float (&v)[KHMAX]) {
+// this thread's column `col` of a [K][ld] fp32 field-array row block
+__device__ __forceinline__ void save_field(const Ctx& c, float* dst, int ld, int col, const float (&v)[KH]) {
+    float* p = dst + (size_t)c.k0 * ld + col;
 #pragma unroll
-    for (int kk = 0; kk < KHMAX; ++kk) {
-        const int k = c.g * c.KH + kk;
-        v[kk] = (kk < c.KH && k < c.K) ? src[(size_t)k * ld + col] : 0.f;
-    }
+    for (int kk = 0; kk < KH; ++kk) if (kk < c.nk) p[kk * ld] = v[kk];
+}
+__device__ __forceinline__ void load_field(const Ctx& c, const float* src, int ld, int col, float (&v)[KH]) {
+    const float* p = src + (size_t)c.k0 * ld + col;
+#pragma unroll
+    for (int kk = 0; kk < KH; ++kk) v[kk] = (kk < c.nk) ? p[kk * ld] : 0.f;
 }
 
 // per-slot mean / rstd over the 128 features (torch LayerNorm: biased variance, two-pass), via the scratch tile
-__device__ __forceinline__ void slot_stats(const Ctx& c, const float (&v)[KHMAX], float eps) {
+__device__ __forceinline__ void slot_stats(const Ctx& c, const float (&v)[KH], float eps) {
     float* scr = reinterpret_cast<float*>(c.sm + c.L.scratch);
     float2* st = reinterpret_cast<float2*>(c.sm + c.L.stats);
+    float* p = scr + c.k0 * F + c.o;
 #pragma unroll
-    for (int kk = 0; kk < KHMAX; ++kk) {
-        const int k = c.g * c.KH + kk;
-        if (kk < c.KH && k < c.K) scr[k * F + c.o] = v[kk];
-    }
-    bar_sync_compute(1);
+    for (int kk = 0; kk < KH; ++kk) if (kk < c.nk) p[kk * F] = v[kk];
+    bar_sync_compute();
     for (int k = c.warp; k < c.K; k += NCW) {
         const float4 x = ld4(scr + k * F + c.lane * 4);
         const float mean = warp_sum((x.x + x.y) + (x.z + x.w)) * (1.0f / F);
@@ -220,15 +239,14 @@ __device__ __forceinline__ void slot_stats(const Ctx& c, const float (&v)[KHMAX]
         const float var = warp_sum((a * a + b * b) + (e * e + f * f)) * (1.0f / F);
         if (c.lane == 0) st[k] = make_float2(mean, 1.0f / sqrtf(var + eps));
     }
-    bar_sync_compute(1);
+    bar_sync_compute();
 }
-__device__ __forceinline__ void layer_norm(const Ctx& c, const float (&v)[KHMAX], float (&y)[KHMAX], float gamma, float beta, float eps) {
+__device__ __forceinline__ void layer_norm(const Ctx& c, const float (&v)[KH], float (&y)[KH], float gamma, float beta, float eps) {
     slot_stats(c, v, eps);
-    const float2* st = reinterpret_cast<const float2*>(c.sm + c.L.stats);
+    const float2* st = reinterpret_cast<const float2*>(c.sm + c.L.stats) + c.k0;
 #pragma unroll
-    for (int kk = 0; kk < KHMAX; ++kk) {
-        const int k = c.g * c.KH + kk;
-        if (kk < c.KH && k < c.K) { const float2 s = st[k]; y[kk] = (v[kk] - s.x) * s.y * gamma + beta; }
+    for (int kk = 0; kk < KH; ++kk) {
+        if (kk < c.nk) { const float2 s = st[kk]; y[kk] = (v[kk] - s.x) * s.y * gamma + beta; }
         else y[kk] = 0.f;
     }
 }

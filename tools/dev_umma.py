@@ -36,6 +36,10 @@ def run(B, T, N, K, I, blocks, cluster, bwd=True, seed=0):
     print("B=%d T=%d N=%d K=%d I=%d blocks=%d cluster=%d : %s %s" % (B, T, N, K, I, blocks, cluster, "  ".join(errs), "NONFINITE" if bad else ""), flush=True)
 
 if __name__ == "__main__":
+    if len(sys.argv) > 2:
+        for spec in sys.argv[1:]:
+            run(*[int(v) for v in spec.split(",")])
+        sys.exit(0)
     stage = int(sys.argv[1]) if len(sys.argv) > 1 else 0
     if stage <= 0: run(1, 1, 128, 24, 1, 0, 1)
     if stage <= 1: run(1, 1, 512, 24, 3, 0, 1)

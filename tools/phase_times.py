@@ -10,6 +10,11 @@ NAMES = {0: "top/pred-tail", 1: "copy+LN", 2: "lin q", 3: "lin qk", 4: "token pa
          30: "B: top", 31: "B pred: LNf..dO", 32: "B pred mha core", 33: "B pred: dy..LN1", 34: "B step setup", 35: "B mlp bwd",
          36: "B gru pointwise+colsum", 37: "B lin dh(whh)", 38: "B lin dU(wih)", 39: "B lin dUx + cvec", 40: "B token pass",
          41: "B cluster sync", 42: "B combine", 43: "B lin dq", 44: "B LN st", 45: "B lin dst", 46: "B LN bwd", 50: "tp: stage qk + issue", 51: "tp: wait tile", 52: "tp: phase1 mma", 53: "tp: softmax", 54: "tp: stores+sync", 55: "tp: attn copy", 56: "tp: phase2", 57: "tp: epilogue", 58: "lin: entry+stage X", 59: "lin: sync", 60: "lin: issue B loads", 61: "lin: wait B + MMAs", 62: "lin: epilogue", 63: "lin: final sync"}
+UN = {1: "u: save hp, LN_s, s~ operand", 2: "u: WAIT q", 3: "u: q epilogue", 4: "u: WAIT qk", 5: "u: qk epilogue", 6: "u: softmax tiles (total)",
+      7: "u: WAIT token pass", 8: "u: ld numx + send", 9: "u: WAIT peer", 10: "u: Ux epilogue", 11: "u: WAIT U", 12: "u: U epilogue", 13: "u: WAIT gru",
+      14: "u: gru math + saves", 15: "u: mlp LN + operand", 16: "u: WAIT a", 17: "u: a epilogue", 18: "u: WAIT h2", 19: "u: h2", 20: "u: predictor (total)",
+      50: "  sm: WAIT logits", 51: "  sm: ld + softmax", 52: "  sm: WAIT aw free", 53: "  sm: write A + signal", 54: "  sm: attn out",
+      21: "  q: tmem ld", 22: "  q: save_field", 23: "  q: write_operand", 24: "  q: fence.proxy.async"}
 cfg = sys.argv[1] if len(sys.argv) > 1 else "c2"
 c = dict(bench.CONFIGS[cfg])
 dt = torch.float32 if c["dtype"] == "fp32" else torch.bfloat16
@@ -28,6 +33,13 @@ _lib.lib.savi_debug_set_phase_buffer(buf.data_ptr())
 step(); torch.cuda.synchronize()
 _lib.lib.savi_debug_set_phase_buffer(None)
 v = buf.cpu().tolist()
+if os.environ.get("SAVI_DISABLE_UMMA") is None and c["D"] == 128:
+    tot = sum(v[1:25])
+    print("UMMA forward, compute thread 0 of CTA 0: total %.1f us" % (tot / 1965.0))
+    for i in sorted(UN):
+        if v[i]: print("  %-34s %8.1f us  %5.1f%%" % (UN[i], v[i] / 1965.0, 100.0 * v[i] / tot))
+    for i in range(25): v[i] = 0
+    for i in range(50, 58): v[i] = 0
 tot_f = sum(v[:30]); tot_b = sum(v[30:50])
 print("forward  total %.1f us (cycles @1.965GHz)" % (tot_f / 1965.0))
 for i in range(30):

@@ -1,0 +1,767 @@
+// tcgen05 backward clip kernel: BPTT through the whole recurrence (+ predictor) of one clip per CTA / CTA pair.
+//
+// The reference has no explicit backward (autograd through steve.py:52-105); the closed form is SURVEY.md
+// Appendix A.2 in the folded form, restated and validated against the reference's autograd in
+// oracle/savi_numpy.py.  Execution model: savi_umma_clip.cuh (feature-per-thread, transposed products).
+// Every dX = dY . W product uses the "backward orientation" weight images (rows = input feature).
+// Writes the staged (dY, X) operands of the weight-gradient GEMMs and the per-token coefficients
+// (dL^T, W^T) + dUx of the token-parallel d_inputs kernel, exactly like the mma.sync kernel (savi_bwd.cu).
+#include "savi_umma_clip.cuh"
+
+using namespace uc;
+
+#define UPH(id) do { if (dbg) { const long long t_ = clock64(); dbg[id] += t_ - ph_last; ph_last = t_; } } while (0)
+
+// TMEM columns (64 each)
+enum { TB_A = 0, TB_B = 64, TB_HP = 128, TB_DQK = 192, TB_S0 = 256, TB_G0 = 320, TB_S1 = 384, TB_G1 = 448,
+       TB_F0 = TB_S0,                         // predictor: the four ffn.2^T tiles live where the token-pass accumulators are
+       TB_COLS = 512 };
+enum { B_HP = B_OPND2 };                      // W_hh^T product complete (its operands may be overwritten)
+
+struct BwdUArgs {
+    BwdArgs a;
+    const unsigned char* wimg;
+    WImg wi;
+};
+
+struct TokState { uint32_t cnt_s[2], cnt_a[2]; };
+
+// operand buffers: X0..X3 = opA, opB, opC, aw0 of the shared plan; aw1 + scratch hold the float2 LayerNorm scratch
+__device__ __forceinline__ int xop(const Smem& L, int i) { return i == 0 ? L.opA : i == 1 ? L.opB : i == 2 ? L.opC : L.aw0; }
+
+// ------------------------------------------------------------------------------------------------
+// issuer: attention-step backward products of this CTA's token tiles
+//   P1(i): S[i&1] = xhat_i . [qk_hi | qk_lo],  G[i&1] = xhat_i . [dUx_hi | dUx_lo]
+//   P2(i): DQK   += xhat_i^T . [dL_hi | dL_lo]
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void issue_token_pass_bwd(Ring& r, uint64_t* bars, uint32_t tb, int ntile, TokState& ts,
+                                                     uint32_t qk_op, uint32_t dux_op, uint32_t dl0, uint32_t dl1) {
+    int ts0[2] = {0, 0};
+    auto p2 = [&](int j) {
+        const int g = j & 1;
+        mbar_wait(&bars[B_AREADY + g], ts.cnt_a[g] & 1u);
+        fence_after_sync();
+        const uint32_t x0 = smem_u32(r.base + (size_t)ts0[g] * BLK);
+        const uint32_t dl = g ? dl1 : dl0;
+#pragma unroll 2
+        for (int kt = 0; kt < 8; ++kt)
+            mma_ss(tb + TB_DQK, desc_mnmajor(x0 + kt * 2048, BLK), desc_mnmajor(dl + kt * 2048, BLK), IDESC_MN_MN64, j > 0 || kt > 0);
+        mma_commit(&r.empty[ts0[g]]);
+        mma_commit(&r.empty[ts0[g] + 1]);
+        mma_commit(&bars[B_AFREE + g]);
+        ++ts.cnt_a[g];
+    };
+    for (int i = 0; i < ntile; ++i) {
+        const int g = i & 1;
+        mbar_wait(&bars[B_SFREE + g], (ts.cnt_s[g] & 1u) ^ 1u);
+        fence_after_sync();
+        ts0[g] = r.stage;
+        const uint32_t acc_s = tb + (g ? TB_S1 : TB_S0), acc_g = tb + (g ? TB_G1 : TB_G0);
+#pragma unroll
+        for (int db = 0; db < 2; ++db) {
+            mbar_wait(&r.full[r.stage], r.phase);
+            fence_after_sync();
+            const uint32_t a = smem_u32(r.base + (size_t)r.stage * BLK);
+#pragma unroll
+            for (int k4 = 0; k4 < 4; ++k4) {
+                const uint64_t ad = desc_kmajor(a + k4 * 32);
+                mma_ss(acc_s, ad, desc_mnmajor(qk_op + (db * 4 + k4) * 2048, BLK), IDESC_K_MN64, db > 0 || k4 > 0);
+                mma_ss(acc_g, ad, desc_mnmajor(dux_op + (db * 4 + k4) * 2048, BLK), IDESC_K_MN64, db > 0 || k4 > 0);
+            }
+            r.advance();
+        }
+        mma_commit(&bars[B_SFULL + g]);
+        ++ts.cnt_s[g];
+        if (i >= 1) p2(i - 1);
+    }
+    p2(ntile - 1);
+    mma_commit(&bars[B_TOK]);
+}
+
+// ------------------------------------------------------------------------------------------------
+// compute threads: recompute P, form dL and W for this group's token tiles (thread = token, half of the slots)
+//   dP = (G - c)/S (+ grad_attn);  dL = P (dP - <P, dP>);  W = (P + eps)/S          
+// cv: shared [64] = c[32] | 1/S[32].  coef: staged [2][KC][N] bf16 (dL^T, W^T) of this (b, t, i).
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void softmax_bwd_tiles(const Ctx& c, const Dims& d, int ntile, int tile0, const bf16* gattn_frame,
+                                                  bf16* coef, const float* cv, int dl0_off, int dl1_off, TokState& ts, long long* dbg) {
+    constexpr float LOG2E = 1.4426950408889634f;
+    long long ph_last = clock64();
+    const int K = c.K, p = c.wg >> 1, h = c.wg & 1;
+    const int KHs = (((K + 1) >> 1) + 3) & ~3;
+    const int s0 = h * KHs, ns = min(max(K - s0, 0), KHs);
+    const uint32_t scol = c.tb + c.tlane + (p ? TB_S1 : TB_S0) + s0;
+    const uint32_t gcol = c.tb + c.tlane + (p ? TB_G1 : TB_G0) + s0;
+    unsigned char* dlrow = c.sm + (p ? dl1_off : dl0_off) + c.o * 128;
+    const uint32_t sw = (uint32_t)(c.o & 7);
+    for (int i = p; i < ntile; i += 2) {
+        const int n = (tile0 + i) * 128 + c.o;
+        const bool valid = n < d.N;
+        float ga[16];
+#pragma unroll
+        for (int s = 0; s < 16; ++s) ga[s] = 0.f;
+        if (gattn_frame && valid) {                              // issued before the wait: latency hidden behind the MMAs
+            const bf16* row = gattn_frame + (size_t)n * K + s0;
+            if ((K & 3) == 0) {
+#pragma unroll
+                for (int s = 0; s < 16; s += 4) {
+                    if (s < ns) {
+                        const uint2 v = *reinterpret_cast<const uint2*>(row + s);
+                        const float2 a0 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&v.x));
+                        const float2 a1 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&v.y));
+                        ga[s] = a0.x; ga[s + 1] = a0.y; ga[s + 2] = a1.x; ga[s + 3] = a1.y;
+                    }
+                }
+            } else {
+#pragma unroll
+                for (int s = 0; s < 16; ++s) if (s < ns) ga[s] = __bfloat162float(row[s]);
+            }
+        }
+        mbar_wait(&c.bars[B_SFULL + p], ts.cnt_s[p] & 1u);
+        fence_after_sync();
+        UPH(55);
+        float l[16], gq[16];
+        {
+            float t2[16];
+            tmem_ld16(scol, l); tmem_ld16(scol + 32, t2);
+            tmem_wait_ld();
+#pragma unroll
+            for (int s = 0; s < 16; ++s) l[s] += t2[s];
+            tmem_ld16(gcol, gq); tmem_ld16(gcol + 32, t2);
+            tmem_wait_ld();
+#pragma unroll
+            for (int s = 0; s < 16; ++s) gq[s] += t2[s];
+        }
+        fence_before_sync();
+        __syncwarp();
+        if (c.lane == 0) mbar_arrive(&c.bars[B_SFREE + p]);
+        float mx = -INFINITY;
+#pragma unroll
+        for (int s = 0; s < 16; ++s) if (s < ns) mx = fmaxf(mx, l[s]);
+        mx *= LOG2E;
+        float sum = 0.f;
+#pragma unroll
+        for (int s = 0; s < 16; ++s) { l[s] = (s < ns) ? exp2f(fmaf(l[s], LOG2E, -mx)) : 0.f; sum += l[s]; }
+        float2* xch = reinterpret_cast<float2*>(c.sm + c.L.xch) + ((p * 2 + (ts.cnt_s[p] & 1u)) * 2) * 128;
+        xch[h * 128 + c.o] = make_float2(mx, sum);
+        bar_sync_n(2 + p, 256);
+        const float2 other = xch[(h ^ 1) * 128 + c.o];
+        const float M = fmaxf(mx, other.x);
+        const float wme = exp2f(mx - M);
+        const float scale = wme / (sum * wme + other.y * exp2f(other.x - M));
+        float dot = 0.f;
+#pragma unroll
+        for (int s = 0; s < 16; ++s) {
+            if (s < ns) {
+                l[s] *= scale;                                                           // P
+                const float dp = (gq[s] - cv[s0 + s]) * cv[32 + s0 + s] + ga[s];         // dP
+                gq[s] = dp;
+                dot = fmaf(l[s], dp, dot);
+            }
+        }
+        // second exchange: the dot product over the whole slot axis (separate slots of the same buffer set)
+        float* xd = reinterpret_cast<float*>(c.sm + c.L.xch + 8192) + ((p * 2 + (ts.cnt_s[p] & 1u)) * 2) * 128;
+        xd[h * 128 + c.o] = dot;
+        bar_sync_n(2 + p, 256);
+        dot += xd[(h ^ 1) * 128 + c.o];
+        ++ts.cnt_s[p];
+        UPH(56);
+        mbar_wait(&c.bars[B_AFREE + p], (ts.cnt_a[p] & 1u) ^ 1u);
+        UPH(57);
+#pragma unroll
+        for (int s = 0; s < 16; s += 4) {
+            if (s < KHs) {
+                float dl[4];
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    const bool ok = valid && s + e < ns;
+                    const float pv = l[s + e];
+                    dl[e] = ok ? pv * (gq[s + e] - dot) : 0.f;                                // dL
+                    l[s + e] = ok ? (pv + d.eps) * cv[32 + s0 + s + e] : 0.f;                 // W
+                    gq[s + e] = dl[e];
+                }
+                const __nv_bfloat162 h0 = __floats2bfloat162_rn(dl[0], dl[1]), h1 = __floats2bfloat162_rn(dl[2], dl[3]);
+                const float2 f0 = __bfloat1622float2(h0), f1 = __bfloat1622float2(h1);
+                uint2 hv, lv;
+                hv.x = *reinterpret_cast<const uint32_t*>(&h0); hv.y = *reinterpret_cast<const uint32_t*>(&h1);
+                lv.x = pack_bf16x2(dl[0] - f0.x, dl[1] - f0.y); lv.y = pack_bf16x2(dl[2] - f1.x, dl[3] - f1.y);
+                const uint32_t bo = (uint32_t)(s0 + s) * 2u;
+                *reinterpret_cast<uint2*>(dlrow + ((((bo >> 4) ^ sw)) << 4) + (bo & 15u)) = hv;
+                *reinterpret_cast<uint2*>(dlrow + (((((bo + 64u) >> 4) ^ sw)) << 4) + (bo & 15u)) = lv;
+            }
+        }
+        fence_async_smem();
+        __syncwarp();
+        if (c.lane == 0) mbar_arrive(&c.bars[B_AREADY + p]);
+        ++ts.cnt_a[p];
+        UPH(58);
+        if (valid) {                                             // coefficients of the d_inputs kernel: [slot][token], token contiguous
+            bf16* cl = coef + (size_t)s0 * d.N + n;
+            bf16* cw = coef + (size_t)(d.KC + s0) * d.N + n;
+#pragma unroll
+            for (int s = 0; s < 16; ++s) {
+                if (s < ns) { cl[(size_t)s * d.N] = __float2bfloat16_rn(gq[s]); cw[(size_t)s * d.N] = __float2bfloat16_rn(l[s]); }
+            }
+        }
+        UPH(59);
+    }
+}
+
+// LayerNorm backward in the feature-per-thread layout.  dy: gradient of the LN output; x: its input (this thread's column);
+// st: (mean, rstd) of each slot row.  Accumulates d gamma / d beta of this feature; returns dx.
+__device__ __forceinline__ void ln_bwd(const Ctx& c, const float (&dy)[KH], const float (&x)[KH], const float2* st, float gamma,
+                                       float& dgam, float& dbet, float (&dx)[KH], int scr_off) {
+    float2* scr = reinterpret_cast<float2*>(c.sm + scr_off);                 // [K][128] (dz, dz * xhat)
+    float2* red = reinterpret_cast<float2*>(c.sm + c.L.stats);               // [32] means of the two sums
+    float xh[KH], dz[KH];
+    float2 s_[KH];
+#pragma unroll
+    for (int kk = 0; kk < KH; ++kk) {
+        if (kk < c.nk) {
+            s_[kk] = st[c.k0 + kk];
+            xh[kk] = (x[kk] - s_[kk].x) * s_[kk].y;
+            dz[kk] = dy[kk] * gamma;
+            dgam = fmaf(dy[kk], xh[kk], dgam); dbet += dy[kk];
+            scr[(c.k0 + kk) * F + c.o] = make_float2(dz[kk], dz[kk] * xh[kk]);
+        } else { xh[kk] = 0.f; dz[kk] = 0.f; s_[kk] = make_float2(0.f, 0.f); }
+    }
+    bar_sync_compute();
+    for (int k = c.warp; k < c.K; k += NCW) {
+        const float4 a = *reinterpret_cast<const float4*>(scr + k * F + c.lane * 4);
+        const float4 b = *reinterpret_cast<const float4*>(scr + k * F + c.lane * 4 + 2);
+        const float s1 = warp_sum((a.x + a.z) + (b.x + b.z)), s2 = warp_sum((a.y + a.w) + (b.y + b.w));
+        if (c.lane == 0) red[k] = make_float2(s1 * (1.0f / F), s2 * (1.0f / F));
+    }
+    bar_sync_compute();
+#pragma unroll
+    for (int kk = 0; kk < KH; ++kk) {
+        if (kk < c.nk) { const float2 r = red[c.k0 + kk]; dx[kk] = s_[kk].y * (dz[kk] - r.x - xh[kk] * r.y); }
+        else dx[kk] = 0.f;
+    }
+}
+
+// Backward of the predictor's attention core in shared memory (transformer.py:34-47).  dQ is w.r.t. the UNSCALED projection.
+__device__ __forceinline__ void mha_core_bwd(const Ctx& c, int H, float hscale, const float (&dO)[KH], const float* Qg, const float* Kg,
+                                             const float* Vg, const float* attg, float (&dQ)[KH], float (&dK)[KH], float (&dV)[KH]) {
+    const int K = c.K, ld = F + 1, ka = K | 1, dh = F / H;
+    float* sO = reinterpret_cast<float*>(c.sm + c.L.opA);             // opA .. scratch are contiguous (5 x 16 KB + scratch)
+    float* sQ = sO + K * ld; float* sK = sQ + K * ld; float* sV = sK + K * ld;
+    float* sA = sV + K * ld; float* sD = sA + H * K * ka;
+#pragma unroll
+    for (int kk = 0; kk < KH; ++kk) {
+        const int k = c.k0 + kk;
+        if (kk < c.nk) {
+            sO[k * ld + c.o] = dO[kk]; sQ[k * ld + c.o] = Qg[(size_t)k * F + c.o];
+            sK[k * ld + c.o] = Kg[(size_t)k * F + c.o]; sV[k * ld + c.o] = Vg[(size_t)k * F + c.o];
+        }
+    }
+    for (int idx = c.tid; idx < H * K * K; idx += NCT) sA[(idx / K) * ka + idx % K] = attg[idx];
+    bar_sync_compute();
+    for (int idx = c.tid; idx < H * K * K; idx += NCT) {
+        const int j = idx % K, i = (idx / K) % K, h = idx / (K * K);
+        const float* a = sO + i * ld + h * dh;
+        const float* v = sV + j * ld + h * dh;
+        float s = 0.f;
+        for (int e = 0; e < dh; ++e) s = fmaf(a[e], v[e], s);
+        sD[(h * K + i) * ka + j] = s;
+    }
+    bar_sync_compute();
+    for (int row = c.tid; row < H * K; row += NCT) {
+        const float* a = sA + row * ka;
+        float* da = sD + row * ka;
+        float dot = 0.f;
+        for (int j = 0; j < K; ++j) dot = fmaf(a[j], da[j], dot);
+        for (int j = 0; j < K; ++j) da[j] = a[j] * (da[j] - dot);
+    }
+    bar_sync_compute();
+    const int h = c.o / dh;
+    const float* dlg = sD + h * K * ka;
+    const float* at = sA + h * K * ka;
+#pragma unroll
+    for (int kk = 0; kk < KH; ++kk) {
+        float sq = 0.f, sk = 0.f, sv = 0.f;
+        if (kk < c.nk) {
+            const int i = c.k0 + kk;
+            for (int j = 0; j < K; ++j) {
+                sq = fmaf(dlg[i * ka + j], sK[j * ld + c.o], sq);
+                sk = fmaf(dlg[j * ka + i], sQ[j * ld + c.o], sk);
+                sv = fmaf(at[j * ka + i], sO[j * ld + c.o], sv);
+            }
+        }
+        dQ[kk] = sq * hscale; dK[kk] = sk; dV[kk] = sv;
+    }
+    bar_sync_compute();
+}
+
+__device__ __forceinline__ float sum8(const Ctx& c, const float (&v)[KH]) {
+    float s = 0.f;
+#pragma unroll
+    for (int kk = 0; kk < KH; ++kk) if (kk < c.nk) s += v[kk];
+    return s;
+}
+
+// ------------------------------------------------------------------------------------------------
+// the kernel
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(NTHREADS, 1) savi_bwd_umma_kernel(const __grid_constant__ BwdUArgs ua) {
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    const BwdArgs& a = ua.a;
+    const Dims& d = a.d;
+    const ParamOff& po = a.po;
+    unsigned char* sm = smem_raw;
+    if ((smem_u32(sm) & 1023u) != 0u) __trap();                // SWIZZLE_128B operands need a 1024-byte aligned base
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int CN = d.CN, b = blockIdx.x / CN, rank = blockIdx.x % CN;
+    const int K = d.K, B = d.B, KP = d.KP;
+    const Smem L = plan_smem(K, CN, true);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sm + L.bars);
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + NBAR);
+    const bool lead = (rank == 0);
+    const int per = (d.NTILE + CN - 1) / CN;
+    const int tile0 = min(d.NTILE, rank * per), ntile = min(d.NTILE, tile0 + per) - tile0;
+    const float* P = a.packed;
+    float* G = a.grad_params;
+    const float* fb = reinterpret_cast<const float*>(a.saved + a.sl.fbase);
+    const unsigned char* ximg = a.saved + a.sl.ximg;
+    float* W = a.ws;
+    bf16* coef_base = reinterpret_cast<bf16*>(reinterpret_cast<unsigned char*>(W) + a.wl.coef);
+    const int scr2 = L.aw1;                                   // float2 [K][128] LayerNorm-backward scratch: aw1 + scratch (contiguous, 16 KB + K*512 B)
+    float* cv = reinterpret_cast<float*>(sm + L.stats + 256);  // [64]: c | 1/S
+
+    // ---- one-time setup ----
+    for (int i = tid * 16; i < L.bars; i += NTHREADS * 16) *reinterpret_cast<uint4*>(sm + i) = make_uint4(0u, 0u, 0u, 0u);
+    __syncthreads();
+    if (tid == 0) {
+        for (int s = 0; s < L.nst; ++s) { mbar_init(&bars[B_FULL + s], 1); mbar_init(&bars[B_EMPTY + s], 1); }
+        mbar_init(&bars[B_OPND], NCW); mbar_init(&bars[B_ACC], 1); mbar_init(&bars[B_TOK], 1); mbar_init(&bars[B_HP], 1);
+        for (int g = 0; g < 2; ++g) {
+            mbar_init(&bars[B_SFULL + g], 1); mbar_init(&bars[B_SFREE + g], 8);
+            mbar_init(&bars[B_AREADY + g], 8); mbar_init(&bars[B_AFREE + g], 1);
+            mbar_init(&bars[B_INBOX + g], NCW);
+        }
+        for (int f = 0; f < 4; ++f) { mbar_init(&bars[B_FACC + f], 1); mbar_init(&bars[B_FOPND + f], NCW); }
+        mbar_init_fence();
+    }
+    if (warp == W_MMA) tmem_alloc(tmem_slot, TB_COLS);
+    fence_async_smem();
+    fence_before_sync();
+    __syncthreads();
+    fence_after_sync();
+    if (CN > 1) { cluster_arrive(); cluster_wait(); }
+    const uint32_t tb = *tmem_slot;
+
+    Ring ring;
+    ring.base = sm + L.ring; ring.full = &bars[B_FULL]; ring.empty = &bars[B_EMPTY]; ring.nst = L.nst; ring.stage = 0; ring.phase = 0;
+
+    if (warp == W_PROD) {
+        // =====================================================================================
+        // producer (mirrors the issuer's consumption order)
+        // =====================================================================================
+        if (lane == 0) {
+            const unsigned char* Wi = ua.wimg;
+            const WImg& wi = ua.wi;
+            for (int t = d.T - 1; t >= 0; --t) {
+                if (t < d.T - 1) {
+                    for (int j = d.blocks - 1; j >= 0; --j) {
+                        const WImgBlock& wb = wi.blkT[j];
+                        prod_blocks(ring, Wi + wb.f2, 16);                       // ffn.2^T: 4 row tiles x K = 128
+                        prod_blocks(ring, Wi + wb.f1 + 4 * BLK, 12);             // ffn.0^T: contraction chunks 1, 2, 3, then 0
+                        prod_blocks(ring, Wi + wb.f1, 4);
+                        prod_blocks(ring, Wi + wb.po, 4);
+                        prod_blocks(ring, Wi + wb.pq, 4); prod_blocks(ring, Wi + wb.pk, 4); prod_blocks(ring, Wi + wb.pv, 4);
+                    }
+                }
+                const unsigned char* xf = ximg + ((size_t)(b * d.T + t) * d.NTILE + tile0) * 2 * BLK;
+                for (int it = d.I - 1; it >= 0; --it) {
+                    if (it < d.I - 1) { prod_blocks(ring, Wi + wi.w2T, 4); prod_blocks(ring, Wi + wi.w1T, 4); }
+                    prod_blocks(ring, Wi + wi.wihT, 12);
+                    prod_blocks(ring, Wi + wi.whhT, 12);
+                    prod_blocks(ring, Wi + wi.wvT, 4);
+                    prod_blocks(ring, xf, 2 * ntile);
+                    prod_blocks(ring, Wi + wi.wk, 4);
+                    prod_blocks(ring, Wi + wi.wqT, 4);
+                }
+            }
+        }
+    } else if (warp == W_MMA) {
+        // =====================================================================================
+        // tcgen05.mma issuer
+        // =====================================================================================
+        if (lane == 0) {
+            uint32_t ph_opnd = 0, pcall = 0;
+            TokState ts = {{0, 0}, {0, 0}};
+            const uint32_t X0 = smem_u32(sm + L.opA), X1 = smem_u32(sm + L.opB), X2 = smem_u32(sm + L.opC), X3 = smem_u32(sm + L.aw0);
+            auto wait_opnd = [&]() { mbar_wait(&bars[B_OPND], ph_opnd); ph_opnd ^= 1u; fence_after_sync(); };
+            for (int t = d.T - 1; t >= 0; --t) {
+                if (t < d.T - 1) {
+                    for (int j = d.blocks - 1; j >= 0; --j) {
+                        wait_opnd();                                                       // d x2 in X0
+                        for (int f = 0; f < 4; ++f) { issue_linear(ring, X0, tb + TB_F0 + 64 * f, 1, 2, false); mma_commit(&bars[B_FACC + f]); }   // d f = ffn.2^T d x2
+                        // d l2 = ffn.0^T d f: chunks 1, 2, 3 (X1..X3) then chunk 0 (X0, rewritten after all four tiles above completed)
+                        for (int q = 0; q < 4; ++q) {
+                            const int f = (q + 1) & 3;
+                            mbar_wait(&bars[B_FOPND + f], pcall & 1u); fence_after_sync();
+                            issue_linear(ring, f == 0 ? X0 : f == 1 ? X1 : f == 2 ? X2 : X3, tb + TB_A, 1, 2, q > 0);
+                        }
+                        mma_commit(&bars[B_ACC]);
+                        ++pcall;
+                        wait_opnd();                                                       // d x1 in X0
+                        issue_linear(ring, X0, tb + TB_B, 1, 2, false); mma_commit(&bars[B_ACC]);        // dO = proj_o^T d x1
+                        wait_opnd();                                                       // dQ, dK, dV in X1, X2, X3
+                        issue_linear(ring, X1, tb + TB_A, 1, 2, false);
+                        issue_linear(ring, X2, tb + TB_A, 1, 2, true);
+                        issue_linear(ring, X3, tb + TB_A, 1, 2, true); mma_commit(&bars[B_ACC]);         // dy
+                    }
+                }
+                for (int it = d.I - 1; it >= 0; --it) {
+                    if (it < d.I - 1) {
+                        wait_opnd();                                                       // dh in X0
+                        issue_linear(ring, X0, tb + TB_A, 1, 2, false); mma_commit(&bars[B_ACC]);        // d a = mlp.2^T dh
+                        wait_opnd();                                                       // d a in X1
+                        issue_linear(ring, X1, tb + TB_B, 1, 2, false); mma_commit(&bars[B_ACC]);        // d m = mlp.0^T d a
+                    }
+                    wait_opnd();                                                           // dr, dz, dn, dn*r in X0..X3
+                    issue_linear(ring, X0, tb + TB_A, 1, 2, false);
+                    issue_linear(ring, X1, tb + TB_A, 1, 2, true);
+                    issue_linear(ring, X2, tb + TB_A, 1, 2, true); mma_commit(&bars[B_ACC]);             // dU = W_ih^T dgi
+                    issue_linear(ring, X0, tb + TB_HP, 1, 2, false);
+                    issue_linear(ring, X1, tb + TB_HP, 1, 2, true);
+                    issue_linear(ring, X3, tb + TB_HP, 1, 2, true); mma_commit(&bars[B_HP]);             // W_hh^T dgh (consumed at the end of the step)
+                    wait_opnd();                                                           // dU in X2
+                    issue_linear(ring, X2, tb + TB_B, 1, 2, false); mma_commit(&bars[B_ACC]);            // dUx = W_v^T dU
+                    wait_opnd();                                                           // dUx in X0, qk in X1
+                    issue_token_pass_bwd(ring, bars, tb, ntile, ts, X1, X0, X2, X3);
+                    wait_opnd();                                                           // d qk in X0
+                    issue_linear(ring, X0, tb + TB_A, 1, 2, false); mma_commit(&bars[B_ACC]);            // dq = W_k d qk
+                    wait_opnd();                                                           // dq in X1
+                    issue_linear(ring, X1, tb + TB_B, 1, 2, false); mma_commit(&bars[B_ACC]);            // d s~ = W_q^T dq
+                }
+            }
+        }
+    } else {
+        // =====================================================================================
+        // compute threads
+        // =====================================================================================
+        Ctx c;
+        ctx_init(c, tid, K, sm, L, tb, bars);
+        const int o = c.o;
+        TokState ts = {{0, 0}, {0, 0}};
+        long long* sdbg = reinterpret_cast<long long*>(sm + L.bars + NBAR * 8 + 16);
+        if (a.dbg && blockIdx.x == 0 && tid == 0) for (int i = 0; i < 64; ++i) sdbg[i] = 0;
+        long long* dbg = (a.dbg && blockIdx.x == 0 && tid == 0) ? sdbg : nullptr;
+        long long ph_last = clock64();
+        const float g_s = P[po.ln_s_w + o], g_m = P[po.ln_m_w + o];
+        const float hscale = 1.0f / sqrtf((float)(F / d.heads));
+        // per-feature parameter-gradient accumulators over all steps of this clip (added to the flat buffer at the end)
+        float a_gs = 0.f, a_bs = 0.f, a_gm = 0.f, a_bm = 0.f, a_b1 = 0.f, a_b2 = 0.f;
+        float a_dr = 0.f, a_dz = 0.f, a_dn = 0.f, a_dnr = 0.f;
+        // the padding rows [K, KC) of every coefficient block of this CTA's tokens must be finite: zero them once
+        if (d.KC > K) {
+            const int n_lo = tile0 * 128, n_hi = min(d.N, (tile0 + ntile) * 128);
+            const int padr = d.KC - K, span = n_hi - n_lo;
+            const int64_t items = (int64_t)d.T * d.I * 2 * padr * span;
+            for (int64_t i = tid; i < items; i += NCT) {
+                const int n = n_lo + (int)(i % span);
+                int64_t r = i / span;
+                const int pr = (int)(r % padr); r /= padr;
+                const int which = (int)(r & 1); r >>= 1;                                   // r = t * I + it
+                coef_base[((((size_t)b * d.T * d.I + r) * 2 + which) * d.KC + K + pr) * d.N + n] = __float2bfloat16_rn(0.f);
+            }
+        }
+        float dh[KH];
+#pragma unroll
+        for (int kk = 0; kk < KH; ++kk) dh[kk] = 0.f;
+        uint32_t step = 0, pcall = 0, hpcall = 0;
+        for (int t = d.T - 1; t >= 0; --t) {
+            if (t < d.T - 1) {
+                // ---- predictor backward (transformer.py:106-114, 70-86, 22-49) ----
+                const float* px0 = fb + a.sl.px0 + ((size_t)t * B + b) * K * F;
+                const float* x_last = d.blocks > 0 ? frow(const_cast<float*>(fb), a.sl.px2, (int64_t)(d.blocks - 1) * (d.T - 1) + t, b, B, K, F) : px0;
+                float xin[KH], t0[KH];
+                load_field(c, x_last, F, o, xin);
+                slot_stats(c, xin, d.ln_eps);
+                {
+                    float dg = 0.f, dbt = 0.f;
+                    ln_bwd(c, dh, xin, reinterpret_cast<const float2*>(sm + L.stats) + 0, P[po.lnf_w + o], dg, dbt, t0, scr2);
+                    if (lead) { atomicAdd(G + po.lnf_w + o, dg); atomicAdd(G + po.lnf_b + o, dbt); }
+                }
+                for (int j = d.blocks - 1; j >= 0; --j) {
+                    const int64_t f = (int64_t)j * (d.T - 1) + t;
+                    const BlockOff& bo = po.blk[j];
+                    float* fbw = const_cast<float*>(fb);
+                    const float* p_q = frow(fbw, a.sl.pq, f, b, B, K, F);
+                    const float* p_k = frow(fbw, a.sl.pk, f, b, B, K, F);
+                    const float* p_v = frow(fbw, a.sl.pv, f, b, B, K, F);
+                    const float* p_x1 = frow(fbw, a.sl.px1, f, b, B, K, F);
+                    const float* p_f = frow(fbw, a.sl.pf, f, b, B, K, 4 * F);
+                    const float* p_att = fb + a.sl.patt + (f * B + b) * ((int64_t)d.heads * K * K);
+                    // t0 = d x2
+                    if (lead) { save_field(c, frow(W, a.wl.pdx2, f, b, B, K, F), F, o, t0); atomicAdd(G + bo.f2b + o, sum8(c, t0)); }
+                    write_operand(c, xop(L, 0), t0);
+                    signal_operand(c);
+                    // d f = (ffn.2^T d x2) masked by relu; chunks 1..3 go to X1..X3 at once, chunk 0 to X0 after all four tiles are done
+                    float df0[KH];
+#pragma unroll
+                    for (int ff = 0; ff < 4; ++ff) {
+                        mbar_wait(&bars[B_FACC + ff], pcall & 1u); fence_after_sync();
+                        float v[KH], fm[KH];
+                        load_acc(c, TB_F0 + 64 * ff, v);
+                        load_field(c, p_f, 4 * F, ff * F + o, fm);
+#pragma unroll
+                        for (int kk = 0; kk < KH; ++kk) v[kk] = (fm[kk] > 0.f) ? v[kk] : 0.f;
+                        if (lead) { save_field(c, frow(W, a.wl.pdf, f, b, B, K, 4 * F), 4 * F, ff * F + o, v); atomicAdd(G + bo.f1b + ff * F + o, sum8(c, v)); }
+                        if (ff == 0) {
+#pragma unroll
+                            for (int kk = 0; kk < KH; ++kk) df0[kk] = v[kk];
+                        } else {
+                            write_operand(c, xop(L, ff), v);
+                            signal_operand(c, B_FOPND + ff);
+                        }
+                    }
+                    write_operand(c, xop(L, 0), df0);
+                    signal_operand(c, B_FOPND + 0);
+                    ++pcall;
+                    float t1[KH], dx1[KH], x1v[KH];
+                    wait_acc(c); load_acc(c, TB_A, t1);                                    // d l2
+                    load_field(c, p_x1, F, o, x1v);
+                    slot_stats(c, x1v, d.ln_eps);
+                    {
+                        float dg = 0.f, dbt = 0.f;
+                        ln_bwd(c, t1, x1v, reinterpret_cast<const float2*>(sm + L.stats), P[bo.ln2_w + o], dg, dbt, dx1, scr2);
+                        if (lead) { atomicAdd(G + bo.ln2_w + o, dg); atomicAdd(G + bo.ln2_b + o, dbt); }
+                    }
+#pragma unroll
+                    for (int kk = 0; kk < KH; ++kk) dx1[kk] += t0[kk];
+                    if (lead) save_field(c, frow(W, a.wl.pdx1, f, b, B, K, F), F, o, dx1);
+                    write_operand(c, xop(L, 0), dx1);
+                    signal_operand(c);
+                    float dO[KH], dQ[KH], dK[KH], dV[KH];
+                    wait_acc(c); load_acc(c, TB_B, dO);
+                    mha_core_bwd(c, d.heads, hscale, dO, p_q, p_k, p_v, p_att, dQ, dK, dV);
+                    if (lead) {
+                        save_field(c, frow(W, a.wl.pdq, f, b, B, K, F), F, o, dQ);
+                        save_field(c, frow(W, a.wl.pdk, f, b, B, K, F), F, o, dK);
+                        save_field(c, frow(W, a.wl.pdv, f, b, B, K, F), F, o, dV);
+                    }
+                    write_operand(c, xop(L, 1), dQ); write_operand(c, xop(L, 2), dK); write_operand(c, xop(L, 3), dV);
+                    signal_operand(c);
+                    wait_acc(c); load_acc(c, TB_A, t1);                                    // dy
+                    if (j == 0) {
+#pragma unroll
+                        for (int kk = 0; kk < KH; ++kk) t1[kk] += dx1[kk];                 // residual taken from the normalised input
+                    }
+                    const float* x_in = (j == 0) ? px0 : frow(fbw, a.sl.px2, (int64_t)(j - 1) * (d.T - 1) + t, b, B, K, F);
+                    load_field(c, x_in, F, o, xin);
+                    slot_stats(c, xin, d.ln_eps);
+                    {
+                        float dg = 0.f, dbt = 0.f;
+                        ln_bwd(c, t1, xin, reinterpret_cast<const float2*>(sm + L.stats), P[bo.ln1_w + o], dg, dbt, t0, scr2);
+                        if (lead) { atomicAdd(G + bo.ln1_w + o, dg); atomicAdd(G + bo.ln1_b + o, dbt); }
+                    }
+                    if (j != 0) {
+#pragma unroll
+                        for (int kk = 0; kk < KH; ++kk) t0[kk] += dx1[kk];
+                    }
+                }
+#pragma unroll
+                for (int kk = 0; kk < KH; ++kk) dh[kk] = t0[kk];
+            }
+            {
+                float gsl[KH];
+                load_field(c, a.grad_slots + ((size_t)b * d.T + t) * K * F, F, o, gsl);
+#pragma unroll
+                for (int kk = 0; kk < KH; ++kk) dh[kk] += gsl[kk];
+            }
+            for (int it = d.I - 1; it >= 0; --it, ++step) {
+                const int64_t s = (int64_t)t * d.I + it;
+                float* fbw = const_cast<float*>(fb);
+                UPH(25);
+                if (it < d.I - 1) {
+                    // ---- residual MLP backward (steve.py:92-93) ----
+                    const int64_t smi = (int64_t)t * (d.I - 1) + it;
+                    float am[KH], hg[KH], v[KH];
+                    load_field(c, frow(fbw, a.sl.a, smi, b, B, K, F), F, o, am);
+                    load_field(c, frow(fbw, a.sl.hg, smi, b, B, K, F), F, o, hg);
+                    if (lead) save_field(c, frow(W, a.wl.dhm, smi, b, B, K, F), F, o, dh);
+                    a_b2 += sum8(c, dh);
+                    write_operand(c, xop(L, 0), dh);
+                    signal_operand(c);
+                    wait_acc(c); load_acc(c, TB_A, v);
+#pragma unroll
+                    for (int kk = 0; kk < KH; ++kk) v[kk] = (am[kk] > 0.f) ? v[kk] : 0.f;    // d a
+                    if (lead) save_field(c, frow(W, a.wl.da, smi, b, B, K, F), F, o, v);
+                    a_b1 += sum8(c, v);
+                    write_operand(c, xop(L, 1), v);
+                    signal_operand(c);
+                    wait_acc(c); load_acc(c, TB_B, v);                                     // d m
+                    float dxm[KH];
+                    ln_bwd(c, v, hg, reinterpret_cast<const float2*>(fb + a.sl.lnm) + (smi * B + b) * K, g_m, a_gm, a_bm, dxm, scr2);
+#pragma unroll
+                    for (int kk = 0; kk < KH; ++kk) dh[kk] += dxm[kk];
+                }
+                UPH(26);
+                // ---- GRUCell backward (steve.py:87-89) ----
+                {
+                    float r_[KH], z_[KH], n_[KH], hn[KH], hp[KH];
+                    load_field(c, frow(fbw, a.sl.r, s, b, B, K, F), F, o, r_);
+                    load_field(c, frow(fbw, a.sl.z, s, b, B, K, F), F, o, z_);
+                    load_field(c, frow(fbw, a.sl.n, s, b, B, K, F), F, o, n_);
+                    load_field(c, frow(fbw, a.sl.ghn, s, b, B, K, F), F, o, hn);
+                    load_field(c, frow(fbw, a.sl.hp, s, b, B, K, F), F, o, hp);
+                    float dr[KH], dz[KH], dn[KH], dnr[KH];
+#pragma unroll
+                    for (int kk = 0; kk < KH; ++kk) {
+                        const float g = dh[kk];
+                        dn[kk] = g * (1.0f - z_[kk]) * (1.0f - n_[kk] * n_[kk]);
+                        dz[kk] = g * (hp[kk] - n_[kk]) * z_[kk] * (1.0f - z_[kk]);
+                        dr[kk] = dn[kk] * hn[kk] * r_[kk] * (1.0f - r_[kk]);
+                        dnr[kk] = dn[kk] * r_[kk];
+                        dh[kk] = g * z_[kk];
+                    }
+                    if (lead) {
+                        float* gi = frow(W, a.wl.dgi, s, b, B, K, 3 * F);
+                        float* gh = frow(W, a.wl.dgh, s, b, B, K, 3 * F);
+                        save_field(c, gi, 3 * F, o, dr); save_field(c, gi, 3 * F, F + o, dz); save_field(c, gi, 3 * F, 2 * F + o, dn);
+                        save_field(c, gh, 3 * F, o, dr); save_field(c, gh, 3 * F, F + o, dz); save_field(c, gh, 3 * F, 2 * F + o, dnr);
+                    }
+                    a_dr += sum8(c, dr); a_dz += sum8(c, dz); a_dn += sum8(c, dn); a_dnr += sum8(c, dnr);
+                    write_operand(c, xop(L, 0), dr); write_operand(c, xop(L, 1), dz);
+                    write_operand(c, xop(L, 2), dn); write_operand(c, xop(L, 3), dnr);
+                    signal_operand(c);
+                }
+                UPH(27);
+                float v[KH], dux[KH];
+                wait_acc(c); load_acc(c, TB_A, v);                                         // dU
+                UPH(28);
+                if (lead) save_field(c, frow(W, a.wl.du, s, b, B, K, F), F, o, v);
+                write_operand(c, xop(L, 2), v);
+                signal_operand(c);
+                // operands of the token pass that do not depend on dUx: qk (saved), 1/S
+                float qk[KH], ux[KH];
+                load_field(c, frow(fbw, a.sl.qk, s, b, B, K, F), F, o, qk);
+                load_field(c, frow(fbw, a.sl.ux, s, b, B, K, F), F, o, ux);
+                if (tid < 32) cv[32 + tid] = (tid < K) ? 1.0f / fb[a.sl.ssum + (s * B + b) * KP + tid] : 0.f;
+                wait_acc(c); load_acc(c, TB_B, dux);                                       // dUx
+                UPH(29);
+                if (lead) save_field(c, frow(W, a.wl.duxs, s, b, B, K, F), F, o, dux);
+                // c[k] = <dUx[k,:], Ux[k,:]>: reduce over the 128 features through the scratch tile
+                {
+                    float* scr = reinterpret_cast<float*>(sm + L.scratch);
+#pragma unroll
+                    for (int kk = 0; kk < KH; ++kk) if (kk < c.nk) scr[(c.k0 + kk) * F + o] = dux[kk] * ux[kk];
+                    mbar_wait(&bars[B_HP], hpcall & 1u);                                   // W_hh^T product done: X0, X1, X3 may be rewritten
+                    ++hpcall;
+                    write_operand(c, xop(L, 0), dux);
+                    write_operand(c, xop(L, 1), qk);
+                    bar_sync_compute();
+                    for (int k = c.warp; k < K; k += NCW) {
+                        const float4 x = ld4(scr + k * F + lane * 4);
+                        const float sdot = warp_sum((x.x + x.y) + (x.z + x.w));
+                        if (lane == 0) cv[k] = sdot;
+                    }
+                    bar_sync_compute();
+                }
+                signal_operand(c);
+                UPH(30);
+                // ---- attention step backward over the token tiles ----
+                const bf16* ga = (a.grad_attn && it == d.I - 1) ? reinterpret_cast<const bf16*>(a.grad_attn) + ((size_t)b * d.T + t) * d.N * K : nullptr;
+                bf16* coef = coef_base + ((((size_t)b * d.T + t) * d.I + it) * 2 * d.KC) * d.N;
+                softmax_bwd_tiles(c, d, ntile, tile0, ga, coef, cv, xop(L, 2), xop(L, 3), ts, dbg);
+                UPH(31);
+                mbar_wait(&bars[B_TOK], step & 1u);
+                fence_after_sync();
+                UPH(32);
+                float dqk[KH];
+                load_acc(c, TB_DQK, dqk);
+                if (CN > 1) {
+                    const int buf = step & 1;
+                    float* ib = reinterpret_cast<float*>(sm + L.inbox + buf * L.inbox_stride);
+                    const uint32_t peer = rank ^ 1u;
+                    const uint32_t rb = map_to_rank(ib, peer) + (uint32_t)(c.k0 * F + o) * 4u;
+#pragma unroll
+                    for (int kk = 0; kk < KH; ++kk) if (kk < c.nk) st_cluster_f1(rb + (uint32_t)(kk * F) * 4u, dqk[kk]);
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive_remote(map_to_rank(&bars[B_INBOX + buf], peer));
+                    mbar_wait_cluster(&bars[B_INBOX + buf], (step >> 1) & 1u);
+                    const float* pn = ib + c.k0 * F + o;
+#pragma unroll
+                    for (int kk = 0; kk < KH; ++kk) if (kk < c.nk) dqk[kk] = lead ? dqk[kk] + pn[kk * F] : pn[kk * F] + dqk[kk];
+                }
+                UPH(33);
+                if (lead) save_field(c, frow(W, a.wl.dqk, s, b, B, K, F), F, o, dqk);
+                write_operand(c, xop(L, 0), dqk);
+                signal_operand(c);
+                wait_acc(c); load_acc(c, TB_A, v);                                         // dq = Ds^-1/2 W_k d qk
+#pragma unroll
+                for (int kk = 0; kk < KH; ++kk) v[kk] *= d.qscale;
+                UPH(34);
+                if (lead) save_field(c, frow(W, a.wl.dq, s, b, B, K, F), F, o, v);
+                write_operand(c, xop(L, 1), v);
+                signal_operand(c);
+                float hp[KH], dst[KH], hpv[KH];
+                load_field(c, frow(fbw, a.sl.hp, s, b, B, K, F), F, o, hp);
+                load_acc(c, TB_HP, hpv);                                                   // W_hh^T dgh (B_HP was observed above)
+                wait_acc(c); load_acc(c, TB_B, v);                                         // d s~
+                UPH(35);
+                ln_bwd(c, v, hp, reinterpret_cast<const float2*>(fb + a.sl.lns) + (s * B + b) * K, g_s, a_gs, a_bs, dst, scr2);
+#pragma unroll
+                for (int kk = 0; kk < KH; ++kk) dh[kk] += hpv[kk] + dst[kk];
+                UPH(36);
+            }
+        }
+        // ---- slot initialisation backward (steve.py:56-57) and the accumulated vector-parameter gradients ----
+        if (lead) {
+            const float es = expf(P[po.slot_log_sigma + o]);
+            float nz[KH];
+            load_field(c, a.noise + (size_t)b * K * F, F, o, nz);
+            float smu = 0.f, sls = 0.f;
+#pragma unroll
+            for (int kk = 0; kk < KH; ++kk) {
+                if (kk < c.nk) {
+                    smu += dh[kk]; sls = fmaf(dh[kk] * es, nz[kk], sls);
+                    if (a.grad_noise) a.grad_noise[((size_t)b * K + c.k0 + kk) * F + o] = dh[kk] * es;
+                }
+            }
+            if (c.nk > 0) {
+                atomicAdd(G + po.slot_mu + o, smu); atomicAdd(G + po.slot_log_sigma + o, sls);
+                atomicAdd(G + po.ln_s_w + o, a_gs); atomicAdd(G + po.ln_s_b + o, a_bs);
+                atomicAdd(G + po.ln_m_w + o, a_gm); atomicAdd(G + po.ln_m_b + o, a_bm);
+                atomicAdd(G + po.b1 + o, a_b1); atomicAdd(G + po.b2 + o, a_b2);
+                atomicAdd(G + po.bih + o, a_dr); atomicAdd(G + po.bih + F + o, a_dz); atomicAdd(G + po.bih + 2 * F + o, a_dn);
+                atomicAdd(G + po.bhh + o, a_dr); atomicAdd(G + po.bhh + F + o, a_dz); atomicAdd(G + po.bhh + 2 * F + o, a_dnr);
+            }
+        }
+        if (dbg) for (int i = 0; i < 64; ++i) if (sdbg[i]) a.dbg[i] += sdbg[i];
+    }
+    // ---- teardown ----
+    __syncwarp();
+    fence_before_sync();
+    __syncthreads();
+    if (CN > 1) { cluster_arrive(); cluster_wait(); }
+    if (warp == W_MMA) tmem_dealloc(tb, TB_COLS);
+}
+
+// ------------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------------
+int savi_bwd_umma_smem_bytes(const Dims& d) {
+    return plan_smem(d.K, d.CN, true).total;
+}
+
+cudaError_t savi_launch_bwd_umma(const BwdArgs& a, const unsigned char* wimg, const WImg& wi, cudaStream_t st) {
+    BwdUArgs ua;
+    ua.a = a; ua.wimg = wimg; ua.wi = wi;
+    ua.a.smem_bytes = savi_bwd_umma_smem_bytes(a.d);
+    cudaError_t e = cudaFuncSetAttribute(savi_bwd_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ua.a.smem_bytes);
+    if (e != cudaSuccess) return e;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(a.d.B * a.d.CN);
+    cfg.blockDim = dim3(NTHREADS);
+    cfg.dynamicSmemBytes = ua.a.smem_bytes;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = a.d.CN; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, savi_bwd_umma_kernel, ua);
+}

@@ -212,15 +212,16 @@ __device__ __forceinline__ void mha_core(const Ctx& c, int H, const float (&q)[K
 // the kernel
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(NTHREADS, 1) savi_fwd_umma_kernel(const __grid_constant__ FwdUArgs ua) {
-    extern __shared__ unsigned char smem_raw[];
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
     const FwdArgs& a = ua.a;
     const Dims& d = a.d;
     const ParamOff& po = a.po;
-    unsigned char* sm = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    unsigned char* sm = smem_raw;
+    if ((smem_u32(sm) & 1023u) != 0u) __trap();                // SWIZZLE_128B operands need a 1024-byte aligned base
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int CN = d.CN, b = blockIdx.x / CN, rank = blockIdx.x % CN;
     const int K = d.K, B = d.B, KP = d.KP;
-    const Smem L = plan_smem(K, CN, 0, a.smem_bytes);
+    const Smem L = plan_smem(K, CN, false);
     uint64_t* bars = reinterpret_cast<uint64_t*>(sm + L.bars);
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + NBAR);
     const bool lead = (rank == 0);
@@ -358,7 +359,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) savi_fwd_umma_kernel(const __grid
             for (int kk = 0; kk < KH; ++kk) h[kk] = mu + sg * y[kk];
         }
         uint32_t step = 0, pcall = 0;
-        __shared__ long long sdbg[64];
+        long long* sdbg = reinterpret_cast<long long*>(sm + L.bars + NBAR * 8 + 16);
         if (a.dbg && blockIdx.x == 0 && tid == 0) for (int i = 0; i < 64; ++i) sdbg[i] = 0;
         long long* dbg = (a.dbg && blockIdx.x == 0 && tid == 0) ? sdbg : nullptr;      // counters in shared memory: a global RMW per probe would stall the warp
         long long ph_last = clock64();
@@ -368,7 +369,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) savi_fwd_umma_kernel(const __grid
                 // ---- slots_prev, LayerNorm, q ----
                 if (lead) save_field(c, frow(fb, a.sl.hp, s, b, B, K, F), F, o, h);
                 write_operand(c, L.opC, h);
-                layer_norm(c, h, y, g_s, b_s, d.ln_eps);                                   // :72
+                layer_norm(c, h, y, g_s, b_s, d.ln_eps, lead ? reinterpret_cast<float2*>(fb + a.sl.lns) + (s * B + b) * K : nullptr);   // :72
+                if (lead) save_field(c, frow(fb, a.sl.st, s, b, B, K, F), F, o, y);
                 write_operand(c, L.opA, y);
                 signal_operand(c);
                 UPH(1);
@@ -465,7 +467,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) savi_fwd_umma_kernel(const __grid
                         const int64_t smi = (int64_t)t * (d.I - 1) + it;
                         if (lead) save_field(c, frow(fb, a.sl.hg, smi, b, B, K, F), F, o, h);
                         UPH(14);
-                        layer_norm(c, h, y, g_m, b_m, d.ln_eps);
+                        layer_norm(c, h, y, g_m, b_m, d.ln_eps, lead ? reinterpret_cast<float2*>(fb + a.sl.lnm) + (smi * B + b) * K : nullptr);
+                        if (lead) save_field(c, frow(fb, a.sl.m, smi, b, B, K, F), F, o, y);
                         write_operand(c, L.opB, y);
                         signal_operand(c);
                         UPH(15);
@@ -558,8 +561,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) savi_fwd_umma_kernel(const __grid
 // host side
 // ------------------------------------------------------------------------------------------------
 int savi_fwd_umma_smem_bytes(const Dims& d) {
-    const Smem L = plan_smem(d.K, d.CN, 0, 227 * 1024 - 1024);      // 1 KB left for static shared memory
-    return L.ring + L.nst * BLK + 1024;
+    return plan_smem(d.K, d.CN, false).total;
 }
 
 cudaError_t savi_launch_fwd_umma(const FwdArgs& a, const unsigned char* wimg, const WImg& wi, cudaStream_t st) {

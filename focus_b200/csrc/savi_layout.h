@@ -153,6 +153,9 @@ struct SavedLayout {
     int64_t py, pq, pk, pv, po, px1, pl2, pf, px2;   // widths Ds x7, 4Ds, Ds
     int64_t patt;                                // [Sp*B, heads*K*K]
     int64_t ximg;        // bytes  [B*T][NTILE][D/64][128 rows][64] bf16, SWIZZLE_128B blocks of xhat (tcgen05 path only)
+    // tcgen05 path only (float offsets like the fields above): LayerNorm outputs and statistics the backward reuses
+    int64_t st, m;       // [S*B*K, Ds] s~ = LN_s(slots_prev);  [Sm*B*K, Ds] LN_m(h')
+    int64_t lns, lnm;    // [S*B*K, 2], [Sm*B*K, 2]: (mean, rstd) of those LayerNorms
     int64_t total_bytes;
 };
 
@@ -172,6 +175,8 @@ static inline void savi_saved_layout(const Dims& d, SavedLayout& L) {
     L.py = take(Rp, d.Ds); L.pq = take(Rp, d.Ds); L.pk = take(Rp, d.Ds); L.pv = take(Rp, d.Ds); L.po = take(Rp, d.Ds);
     L.px1 = take(Rp, d.Ds); L.pl2 = take(Rp, d.Ds); L.pf = take(Rp, 4 * d.Ds); L.px2 = take(Rp, d.Ds);
     L.patt = take((int64_t)d.Sp * d.B, (int64_t)d.heads * d.K * d.K);
+    L.st = L.m = L.lns = L.lnm = 0;
+    if (d.umma) { L.st = take(R, d.Ds); L.m = take(Rm, d.Ds); L.lns = take(R, 2); L.lnm = take(Rm, 2); }
     int64_t e = L.fbase + f * 4;
     e = (e + 1023) / 1024 * 1024;
     L.ximg = e;

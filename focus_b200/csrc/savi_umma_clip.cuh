@@ -76,28 +76,29 @@ struct Smem {
     int total;
 };
 constexpr int NBAR = 64;
-__host__ __device__ inline Smem plan_smem(int K, int CN, int aux_bytes, int max_bytes) {
+constexpr int SMEM_MAX = 227 * 1024;             // the kernels use no static shared memory: the whole opt-in window is dynamic
+__host__ __device__ inline Smem plan_smem(int K, int CN, bool bwd) {
     Smem s;
     const int KR = (K + 3) & ~3;
     int p = 0;
     s.opA = p; p += OPB; s.opB = p; p += OPB; s.opC = p; p += OPB;
     s.aw0 = p; p += OPB; s.aw1 = p; p += OPB;
     s.scratch = p; p += KR * F * 4;
-    s.stats = p; p += 32 * 8;
-    s.xch = p; p += 2 * 2 * 2 * 128 * 8;           // [pair][tile parity][half][token] float2
+    s.stats = p; p += 512;                         // float2 [32] LayerNorm statistics | float [64] c, 1/S (backward)
+    s.xch = p; p += bwd ? 12288 : 8192;            // float2 [pair][tile parity][half][token] (+ float [..] for the backward's dot product)
     p = (p + 1023) & ~1023;
-    s.ones = p; p += 4096;
-    s.inbox_stride = (KR * F * 4 + 32 * 4 + 127) & ~127;
+    s.ones = p; p += bwd ? 0 : 4096;
+    s.inbox_stride = (KR * F * 4 + (bwd ? 0 : 32 * 4) + 127) & ~127;
     s.inbox = p; p += (CN > 1) ? 2 * s.inbox_stride : 0;
-    s.aux = p; p += aux_bytes;
+    s.aux = p;
     p = (p + 15) & ~15;
-    s.bars = p; p += NBAR * 8 + 16;
+    s.bars = p; p += NBAR * 8 + 16 + 512;          // mbarriers, TMEM base, development counters
     p = (p + 1023) & ~1023;
     s.ring = p;
-    s.nst = (max_bytes - 1024 - p) / BLK;        // 1024: base alignment slack
+    s.nst = (SMEM_MAX - p) / BLK;
     if (s.nst > 12) s.nst = 12;
     s.nst &= ~1;                                 // even: a token tile's two blocks never wrap around the ring
-    s.total = p + s.nst * BLK + 1024;
+    s.total = p + s.nst * BLK;
     return s;
 }
 
@@ -241,9 +242,15 @@ __device__ __forceinline__ void slot_stats(const Ctx& c, const float (&v)[KH], f
     }
     bar_sync_compute();
 }
-__device__ __forceinline__ void layer_norm(const Ctx& c, const float (&v)[KH], float (&y)[KH], float gamma, float beta, float eps) {
+// stats_out (nullable): global [K][2] record of (mean, rstd), written by one thread per warpgroup
+__device__ __forceinline__ void layer_norm(const Ctx& c, const float (&v)[KH], float (&y)[KH], float gamma, float beta, float eps,
+                                           float2* stats_out = nullptr) {
     slot_stats(c, v, eps);
     const float2* st = reinterpret_cast<const float2*>(c.sm + c.L.stats) + c.k0;
+    if (stats_out && c.o == 0) {
+#pragma unroll
+        for (int kk = 0; kk < KH; ++kk) if (kk < c.nk) stats_out[c.k0 + kk] = st[kk];
+    }
 #pragma unroll
     for (int kk = 0; kk < KH; ++kk) {
         if (kk < c.nk) { const float2 s = st[kk]; y[kk] = (v[kk] - s.x) * s.y * gamma + beta; }

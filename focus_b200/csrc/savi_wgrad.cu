@@ -1,5 +1,6 @@
 // Weight-gradient GEMM and the backward launch sequence.
 #include "savi_dev.cuh"
+#include <cstdlib>
 #include "savi_args.h"
 
 // ---------------------------------------------------------------------------
@@ -81,7 +82,12 @@ cudaError_t savi_launch_backward(const BwdArgs& a, const void* inputs, void* gra
     cudaError_t e = cudaMemsetAsync(a.grad_params, 0, (size_t)a.po.total * sizeof(float), st);
     if (e != cudaSuccess) return e;
     savi_prof_begin(3, st);
-    if (d.tok_bytes == 4) e = savi_launch_bwd_clip_f32(a, st); else e = savi_launch_bwd_clip_bf16(a, st);
+    const bool umma_bwd = d.umma && !getenv("SAVI_UMMA_FWD_ONLY");
+    if (umma_bwd) {
+        WImg wi;
+        savi_wimg_layout(d.D, d.Ds, d.M, d.blocks, wi);
+        e = savi_launch_bwd_umma(a, reinterpret_cast<const unsigned char*>(a.packed) + savi_wimg_base(a.po.packed_total), wi, st);
+    } else if (d.tok_bytes == 4) e = savi_launch_bwd_clip_f32(a, st); else e = savi_launch_bwd_clip_bf16(a, st);
     savi_prof_end(3, st);
     if (e != cudaSuccess) return e;
     *launches += 1;
@@ -92,12 +98,15 @@ cudaError_t savi_launch_backward(const BwdArgs& a, const void* inputs, void* gra
     const int Ds = d.Ds, D = d.D, M = d.M;
     const int64_t R = (int64_t)d.S * d.B * d.K, Rm = (int64_t)d.Sm * d.B * d.K, Rb = (int64_t)(d.T - 1) * d.B * d.K;
     WgradArgs wa; wa.njobs = 0;
-    add_job(wa, W + a.wl.dq, Ds, W + a.wl.st, Ds, G + a.po.wq, R, Ds, Ds, 1.0f);
+    // the tcgen05 forward saves s~ and LN_m(h'): its backward does not restage them
+    const float* st_rows = umma_bwd ? fb + a.sl.st : W + a.wl.st;
+    const float* m_rows = umma_bwd ? fb + a.sl.m : W + a.wl.m;
+    add_job(wa, W + a.wl.dq, Ds, st_rows, Ds, G + a.po.wq, R, Ds, Ds, 1.0f);
     add_job(wa, fb + a.sl.q, Ds, W + a.wl.dqk, D, G + a.po.wk, R, Ds, D, d.qscale);
     add_job(wa, W + a.wl.du, Ds, fb + a.sl.ux, D, G + a.po.wv, R, Ds, D, 1.0f);
     add_job(wa, W + a.wl.dgi, 3 * Ds, fb + a.sl.u, Ds, G + a.po.wih, R, 3 * Ds, Ds, 1.0f);
     add_job(wa, W + a.wl.dgh, 3 * Ds, fb + a.sl.hp, Ds, G + a.po.whh, R, 3 * Ds, Ds, 1.0f);
-    add_job(wa, W + a.wl.da, M, W + a.wl.m, Ds, G + a.po.w1, Rm, M, Ds, 1.0f);
+    add_job(wa, W + a.wl.da, M, m_rows, Ds, G + a.po.w1, Rm, M, Ds, 1.0f);
     add_job(wa, W + a.wl.dhm, Ds, fb + a.sl.a, M, G + a.po.w2, Rm, Ds, M, 1.0f);
     for (int j = 0; j < d.blocks; ++j) {
         const int64_t ro = (int64_t)j * Rb;      // block j's rows are contiguous: f = j*(T-1)+t

@@ -34,23 +34,28 @@ __device__ __forceinline__ int xop(const Smem& L, int i) { return i == 0 ? L.opA
 //   P1(i): S[i&1] = xhat_i . [qk_hi | qk_lo],  G[i&1] = xhat_i . [dUx_hi | dUx_lo]
 //   P2(i): DQK   += xhat_i^T . [dL_hi | dL_lo]
 // ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ void issue_token_pass_bwd(Ring& r, uint64_t* bars, uint32_t tb, int ntile, TokState& ts,
+__device__ __forceinline__ void issue_token_pass_bwd(Ring& r, bool el, uint64_t* bars, uint32_t tb, int ntile, TokState& ts,
                                                      uint32_t qk_op, uint32_t dux_op, uint32_t dl0, uint32_t dl1) {
     int ts0[2] = {0, 0};
+    const uint32_t rb = smem_u32(r.base);
     auto p2 = [&](int j) {
         const int g = j & 1;
         mbar_wait(&bars[B_AREADY + g], ts.cnt_a[g] & 1u);
         fence_after_sync();
-        const uint32_t x0 = smem_u32(r.base + (size_t)ts0[g] * BLK);
-        const uint32_t dl = g ? dl1 : dl0;
-#pragma unroll 2
-        for (int kt = 0; kt < 8; ++kt)
-            mma_ss(tb + TB_DQK, desc_mnmajor(x0 + kt * 2048, BLK), desc_mnmajor(dl + kt * 2048, BLK), IDESC_MN_MN64, j > 0 || kt > 0);
-        mma_commit(&r.empty[ts0[g]]);
-        mma_commit(&r.empty[ts0[g] + 1]);
-        mma_commit(&bars[B_AFREE + g]);
+        const uint32_t x0 = dlo_mn(rb + ts0[g] * BLK, BLK);
+        const uint32_t dl = dlo_mn(g ? dl1 : dl0, BLK);
+        if (el) {
+            mma_lo(tb + TB_DQK, x0, dl, IDESC_MN_MN64, j > 0 ? 1u : 0u);
+#pragma unroll
+            for (int kt = 1; kt < 8; ++kt) mma_lo(tb + TB_DQK, x0 + kt * 128, dl + kt * 128, IDESC_MN_MN64, 1u);
+            mma_commit(&r.empty[ts0[g]]);
+            mma_commit(&r.empty[ts0[g] + 1]);
+            mma_commit(&bars[B_AFREE + g]);
+        }
+        __syncwarp();
         ++ts.cnt_a[g];
     };
+    const uint32_t qk0 = dlo_mn(qk_op, BLK), du0 = dlo_mn(dux_op, BLK);
     for (int i = 0; i < ntile; ++i) {
         const int g = i & 1;
         mbar_wait(&bars[B_SFREE + g], (ts.cnt_s[g] & 1u) ^ 1u);
@@ -61,21 +66,26 @@ __device__ __forceinline__ void issue_token_pass_bwd(Ring& r, uint64_t* bars, ui
         for (int db = 0; db < 2; ++db) {
             mbar_wait(&r.full[r.stage], r.phase);
             fence_after_sync();
-            const uint32_t a = smem_u32(r.base + (size_t)r.stage * BLK);
+            const uint32_t a = dlo_k(rb + r.stage * BLK);
+            if (el) {
 #pragma unroll
-            for (int k4 = 0; k4 < 4; ++k4) {
-                const uint64_t ad = desc_kmajor(a + k4 * 32);
-                mma_ss(acc_s, ad, desc_mnmajor(qk_op + (db * 4 + k4) * 2048, BLK), IDESC_K_MN64, db > 0 || k4 > 0);
-                mma_ss(acc_g, ad, desc_mnmajor(dux_op + (db * 4 + k4) * 2048, BLK), IDESC_K_MN64, db > 0 || k4 > 0);
+                for (int k4 = 0; k4 < 4; ++k4) {
+                    const uint32_t acc = (db > 0 || k4 > 0) ? 1u : 0u;
+                    mma_lo(acc_s, a + k4 * 2, qk0 + (db * 4 + k4) * 128, IDESC_K_MN64, acc);
+                    mma_lo(acc_g, a + k4 * 2, du0 + (db * 4 + k4) * 128, IDESC_K_MN64, acc);
+                }
             }
+            __syncwarp();
             r.advance();
         }
-        mma_commit(&bars[B_SFULL + g]);
+        if (el) mma_commit(&bars[B_SFULL + g]);
+        __syncwarp();
         ++ts.cnt_s[g];
         if (i >= 1) p2(i - 1);
     }
     p2(ntile - 1);
-    mma_commit(&bars[B_TOK]);
+    if (el) mma_commit(&bars[B_TOK]);
+    __syncwarp();
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -241,8 +251,9 @@ __device__ __forceinline__ void ln_bwd(const Ctx& c, const float (&dy)[KH], cons
 }
 
 // Backward of the predictor's attention core in shared memory (transformer.py:34-47).  dQ is w.r.t. the UNSCALED projection.
-__device__ __forceinline__ void mha_core_bwd(const Ctx& c, int H, float hscale, const float (&dO)[KH], const float* Qg, const float* Kg,
-                                             const float* Vg, const float* attg, float (&dQ)[KH], float (&dK)[KH], float (&dV)[KH]) {
+constexpr int ATT_PT = 8;     // attention-matrix elements per thread: heads * K * K <= 8 * 512
+__device__ __forceinline__ void mha_core_bwd(const Ctx& c, int H, float hscale, const float (&dO)[KH], const float (&Qv)[KH], const float (&Kv)[KH],
+                                             const float (&Vv)[KH], const float (&attv)[ATT_PT], float (&dQ)[KH], float (&dK)[KH], float (&dV)[KH]) {
     const int K = c.K, ld = F + 1, ka = K | 1, dh = F / H;
     float* sO = reinterpret_cast<float*>(c.sm + c.L.opA);             // opA .. scratch are contiguous (5 x 16 KB + scratch)
     float* sQ = sO + K * ld; float* sK = sQ + K * ld; float* sV = sK + K * ld;
@@ -250,12 +261,10 @@ __device__ __forceinline__ void mha_core_bwd(const Ctx& c, int H, float hscale, 
 #pragma unroll
     for (int kk = 0; kk < KH; ++kk) {
         const int k = c.k0 + kk;
-        if (kk < c.nk) {
-            sO[k * ld + c.o] = dO[kk]; sQ[k * ld + c.o] = Qg[(size_t)k * F + c.o];
-            sK[k * ld + c.o] = Kg[(size_t)k * F + c.o]; sV[k * ld + c.o] = Vg[(size_t)k * F + c.o];
-        }
+        if (kk < c.nk) { sO[k * ld + c.o] = dO[kk]; sQ[k * ld + c.o] = Qv[kk]; sK[k * ld + c.o] = Kv[kk]; sV[k * ld + c.o] = Vv[kk]; }
     }
-    for (int idx = c.tid; idx < H * K * K; idx += NCT) sA[(idx / K) * ka + idx % K] = attg[idx];
+#pragma unroll
+    for (int e = 0; e < ATT_PT; ++e) { const int idx = c.tid + e * NCT; if (idx < H * K * K) sA[(idx / K) * ka + idx % K] = attv[e]; }
     bar_sync_compute();
     for (int idx = c.tid; idx < H * K * K; idx += NCT) {
         const int j = idx % K, i = (idx / K) % K, h = idx / (K * K);
@@ -352,6 +361,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) savi_bwd_umma_kernel(const __grid
 
     Ring ring;
     ring.base = sm + L.ring; ring.full = &bars[B_FULL]; ring.empty = &bars[B_EMPTY]; ring.nst = L.nst; ring.stage = 0; ring.phase = 0;
+    ring.wait_cycles = nullptr;
 
     if (warp == W_PROD) {
         // =====================================================================================
@@ -387,7 +397,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) savi_bwd_umma_kernel(const __grid
         // =====================================================================================
         // tcgen05.mma issuer
         // =====================================================================================
-        if (lane == 0) {
+        {
+            const bool el = elect_one();
             uint32_t ph_opnd = 0, pcall = 0;
             TokState ts = {{0, 0}, {0, 0}};
             const uint32_t X0 = smem_u32(sm + L.opA), X1 = smem_u32(sm + L.opB), X2 = smem_u32(sm + L.opC), X3 = smem_u32(sm + L.aw0);
@@ -396,45 +407,45 @@ __global__ void __launch_bounds__(NTHREADS, 1) savi_bwd_umma_kernel(const __grid
                 if (t < d.T - 1) {
                     for (int j = d.blocks - 1; j >= 0; --j) {
                         wait_opnd();                                                       // d x2 in X0
-                        for (int f = 0; f < 4; ++f) { issue_linear(ring, X0, tb + TB_F0 + 64 * f, 1, 2, false); mma_commit(&bars[B_FACC + f]); }   // d f = ffn.2^T d x2
+                        for (int f = 0; f < 4; ++f) { issue_linear(ring, el, X0, tb + TB_F0 + 64 * f, 1, 2, false); if (el) mma_commit(&bars[B_FACC + f]); }   // d f = ffn.2^T d x2
                         // d l2 = ffn.0^T d f: chunks 1, 2, 3 (X1..X3) then chunk 0 (X0, rewritten after all four tiles above completed)
                         for (int q = 0; q < 4; ++q) {
                             const int f = (q + 1) & 3;
                             mbar_wait(&bars[B_FOPND + f], pcall & 1u); fence_after_sync();
-                            issue_linear(ring, f == 0 ? X0 : f == 1 ? X1 : f == 2 ? X2 : X3, tb + TB_A, 1, 2, q > 0);
+                            issue_linear(ring, el, f == 0 ? X0 : f == 1 ? X1 : f == 2 ? X2 : X3, tb + TB_A, 1, 2, q > 0);
                         }
-                        mma_commit(&bars[B_ACC]);
+                        if (el) mma_commit(&bars[B_ACC]);
                         ++pcall;
                         wait_opnd();                                                       // d x1 in X0
-                        issue_linear(ring, X0, tb + TB_B, 1, 2, false); mma_commit(&bars[B_ACC]);        // dO = proj_o^T d x1
+                        issue_linear(ring, el, X0, tb + TB_B, 1, 2, false); if (el) mma_commit(&bars[B_ACC]);        // dO = proj_o^T d x1
                         wait_opnd();                                                       // dQ, dK, dV in X1, X2, X3
-                        issue_linear(ring, X1, tb + TB_A, 1, 2, false);
-                        issue_linear(ring, X2, tb + TB_A, 1, 2, true);
-                        issue_linear(ring, X3, tb + TB_A, 1, 2, true); mma_commit(&bars[B_ACC]);         // dy
+                        issue_linear(ring, el, X1, tb + TB_A, 1, 2, false);
+                        issue_linear(ring, el, X2, tb + TB_A, 1, 2, true);
+                        issue_linear(ring, el, X3, tb + TB_A, 1, 2, true); if (el) mma_commit(&bars[B_ACC]);         // dy
                     }
                 }
                 for (int it = d.I - 1; it >= 0; --it) {
                     if (it < d.I - 1) {
                         wait_opnd();                                                       // dh in X0
-                        issue_linear(ring, X0, tb + TB_A, 1, 2, false); mma_commit(&bars[B_ACC]);        // d a = mlp.2^T dh
+                        issue_linear(ring, el, X0, tb + TB_A, 1, 2, false); if (el) mma_commit(&bars[B_ACC]);        // d a = mlp.2^T dh
                         wait_opnd();                                                       // d a in X1
-                        issue_linear(ring, X1, tb + TB_B, 1, 2, false); mma_commit(&bars[B_ACC]);        // d m = mlp.0^T d a
+                        issue_linear(ring, el, X1, tb + TB_B, 1, 2, false); if (el) mma_commit(&bars[B_ACC]);        // d m = mlp.0^T d a
                     }
                     wait_opnd();                                                           // dr, dz, dn, dn*r in X0..X3
-                    issue_linear(ring, X0, tb + TB_A, 1, 2, false);
-                    issue_linear(ring, X1, tb + TB_A, 1, 2, true);
-                    issue_linear(ring, X2, tb + TB_A, 1, 2, true); mma_commit(&bars[B_ACC]);             // dU = W_ih^T dgi
-                    issue_linear(ring, X0, tb + TB_HP, 1, 2, false);
-                    issue_linear(ring, X1, tb + TB_HP, 1, 2, true);
-                    issue_linear(ring, X3, tb + TB_HP, 1, 2, true); mma_commit(&bars[B_HP]);             // W_hh^T dgh (consumed at the end of the step)
+                    issue_linear(ring, el, X0, tb + TB_A, 1, 2, false);
+                    issue_linear(ring, el, X1, tb + TB_A, 1, 2, true);
+                    issue_linear(ring, el, X2, tb + TB_A, 1, 2, true); if (el) mma_commit(&bars[B_ACC]);             // dU = W_ih^T dgi
+                    issue_linear(ring, el, X0, tb + TB_HP, 1, 2, false);
+                    issue_linear(ring, el, X1, tb + TB_HP, 1, 2, true);
+                    issue_linear(ring, el, X3, tb + TB_HP, 1, 2, true); if (el) mma_commit(&bars[B_HP]);             // W_hh^T dgh (consumed at the end of the step)
                     wait_opnd();                                                           // dU in X2
-                    issue_linear(ring, X2, tb + TB_B, 1, 2, false); mma_commit(&bars[B_ACC]);            // dUx = W_v^T dU
+                    issue_linear(ring, el, X2, tb + TB_B, 1, 2, false); if (el) mma_commit(&bars[B_ACC]);            // dUx = W_v^T dU
                     wait_opnd();                                                           // dUx in X0, qk in X1
-                    issue_token_pass_bwd(ring, bars, tb, ntile, ts, X1, X0, X2, X3);
+                    issue_token_pass_bwd(ring, el, bars, tb, ntile, ts, X1, X0, X2, X3);
                     wait_opnd();                                                           // d qk in X0
-                    issue_linear(ring, X0, tb + TB_A, 1, 2, false); mma_commit(&bars[B_ACC]);            // dq = W_k d qk
+                    issue_linear(ring, el, X0, tb + TB_A, 1, 2, false); if (el) mma_commit(&bars[B_ACC]);            // dq = W_k d qk
                     wait_opnd();                                                           // dq in X1
-                    issue_linear(ring, X1, tb + TB_B, 1, 2, false); mma_commit(&bars[B_ACC]);            // d s~ = W_q^T dq
+                    issue_linear(ring, el, X1, tb + TB_B, 1, 2, false); if (el) mma_commit(&bars[B_ACC]);            // d s~ = W_q^T dq
                 }
             }
         }
@@ -503,10 +514,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) savi_bwd_umma_kernel(const __grid
                     float df0[KH];
 #pragma unroll
                     for (int ff = 0; ff < 4; ++ff) {
-                        mbar_wait(&bars[B_FACC + ff], pcall & 1u); fence_after_sync();
                         float v[KH], fm[KH];
+                        load_field(c, p_f, 4 * F, ff * F + o, fm);                         // issued before the wait: latency hidden behind the MMAs
+                        mbar_wait(&bars[B_FACC + ff], pcall & 1u); fence_after_sync();
                         load_acc(c, TB_F0 + 64 * ff, v);
-                        load_field(c, p_f, 4 * F, ff * F + o, fm);
 #pragma unroll
                         for (int kk = 0; kk < KH; ++kk) v[kk] = (fm[kk] > 0.f) ? v[kk] : 0.f;
                         if (lead) { save_field(c, frow(W, a.wl.pdf, f, b, B, K, 4 * F), 4 * F, ff * F + o, v); atomicAdd(G + bo.f1b + ff * F + o, sum8(c, v)); }
@@ -522,8 +533,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) savi_bwd_umma_kernel(const __grid
                     signal_operand(c, B_FOPND + 0);
                     ++pcall;
                     float t1[KH], dx1[KH], x1v[KH];
-                    wait_acc(c); load_acc(c, TB_A, t1);                                    // d l2
                     load_field(c, p_x1, F, o, x1v);
+                    wait_acc(c); load_acc(c, TB_A, t1);                                    // d l2
                     slot_stats(c, x1v, d.ln_eps);
                     {
                         float dg = 0.f, dbt = 0.f;
@@ -536,8 +547,14 @@ __global__ void __launch_bounds__(NTHREADS, 1) savi_bwd_umma_kernel(const __grid
                     write_operand(c, xop(L, 0), dx1);
                     signal_operand(c);
                     float dO[KH], dQ[KH], dK[KH], dV[KH];
-                    wait_acc(c); load_acc(c, TB_B, dO);
-                    mha_core_bwd(c, d.heads, hscale, dO, p_q, p_k, p_v, p_att, dQ, dK, dV);
+                    {
+                        float qv[KH], kv[KH], vv[KH], attv[ATT_PT];
+                        load_field(c, p_q, F, o, qv); load_field(c, p_k, F, o, kv); load_field(c, p_v, F, o, vv);
+#pragma unroll
+                        for (int e = 0; e < ATT_PT; ++e) { const int idx = tid + e * NCT; attv[e] = (idx < d.heads * K * K) ? p_att[idx] : 0.f; }
+                        wait_acc(c); load_acc(c, TB_B, dO);
+                        mha_core_bwd(c, d.heads, hscale, dO, qv, kv, vv, attv, dQ, dK, dV);
+                    }
                     if (lead) {
                         save_field(c, frow(W, a.wl.pdq, f, b, B, K, F), F, o, dQ);
                         save_field(c, frow(W, a.wl.pdk, f, b, B, K, F), F, o, dK);
@@ -545,13 +562,13 @@ __global__ void __launch_bounds__(NTHREADS, 1) savi_bwd_umma_kernel(const __grid
                     }
                     write_operand(c, xop(L, 1), dQ); write_operand(c, xop(L, 2), dK); write_operand(c, xop(L, 3), dV);
                     signal_operand(c);
+                    const float* x_in = (j == 0) ? px0 : frow(fbw, a.sl.px2, (int64_t)(j - 1) * (d.T - 1) + t, b, B, K, F);
+                    load_field(c, x_in, F, o, xin);
                     wait_acc(c); load_acc(c, TB_A, t1);                                    // dy
                     if (j == 0) {
 #pragma unroll
                         for (int kk = 0; kk < KH; ++kk) t1[kk] += dx1[kk];                 // residual taken from the normalised input
                     }
-                    const float* x_in = (j == 0) ? px0 : frow(fbw, a.sl.px2, (int64_t)(j - 1) * (d.T - 1) + t, b, B, K, F);
-                    load_field(c, x_in, F, o, xin);
                     slot_stats(c, xin, d.ln_eps);
                     {
                         float dg = 0.f, dbt = 0.f;
@@ -576,6 +593,30 @@ __global__ void __launch_bounds__(NTHREADS, 1) savi_bwd_umma_kernel(const __grid
                 const int64_t s = (int64_t)t * d.I + it;
                 float* fbw = const_cast<float*>(fb);
                 UPH(25);
+                if (tid == 32 && s > 0) {
+                    // The saved records are read in reverse order of their creation and do not fit L2 as a whole:
+                    // pull the previous step's rows (the next ones this kernel needs) into L2 while this step runs.
+                    const int64_t sp = s - 1;
+                    const uint32_t rowb = (uint32_t)K * F * 4u;
+                    prefetch_l2(frow(fbw, a.sl.r, sp, b, B, K, F), rowb); prefetch_l2(frow(fbw, a.sl.z, sp, b, B, K, F), rowb);
+                    prefetch_l2(frow(fbw, a.sl.n, sp, b, B, K, F), rowb); prefetch_l2(frow(fbw, a.sl.ghn, sp, b, B, K, F), rowb);
+                    prefetch_l2(frow(fbw, a.sl.hp, sp, b, B, K, F), rowb); prefetch_l2(frow(fbw, a.sl.qk, sp, b, B, K, F), rowb);
+                    prefetch_l2(frow(fbw, a.sl.ux, sp, b, B, K, F), rowb);
+                    const int itp = (it > 0) ? it - 1 : d.I - 1, tp = (it > 0) ? t : t - 1;
+                    if (itp < d.I - 1) {
+                        const int64_t smp = (int64_t)tp * (d.I - 1) + itp;
+                        prefetch_l2(frow(fbw, a.sl.a, smp, b, B, K, F), rowb); prefetch_l2(frow(fbw, a.sl.hg, smp, b, B, K, F), rowb);
+                    }
+                    if (it == 0 && t > 0) {                                                // the predictor link of frame t-1 comes next
+                        prefetch_l2(fb + a.sl.px0 + ((size_t)(t - 1) * B + b) * K * F, rowb);
+                        for (int j = 0; j < d.blocks; ++j) {
+                            const int64_t f = (int64_t)j * (d.T - 1) + (t - 1);
+                            prefetch_l2(frow(fbw, a.sl.px2, f, b, B, K, F), rowb); prefetch_l2(frow(fbw, a.sl.px1, f, b, B, K, F), rowb);
+                            prefetch_l2(frow(fbw, a.sl.pq, f, b, B, K, F), rowb); prefetch_l2(frow(fbw, a.sl.pk, f, b, B, K, F), rowb);
+                            prefetch_l2(frow(fbw, a.sl.pv, f, b, B, K, F), rowb); prefetch_l2(frow(fbw, a.sl.pf, f, b, B, K, 4 * F), 4 * rowb);
+                        }
+                    }
+                }
                 if (it < d.I - 1) {
                     // ---- residual MLP backward (steve.py:92-93) ----
                     const int64_t smi = (int64_t)t * (d.I - 1) + it;
@@ -631,16 +672,17 @@ __global__ void __launch_bounds__(NTHREADS, 1) savi_bwd_umma_kernel(const __grid
                 }
                 UPH(27);
                 float v[KH], dux[KH];
+                // operands of the token pass that do not depend on dUx: qk (saved), Ux, 1/S (loads issued before the wait)
+                float qk[KH], ux[KH];
+                load_field(c, frow(fbw, a.sl.qk, s, b, B, K, F), F, o, qk);
+                load_field(c, frow(fbw, a.sl.ux, s, b, B, K, F), F, o, ux);
+                const float ssv = (tid < K) ? fb[a.sl.ssum + (s * B + b) * KP + tid] : 1.f;
                 wait_acc(c); load_acc(c, TB_A, v);                                         // dU
                 UPH(28);
                 if (lead) save_field(c, frow(W, a.wl.du, s, b, B, K, F), F, o, v);
                 write_operand(c, xop(L, 2), v);
                 signal_operand(c);
-                // operands of the token pass that do not depend on dUx: qk (saved), 1/S
-                float qk[KH], ux[KH];
-                load_field(c, frow(fbw, a.sl.qk, s, b, B, K, F), F, o, qk);
-                load_field(c, frow(fbw, a.sl.ux, s, b, B, K, F), F, o, ux);
-                if (tid < 32) cv[32 + tid] = (tid < K) ? 1.0f / fb[a.sl.ssum + (s * B + b) * KP + tid] : 0.f;
+                if (tid < 32) cv[32 + tid] = (tid < K) ? 1.0f / ssv : 0.f;
                 wait_acc(c); load_acc(c, TB_B, dux);                                       // dUx
                 UPH(29);
                 if (lead) save_field(c, frow(W, a.wl.duxs, s, b, B, K, F), F, o, dux);
@@ -731,7 +773,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) savi_bwd_umma_kernel(const __grid
                 atomicAdd(G + po.bhh + o, a_dr); atomicAdd(G + po.bhh + F + o, a_dz); atomicAdd(G + po.bhh + 2 * F + o, a_dnr);
             }
         }
-        if (dbg) for (int i = 0; i < 64; ++i) if (sdbg[i]) a.dbg[i] += sdbg[i];
+        if (dbg) for (int i = 0; i < 60; ++i) if (sdbg[i]) a.dbg[i] += sdbg[i];
     }
     // ---- teardown ----
     __syncwarp();

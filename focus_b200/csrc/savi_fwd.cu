@@ -2,6 +2,7 @@
 //
 // Reference semantics: /root/reference/slowfast/models/STEVE/steve.py:52-105
 // (SlotAttentionVideo.forward) and transformer.py:22-49, 70-86, 106-114.
+#include <cstdlib>
 #include "savi_token_mma.cuh"
 #include "savi_args.h"
 
@@ -66,7 +67,7 @@ __global__ void __launch_bounds__(NT) ln_tokens_fwd_kernel(const TokT* __restric
                     o.y = (v[j][e + 1] - mean) * rstd * gg.y + bb.y;
                     o.z = (v[j][e + 2] - mean) * rstd * gg.z + bb.z;
                     o.w = (v[j][e + 3] - mean) * rstd * gg.w + bb.w;
-                    Tok<TokT>::store4(yr + d, o);
+                    if (xhat) Tok<TokT>::store4(yr + d, o);
                     if (ximg) {
                         __nv_bfloat162 p0 = __floats2bfloat162_rn(o.x, o.y), p1 = __floats2bfloat162_rn(o.z, o.w);
                         uint2 t; t.x = *reinterpret_cast<unsigned*>(&p0); t.y = *reinterpret_cast<unsigned*>(&p1);
@@ -85,6 +86,54 @@ __global__ void __launch_bounds__(NT) ln_tokens_fwd_kernel(const TokT* __restric
             const int n = N + (int)(t % pad);
             *reinterpret_cast<uint4*>(ximg_chunk(ximg, t / pad, n, c * 8, NTILE, D)) = make_uint4(0u, 0u, 0u, 0u);
         }
+    }
+}
+
+// tcgen05 path, D = 128 bf16: 16 lanes per token (one 16-byte chunk each), two tokens per warp, output written
+// only as SWIZZLE_128B operand blocks.  Reads 256 B and writes 256 B per token with full 16-byte accesses.
+static __global__ void __launch_bounds__(256) ln_tokens_fwd_img128_kernel(const __nv_bfloat16* __restrict__ x, float2* __restrict__ stats,
+                                                                   const float* __restrict__ g, const float* __restrict__ b, int64_t rows,
+                                                                   float eps, unsigned char* __restrict__ ximg, int N, int NTILE) {
+    const int lane = threadIdx.x & 31, sub = lane & 15, half = lane >> 4;
+    float gg[8], bb[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) { gg[e] = __ldg(g + sub * 8 + e); bb[e] = __ldg(b + sub * 8 + e); }
+    const int64_t npair = ((int64_t)(rows / N) * NTILE * 128 + 1) / 2;            // padded rows, two per warp
+    for (int64_t pr = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5); pr < npair; pr += (int64_t)gridDim.x * 8) {
+        const int64_t prow = pr * 2 + half;                                       // padded row index: frame * NTILE*128 + n
+        const int64_t frame = prow / (NTILE * 128);
+        const int n = (int)(prow - frame * (NTILE * 128));
+        const bool real = n < N;
+        float v[8];
+        if (real) Tok<__nv_bfloat16>::load(x + (frame * N + n) * 128 + sub * 8, v);
+        else {
+#pragma unroll
+            for (int e = 0; e < 8; ++e) v[e] = 0.f;
+        }
+        float s = 0.f;
+#pragma unroll
+        for (int e = 0; e < 8; ++e) s += v[e];
+#pragma unroll
+        for (int o = 8; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+        const float mean = s * (1.0f / 128.0f);
+        float q = 0.f;
+#pragma unroll
+        for (int e = 0; e < 8; ++e) { const float t = v[e] - mean; q = fmaf(t, t, q); }
+#pragma unroll
+        for (int o = 8; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
+        const float rstd = 1.0f / sqrtf(q * (1.0f / 128.0f) + eps);
+        uint4 out = make_uint4(0u, 0u, 0u, 0u);
+        if (real) {
+            if (sub == 0) stats[frame * N + n] = make_float2(mean, rstd);
+            float y[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) y[e] = (v[e] - mean) * rstd * gg[e] + bb[e];
+            __nv_bfloat162 p0 = __floats2bfloat162_rn(y[0], y[1]), p1 = __floats2bfloat162_rn(y[2], y[3]);
+            __nv_bfloat162 p2 = __floats2bfloat162_rn(y[4], y[5]), p3 = __floats2bfloat162_rn(y[6], y[7]);
+            out.x = *reinterpret_cast<unsigned*>(&p0); out.y = *reinterpret_cast<unsigned*>(&p1);
+            out.z = *reinterpret_cast<unsigned*>(&p2); out.w = *reinterpret_cast<unsigned*>(&p3);
+        }
+        *reinterpret_cast<uint4*>(ximg_chunk(ximg, frame, n, sub * 8, NTILE, 128)) = out;   // padding rows are zero-filled
     }
 }
 
@@ -464,10 +513,23 @@ __global__ void __launch_bounds__(NT, 1) savi_fwd_kernel(const __grid_constant__
 template <typename TokT>
 static cudaError_t launch_ln_fwd(const FwdArgs& a, const void* inputs, cudaStream_t st) {
     const int64_t rows = (int64_t)a.d.B * a.d.T * a.d.N;
+    if constexpr (sizeof(TokT) == 2) {
+        if (a.d.umma && a.d.D == 128 && !getenv("SAVI_UMMA_FWD_ONLY")) {
+            const int64_t npair = ((int64_t)a.d.B * a.d.T * a.d.NTILE * 128 + 1) / 2;
+            int grid = (int)((npair + 7) / 8);
+            if (grid > 148 * 16) grid = 148 * 16;
+            ln_tokens_fwd_img128_kernel<<<grid, 256, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(inputs),
+                reinterpret_cast<float2*>(a.saved + a.sl.stats), a.packed + a.po.ln_in_w, a.packed + a.po.ln_in_b, rows, a.d.ln_eps,
+                a.saved + a.sl.ximg, a.d.N, a.d.NTILE);
+            return cudaGetLastError();
+        }
+    }
     int grid = (int)((rows + NW - 1) / NW);
     if (grid > 148 * 16) grid = 148 * 16;
     ln_tokens_fwd_kernel<TokT><<<grid, NT, 0, st>>>(
-        reinterpret_cast<const TokT*>(inputs), reinterpret_cast<TokT*>(a.saved + a.sl.xhat),
+        reinterpret_cast<const TokT*>(inputs),
+        // the tcgen05 kernels read only the blocked image; the row-major copy is kept for the mma.sync backward (development toggle)
+        (a.d.umma && !getenv("SAVI_UMMA_FWD_ONLY")) ? nullptr : reinterpret_cast<TokT*>(a.saved + a.sl.xhat),
         reinterpret_cast<float2*>(a.saved + a.sl.stats), a.packed + a.po.ln_in_w, a.packed + a.po.ln_in_b, rows, a.d.D,
         a.d.ln_eps, a.d.umma ? a.saved + a.sl.ximg : nullptr, a.d.N, a.d.NTILE);
     return cudaGetLastError();

@@ -30,28 +30,34 @@ struct FwdUArgs {
 // ------------------------------------------------------------------------------------------------
 struct TokState { uint32_t cnt_s[2], cnt_a[2]; };
 
-__device__ __forceinline__ void issue_token_pass(Ring& r, unsigned char* sm, const Smem& L, uint64_t* bars, uint32_t tb, int ntile,
+__device__ __forceinline__ void issue_token_pass(Ring& r, bool el, unsigned char* sm, const Smem& L, uint64_t* bars, uint32_t tb, int ntile,
                                                  TokState& ts, uint32_t qk_op) {
     int ts0[2] = {0, 0};
-    const uint32_t ones = smem_u32(sm + L.ones);
+    const uint32_t ones = dlo_mn(smem_u32(sm + L.ones), 2048);
+    const uint32_t rb = smem_u32(r.base);
     auto p2 = [&](int j) {
         const int g = j & 1;
         mbar_wait(&bars[B_AREADY + g], ts.cnt_a[g] & 1u);
         fence_after_sync();
-        const uint32_t x0 = smem_u32(r.base + (size_t)ts0[g] * BLK);
-        const uint32_t aw = smem_u32(sm + (g ? L.aw1 : L.aw0));
-#pragma unroll 2
-        for (int kt = 0; kt < 8; ++kt) {                              // 16 tokens per k-step
-            const uint64_t bw = desc_mnmajor(aw + kt * 2048, BLK);
-            const bool acc = j > 0 || kt > 0;
-            mma_ss(tb + TC_NUMX, desc_mnmajor(x0 + kt * 2048, BLK), bw, IDESC_MN_MN64, acc);
-            mma_ss(tb + TC_SSUM, desc_mnmajor(ones, 2048), bw, IDESC_MN_MN64, acc);
+        const uint32_t x0 = dlo_mn(rb + ts0[g] * BLK, BLK);
+        const uint32_t aw = dlo_mn(smem_u32(sm + (g ? L.aw1 : L.aw0)), BLK);
+        const uint32_t acc0 = j > 0 ? 1u : 0u;
+        if (el) {
+            mma_lo(tb + TC_NUMX, x0, aw, IDESC_MN_MN64, acc0);
+            mma_lo(tb + TC_SSUM, ones, aw, IDESC_MN_MN64, acc0);
+#pragma unroll
+            for (int kt = 1; kt < 8; ++kt) {                              // 16 tokens per k-step
+                mma_lo(tb + TC_NUMX, x0 + kt * 128, aw + kt * 128, IDESC_MN_MN64, 1u);
+                mma_lo(tb + TC_SSUM, ones, aw + kt * 128, IDESC_MN_MN64, 1u);
+            }
+            mma_commit(&r.empty[ts0[g]]);
+            mma_commit(&r.empty[ts0[g] + 1]);
+            mma_commit(&bars[B_AFREE + g]);
         }
-        mma_commit(&r.empty[ts0[g]]);
-        mma_commit(&r.empty[ts0[g] + 1]);
-        mma_commit(&bars[B_AFREE + g]);
+        __syncwarp();
         ++ts.cnt_a[g];
     };
+    const uint32_t qk0 = dlo_mn(qk_op, BLK);
     for (int i = 0; i < ntile; ++i) {
         const int g = i & 1;
         mbar_wait(&bars[B_SFREE + g], (ts.cnt_s[g] & 1u) ^ 1u);
@@ -62,18 +68,23 @@ __device__ __forceinline__ void issue_token_pass(Ring& r, unsigned char* sm, con
         for (int db = 0; db < 2; ++db) {
             mbar_wait(&r.full[r.stage], r.phase);
             fence_after_sync();
-            const uint32_t a = smem_u32(r.base + (size_t)r.stage * BLK);
+            const uint32_t a = dlo_k(rb + r.stage * BLK);
+            if (el) {
 #pragma unroll
-            for (int k4 = 0; k4 < 4; ++k4)
-                mma_ss(acc_s, desc_kmajor(a + k4 * 32), desc_mnmajor(qk_op + (db * 4 + k4) * 2048, BLK), IDESC_K_MN64, db > 0 || k4 > 0);
+                for (int k4 = 0; k4 < 4; ++k4)
+                    mma_lo(acc_s, a + k4 * 2, qk0 + (db * 4 + k4) * 128, IDESC_K_MN64, (db > 0 || k4 > 0) ? 1u : 0u);
+            }
+            __syncwarp();
             r.advance();
         }
-        mma_commit(&bars[B_SFULL + g]);
+        if (el) mma_commit(&bars[B_SFULL + g]);
+        __syncwarp();
         ++ts.cnt_s[g];
         if (i >= 1) p2(i - 1);
     }
     p2(ntile - 1);
-    mma_commit(&bars[B_TOK]);
+    if (el) mma_commit(&bars[B_TOK]);
+    __syncwarp();
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -257,6 +268,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) savi_fwd_umma_kernel(const __grid
 
     Ring ring;
     ring.base = sm + L.ring; ring.full = &bars[B_FULL]; ring.empty = &bars[B_EMPTY]; ring.nst = L.nst; ring.stage = 0; ring.phase = 0;
+    ring.wait_cycles = nullptr;
 
     if (warp == W_PROD) {
         // =====================================================================================
@@ -291,52 +303,63 @@ __global__ void __launch_bounds__(NTHREADS, 1) savi_fwd_umma_kernel(const __grid
         // =====================================================================================
         // tcgen05.mma issuer
         // =====================================================================================
-        if (lane == 0) {
+        {
+            const bool el = elect_one();
             uint32_t ph_opnd = 0, pcall = 0;
             TokState ts = {{0, 0}, {0, 0}};
             const uint32_t opA = smem_u32(sm + L.opA), opB = smem_u32(sm + L.opB), opC = smem_u32(sm + L.opC);
             const uint32_t aw0 = smem_u32(sm + L.aw0), aw1 = smem_u32(sm + L.aw1);
-            auto wait_opnd = [&]() { mbar_wait(&bars[B_OPND], ph_opnd); ph_opnd ^= 1u; fence_after_sync(); };
+            // development counters of the issuer (CTA 0): [60] waiting for operands, [61] waiting for ring blocks, [62] token pass, [63] total
+            long long* idbg = (a.dbg && blockIdx.x == 0 && el) ? reinterpret_cast<long long*>(sm + L.bars + NBAR * 8 + 16) : nullptr;
+            long long i_opnd = 0, i_ring = 0, i_tok = 0;
+            const long long i_t0 = clock64();
+            if (a.dbg && blockIdx.x == 0) ring.wait_cycles = &i_ring;
+            auto wait_opnd = [&]() {
+                const long long t0 = clock64();
+                mbar_wait(&bars[B_OPND], ph_opnd); ph_opnd ^= 1u; fence_after_sync();
+                i_opnd += clock64() - t0;
+            };
             for (int t = 0; t < d.T; ++t) {
                 for (int it = 0; it < d.I; ++it) {
                     wait_opnd();                                                          // s~ in opA, h_prev in opC
-                    issue_linear(ring, opA, tb + TC_A, 1, 2, false); mma_commit(&bars[B_ACC]);          // q   (steve.py:75)
+                    issue_linear(ring, el, opA, tb + TC_A, 1, 2, false); if (el) mma_commit(&bars[B_ACC]);          // q   (steve.py:75)
                     wait_opnd();                                                          // q in opB
-                    issue_linear(ring, opB, tb + TC_B, 1, 2, false); mma_commit(&bars[B_ACC]);          // qk  (fold of :61,63,76)
+                    issue_linear(ring, el, opB, tb + TC_B, 1, 2, false); if (el) mma_commit(&bars[B_ACC]);          // qk  (fold of :61,63,76)
                     wait_opnd();                                                          // qk in opA
-                    issue_token_pass(ring, sm, L, bars, tb, ntile, ts, opA);
+                    { const long long t0 = clock64(); issue_token_pass(ring, el, sm, L, bars, tb, ntile, ts, opA); i_tok += clock64() - t0; }
                     // GRU hidden-side product, off the critical path: runs while the compute threads combine the partial sums.
                     // (It must not be streamed while token tiles are held in the ring: the ring is filled in order.)
-                    issue_linear(ring, opC, tb + TC_R, 3, 2, false);                      // R, Z, HN = W_hh . h_prev
+                    issue_linear(ring, el, opC, tb + TC_R, 3, 2, false);                      // R, Z, HN = W_hh . h_prev
                     wait_opnd();                                                          // Ux in opB
-                    issue_linear(ring, opB, tb + TC_A, 1, 2, false); mma_commit(&bars[B_ACC]);          // updates (:83)
+                    issue_linear(ring, el, opB, tb + TC_A, 1, 2, false); if (el) mma_commit(&bars[B_ACC]);          // updates (:83)
                     wait_opnd();                                                          // U in opA
-                    issue_linear(ring, opA, tb + TC_R, 2, 2, true);                                      // R, Z += W_i{r,z} . U
-                    issue_linear(ring, opA, tb + TC_IN, 1, 2, false); mma_commit(&bars[B_ACC]);         // IN = W_in . U   (:87)
+                    issue_linear(ring, el, opA, tb + TC_R, 2, 2, true);                                      // R, Z += W_i{r,z} . U
+                    issue_linear(ring, el, opA, tb + TC_IN, 1, 2, false); if (el) mma_commit(&bars[B_ACC]);         // IN = W_in . U   (:87)
                     if (it < d.I - 1) {
                         wait_opnd();                                                      // LN_m(h') in opB
-                        issue_linear(ring, opB, tb + TC_A, 1, 2, false); mma_commit(&bars[B_ACC]);      // mlp.0 (:92)
+                        issue_linear(ring, el, opB, tb + TC_A, 1, 2, false); if (el) mma_commit(&bars[B_ACC]);      // mlp.0 (:92)
                         wait_opnd();                                                      // a in opA
-                        issue_linear(ring, opA, tb + TC_B, 1, 2, false); mma_commit(&bars[B_ACC]);      // mlp.2
+                        issue_linear(ring, el, opA, tb + TC_B, 1, 2, false); if (el) mma_commit(&bars[B_ACC]);      // mlp.2
                     }
                 }
                 if (t < d.T - 1) {
                     for (int j = 0; j < d.blocks; ++j) {
                         wait_opnd();                                                      // y in opA
-                        issue_linear(ring, opA, tb + TC_R, 3, 2, false); mma_commit(&bars[B_ACC]);      // q, k, v -> R, Z, HN columns
+                        issue_linear(ring, el, opA, tb + TC_R, 3, 2, false); if (el) mma_commit(&bars[B_ACC]);      // q, k, v -> R, Z, HN columns
                         wait_opnd();                                                      // attention output in opB
-                        issue_linear(ring, opB, tb + TC_A, 1, 2, false); mma_commit(&bars[B_ACC]);      // proj_o
+                        issue_linear(ring, el, opB, tb + TC_A, 1, 2, false); if (el) mma_commit(&bars[B_ACC]);      // proj_o
                         wait_opnd();                                                      // LN2 in opA
-                        for (int f = 0; f < 4; ++f) { issue_linear(ring, opA, tb + TC_F0 + 64 * f, 1, 2, false); mma_commit(&bars[B_FACC + f]); }   // ffn.0
+                        for (int f = 0; f < 4; ++f) { issue_linear(ring, el, opA, tb + TC_F0 + 64 * f, 1, 2, false); if (el) mma_commit(&bars[B_FACC + f]); }   // ffn.0
                         for (int f = 0; f < 4; ++f) {                                     // ffn.2, contraction split in 4 chunks of 128
                             mbar_wait(&bars[B_FOPND + f], pcall & 1u); fence_after_sync();
-                            issue_linear(ring, f == 0 ? opB : f == 1 ? opC : f == 2 ? aw0 : aw1, tb + TC_B, 1, 2, f > 0);
+                            issue_linear(ring, el, f == 0 ? opB : f == 1 ? opC : f == 2 ? aw0 : aw1, tb + TC_B, 1, 2, f > 0);
                         }
-                        mma_commit(&bars[B_ACC]);
+                        if (el) mma_commit(&bars[B_ACC]);
                         ++pcall;
                     }
                 }
             }
+            if (idbg) { a.dbg[60] += i_opnd; a.dbg[61] += i_ring; a.dbg[62] += i_tok; a.dbg[63] += clock64() - i_t0; }
         }
     } else {
         // =====================================================================================
@@ -547,7 +570,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) savi_fwd_umma_kernel(const __grid
                 UPH(20);
             }
         }
-        if (dbg) for (int i = 0; i < 64; ++i) if (sdbg[i]) a.dbg[i] += sdbg[i];
+        if (dbg) for (int i = 0; i < 60; ++i) if (sdbg[i]) a.dbg[i] += sdbg[i];
     }
     // ---- teardown ----
     __syncwarp();

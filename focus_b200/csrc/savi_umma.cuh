@@ -52,9 +52,28 @@ __device__ __forceinline__ void mma_ss(uint32_t d_tmem, uint64_t adesc, uint64_t
                  "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}\n"
                  :: "r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"((uint32_t)accumulate) : "memory");
 }
+// Issue-efficient form for the hot loops: the single issuing thread is latency-bound on its own instruction
+// stream, so the descriptors are kept as (lo, hi) register pairs; hi is a compile-time constant per layout and
+// stepping along K is one 32-bit add on lo (start address field, 16-byte units).
+constexpr uint32_t DHI = (1024u >> 4) | (1u << 14) | (2u << 29);       // SBO = 1024 B, version 1, SWIZZLE_128B
+// (inside a cluster the shared::cta window address carries the CTA's rank in its upper bits: keep the 18-bit mask)
+__device__ __forceinline__ constexpr uint32_t dlo_k(uint32_t saddr) { return ((saddr & 0x3FFFFu) >> 4) | ((16u >> 4) << 16); }
+__device__ __forceinline__ constexpr uint32_t dlo_mn(uint32_t saddr, uint32_t blk_stride) { return ((saddr & 0x3FFFFu) >> 4) | ((blk_stride >> 4) << 16); }
+__device__ __forceinline__ void mma_lo(uint32_t d_tmem, uint32_t alo, uint32_t blo, uint32_t idesc, uint32_t accumulate) {
+    asm volatile("{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\tmov.b64 da, {%1, %5};\n\tmov.b64 db, {%2, %5};\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                 "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %3, p;\n\t}\n"
+                 :: "r"(d_tmem), "r"(alo), "r"(blo), "r"(idesc), "r"(accumulate), "r"(DHI) : "memory");
+}
 // all MMAs issued so far by this thread arrive on `bar` when they have completed (implies fence::before_thread_sync)
 __device__ __forceinline__ void mma_commit(uint64_t* bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n" :: "r"(smem_u32(bar)) : "memory");
+}
+
+// one lane of a fully active warp
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}\n" : "=r"(pred));
+    return pred != 0;
 }
 
 // ---- TMEM ------------------------------------------------------------------------------------
@@ -138,6 +157,10 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t by
 __device__ __forceinline__ void bulk_g2s_mcast(void* dst, const void* src, uint32_t bytes, uint64_t* bar, uint16_t mask) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1], %2, [%3], %4;\n"
                  :: "r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)), "h"(mask) : "memory");
+}
+// bring `bytes` (multiple of 16, 16-byte aligned) of global memory into L2; fire and forget
+__device__ __forceinline__ void prefetch_l2(const void* src, uint32_t bytes) {
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;\n" :: "l"(src), "r"(bytes) : "memory");
 }
 // generic-proxy shared-memory writes -> visible to the async proxy (tensor core / TMA reads)
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory"); }

@@ -112,6 +112,7 @@ enum { B_FULL = 0, B_EMPTY = 12, B_OPND = 24, B_ACC = 25, B_SFULL = 26, B_SFREE 
 
 struct Ring {
     unsigned char* base; uint64_t* full; uint64_t* empty; int nst; int stage; uint32_t phase;
+    long long* wait_cycles;      // development: cycles the issuer spent waiting for ring blocks (nullptr = off)
     __device__ __forceinline__ void advance() { if (++stage == nst) { stage = 0; phase ^= 1u; } }
 };
 
@@ -129,26 +130,36 @@ __device__ __forceinline__ void prod_blocks(Ring& r, const unsigned char* src, i
 // One linear layer, transposed: acc[rt] (+)= Wimg[rt] . X^T.  Weight blocks arrive through the ring in image
 // order (rt, cb, hi, lo).  xop: shared address of the activation operand; its rows [cb*64, cb*64 + 64) are the
 // contraction range of block cb.  Accumulators are 64 columns wide (32 slots x {hi, lo} of X).
-__device__ __forceinline__ void issue_linear(Ring& r, uint32_t xop, uint32_t tacc, int ntile, int ncb, bool accumulate) {
+// The WHOLE issuer warp runs this code with warp-uniform values and only the tcgen05 instructions are predicated
+// on one elected lane `el`: the descriptors then live in uniform registers.  (Issued from single-lane divergent
+// code, every tcgen05.mma is wrapped in a register-to-uniform "waterfall" loop of ~100 cycles.)
+__device__ __forceinline__ void issue_linear(Ring& r, bool el, uint32_t xop, uint32_t tacc, int ntile, int ncb, bool accumulate) {
     for (int rt = 0; rt < ntile; ++rt) {
         const uint32_t d = tacc + rt * 64;
         for (int cb = 0; cb < ncb; ++cb) {
-            const uint32_t xb = xop + cb * 8192;                         // 64 rows x 128 B
-            mbar_wait(&r.full[r.stage], r.phase);
+            const uint32_t xb = dlo_mn(xop + cb * 8192, BLK);              // 64 rows x 128 B of the activation operand
+            if (r.wait_cycles) { const long long t0 = clock64(); mbar_wait(&r.full[r.stage], r.phase); if (el) *r.wait_cycles += clock64() - t0; }
+            else mbar_wait(&r.full[r.stage], r.phase);
             fence_after_sync();
-            uint32_t a = smem_u32(r.base + (size_t)r.stage * BLK);
+            uint32_t a = dlo_k(smem_u32(r.base) + r.stage * BLK);
+            if (el) {
+                mma_lo(d, a, xb, IDESC_K_MN64, (accumulate || cb > 0) ? 1u : 0u);
 #pragma unroll
-            for (int k4 = 0; k4 < 4; ++k4)
-                mma_ss(d, desc_kmajor(a + k4 * 32), desc_mnmajor(xb + k4 * 2048, BLK), IDESC_K_MN64, accumulate || cb > 0 || k4 > 0);
-            mma_commit(&r.empty[r.stage]);
+                for (int k4 = 1; k4 < 4; ++k4) mma_lo(d, a + k4 * 2, xb + k4 * 128, IDESC_K_MN64, 1u);
+                mma_commit(&r.empty[r.stage]);
+            }
+            __syncwarp();
             r.advance();
-            mbar_wait(&r.full[r.stage], r.phase);
+            if (r.wait_cycles) { const long long t0 = clock64(); mbar_wait(&r.full[r.stage], r.phase); if (el) *r.wait_cycles += clock64() - t0; }
+            else mbar_wait(&r.full[r.stage], r.phase);
             fence_after_sync();
-            a = smem_u32(r.base + (size_t)r.stage * BLK);
+            a = dlo_k(smem_u32(r.base) + r.stage * BLK);
+            if (el) {
 #pragma unroll
-            for (int k4 = 0; k4 < 4; ++k4)
-                mma_ss(d, desc_kmajor(a + k4 * 32), desc_mnmajor(xb + k4 * 2048, BLK), IDESC_K_MN32, true);
-            mma_commit(&r.empty[r.stage]);
+                for (int k4 = 0; k4 < 4; ++k4) mma_lo(d, a + k4 * 2, xb + k4 * 128, IDESC_K_MN32, 1u);
+                mma_commit(&r.empty[r.stage]);
+            }
+            __syncwarp();
             r.advance();
         }
     }

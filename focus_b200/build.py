@@ -13,6 +13,7 @@ UNITS = [("savi_api.cu", "savi_api.o", []),
          ("savi_wgrad.cu", "savi_wgrad.o", []),
          ("savi_fwd_umma.cu", "savi_fwd_umma.o", []),
          ("savi_bwd_umma.cu", "savi_bwd_umma.o", []),
+         ("savi_dx_umma.cu", "savi_dx_umma.o", []),
          ("savi_fwd.cu", "savi_fwd_f32.o", ["-DSAVI_TOK=float", "-DSAVI_SUFFIX=f32"]),
          ("savi_fwd.cu", "savi_fwd_bf16.o", ["-DSAVI_TOK=__nv_bfloat16", "-DSAVI_SUFFIX=bf16"]),
          ("savi_bwd.cu", "savi_bwd_f32.o", ["-DSAVI_TOK=float", "-DSAVI_SUFFIX=f32"]),

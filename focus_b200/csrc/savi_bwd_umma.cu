@@ -91,10 +91,10 @@ __device__ __forceinline__ void issue_token_pass_bwd(Ring& r, bool el, uint64_t*
 // ------------------------------------------------------------------------------------------------
 // compute threads: recompute P, form dL and W for this group's token tiles (thread = token, half of the slots)
 //   dP = (G - c)/S (+ grad_attn);  dL = P (dP - <P, dP>);  W = (P + eps)/S          
-// cv: shared [64] = c[32] | 1/S[32].  coef: staged [2][KC][N] bf16 (dL^T, W^T) of this (b, t, i).
+// cv: shared [64] = c[32] | 1/S[32].  coef: first coefficient block of this (frame, iteration): tile j's block is j * I * 16 KB further.
 // ------------------------------------------------------------------------------------------------
 __device__ __forceinline__ void softmax_bwd_tiles(const Ctx& c, const Dims& d, int ntile, int tile0, const bf16* gattn_frame,
-                                                  bf16* coef, const float* cv, int dl0_off, int dl1_off, TokState& ts, long long* dbg) {
+                                                  unsigned char* coef, const float* cv, int dl0_off, int dl1_off, TokState& ts, long long* dbg) {
     constexpr float LOG2E = 1.4426950408889634f;
     long long ph_last = clock64();
     const int K = c.K, p = c.wg >> 1, h = c.wg & 1;
@@ -205,12 +205,26 @@ __device__ __forceinline__ void softmax_bwd_tiles(const Ctx& c, const Dims& d, i
         if (c.lane == 0) mbar_arrive(&c.bars[B_AREADY + p]);
         ++ts.cnt_a[p];
         UPH(58);
-        if (valid) {                                             // coefficients of the d_inputs kernel: [slot][token], token contiguous
-            bf16* cl = coef + (size_t)s0 * d.N + n;
-            bf16* cw = coef + (size_t)(d.KC + s0) * d.N + n;
+        if (valid) {
+            // coefficients of the d_inputs kernel: this token's row of the iteration's K-major operand block,
+            // [128 tokens][32 dL | 32 W] bf16, SWIZZLE_128B (savi_dx_umma.cu fetches the block with one bulk copy)
+            unsigned char* row = coef + (size_t)(tile0 + i) * d.I * 16384 + (size_t)c.o * 128;
 #pragma unroll
-            for (int s = 0; s < 16; ++s) {
-                if (s < ns) { cl[(size_t)s * d.N] = __float2bfloat16_rn(gq[s]); cw[(size_t)s * d.N] = __float2bfloat16_rn(l[s]); }
+            for (int s = 0; s < 16; s += 4) {
+                if (s < KHs) {
+                    const uint32_t bo = (uint32_t)(s0 + s) * 2u;
+                    *reinterpret_cast<uint2*>(row + (((bo >> 4) ^ sw) << 4) + (bo & 15u)) =
+                        make_uint2(pack_bf16x2(gq[s], gq[s + 1]), pack_bf16x2(gq[s + 2], gq[s + 3]));
+                    *reinterpret_cast<uint2*>(row + ((((bo + 64u) >> 4) ^ sw) << 4) + (bo & 15u)) =
+                        make_uint2(pack_bf16x2(l[s], l[s + 1]), pack_bf16x2(l[s + 2], l[s + 3]));
+                }
+            }
+            if (h == 1) {                                        // slots [2 KHs, 32) belong to nobody: keep them finite (zero)
+                for (int sp = 2 * KHs; sp < 32; sp += 4) {
+                    const uint32_t bo = (uint32_t)sp * 2u;
+                    *reinterpret_cast<uint2*>(row + (((bo >> 4) ^ sw) << 4) + (bo & 15u)) = make_uint2(0u, 0u);
+                    *reinterpret_cast<uint2*>(row + ((((bo + 64u) >> 4) ^ sw) << 4) + (bo & 15u)) = make_uint2(0u, 0u);
+                }
             }
         }
         UPH(59);
@@ -333,7 +347,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) savi_bwd_umma_kernel(const __grid
     const float* fb = reinterpret_cast<const float*>(a.saved + a.sl.fbase);
     const unsigned char* ximg = a.saved + a.sl.ximg;
     float* W = a.ws;
-    bf16* coef_base = reinterpret_cast<bf16*>(reinterpret_cast<unsigned char*>(W) + a.wl.coef);
+    unsigned char* coef_base = reinterpret_cast<unsigned char*>(W) + a.wl.coef;
     const int scr2 = L.aw1;                                   // float2 [K][128] LayerNorm-backward scratch: aw1 + scratch (contiguous, 16 KB + K*512 B)
     float* cv = reinterpret_cast<float*>(sm + L.stats + 256);  // [64]: c | 1/S
 
@@ -466,19 +480,6 @@ __global__ void __launch_bounds__(NTHREADS, 1) savi_bwd_umma_kernel(const __grid
         // per-feature parameter-gradient accumulators over all steps of this clip (added to the flat buffer at the end)
         float a_gs = 0.f, a_bs = 0.f, a_gm = 0.f, a_bm = 0.f, a_b1 = 0.f, a_b2 = 0.f;
         float a_dr = 0.f, a_dz = 0.f, a_dn = 0.f, a_dnr = 0.f;
-        // the padding rows [K, KC) of every coefficient block of this CTA's tokens must be finite: zero them once
-        if (d.KC > K) {
-            const int n_lo = tile0 * 128, n_hi = min(d.N, (tile0 + ntile) * 128);
-            const int padr = d.KC - K, span = n_hi - n_lo;
-            const int64_t items = (int64_t)d.T * d.I * 2 * padr * span;
-            for (int64_t i = tid; i < items; i += NCT) {
-                const int n = n_lo + (int)(i % span);
-                int64_t r = i / span;
-                const int pr = (int)(r % padr); r /= padr;
-                const int which = (int)(r & 1); r >>= 1;                                   // r = t * I + it
-                coef_base[((((size_t)b * d.T * d.I + r) * 2 + which) * d.KC + K + pr) * d.N + n] = __float2bfloat16_rn(0.f);
-            }
-        }
         float dh[KH];
 #pragma unroll
         for (int kk = 0; kk < KH; ++kk) dh[kk] = 0.f;
@@ -506,6 +507,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) savi_bwd_umma_kernel(const __grid
                     const float* p_x1 = frow(fbw, a.sl.px1, f, b, B, K, F);
                     const float* p_f = frow(fbw, a.sl.pf, f, b, B, K, 4 * F);
                     const float* p_att = fb + a.sl.patt + (f * B + b) * ((int64_t)d.heads * K * K);
+                    UPH(37);
                     // t0 = d x2
                     if (lead) { save_field(c, frow(W, a.wl.pdx2, f, b, B, K, F), F, o, t0); atomicAdd(G + bo.f2b + o, sum8(c, t0)); }
                     write_operand(c, xop(L, 0), t0);
@@ -532,9 +534,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) savi_bwd_umma_kernel(const __grid
                     write_operand(c, xop(L, 0), df0);
                     signal_operand(c, B_FOPND + 0);
                     ++pcall;
+                    UPH(38);
                     float t1[KH], dx1[KH], x1v[KH];
                     load_field(c, p_x1, F, o, x1v);
                     wait_acc(c); load_acc(c, TB_A, t1);                                    // d l2
+                    UPH(39);
                     slot_stats(c, x1v, d.ln_eps);
                     {
                         float dg = 0.f, dbt = 0.f;
@@ -546,6 +550,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) savi_bwd_umma_kernel(const __grid
                     if (lead) save_field(c, frow(W, a.wl.pdx1, f, b, B, K, F), F, o, dx1);
                     write_operand(c, xop(L, 0), dx1);
                     signal_operand(c);
+                    UPH(40);
                     float dO[KH], dQ[KH], dK[KH], dV[KH];
                     {
                         float qv[KH], kv[KH], vv[KH], attv[ATT_PT];
@@ -553,7 +558,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) savi_bwd_umma_kernel(const __grid
 #pragma unroll
                         for (int e = 0; e < ATT_PT; ++e) { const int idx = tid + e * NCT; attv[e] = (idx < d.heads * K * K) ? p_att[idx] : 0.f; }
                         wait_acc(c); load_acc(c, TB_B, dO);
+                        UPH(41);
                         mha_core_bwd(c, d.heads, hscale, dO, qv, kv, vv, attv, dQ, dK, dV);
+                        UPH(42);
                     }
                     if (lead) {
                         save_field(c, frow(W, a.wl.pdq, f, b, B, K, F), F, o, dQ);
@@ -564,7 +571,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) savi_bwd_umma_kernel(const __grid
                     signal_operand(c);
                     const float* x_in = (j == 0) ? px0 : frow(fbw, a.sl.px2, (int64_t)(j - 1) * (d.T - 1) + t, b, B, K, F);
                     load_field(c, x_in, F, o, xin);
+                    UPH(43);
                     wait_acc(c); load_acc(c, TB_A, t1);                                    // dy
+                    UPH(44);
                     if (j == 0) {
 #pragma unroll
                         for (int kk = 0; kk < KH; ++kk) t1[kk] += dx1[kk];                 // residual taken from the normalised input
@@ -707,7 +716,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) savi_bwd_umma_kernel(const __grid
                 UPH(30);
                 // ---- attention step backward over the token tiles ----
                 const bf16* ga = (a.grad_attn && it == d.I - 1) ? reinterpret_cast<const bf16*>(a.grad_attn) + ((size_t)b * d.T + t) * d.N * K : nullptr;
-                bf16* coef = coef_base + ((((size_t)b * d.T + t) * d.I + it) * 2 * d.KC) * d.N;
+                unsigned char* coef = coef_base + (((size_t)b * d.T + t) * d.NTILE * d.I + it) * 16384;
                 softmax_bwd_tiles(c, d, ntile, tile0, ga, coef, cv, xop(L, 2), xop(L, 3), ts, dbg);
                 UPH(31);
                 mbar_wait(&bars[B_TOK], step & 1u);

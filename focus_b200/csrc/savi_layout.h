@@ -271,5 +271,8 @@ static inline void savi_bwd_ws_layout(const Dims& d, BwdWsLayout& L) {
     L.cta = g; g += (int64_t)d.B * d.CN * L.cta_floats;
     g = (g + 63) / 64 * 64;
     L.coef = g * 4;
-    L.total_bytes = g * 4 + (d.mma ? (int64_t)d.B * d.T * d.I * 2 * d.KC * d.N * 2 : 0);
+    // tcgen05 path: one 16 KB K-major operand block [128 tokens][32 dL | 32 W] per (frame, tile, iteration)
+    if (d.umma) L.total_bytes = (g * 4 + 1023) / 1024 * 1024 + (int64_t)d.B * d.T * d.NTILE * d.I * 16384;
+    else L.total_bytes = g * 4 + (d.mma ? (int64_t)d.B * d.T * d.I * 2 * d.KC * d.N * 2 : 0);
+    if (d.umma) L.coef = (g * 4 + 1023) / 1024 * 1024;
 }

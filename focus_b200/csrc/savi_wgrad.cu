@@ -136,7 +136,8 @@ cudaError_t savi_launch_backward(const BwdArgs& a, const void* inputs, void* gra
         *launches += 1;
     }
     savi_prof_begin(5, st);
-    if (d.mma) e = savi_launch_dx_mma(a, inputs, grad_inputs, st);
+    if (umma_bwd) e = savi_launch_dx_umma(a, inputs, grad_inputs, st);
+    else if (d.mma) e = savi_launch_dx_mma(a, inputs, grad_inputs, st);
     else if (d.tok_bytes == 4) e = savi_launch_ln_bwd_f32(a, inputs, grad_inputs, st);
     else e = savi_launch_ln_bwd_bf16(a, inputs, grad_inputs, st);
     savi_prof_end(5, st);

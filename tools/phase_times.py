@@ -44,14 +44,15 @@ if os.environ.get("SAVI_DISABLE_UMMA") is None and c["D"] == 128:
     for i in range(60, 64): v[i] = 0
     BN = {25: "b: predictor bwd + grad_slots (per frame)", 26: "b: mlp bwd", 27: "b: gru bwd + operands", 28: "b: WAIT dU", 29: "b: dU epi + loads + WAIT dUx",
           30: "b: c vector + operands", 31: "b: softmax-bwd tiles (total)", 32: "b: WAIT token pass", 33: "b: dqk + exchange", 34: "b: dqk op + WAIT dq",
-          35: "b: dq op + WAIT ds~", 36: "b: LN_s bwd", 55: "  sb: WAIT logits (incl. grad_attn load)", 56: "  sb: ld + softmax + dP + dot", 57: "  sb: WAIT dl free",
+          35: "b: dq op + WAIT ds~", 36: "b: LN_s bwd", 37: "  pb: LN_f / LN1 bwd (+ frame top)", 38: "  pb: dx2 operand, 4 ffn.2^T tiles, df chunks", 39: "  pb: WAIT d l2", 40: "  pb: LN2 bwd + dx1 operand", 41: "  pb: loads + WAIT dO", 42: "  pb: mha core bwd", 43: "  pb: saves + 3 operands", 44: "  pb: WAIT dy",
+          55: "  sb: WAIT logits (incl. grad_attn load)", 56: "  sb: ld + softmax + dP + dot", 57: "  sb: WAIT dl free",
           58: "  sb: write dL + signal", 59: "  sb: coef stores"}
     tot = sum(v[25:37])
     if tot:
         print("UMMA backward, compute thread 0 of CTA 0: total %.1f us" % (tot / 1965.0))
         for i in sorted(BN):
             if v[i]: print("  %-42s %8.1f us  %5.1f%%" % (BN[i], v[i] / 1965.0, 100.0 * v[i] / tot))
-        for i in list(range(25, 37)) + list(range(55, 60)): v[i] = 0
+        for i in list(range(25, 50)) + list(range(55, 60)): v[i] = 0
 tot_f = sum(v[:30]); tot_b = sum(v[30:50])
 print("forward  total %.1f us (cycles @1.965GHz)" % (tot_f / 1965.0))
 for i in range(30):

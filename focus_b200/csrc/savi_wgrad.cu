@@ -118,7 +118,13 @@ cudaError_t savi_launch_backward(const BwdArgs& a, const void* inputs, void* gra
         add_job(wa, W + a.wl.pdf + ro * 4 * Ds, 4 * Ds, fb + a.sl.pl2 + ro * Ds, Ds, G + bo.f1, Rb, 4 * Ds, Ds, 1.0f);
         add_job(wa, W + a.wl.pdx2 + ro * Ds, Ds, fb + a.sl.pf + ro * 4 * Ds, 4 * Ds, G + bo.f2, Rb, Ds, 4 * Ds, 1.0f);
     }
-    if (wa.njobs > 0) {
+    if (wa.njobs > 0 && umma_bwd) {
+        savi_prof_begin(4, st);
+        e = savi_launch_wgrad_umma(wa, st);
+        savi_prof_end(4, st);
+        if (e != cudaSuccess) return e;
+        *launches += 1;
+    } else if (wa.njobs > 0) {
         int maxR = 0, maxTiles = 0;
         for (int j = 0; j < wa.njobs; ++j) {
             maxR = wa.job[j].R > maxR ? wa.job[j].R : maxR;

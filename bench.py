@@ -150,7 +150,8 @@ def config_dict(args, cfg, n):
             else "BASELINE.json config %s" % args.config,
             "clips_per_gpu": cfg["B"], "global_clips": cfg["B"] * n, "T": cfg["T"], "N": cfg["N"], "D": cfg["D"],
             "Ds": cfg["Ds"], "M": cfg["M"], "K": cfg["K"], "iters": cfg["I"], "predictor": "%d block x %d heads" % (cfg["blocks"], cfg["heads"]),
-            "token_dtype": cfg["dtype"], "grad_attn": "dense N(0,1)", "parallelism": "dp%d" % n,
+            "token_dtype": cfg["dtype"], "grad_attn": "dense N(0,1)",
+            "parallelism": "dp%d" % n + ("" if n == 1 else " (torch DDP)" if args.ddp else " (one flat NCCL gradient all-reduce inside backward)"),
             "l2": "flushed between timed steps (256 MiB write outside the event brackets); step working set >> 126 MB L2"}
 
 
@@ -170,9 +171,12 @@ def run_ours(args, cfg, rank, world, local_rank):
     dt = torch.float32 if c["dtype"] == "fp32" else torch.bfloat16
     model = make_params_like(c).to(dev)
     ddp = model
-    if world > 1:
+    if world > 1 and args.ddp:       # stock DistributedDataParallel, what the reference wraps the model in (models/build.py:79-83)
         ddp = torch.nn.parallel.DistributedDataParallel(model, device_ids=[local_rank], output_device=local_rank,
                                                         gradient_as_bucket_view=True, bucket_cap_mb=64)
+    elif world > 1:                  # the path's own exchange step: ONE NCCL all-reduce of the flat gradient buffer inside backward
+        from focus_b200.distributed import attach_grad_sync
+        attach_grad_sync(model)
     g = torch.Generator(device="cpu").manual_seed(1 + rank)
     B, T, N, D, K, Ds = c["B"], c["T"], c["N"], c["D"], c["K"], c["Ds"]
     x_host = torch.randn(B, T, N, D, generator=g).to(dt).pin_memory()
@@ -328,6 +332,7 @@ def main():
     ap.add_argument("--config", default="c2", choices=sorted(CONFIGS))
     ap.add_argument("--clips", type=int, default=0, help="override clips per GPU")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--ddp", action="store_true", help="N>1: wrap the module in torch DDP instead of the fused flat all-reduce")
     args = ap.parse_args()
     cfg = dict(CONFIGS[args.config])
     if args.clips:

@@ -104,7 +104,7 @@ static int validate(const SaviShape* s, Dims& d) {
     d.NTILE = (s->N + 127) / 128;
     d.umma = 0;
     if (d.mma && s->D == 128 && s->Ds == 128 && s->M == 128 && s->K <= 24 && (s->cluster == 0 || s->cluster <= 2) &&
-        (int64_t)s->heads * s->K * (s->K | 1) * 4 <= 16384 && savi_dx_umma_smem_bytes(s->I) <= kMaxSmem && !getenv("SAVI_DISABLE_UMMA")) {
+        savi_umma_mha_fits(s->K, s->heads) && savi_dx_umma_smem_bytes(s->I) <= kMaxSmem && !getenv("SAVI_DISABLE_UMMA")) {
         d.umma = 1;
         d.CN = s->cluster ? s->cluster : ((int64_t)s->B * 2 <= 148 ? 2 : 1);
         if (d.NTILE < d.CN) d.CN = 1;

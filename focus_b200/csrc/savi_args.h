@@ -75,6 +75,7 @@ size_t savi_dx_smem_bytes(const Dims& d);
 static inline int savi_fwd_kmax(int K) { return K <= 8 ? 8 : K <= 16 ? 16 : K <= 24 ? 24 : K <= 32 ? 32 : 64; }
 cudaError_t savi_launch_fwd_umma(const FwdArgs& a, const unsigned char* wimg, const WImg& wi, cudaStream_t st);
 int savi_fwd_umma_smem_bytes(const Dims& d);
+int savi_umma_mha_fits(int K, int heads);        // predictor attention core of the tcgen05 clip kernels fits its shared-memory windows
 cudaError_t savi_launch_bwd_umma(const BwdArgs& a, const unsigned char* wimg, const WImg& wi, cudaStream_t st);
 int savi_bwd_umma_smem_bytes(const Dims& d);
 cudaError_t savi_launch_dx_umma(const BwdArgs& a, const void* inputs, void* grad_inputs, cudaStream_t st);

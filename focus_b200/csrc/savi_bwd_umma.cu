@@ -268,10 +268,13 @@ __device__ __forceinline__ void ln_bwd(const Ctx& c, const float (&dy)[KH], cons
 constexpr int ATT_PT = 8;     // attention-matrix elements per thread: heads * K * K <= 8 * 512
 __device__ __forceinline__ void mha_core_bwd(const Ctx& c, int H, float hscale, const float (&dO)[KH], const float (&Qv)[KH], const float (&Kv)[KH],
                                              const float (&Vv)[KH], const float (&attv)[ATT_PT], float (&dQ)[KH], float (&dK)[KH], float (&dV)[KH]) {
-    const int K = c.K, ld = F + 1, ka = K | 1, dh = F / H;
+    // layout as in the forward core (savi_fwd_umma.cu: mha_core): 16-byte aligned rows, attention rows padded to ka
+    const int K = c.K, ld = MHA_LD, ka = mha_ka(K), dh = F / H;
     float* sO = reinterpret_cast<float*>(c.sm + c.L.opA);             // opA .. scratch are contiguous (5 x 16 KB + scratch)
     float* sQ = sO + K * ld; float* sK = sQ + K * ld; float* sV = sK + K * ld;
-    float* sA = sV + K * ld; float* sD = sA + H * K * ka;
+    float* sA = sV + K * ld;                                          // [H][query][ka key]   probabilities
+    float* sD = sA + H * K * ka;                                      // [H][query][ka key]   d attention -> d logits
+    float* sDT = sD + H * K * ka;                                     // [H][key][ka query]   d logits, transposed
 #pragma unroll
     for (int kk = 0; kk < KH; ++kk) {
         const int k = c.k0 + kk;
@@ -280,39 +283,49 @@ __device__ __forceinline__ void mha_core_bwd(const Ctx& c, int H, float hscale, 
 #pragma unroll
     for (int e = 0; e < ATT_PT; ++e) { const int idx = c.tid + e * NCT; if (idx < H * K * K) sA[(idx / K) * ka + idx % K] = attv[e]; }
     bar_sync_compute();
-    for (int idx = c.tid; idx < H * K * K; idx += NCT) {
+    for (int idx = c.tid; idx < H * K * K; idx += NCT) {              // d attention = dO_h . V_h^T
         const int j = idx % K, i = (idx / K) % K, h = idx / (K * K);
-        const float* a = sO + i * ld + h * dh;
-        const float* v = sV + j * ld + h * dh;
+        const float4* a = reinterpret_cast<const float4*>(sO + i * ld + h * dh);
+        const float4* v = reinterpret_cast<const float4*>(sV + j * ld + h * dh);
         float s = 0.f;
-        for (int e = 0; e < dh; ++e) s = fmaf(a[e], v[e], s);
+        for (int e = 0; e < dh / 4; ++e) {
+            const float4 x = a[e], y = v[e];
+            s = fmaf(x.x, y.x, s); s = fmaf(x.y, y.y, s); s = fmaf(x.z, y.z, s); s = fmaf(x.w, y.w, s);
+        }
         sD[(h * K + i) * ka + j] = s;
     }
     bar_sync_compute();
-    for (int row = c.tid; row < H * K; row += NCT) {
-        const float* a = sA + row * ka;
-        float* da = sD + row * ka;
-        float dot = 0.f;
-        for (int j = 0; j < K; ++j) dot = fmaf(a[j], da[j], dot);
-        for (int j = 0; j < K; ++j) da[j] = a[j] * (da[j] - dot);
+    for (int row = c.warp; row < H * K; row += NCW) {                 // softmax backward: one warp per (head, query) row, lane = key
+        const bool on = c.lane < K;
+        const float a = on ? sA[row * ka + c.lane] : 0.f, da = on ? sD[row * ka + c.lane] : 0.f;
+        const float dl = a * (da - warp_sum(a * da));
+        if (on) { sD[row * ka + c.lane] = dl; sDT[((row / K) * K + c.lane) * ka + row % K] = dl; }
     }
     bar_sync_compute();
-    const int h = c.o / dh;
-    const float* dlg = sD + h * K * ka;
-    const float* at = sA + h * K * ka;
+    const int hb = (c.o / dh) * K * ka + c.k0;
+    const float* dlt = sDT + hb;                                      // row j: d logits [i][j] over this warpgroup's 8 slots i
+    const float* dlg = sD + hb;                                       // row j: d logits [j][i]
+    const float* at = sA + hb;                                        // row j: attention [j][i]
+    float sq[KH], sk[KH], sv[KH];
 #pragma unroll
-    for (int kk = 0; kk < KH; ++kk) {
-        float sq = 0.f, sk = 0.f, sv = 0.f;
-        if (kk < c.nk) {
-            const int i = c.k0 + kk;
-            for (int j = 0; j < K; ++j) {
-                sq = fmaf(dlg[i * ka + j], sK[j * ld + c.o], sq);
-                sk = fmaf(dlg[j * ka + i], sQ[j * ld + c.o], sk);
-                sv = fmaf(at[j * ka + i], sO[j * ld + c.o], sv);
+    for (int kk = 0; kk < KH; ++kk) { sq[kk] = 0.f; sk[kk] = 0.f; sv[kk] = 0.f; }
+    if (c.nk > 0) {
+        for (int j = 0; j < K; ++j) {
+            const float kj = sK[j * ld + c.o], qj = sQ[j * ld + c.o], oj = sO[j * ld + c.o];
+            float t[KH], u[KH], w[KH];                                // warp-uniform 16-byte reads
+            *reinterpret_cast<float4*>(t) = ld4(dlt + j * ka); *reinterpret_cast<float4*>(t + 4) = ld4(dlt + j * ka + 4);
+            *reinterpret_cast<float4*>(u) = ld4(dlg + j * ka); *reinterpret_cast<float4*>(u + 4) = ld4(dlg + j * ka + 4);
+            *reinterpret_cast<float4*>(w) = ld4(at + j * ka); *reinterpret_cast<float4*>(w + 4) = ld4(at + j * ka + 4);
+#pragma unroll
+            for (int kk = 0; kk < KH; ++kk) {
+                sq[kk] = fmaf(t[kk], kj, sq[kk]);
+                sk[kk] = fmaf(u[kk], qj, sk[kk]);
+                sv[kk] = fmaf(w[kk], oj, sv[kk]);
             }
         }
-        dQ[kk] = sq * hscale; dK[kk] = sk; dV[kk] = sv;
     }
+#pragma unroll
+    for (int kk = 0; kk < KH; ++kk) { dQ[kk] = sq[kk] * hscale; dK[kk] = sk[kk]; dV[kk] = sv[kk]; }
     bar_sync_compute();
 }
 
@@ -340,6 +353,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) savi_bwd_umma_kernel(const __grid
     uint64_t* bars = reinterpret_cast<uint64_t*>(sm + L.bars);
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + NBAR);
     const bool lead = (rank == 0);
+    // both CTAs of a pair carry bit-identical slot-state gradients: the staged records are split between them
+    const bool svA = lead, svB = (rank == CN - 1);
     const int per = (d.NTILE + CN - 1) / CN;
     const int tile0 = min(d.NTILE, rank * per), ntile = min(d.NTILE, tile0 + per) - tile0;
     const float* P = a.packed;
@@ -509,7 +524,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) savi_bwd_umma_kernel(const __grid
                     const float* p_att = fb + a.sl.patt + (f * B + b) * ((int64_t)d.heads * K * K);
                     UPH(37);
                     // t0 = d x2
-                    if (lead) { save_field(c, frow(W, a.wl.pdx2, f, b, B, K, F), F, o, t0); atomicAdd(G + bo.f2b + o, sum8(c, t0)); }
+                    if (svB) save_field(c, frow(W, a.wl.pdx2, f, b, B, K, F), F, o, t0);
+                    if (lead) atomicAdd(G + bo.f2b + o, sum8(c, t0));
                     write_operand(c, xop(L, 0), t0);
                     signal_operand(c);
                     // d f = (ffn.2^T d x2) masked by relu; chunks 1..3 go to X1..X3 at once, chunk 0 to X0 after all four tiles are done
@@ -522,7 +538,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) savi_bwd_umma_kernel(const __grid
                         load_acc(c, TB_F0 + 64 * ff, v);
 #pragma unroll
                         for (int kk = 0; kk < KH; ++kk) v[kk] = (fm[kk] > 0.f) ? v[kk] : 0.f;
-                        if (lead) { save_field(c, frow(W, a.wl.pdf, f, b, B, K, 4 * F), 4 * F, ff * F + o, v); atomicAdd(G + bo.f1b + ff * F + o, sum8(c, v)); }
+                        if ((ff & 1) ? svB : svA) { save_field(c, frow(W, a.wl.pdf, f, b, B, K, 4 * F), 4 * F, ff * F + o, v); atomicAdd(G + bo.f1b + ff * F + o, sum8(c, v)); }
                         if (ff == 0) {
 #pragma unroll
                             for (int kk = 0; kk < KH; ++kk) df0[kk] = v[kk];
@@ -547,7 +563,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) savi_bwd_umma_kernel(const __grid
                     }
 #pragma unroll
                     for (int kk = 0; kk < KH; ++kk) dx1[kk] += t0[kk];
-                    if (lead) save_field(c, frow(W, a.wl.pdx1, f, b, B, K, F), F, o, dx1);
+                    if (svB) save_field(c, frow(W, a.wl.pdx1, f, b, B, K, F), F, o, dx1);
                     write_operand(c, xop(L, 0), dx1);
                     signal_operand(c);
                     UPH(40);
@@ -562,11 +578,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) savi_bwd_umma_kernel(const __grid
                         mha_core_bwd(c, d.heads, hscale, dO, qv, kv, vv, attv, dQ, dK, dV);
                         UPH(42);
                     }
-                    if (lead) {
+                    if (svA) {
                         save_field(c, frow(W, a.wl.pdq, f, b, B, K, F), F, o, dQ);
-                        save_field(c, frow(W, a.wl.pdk, f, b, B, K, F), F, o, dK);
                         save_field(c, frow(W, a.wl.pdv, f, b, B, K, F), F, o, dV);
                     }
+                    if (svB) save_field(c, frow(W, a.wl.pdk, f, b, B, K, F), F, o, dK);
                     write_operand(c, xop(L, 1), dQ); write_operand(c, xop(L, 2), dK); write_operand(c, xop(L, 3), dV);
                     signal_operand(c);
                     const float* x_in = (j == 0) ? px0 : frow(fbw, a.sl.px2, (int64_t)(j - 1) * (d.T - 1) + t, b, B, K, F);
@@ -632,14 +648,14 @@ __global__ void __launch_bounds__(NTHREADS, 1) savi_bwd_umma_kernel(const __grid
                     float am[KH], hg[KH], v[KH];
                     load_field(c, frow(fbw, a.sl.a, smi, b, B, K, F), F, o, am);
                     load_field(c, frow(fbw, a.sl.hg, smi, b, B, K, F), F, o, hg);
-                    if (lead) save_field(c, frow(W, a.wl.dhm, smi, b, B, K, F), F, o, dh);
+                    if (svA) save_field(c, frow(W, a.wl.dhm, smi, b, B, K, F), F, o, dh);
                     a_b2 += sum8(c, dh);
                     write_operand(c, xop(L, 0), dh);
                     signal_operand(c);
                     wait_acc(c); load_acc(c, TB_A, v);
 #pragma unroll
                     for (int kk = 0; kk < KH; ++kk) v[kk] = (am[kk] > 0.f) ? v[kk] : 0.f;    // d a
-                    if (lead) save_field(c, frow(W, a.wl.da, smi, b, B, K, F), F, o, v);
+                    if (svB) save_field(c, frow(W, a.wl.da, smi, b, B, K, F), F, o, v);
                     a_b1 += sum8(c, v);
                     write_operand(c, xop(L, 1), v);
                     signal_operand(c);
@@ -668,10 +684,12 @@ __global__ void __launch_bounds__(NTHREADS, 1) savi_bwd_umma_kernel(const __grid
                         dnr[kk] = dn[kk] * r_[kk];
                         dh[kk] = g * z_[kk];
                     }
-                    if (lead) {
+                    if (svA) {
                         float* gi = frow(W, a.wl.dgi, s, b, B, K, 3 * F);
-                        float* gh = frow(W, a.wl.dgh, s, b, B, K, 3 * F);
                         save_field(c, gi, 3 * F, o, dr); save_field(c, gi, 3 * F, F + o, dz); save_field(c, gi, 3 * F, 2 * F + o, dn);
+                    }
+                    if (svB) {
+                        float* gh = frow(W, a.wl.dgh, s, b, B, K, 3 * F);
                         save_field(c, gh, 3 * F, o, dr); save_field(c, gh, 3 * F, F + o, dz); save_field(c, gh, 3 * F, 2 * F + o, dnr);
                     }
                     a_dr += sum8(c, dr); a_dz += sum8(c, dz); a_dn += sum8(c, dn); a_dnr += sum8(c, dnr);
@@ -688,13 +706,13 @@ __global__ void __launch_bounds__(NTHREADS, 1) savi_bwd_umma_kernel(const __grid
                 const float ssv = (tid < K) ? fb[a.sl.ssum + (s * B + b) * KP + tid] : 1.f;
                 wait_acc(c); load_acc(c, TB_A, v);                                         // dU
                 UPH(28);
-                if (lead) save_field(c, frow(W, a.wl.du, s, b, B, K, F), F, o, v);
+                if (svA) save_field(c, frow(W, a.wl.du, s, b, B, K, F), F, o, v);
                 write_operand(c, xop(L, 2), v);
                 signal_operand(c);
                 if (tid < 32) cv[32 + tid] = (tid < K) ? 1.0f / ssv : 0.f;
                 wait_acc(c); load_acc(c, TB_B, dux);                                       // dUx
                 UPH(29);
-                if (lead) save_field(c, frow(W, a.wl.duxs, s, b, B, K, F), F, o, dux);
+                if (svB) save_field(c, frow(W, a.wl.duxs, s, b, B, K, F), F, o, dux);
                 // c[k] = <dUx[k,:], Ux[k,:]>: reduce over the 128 features through the scratch tile
                 {
                     float* scr = reinterpret_cast<float*>(sm + L.scratch);
@@ -739,14 +757,14 @@ __global__ void __launch_bounds__(NTHREADS, 1) savi_bwd_umma_kernel(const __grid
                     for (int kk = 0; kk < KH; ++kk) if (kk < c.nk) dqk[kk] = lead ? dqk[kk] + pn[kk * F] : pn[kk * F] + dqk[kk];
                 }
                 UPH(33);
-                if (lead) save_field(c, frow(W, a.wl.dqk, s, b, B, K, F), F, o, dqk);
+                if (svA) save_field(c, frow(W, a.wl.dqk, s, b, B, K, F), F, o, dqk);
                 write_operand(c, xop(L, 0), dqk);
                 signal_operand(c);
                 wait_acc(c); load_acc(c, TB_A, v);                                         // dq = Ds^-1/2 W_k d qk
 #pragma unroll
                 for (int kk = 0; kk < KH; ++kk) v[kk] *= d.qscale;
                 UPH(34);
-                if (lead) save_field(c, frow(W, a.wl.dq, s, b, B, K, F), F, o, v);
+                if (svB) save_field(c, frow(W, a.wl.dq, s, b, B, K, F), F, o, v);
                 write_operand(c, xop(L, 1), v);
                 signal_operand(c);
                 float hp[KH], dst[KH], hpv[KH];

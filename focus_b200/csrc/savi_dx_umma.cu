@@ -4,9 +4,10 @@
 // The clip kernel stages the per-token coefficients as ready-made K-major SWIZZLE_128B operand blocks
 // (one 16 KB block per iteration: [128 tokens][32 dL | 32 W]), so a 128-token tile is fetched with one bulk copy and
 // multiplied by the [64 I x 128] right-hand side (qk_i, dUx_i rows, bf16) with 4 I tcgen05.mma (M = N = 128).
-// Epilogue: thread = token (accumulator row = TMEM lane), so the LayerNorm-backward row sums are thread-local;
-// the d gamma / d beta column sums over tokens are two more products with a ones matrix, accumulated in TMEM over
-// all tiles of the CTA.  HBM traffic = coefficients + inputs + d_inputs, each once.
+// Epilogue: thread = token (accumulator row = TMEM lane), so the LayerNorm-backward row sums are thread-local; two
+// warpgroups drain alternate tiles (two TMEM accumulators), each thread fetching its whole input row (16 x 16 B) before
+// it waits for the accumulator; the d gamma / d beta column sums over tokens are fp32 recursive-halving warp shuffles
+// accumulated in registers over all tiles of the CTA.  HBM traffic = coefficients + inputs + d_inputs, each once.
 #include "savi_umma.cuh"
 #include "savi_dev.cuh"
 #include "savi_args.h"
@@ -19,11 +20,17 @@ __device__ __forceinline__ uint32_t pack2(float lo, float hi) {
     __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
     return *reinterpret_cast<uint32_t*>(&v);
 }
-constexpr int DX_THREADS = 160;                 // warps 0-3: epilogue (thread = token); warp 4: loader + MMA issuer
+// 16-byte global load the compiler may not merge with an earlier load of the same address (the row is deliberately fetched twice)
+__device__ __forceinline__ uint4 ldg_v4_again(const void* p) {
+    uint4 v;
+    asm volatile("ld.global.nc.v4.u32 {%0, %1, %2, %3}, [%4];\n" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+    return v;
+}
+constexpr int DX_EPI_WARPS = 8;                 // two epilogue warpgroups (thread = token); tile j is drained by warpgroup j & 1
+constexpr int DX_THREADS = (DX_EPI_WARPS + 1) * 32;   // + warp 8: loader + MMA issuer
 constexpr int D128 = 128;
 constexpr uint32_t IDESC_A_K_B_MN_128 = idesc_bf16(128, 128, false, true);
-constexpr uint32_t IDESC_A_MN_B_MN_128 = idesc_bf16(128, 128, true, true);
-enum { TD_ACC0 = 0, TD_ACC1 = 128, TD_SUM1 = 256, TD_SUM2 = 384, TD_COLS = 512 };
+enum { TD_ACC0 = 0, TD_ACC1 = 128, TD_COLS = 256 };
 
 struct DxUArgs {
     const bf16* x;              // inputs [B*T][N][128]
@@ -37,9 +44,26 @@ struct DxUArgs {
     int B, T, N, K, I, NTILE, tiles_per_cta;
 };
 
-// shared memory plan (bytes): rhs [2 blocks][64 I rows][128 B] | coef tiles x2 [I][16 KB] | dxh, dxhz operands [2 blocks][128 rows][128 B] each | ones 4 KB | gamma, bars
+// shared memory plan (bytes): rhs [2 blocks][64 I rows][128 B] | coef tiles x2 [I][16 KB] | column-sum scratch [8 warps][256] fp32 | gamma, bars
 __host__ __device__ inline int dx_rhs_bytes(int I) { return 2 * 64 * I * 128; }
-__host__ __device__ inline int dx_smem_total(int I) { return dx_rhs_bytes(I) + 2 * I * 16384 + 2 * 32768 + 4096 + 1024; }
+__host__ __device__ inline int dx_smem_total(int I) { return dx_rhs_bytes(I) + 2 * I * 16384 + DX_EPI_WARPS * 256 * 4 + 1024; }
+
+// v[j] of lane l = element (row l, column j) of a 32 x 32 block; returns to lane l the sum of column l over the 32 rows
+// (recursive halving: 31 shuffles instead of 32 x 5)
+template <int H>
+__device__ __forceinline__ void colsum_step(float (&v)[32], int lane) {
+    const bool up = (lane & H) != 0;
+#pragma unroll
+    for (int i = 0; i < H; ++i) {
+        const float send = up ? v[i] : v[i + H];
+        const float keep = up ? v[i + H] : v[i];
+        v[i] = keep + __shfl_xor_sync(0xffffffffu, send, H);
+    }
+}
+__device__ __forceinline__ float warp_colsum32(float (&v)[32], int lane) {
+    colsum_step<16>(v, lane); colsum_step<8>(v, lane); colsum_step<4>(v, lane); colsum_step<2>(v, lane); colsum_step<1>(v, lane);
+    return v[0];
+}
 
 __global__ void __launch_bounds__(DX_THREADS, 1) dx_umma_kernel(const __grid_constant__ DxUArgs a) {
     extern __shared__ __align__(1024) unsigned char sm[];
@@ -49,26 +73,28 @@ __global__ void __launch_bounds__(DX_THREADS, 1) dx_umma_kernel(const __grid_con
     const int f = blockIdx.y, b = f / a.T, t = f - b * a.T;
     unsigned char* rhs = sm;
     unsigned char* ct = rhs + dx_rhs_bytes(I);                 // 2 stages of I blocks
-    unsigned char* s1op = ct + 2 * I * 16384;
-    unsigned char* s2op = s1op + 32768;
-    unsigned char* ones = s2op + 32768;
-    float* gam = reinterpret_cast<float*>(ones + 4096);        // [128]
-    uint64_t* bars = reinterpret_cast<uint64_t*>(ones + 4096 + 512);   // full[2], accfull[2], accfree[2], sumrdy, sumfree
+    float* csum = reinterpret_cast<float*>(ct + 2 * I * 16384);   // [8 warps][2][128]
+    float* gam = csum + DX_EPI_WARPS * 256;                    // [128]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(gam + 128);   // full[2], accfull[2], accfree[2]
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
-    enum { BF = 0, BAF = 2, BAE = 4, BSR = 6, BSF = 7 };
+    enum { BF = 0, BAF = 2, BAE = 4 };
     const int tile_lo = blockIdx.x * a.tiles_per_cta, tile_hi = min(a.NTILE, tile_lo + a.tiles_per_cta), nt = tile_hi - tile_lo;
+    const unsigned char* coef_f = a.coef + ((size_t)f * a.NTILE + tile_lo) * I * 16384;
 
     if (tid == 0) {
         mbar_init(&bars[BF], 1); mbar_init(&bars[BF + 1], 1);
         mbar_init(&bars[BAF], 1); mbar_init(&bars[BAF + 1], 1);
         mbar_init(&bars[BAE], 4); mbar_init(&bars[BAE + 1], 4);
-        mbar_init(&bars[BSR], 4); mbar_init(&bars[BSF], 1);
         mbar_init_fence();
     }
-    if (warp == 4) tmem_alloc(tmem_slot, TD_COLS);
-    for (int i = tid; i < 2048; i += DX_THREADS) reinterpret_cast<uint16_t*>(ones)[i] = 0x3F80;
+    if (warp == DX_EPI_WARPS) tmem_alloc(tmem_slot, TD_COLS);
+    __syncthreads();                                           // barriers exist before the first bulk copy is issued
+    if (tid == DX_EPI_WARPS * 32 && nt > 0) {                  // the first coefficient tile streams in while the right-hand side is staged
+        mbar_expect_tx(&bars[BF], I * 16384); bulk_g2s(ct, coef_f, I * 16384, &bars[BF]);
+    }
     for (int i = tid; i < 128; i += DX_THREADS) gam[i] = a.gamma[i];
     // right-hand side rows: iteration i -> rows [64 i, 64 i + 64): qk_i (32 rows, zero beyond K) then dUx_i; MN-major, two 64-column blocks
+#pragma unroll 4
     for (int idx = tid; idx < KT * 16; idx += DX_THREADS) {
         const int k = idx >> 4, c8 = (idx & 15) * 8;            // row, first of 8 columns
         const int i = k >> 6, which = (k >> 5) & 1, s = k & 31;
@@ -76,10 +102,7 @@ __global__ void __launch_bounds__(DX_THREADS, 1) dx_umma_kernel(const __grid_con
         if (s < K) {
             const float* src = (which == 0 ? a.qk : a.dux) + ((((size_t)t * I + i) * a.B + b) * K + s) * D128 + c8;
             const float4 p = ld4(src), q = ld4(src + 4);
-            __nv_bfloat162 h0 = __floats2bfloat162_rn(p.x, p.y), h1 = __floats2bfloat162_rn(p.z, p.w);
-            __nv_bfloat162 h2 = __floats2bfloat162_rn(q.x, q.y), h3 = __floats2bfloat162_rn(q.z, q.w);
-            v.x = *reinterpret_cast<unsigned*>(&h0); v.y = *reinterpret_cast<unsigned*>(&h1);
-            v.z = *reinterpret_cast<unsigned*>(&h2); v.w = *reinterpret_cast<unsigned*>(&h3);
+            v.x = pack2(p.x, p.y); v.y = pack2(p.z, p.w); v.z = pack2(q.x, q.y); v.w = pack2(q.z, q.w);
         }
         *reinterpret_cast<uint4*>(rhs + (c8 >> 6) * (KT * 128) + k * 128 + ((((c8 & 63) >> 3) ^ (k & 7)) << 4)) = v;
     }
@@ -88,16 +111,11 @@ __global__ void __launch_bounds__(DX_THREADS, 1) dx_umma_kernel(const __grid_con
     __syncthreads();
     fence_after_sync();
     const uint32_t tb = *tmem_slot;
-    const unsigned char* coef_f = a.coef + ((size_t)f * a.NTILE + tile_lo) * I * 16384;
 
-    if (warp == 4) {
+    if (warp == DX_EPI_WARPS) {
         // ---- loader + issuer (warp-uniform, one elected lane issues) ----
-        const bool el = elect_one();
-        if (el && nt > 0) { mbar_expect_tx(&bars[BF], I * 16384); bulk_g2s(ct, coef_f, I * 16384, &bars[BF]); }
-        __syncwarp();
+        const bool el = (lane == 0);                           // lane 0 issued the first copy: keep one issuing thread
         const uint32_t rhs0 = dlo_mn(smem_u32(rhs), KT * 128);
-        const uint32_t one0 = dlo_mn(smem_u32(ones), 2048);
-        const uint32_t s1d = dlo_mn(smem_u32(s1op), 16384), s2d = dlo_mn(smem_u32(s2op), 16384);
         for (int j = 0; j < nt; ++j) {
             const int st = j & 1;
             // prefetch the next tile's coefficient blocks (its stage was released when the MMAs of tile j-1 completed)
@@ -116,91 +134,60 @@ __global__ void __launch_bounds__(DX_THREADS, 1) dx_umma_kernel(const __grid_con
                 mma_commit(&bars[BAF + st]);
             }
             __syncwarp();
-            // column sums of the previous tile (its operands were written by the epilogue)
-            if (j >= 1) {
-                mbar_wait(&bars[BSR], (j - 1) & 1u);
-                fence_after_sync();
-                if (el) {
-                    for (int kt = 0; kt < 8; ++kt) {
-                        mma_lo(tb + TD_SUM1, one0, s1d + kt * 128, IDESC_A_MN_B_MN_128, (j > 1 || kt > 0) ? 1u : 0u);
-                        mma_lo(tb + TD_SUM2, one0, s2d + kt * 128, IDESC_A_MN_B_MN_128, (j > 1 || kt > 0) ? 1u : 0u);
-                    }
-                    mma_commit(&bars[BSF]);
-                }
-                __syncwarp();
-            }
-        }
-        if (nt > 0) {
-            mbar_wait(&bars[BSR], (nt - 1) & 1u);
-            fence_after_sync();
-            if (el) {
-                for (int kt = 0; kt < 8; ++kt) {
-                    mma_lo(tb + TD_SUM1, one0, s1d + kt * 128, IDESC_A_MN_B_MN_128, (nt > 1 || kt > 0) ? 1u : 0u);
-                    mma_lo(tb + TD_SUM2, one0, s2d + kt * 128, IDESC_A_MN_B_MN_128, (nt > 1 || kt > 0) ? 1u : 0u);
-                }
-                mma_commit(&bars[BSF]);
-            }
-            __syncwarp();
         }
     } else {
-        // ---- epilogue: thread = token ----
-        const uint32_t tl = (uint32_t)(warp * 32) << 16;
-        const int r = tid;                                                // row inside the tile
-        for (int j = 0; j < nt; ++j) {
-            const int st = j & 1;
+        // ---- epilogue: thread = token; warpgroup g drains the tiles with j & 1 == g ----
+        const int g = warp >> 2;
+        const uint32_t tl = (uint32_t)((warp & 3) * 32) << 16;
+        const int r = tid & 127;                                          // row inside the tile
+        float cs1[4] = {0.f, 0.f, 0.f, 0.f}, cs2[4] = {0.f, 0.f, 0.f, 0.f};   // column sums (d beta, d gamma) of columns 32 c + lane over this warp's rows
+        for (int j = g; j < nt; j += 2) {
             const int n = (tile_lo + j) * 128 + r;
             const bool valid = n < N;
             const float2 ms = valid ? a.stats[(size_t)f * N + n] : make_float2(0.f, 0.f);
             const bf16* xrow = a.x + ((size_t)f * N + (valid ? n : 0)) * D128;
             bf16* orow = a.dx + ((size_t)f * N + (valid ? n : 0)) * D128;
-            mbar_wait(&bars[BAF + st], (j >> 1) & 1u);
-            fence_after_sync();
-            if (j >= 1) mbar_wait(&bars[BSF], (j - 1) & 1u);              // the previous tile's column-sum products have read their operands
-            const uint32_t acc = tb + tl + (st ? TD_ACC1 : TD_ACC0);
-            float s1 = 0.f, s2 = 0.f;
-#pragma unroll 1
-            for (int c = 0; c < 4; ++c) {                                 // pass 1: row sums + column-sum operands
-                float v[32];
-                tmem_ld32(acc + c * 32, v);
-                uint4 xq[4];
+            uint4 xq[16];                                                 // the whole input row, in flight before the accumulator is awaited
 #pragma unroll
-                for (int q = 0; q < 4; ++q) xq[q] = valid ? *reinterpret_cast<const uint4*>(xrow + c * 32 + q * 8) : make_uint4(0u, 0u, 0u, 0u);
+            for (int q = 0; q < 16; ++q) xq[q] = valid ? ldg_v4_again(xrow + q * 8) : make_uint4(0u, 0u, 0u, 0u);
+            mbar_wait(&bars[BAF + g], (j >> 1) & 1u);
+            fence_after_sync();
+            const uint32_t acc = tb + tl + (g ? TD_ACC1 : TD_ACC0);
+            float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {                                 // pass 1: row sums + column sums
+                float v[32], w[32];
+                tmem_ld32(acc + c * 32, v);
                 tmem_wait_ld();
 #pragma unroll
                 for (int q = 0; q < 4; ++q) {
-                    const __nv_bfloat162* xp = reinterpret_cast<const __nv_bfloat162*>(&xq[q]);
-                    uint32_t o1[4], o2[4];
+                    const __nv_bfloat162* xp = reinterpret_cast<const __nv_bfloat162*>(&xq[c * 4 + q]);
 #pragma unroll
                     for (int e = 0; e < 4; ++e) {
                         const float2 xf = __bfloat1622float2(xp[e]);
-                        const int col = c * 32 + q * 8 + e * 2;
+                        const int col = c * 32 + q * 8 + e * 2, u = q * 8 + e * 2;
                         const float z0 = (xf.x - ms.x) * ms.y, z1 = (xf.y - ms.x) * ms.y;
-                        const float d0 = valid ? v[q * 8 + e * 2] : 0.f, d1 = valid ? v[q * 8 + e * 2 + 1] : 0.f;
+                        const float d0 = valid ? v[u] : 0.f, d1 = valid ? v[u + 1] : 0.f;
                         const float dz0 = d0 * gam[col], dz1 = d1 * gam[col + 1];
                         s1 += dz0 + dz1; s2 = fmaf(dz0, z0, fmaf(dz1, z1, s2));
-                        o1[e] = pack2(d0, d1); o2[e] = pack2(d0 * z0, d1 * z1);
+                        v[u] = d0; v[u + 1] = d1; w[u] = d0 * z0; w[u + 1] = d1 * z1;
                     }
-                    const int col8 = c * 32 + q * 8;                      // MN-major B operand [128 token rows][128 columns], two 64-column blocks
-                    const uint32_t off = (uint32_t)(col8 >> 6) * 16384u + (uint32_t)r * 128u + (((((uint32_t)col8 & 63u) >> 3) ^ ((uint32_t)r & 7u)) << 4);
-                    *reinterpret_cast<uint4*>(s1op + off) = make_uint4(o1[0], o1[1], o1[2], o1[3]);
-                    *reinterpret_cast<uint4*>(s2op + off) = make_uint4(o2[0], o2[1], o2[2], o2[3]);
                 }
+                cs2[c] += warp_colsum32(w, lane);
+                cs1[c] += warp_colsum32(v, lane);
             }
-            fence_async_smem();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&bars[BSR]);
             s1 *= (1.0f / D128); s2 *= (1.0f / D128);
-#pragma unroll 1
+            // the row again (L1 / L2 hit): keeping it in registers across the column sums would spill
+#pragma unroll
+            for (int q = 0; q < 16; ++q) xq[q] = valid ? ldg_v4_again(xrow + q * 8) : make_uint4(0u, 0u, 0u, 0u);
+#pragma unroll
             for (int c = 0; c < 4; ++c) {                                 // pass 2: d_inputs row
                 float v[32];
                 tmem_ld32(acc + c * 32, v);
-                uint4 xq[4];
-#pragma unroll
-                for (int q = 0; q < 4; ++q) xq[q] = valid ? *reinterpret_cast<const uint4*>(xrow + c * 32 + q * 8) : make_uint4(0u, 0u, 0u, 0u);
                 tmem_wait_ld();
 #pragma unroll
                 for (int q = 0; q < 4; ++q) {
-                    const __nv_bfloat162* xp = reinterpret_cast<const __nv_bfloat162*>(&xq[q]);
+                    const __nv_bfloat162* xp = reinterpret_cast<const __nv_bfloat162*>(&xq[c * 4 + q]);
                     uint32_t o[4];
 #pragma unroll
                     for (int e = 0; e < 4; ++e) {
@@ -215,31 +202,22 @@ __global__ void __launch_bounds__(DX_THREADS, 1) dx_umma_kernel(const __grid_con
             }
             fence_before_sync();
             __syncwarp();
-            if (lane == 0) mbar_arrive(&bars[BAE + st]);
+            if (lane == 0) mbar_arrive(&bars[BAE + g]);
         }
-        // d gamma / d beta: every row of the ones-products holds the column sums; lanes 0..127 each add one column
+        // d gamma / d beta: combine the 8 warps' column sums, one atomic per column and CTA
+#pragma unroll
+        for (int c = 0; c < 4; ++c) { csum[warp * 256 + c * 32 + lane] = cs1[c]; csum[warp * 256 + 128 + c * 32 + lane] = cs2[c]; }
+        asm volatile("bar.sync 1, %0;\n" :: "r"(DX_EPI_WARPS * 32) : "memory");
         if (nt > 0) {
-            mbar_wait(&bars[BSF], (nt - 1) & 1u);
-            fence_after_sync();
-            // thread r reads row r (any row would do) but only its own column r: load the 32-column chunk that contains it
-            float v[32];
-            tmem_ld32(tb + tl + TD_SUM2 + (r & ~31), v);
-            tmem_wait_ld();
-            float dgv = 0.f;
+            float tot = 0.f;
 #pragma unroll
-            for (int e = 0; e < 32; ++e) if (e == (r & 31)) dgv = v[e];
-            tmem_ld32(tb + tl + TD_SUM1 + (r & ~31), v);
-            tmem_wait_ld();
-            float dbv = 0.f;
-#pragma unroll
-            for (int e = 0; e < 32; ++e) if (e == (r & 31)) dbv = v[e];
-            atomicAdd(a.dgamma + r, dgv);
-            atomicAdd(a.dbeta + r, dbv);
+            for (int w8 = 0; w8 < DX_EPI_WARPS; ++w8) tot += csum[w8 * 256 + tid];
+            atomicAdd((tid < 128 ? a.dbeta : a.dgamma - 128) + tid, tot);
         }
     }
     fence_before_sync();
     __syncthreads();
-    if (warp == 4) tmem_dealloc(tb, TD_COLS);
+    if (warp == DX_EPI_WARPS) tmem_dealloc(tb, TD_COLS);
 }
 }  // namespace
 
@@ -255,7 +233,8 @@ cudaError_t savi_launch_dx_umma(const BwdArgs& a, const void* inputs, void* grad
     x.dx = reinterpret_cast<bf16*>(grad_inputs);
     x.dgamma = a.grad_params + a.po.ln_in_w; x.dbeta = a.grad_params + a.po.ln_in_b;
     x.B = d.B; x.T = d.T; x.N = d.N; x.K = d.K; x.I = d.I; x.NTILE = d.NTILE;
-    x.tiles_per_cta = d.NTILE >= 8 ? 4 : d.NTILE;                           // >= 2 CTAs per frame once frames have 8 tiles
+    // whole frames per CTA (one staging of the right-hand side) once there are >= 2 waves of frames; else >= 2 CTAs per frame
+    x.tiles_per_cta = d.NTILE <= 8 ? ((d.B * d.T >= 2 * 148 || d.NTILE < 8) ? d.NTILE : 4) : 8;
     const int smem = dx_smem_total(d.I);
     cudaError_t e = cudaFuncSetAttribute(dx_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) return e;

@@ -175,11 +175,14 @@ __device__ __forceinline__ void softmax_tiles(const Ctx& c, const Dims& d, int n
 // ------------------------------------------------------------------------------------------------
 __device__ __forceinline__ void mha_core(const Ctx& c, int H, const float (&q)[KH], const float (&kx)[KH], const float (&v)[KH],
                                          float (&out)[KH], float* att_g /* nullable: [H][K][K] saved */) {
-    const int K = c.K, ld = F + 1, ka = K | 1, dh = F / H;
+    // rows of sQ / sK / sV are 16-byte aligned (ld % 4 == 0) and 4 banks apart: float4 reads along a head's features are
+    // conflict-free across slots, column reads [k][o] across o.  Attention rows are padded to ka = 4-aligned K.
+    const int K = c.K, ld = MHA_LD, ka = mha_ka(K), dh = F / H;
     float* sQ = reinterpret_cast<float*>(c.sm + c.L.aw0);            // aw0 | aw1 | scratch are contiguous
     float* sK = sQ + K * ld;
     float* sV = sK + K * ld;
-    float* sA = reinterpret_cast<float*>(c.sm + c.L.opC);            // [H*K][ka]
+    float* sA = reinterpret_cast<float*>(c.sm + c.L.opB);            // [H*K][ka] logits -> probabilities (opB | opC are free here)
+    float* sAT = sA + H * K * ka;                                    // [H][K key][ka query]: the transposed probabilities
 #pragma unroll
     for (int kk = 0; kk < KH; ++kk) {
         const int k = c.k0 + kk;
@@ -188,33 +191,40 @@ __device__ __forceinline__ void mha_core(const Ctx& c, int H, const float (&q)[K
     bar_sync_compute();
     for (int idx = c.tid; idx < H * K * K; idx += NCT) {
         const int j = idx % K, i = (idx / K) % K, h = idx / (K * K);
-        const float* a = sQ + i * ld + h * dh;
-        const float* b = sK + j * ld + h * dh;
+        const float4* a = reinterpret_cast<const float4*>(sQ + i * ld + h * dh);
+        const float4* b = reinterpret_cast<const float4*>(sK + j * ld + h * dh);
         float s = 0.f;
-        for (int e = 0; e < dh; ++e) s = fmaf(a[e], b[e], s);
+        for (int e = 0; e < dh / 4; ++e) {
+            const float4 x = a[e], y = b[e];
+            s = fmaf(x.x, y.x, s); s = fmaf(x.y, y.y, s); s = fmaf(x.z, y.z, s); s = fmaf(x.w, y.w, s);
+        }
         sA[(h * K + i) * ka + j] = s;
     }
     bar_sync_compute();
-    for (int row = c.tid; row < H * K; row += NCT) {
-        float* a = sA + row * ka;
-        float mx = -INFINITY;
-        for (int j = 0; j < K; ++j) mx = fmaxf(mx, a[j]);
-        float sum = 0.f;
-        for (int j = 0; j < K; ++j) { const float e = expf(a[j] - mx); a[j] = e; sum += e; }
-        const float inv = 1.0f / sum;
-        for (int j = 0; j < K; ++j) a[j] *= inv;
+    for (int row = c.warp; row < H * K; row += NCW) {                // softmax over the keys: one warp per (head, query) row, lane = key
+        const bool on = c.lane < K;
+        const float x = on ? sA[row * ka + c.lane] : -INFINITY;
+        float mx = x;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+        const float e = on ? expf(x - mx) : 0.f;
+        const float pr = e * (1.0f / warp_sum(e));
+        if (on) {
+            sAT[((row / K) * K + c.lane) * ka + row % K] = pr;
+            if (att_g) att_g[row * K + c.lane] = pr;
+        }
     }
     bar_sync_compute();
-    if (att_g) for (int idx = c.tid; idx < H * K * K; idx += NCT) att_g[idx] = sA[(idx / K) * ka + idx % K];
-    const int h = c.o / dh;
+    const float* at = sAT + (c.o / dh) * K * ka + c.k0;
 #pragma unroll
-    for (int kk = 0; kk < KH; ++kk) {
-        float s = 0.f;
-        if (kk < c.nk) {
-            const float* a = sA + (h * K + c.k0 + kk) * ka;
-            for (int j = 0; j < K; ++j) s = fmaf(a[j], sV[j * ld + c.o], s);
+    for (int kk = 0; kk < KH; ++kk) out[kk] = 0.f;
+    if (c.nk > 0) {
+        for (int j = 0; j < K; ++j) {
+            const float vj = sV[j * ld + c.o];
+            const float4 p0 = ld4(at + j * ka), p1 = ld4(at + j * ka + 4);       // this warpgroup's 8 queries (warp-uniform address)
+            out[0] = fmaf(p0.x, vj, out[0]); out[1] = fmaf(p0.y, vj, out[1]); out[2] = fmaf(p0.z, vj, out[2]); out[3] = fmaf(p0.w, vj, out[3]);
+            out[4] = fmaf(p1.x, vj, out[4]); out[5] = fmaf(p1.y, vj, out[5]); out[6] = fmaf(p1.z, vj, out[6]); out[7] = fmaf(p1.w, vj, out[7]);
         }
-        out[kk] = s;
     }
     bar_sync_compute();                                              // sQ/sK/sV/sA are free again
 }
@@ -236,6 +246,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) savi_fwd_umma_kernel(const __grid
     uint64_t* bars = reinterpret_cast<uint64_t*>(sm + L.bars);
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + NBAR);
     const bool lead = (rank == 0);
+    // both CTAs of a pair hold bit-identical slot state: the saved-for-backward records are split between them
+    const bool svA = lead, svB = (rank == CN - 1);
     // token tiles of this CTA
     const int per = (d.NTILE + CN - 1) / CN;
     const int tile0 = min(d.NTILE, rank * per), ntile = min(d.NTILE, tile0 + per) - tile0;
@@ -390,22 +402,22 @@ __global__ void __launch_bounds__(NTHREADS, 1) savi_fwd_umma_kernel(const __grid
             for (int it = 0; it < d.I; ++it, ++step) {
                 const int64_t s = (int64_t)t * d.I + it;
                 // ---- slots_prev, LayerNorm, q ----
-                if (lead) save_field(c, frow(fb, a.sl.hp, s, b, B, K, F), F, o, h);
+                if (svA) save_field(c, frow(fb, a.sl.hp, s, b, B, K, F), F, o, h);
                 write_operand(c, L.opC, h);
                 layer_norm(c, h, y, g_s, b_s, d.ln_eps, lead ? reinterpret_cast<float2*>(fb + a.sl.lns) + (s * B + b) * K : nullptr);   // :72
-                if (lead) save_field(c, frow(fb, a.sl.st, s, b, B, K, F), F, o, y);
+                if (svB) save_field(c, frow(fb, a.sl.st, s, b, B, K, F), F, o, y);
                 write_operand(c, L.opA, y);
                 signal_operand(c);
                 UPH(1);
                 wait_acc(c); UPH(2); load_acc(c, TC_A, y);                                  // q
-                if (lead) save_field(c, frow(fb, a.sl.q, s, b, B, K, F), F, o, y);
+                if (svA) save_field(c, frow(fb, a.sl.q, s, b, B, K, F), F, o, y);
                 write_operand(c, L.opB, y);
                 signal_operand(c);
                 UPH(3);
                 wait_acc(c); UPH(4); load_acc(c, TC_B, y);                                  // qk = Ds^-1/2 q Wk
 #pragma unroll
                 for (int kk = 0; kk < KH; ++kk) y[kk] *= d.qscale;
-                if (lead) save_field(c, frow(fb, a.sl.qk, s, b, B, K, F), F, o, y);
+                if (svB) save_field(c, frow(fb, a.sl.qk, s, b, B, K, F), F, o, y);
                 write_operand(c, L.opA, y);
                 signal_operand(c);
                 // ---- attention step over the token tiles ----
@@ -460,7 +472,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) savi_fwd_umma_kernel(const __grid
                 signal_operand(c);
                 UPH(10);
                 wait_acc(c); UPH(11); load_acc(c, TC_A, y);                                 // updates U (:83)
-                if (lead) save_field(c, frow(fb, a.sl.u, s, b, B, K, F), F, o, y);
+                if (svB) save_field(c, frow(fb, a.sl.u, s, b, B, K, F), F, o, y);
                 write_operand(c, L.opA, y);
                 signal_operand(c);
                 // ---- GRUCell (:87-89) ----
@@ -480,25 +492,27 @@ __global__ void __launch_bounds__(NTHREADS, 1) savi_fwd_umma_kernel(const __grid
                         r_[kk] = vr; z_[kk] = vz; n_[kk] = vn; hn[kk] = hnb;
                         h[kk] = (1.0f - vz) * vn + vz * h[kk];
                     }
-                    if (lead) {
+                    if (svA) {
                         save_field(c, frow(fb, a.sl.r, s, b, B, K, F), F, o, r_);
-                        save_field(c, frow(fb, a.sl.z, s, b, B, K, F), F, o, z_);
                         save_field(c, frow(fb, a.sl.n, s, b, B, K, F), F, o, n_);
+                    }
+                    if (svB) {
+                        save_field(c, frow(fb, a.sl.z, s, b, B, K, F), F, o, z_);
                         save_field(c, frow(fb, a.sl.ghn, s, b, B, K, F), F, o, hn);
                     }
                     if (mlp) {                                                             // residual MLP (:92-93)
                         const int64_t smi = (int64_t)t * (d.I - 1) + it;
-                        if (lead) save_field(c, frow(fb, a.sl.hg, smi, b, B, K, F), F, o, h);
+                        if (svA) save_field(c, frow(fb, a.sl.hg, smi, b, B, K, F), F, o, h);
                         UPH(14);
-                        layer_norm(c, h, y, g_m, b_m, d.ln_eps, lead ? reinterpret_cast<float2*>(fb + a.sl.lnm) + (smi * B + b) * K : nullptr);
-                        if (lead) save_field(c, frow(fb, a.sl.m, smi, b, B, K, F), F, o, y);
+                        layer_norm(c, h, y, g_m, b_m, d.ln_eps, svB ? reinterpret_cast<float2*>(fb + a.sl.lnm) + (smi * B + b) * K : nullptr);
+                        if (svB) save_field(c, frow(fb, a.sl.m, smi, b, B, K, F), F, o, y);
                         write_operand(c, L.opB, y);
                         signal_operand(c);
                         UPH(15);
                         wait_acc(c); UPH(16); load_acc(c, TC_A, y);
 #pragma unroll
                         for (int kk = 0; kk < KH; ++kk) y[kk] = fmaxf(y[kk] + b1, 0.f);
-                        if (lead) save_field(c, frow(fb, a.sl.a, smi, b, B, K, F), F, o, y);
+                        if (svA) save_field(c, frow(fb, a.sl.a, smi, b, B, K, F), F, o, y);
                         write_operand(c, L.opA, y);
                         signal_operand(c);
                         UPH(17);
@@ -509,10 +523,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) savi_fwd_umma_kernel(const __grid
                     UPH(19);
                 }
             }
-            if (lead) save_field(c, a.slots_out + ((size_t)b * d.T + t) * K * F, F, o, h);      // collect (:96-97)
+            if (svB) save_field(c, a.slots_out + ((size_t)b * d.T + t) * K * F, F, o, h);      // collect (:96-97)
             if (t < d.T - 1) {
                 // ---- predictor (:100; transformer.py:106-114) ----
-                if (lead) save_field(c, fb + a.sl.px0 + ((size_t)t * B + b) * K * F, F, o, h);
+                if (svA) save_field(c, fb + a.sl.px0 + ((size_t)t * B + b) * K * F, F, o, h);
                 const float hscale = 1.0f / sqrtf((float)(F / d.heads));
                 float x[KH];
 #pragma unroll
@@ -522,30 +536,30 @@ __global__ void __launch_bounds__(NTHREADS, 1) savi_fwd_umma_kernel(const __grid
                     const BlockOff& bo = po.blk[j];
                     float yv[KH], q[KH], kx[KH], v[KH], x1[KH];
                     layer_norm(c, x, yv, P[bo.ln1_w + o], P[bo.ln1_b + o], d.ln_eps);
-                    if (lead) save_field(c, frow(fb, a.sl.py, f, b, B, K, F), F, o, yv);
+                    if (svB) save_field(c, frow(fb, a.sl.py, f, b, B, K, F), F, o, yv);
                     write_operand(c, L.opA, yv);
                     signal_operand(c);
                     wait_acc(c);
                     load_acc(c, TC_R, q); load_acc(c, TC_Z, kx); load_acc(c, TC_HN, v);
 #pragma unroll
                     for (int kk = 0; kk < KH; ++kk) q[kk] *= hscale;
-                    if (lead) {
+                    if (svA) {
                         save_field(c, frow(fb, a.sl.pq, f, b, B, K, F), F, o, q);
-                        save_field(c, frow(fb, a.sl.pk, f, b, B, K, F), F, o, kx);
                         save_field(c, frow(fb, a.sl.pv, f, b, B, K, F), F, o, v);
                     }
+                    if (svB) save_field(c, frow(fb, a.sl.pk, f, b, B, K, F), F, o, kx);
                     float ov[KH];
-                    mha_core(c, d.heads, q, kx, v, ov, lead ? fb + a.sl.patt + (f * B + b) * ((int64_t)d.heads * K * K) : nullptr);
-                    if (lead) save_field(c, frow(fb, a.sl.po, f, b, B, K, F), F, o, ov);
+                    mha_core(c, d.heads, q, kx, v, ov, svB ? fb + a.sl.patt + (f * B + b) * ((int64_t)d.heads * K * K) : nullptr);
+                    if (svA) save_field(c, frow(fb, a.sl.po, f, b, B, K, F), F, o, ov);
                     write_operand(c, L.opB, ov);
                     signal_operand(c);
                     wait_acc(c); load_acc(c, TC_A, x1);
                     // the first block adds the residual to the NORMALISED input (transformer.py:75-78)
 #pragma unroll
                     for (int kk = 0; kk < KH; ++kk) x1[kk] += (j == 0) ? yv[kk] : x[kk];
-                    if (lead) save_field(c, frow(fb, a.sl.px1, f, b, B, K, F), F, o, x1);
+                    if (svB) save_field(c, frow(fb, a.sl.px1, f, b, B, K, F), F, o, x1);
                     layer_norm(c, x1, yv, P[bo.ln2_w + o], P[bo.ln2_b + o], d.ln_eps);
-                    if (lead) save_field(c, frow(fb, a.sl.pl2, f, b, B, K, F), F, o, yv);
+                    if (svA) save_field(c, frow(fb, a.sl.pl2, f, b, B, K, F), F, o, yv);
                     write_operand(c, L.opA, yv);
                     signal_operand(c);
 #pragma unroll
@@ -555,7 +569,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) savi_fwd_umma_kernel(const __grid
                         const float bb = P[bo.f1b + ff * F + o];
 #pragma unroll
                         for (int kk = 0; kk < KH; ++kk) yv[kk] = fmaxf(yv[kk] + bb, 0.f);
-                        if (lead) save_field(c, frow(fb, a.sl.pf, f, b, B, K, 4 * F), 4 * F, ff * F + o, yv);
+                        if ((ff & 1) ? svB : svA) save_field(c, frow(fb, a.sl.pf, f, b, B, K, 4 * F), 4 * F, ff * F + o, yv);
                         write_operand(c, ff == 0 ? L.opB : ff == 1 ? L.opC : ff == 2 ? L.aw0 : L.aw1, yv);
                         signal_operand(c, B_FOPND + ff);
                     }
@@ -564,7 +578,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) savi_fwd_umma_kernel(const __grid
                     const float bb2 = P[bo.f2b + o];
 #pragma unroll
                     for (int kk = 0; kk < KH; ++kk) x[kk] = x1[kk] + yv[kk] + bb2;
-                    if (lead) save_field(c, frow(fb, a.sl.px2, f, b, B, K, F), F, o, x);
+                    if (svB) save_field(c, frow(fb, a.sl.px2, f, b, B, K, F), F, o, x);
                 }
                 layer_norm(c, x, h, P[po.lnf_w + o], P[po.lnf_b + o], d.ln_eps);
                 UPH(20);
@@ -583,6 +597,15 @@ __global__ void __launch_bounds__(NTHREADS, 1) savi_fwd_umma_kernel(const __grid
 // ------------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------------
+int savi_umma_mha_fits(int K, int heads) {
+    if (heads < 1 || F % heads || (F / heads) % 4) return 0;
+    const int KR = (K + 3) & ~3, ka = mha_ka(K);
+    const int win_bwd = 5 * OPB + KR * F * 4;                 // opA .. scratch
+    const int win_fwd = 2 * OPB + KR * F * 4;                 // aw0 .. scratch (q, k, v tiles); the attention matrices take opB | opC
+    return heads * K * K <= 8 * NCT && mha_bwd_bytes(K, heads) <= win_bwd &&
+           3 * K * MHA_LD * 4 <= win_fwd && 2 * heads * K * ka * 4 <= 2 * OPB;
+}
+
 int savi_fwd_umma_smem_bytes(const Dims& d) {
     return plan_smem(d.K, d.CN, false).total;
 }

@@ -36,6 +36,12 @@ constexpr uint32_t IDESC_K_MN64 = idesc_bf16(128, 64, false, true);    // A K-ma
 constexpr uint32_t IDESC_K_MN32 = idesc_bf16(128, 32, false, true);    //                          N = 32 (hi half of B's rows)
 constexpr uint32_t IDESC_MN_MN64 = idesc_bf16(128, 64, true, true);    // A MN-major, B MN-major, N = 64
 
+// predictor attention core (shared-memory, SIMT): row stride of the q / k / v / dO tiles and of the attention matrices
+constexpr int MHA_LD = F + 4;
+__host__ __device__ __forceinline__ constexpr int mha_ka(int K) { return (K + 3) & ~3; }
+// bytes the backward core needs from opA on (dO, q, k, v tiles + A, dL, dL^T); the forward needs less
+__host__ __device__ __forceinline__ constexpr int mha_bwd_bytes(int K, int H) { return (4 * K * MHA_LD + 3 * H * K * mha_ka(K)) * 4 + 64; }
+
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
     __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
     return *reinterpret_cast<uint32_t*>(&v);

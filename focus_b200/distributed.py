@@ -18,6 +18,50 @@ def shard_range(n_clips, rank, world):
     return lo, lo + base + (1 if rank < extra else 0)
 
 
+def all_reduce_flat_(flat, group=None, average=True):
+    """ONE collective, in place, on a flat gradient buffer: sum (or mean) over the ranks of `group`."""
+    if not (dist.is_available() and dist.is_initialized()):
+        return flat
+    world = dist.get_world_size(group)
+    if world == 1:
+        return flat
+    if average and dist.get_backend(group) == "nccl":
+        dist.all_reduce(flat, op=dist.ReduceOp.AVG, group=group)     # averaged inside the collective (NVLS / ring), no extra pass
+    else:
+        dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
+        if average:
+            flat.div_(world)
+    return flat
+
+
+class GradSync:
+    """Gradient exchange of a standalone data-parallel `SlotAttentionVideo` (what DDP does for the reference,
+    slowfast/models/build.py:79-83), fused into its backward: the CUDA library already writes every parameter
+    gradient into one flat fp32 buffer, so the module all-reduces THAT buffer once, in place, on the backward's
+    stream, and hands views of it to autograd: no bucket copies, one NCCL launch per step.
+
+        sync = attach_grad_sync(module)          # after init_process_group; parameters must start identical
+        slots, attn = module(x); loss.backward() # .grad now holds the rank-averaged gradients
+
+    Do not combine with DistributedDataParallel on the same module (the gradients would be reduced twice); when the
+    module is embedded in a DDP-wrapped STEVE, leave it detached and DDP handles it like any other sub-module."""
+
+    def __init__(self, group=None, average=True):
+        self.group, self.average = group, average
+
+    def __call__(self, flat):
+        return all_reduce_flat_(flat, self.group, self.average)
+
+
+def attach_grad_sync(module, group=None, average=True, broadcast_parameters=True):
+    """Enable the fused flat-gradient all-reduce on `module`; rank 0's parameters are broadcast first (as DDP does)."""
+    if broadcast_parameters and dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+        for t in list(module.parameters()) + list(module.buffers()):
+            dist.broadcast(t.data, src=dist.get_global_rank(group, 0) if group is not None else 0, group=group)
+    module.grad_sync = GradSync(group, average)
+    return module.grad_sync
+
+
 class FlatGradAllReduce:
     """Average the gradients of `params` across ranks with a single all-reduce on a flat buffer."""
 

@@ -82,7 +82,7 @@ class _SaviFunction(torch.autograd.Function):
     """autograd.Function over the C ABI: savi_pack_params + savi_forward / savi_backward."""
 
     @staticmethod
-    def forward(ctx, shape, inputs, noise, *params):
+    def forward(ctx, shape, grad_sync, inputs, noise, *params):
         dev = inputs.device
         sizes = _lib.query(shape)
         stream = ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
@@ -102,6 +102,7 @@ class _SaviFunction(torch.autograd.Function):
                                          _ptr(attn), _ptr(saved), _ptr(ws), stream), "savi_forward")
         _SaviFunction.last_launches = launches + _lib.lib.savi_last_launch_count()
         ctx.shape = shape
+        ctx.grad_sync = grad_sync
         ctx.sizes = sizes
         ctx.param_meta = [(p.shape, p.dtype) for p in params]
         ctx.save_for_backward(inputs, noise, packed, saved)
@@ -122,17 +123,19 @@ class _SaviFunction(torch.autograd.Function):
         ws = torch.empty(max(sizes.bwd_ws_bytes, 16), dtype=torch.uint8, device=dev)
         g_in = torch.empty_like(inputs)
         g_par = torch.empty(sizes.param_floats, dtype=torch.float32, device=dev)
-        g_noise = torch.empty_like(noise) if ctx.needs_input_grad[2] else None
+        g_noise = torch.empty_like(noise) if ctx.needs_input_grad[3] else None
         _lib.check(_lib.lib.savi_backward(ctypes.byref(shape), _ptr(packed), _ptr(inputs), _ptr(noise), _ptr(saved),
                                           _ptr(g_slots), _ptr(g_attn), _ptr(g_in), _ptr(g_par), _ptr(g_noise),
                                           _ptr(ws), stream), "savi_backward")
         _SaviFunction.last_launches = _lib.lib.savi_last_launch_count()
+        if ctx.grad_sync is not None:                # data parallel: ONE all-reduce of the flat buffer (focus_b200/distributed.py)
+            ctx.grad_sync(g_par)
         off, num = _lib.param_layout(shape, len(ctx.param_meta))
         grads = []
         for (shp, dt), o, n in zip(ctx.param_meta, off, num):
             g = g_par[o:o + n].view(shp)           # every parameter gets a tensor (zeros when unused): DDP-safe
             grads.append(g if dt == torch.float32 else g.to(dt))
-        return (None, g_in if ctx.needs_input_grad[1] else None, g_noise) + tuple(grads)
+        return (None, None, g_in if ctx.needs_input_grad[2] else None, g_noise) + tuple(grads)
 
 
 _SaviFunction.last_launches = 0
@@ -154,6 +157,7 @@ class SlotAttentionVideo(nn.Module):
         self.num_predictor_heads = num_predictor_heads
         self.dropout = dropout
         self.cluster = 0               # CTAs per clip; 0 lets the library choose
+        self.grad_sync = None          # focus_b200.distributed.attach_grad_sync: flat gradient all-reduce inside backward
 
         # creation order == reference order, so torch.manual_seed(s) gives identical initial weights
         self.slot_mu = nn.Parameter(torch.Tensor(1, 1, slot_size))
@@ -215,4 +219,5 @@ class SlotAttentionVideo(nn.Module):
         inputs = inputs.contiguous()
         shape = self.make_shape(B, T, N, inputs.dtype)
         with torch.cuda.device(inputs.device):
-            return _SaviFunction.apply(shape, inputs, noise, *self._ordered_params())
+            return _SaviFunction.apply(shape, self.grad_sync if torch.is_grad_enabled() else None, inputs, noise,
+                                        *self._ordered_params())

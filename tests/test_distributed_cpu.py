@@ -9,7 +9,7 @@ import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
 
-from focus_b200.distributed import FlatGradAllReduce, shard_range
+from focus_b200.distributed import FlatGradAllReduce, GradSync, shard_range
 
 
 def test_shard_range_partitions_every_clip_once():
@@ -48,6 +48,11 @@ def _worker(rank, world, port, out):
     for p, k in zip(params, P):
         p.grad = G[k].float().clone()
     FlatGradAllReduce(params)(weight=(hi - lo) / Bg)
+    # the fused variant used by SlotAttentionVideo.backward: one in-place collective on the library's flat gradient buffer
+    flat = torch.cat([G[k].float().reshape(-1) for k in P]) * ((hi - lo) * world / Bg)
+    GradSync(average=True)(flat)
+    flat_ref = torch.cat([p.grad.reshape(-1) for p in params])
+    assert float((flat - flat_ref).abs().max()) <= 1e-6 * float(flat_ref.abs().max())
     if rank == 0:
         _, _, _, Gfull = OT.forward_backward(P, x, noise, I, heads, gs / Bg)
         worst = max(float((p.grad.double() - Gfull[k]).abs().max() / Gfull[k].abs().max().clamp_min(1e-30))

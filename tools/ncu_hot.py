@@ -1,8 +1,9 @@
 """Summarise an ncu report's source page per CUDA source line: stall samples + dominant stall reasons.
-usage: python tools/ncu_hot.py report.ncu-rep [topN]"""
+usage: python tools/ncu_hot.py report.ncu-rep [topN] [kernel-regex]"""
 import csv, subprocess, sys, io, collections
 rep = sys.argv[1]; topn = int(sys.argv[2]) if len(sys.argv) > 2 else 25
-out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--print-source", "cuda,sass"], capture_output=True, text=True).stdout
+kf = ["-k", "regex:" + sys.argv[3]] if len(sys.argv) > 3 else []
+out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--print-source", "cuda,sass"] + kf, capture_output=True, text=True).stdout
 rows = list(csv.reader(io.StringIO(out)))
 fname = "?"; hdr = None; cur = None
 agg = collections.defaultdict(lambda: collections.Counter()); src = {}

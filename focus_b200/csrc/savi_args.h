@@ -78,7 +78,8 @@ int savi_fwd_umma_smem_bytes(const Dims& d);
 int savi_umma_mha_fits(int K, int heads);        // predictor attention core of the tcgen05 clip kernels fits its shared-memory windows
 cudaError_t savi_launch_bwd_umma(const BwdArgs& a, const unsigned char* wimg, const WImg& wi, cudaStream_t st);
 int savi_bwd_umma_smem_bytes(const Dims& d);
-cudaError_t savi_launch_dx_umma(const BwdArgs& a, const void* inputs, void* grad_inputs, cudaStream_t st);
+cudaError_t savi_launch_dx_umma(const BwdArgs& a, const void* inputs, void* grad_inputs, bool overlap, cudaStream_t st);
+bool savi_prof_enabled();
 int savi_dx_umma_smem_bytes(int I);
 cudaError_t savi_launch_wgrad_umma(const WgradArgs& wa, cudaStream_t st);
 size_t savi_fwd_smem_bytes(const Dims& d, int TN);

@@ -20,6 +20,7 @@ enum { B_HP = B_OPND2 };                      // W_hh^T product complete (its op
 
 struct BwdUArgs {
     BwdArgs a;
+    long long* trace;              // development (SAVI_DX_TRACE): globaltimer of CTA 0 at start / end
     const unsigned char* wimg;
     WImg wi;
 };
@@ -387,6 +388,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) savi_bwd_umma_kernel(const __grid
     fence_after_sync();
     if (CN > 1) { cluster_arrive(); cluster_wait(); }
     const uint32_t tb = *tmem_slot;
+    // every CTA of this grid is resident from here on: the dependent d_inputs grid may take the idle SMs (it waits on the frame flags)
+    asm volatile("griddepcontrol.launch_dependents;\n" ::: "memory");
+    if (ua.trace && tid == 0) { long long t_; asm volatile("mov.u64 %0, %%globaltimer;\n" : "=l"(t_)); atomicMin(ua.trace, t_); }
 
     Ring ring;
     ring.base = sm + L.ring; ring.full = &bars[B_FULL]; ring.empty = &bars[B_EMPTY]; ring.nst = L.nst; ring.stage = 0; ring.phase = 0;
@@ -777,6 +781,13 @@ __global__ void __launch_bounds__(NTHREADS, 1) savi_bwd_umma_kernel(const __grid
                 for (int kk = 0; kk < KH; ++kk) dh[kk] += hpv[kk] + dst[kk];
                 UPH(36);
             }
+            // frame t is fully staged (coefficient blocks, d(Ux) rows): release it to the d_inputs kernel, which runs
+            // concurrently on the SMs this grid leaves idle (programmatic dependent launch, savi_dx_umma.cu)
+            bar_sync_compute();
+            if (tid == 0) {
+                __threadfence();
+                atomicAdd(reinterpret_cast<int*>(reinterpret_cast<unsigned char*>(a.ws) + a.wl.flags) + b * d.T + t, 1);
+            }
         }
         // ---- slot initialisation backward (steve.py:56-57) and the accumulated vector-parameter gradients ----
         if (lead) {
@@ -806,6 +817,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) savi_bwd_umma_kernel(const __grid
     __syncwarp();
     fence_before_sync();
     __syncthreads();
+    if (ua.trace && tid == 0) { long long t_; asm volatile("mov.u64 %0, %%globaltimer;\n" : "=l"(t_)); atomicMax(ua.trace + 1, t_); }
     if (CN > 1) { cluster_arrive(); cluster_wait(); }
     if (warp == W_MMA) tmem_dealloc(tb, TB_COLS);
 }
@@ -820,6 +832,8 @@ int savi_bwd_umma_smem_bytes(const Dims& d) {
 cudaError_t savi_launch_bwd_umma(const BwdArgs& a, const unsigned char* wimg, const WImg& wi, cudaStream_t st) {
     BwdUArgs ua;
     ua.a = a; ua.wimg = wimg; ua.wi = wi;
+    ua.trace = (a.dbg && getenv("SAVI_DX_TRACE")) ? a.dbg + 64 + 3 * 4096 : nullptr;      // [0] = min start (preset to LLONG_MAX), [1] = max end
+    if (ua.trace) ua.a.dbg = nullptr;                                                         // no phase counters in a trace run
     ua.a.smem_bytes = savi_bwd_umma_smem_bytes(a.d);
     cudaError_t e = cudaFuncSetAttribute(savi_bwd_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ua.a.smem_bytes);
     if (e != cudaSuccess) return e;

@@ -42,6 +42,9 @@ struct DxUArgs {
     bf16* dx;
     float* dgamma; float* dbeta;
     int B, T, N, K, I, NTILE, tiles_per_cta;
+    const int* flags;           // [B*T] frame-staged counters of the clip kernel (nullptr: not overlapped)
+    int flag_target;            // CTAs per clip
+    long long* trace;           // development (SAVI_DX_TRACE): per CTA globaltimer at start, after the flag wait, at the end
 };
 
 // shared memory plan (bytes): rhs [2 blocks][64 I rows][128 B] | coef tiles x2 [I][16 KB] | column-sum scratch [8 warps][256] fp32 | gamma, bars
@@ -70,7 +73,8 @@ __global__ void __launch_bounds__(DX_THREADS, 1) dx_umma_kernel(const __grid_con
     if ((smem_u32(sm) & 1023u) != 0u) __trap();
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int I = a.I, K = a.K, N = a.N, KT = 64 * I;
-    const int f = blockIdx.y, b = f / a.T, t = f - b * a.T;
+    // frames in the order the backward clip kernel finishes them: t descending, all clips of a frame together
+    const int t = a.T - 1 - (int)blockIdx.y / a.B, b = (int)blockIdx.y % a.B, f = b * a.T + t;
     unsigned char* rhs = sm;
     unsigned char* ct = rhs + dx_rhs_bytes(I);                 // 2 stages of I blocks
     float* csum = reinterpret_cast<float*>(ct + 2 * I * 16384);   // [8 warps][2][128]
@@ -88,11 +92,26 @@ __global__ void __launch_bounds__(DX_THREADS, 1) dx_umma_kernel(const __grid_con
         mbar_init_fence();
     }
     if (warp == DX_EPI_WARPS) tmem_alloc(tmem_slot, TD_COLS);
-    __syncthreads();                                           // barriers exist before the first bulk copy is issued
+    for (int i = tid; i < 128; i += DX_THREADS) gam[i] = a.gamma[i];
+    long long t_start = 0;
+    if (a.trace && tid == 0) asm volatile("mov.u64 %0, %%globaltimer;\n" : "=l"(t_start));
+    if (tid == 0 && a.flags) {
+        // launched as a programmatic dependent of the clip kernel: wait (acquire) until this frame's records are staged
+        int v;
+        do {
+            asm volatile("ld.acquire.gpu.global.s32 %0, [%1];\n" : "=r"(v) : "l"(a.flags + f) : "memory");
+            if (v < a.flag_target) __nanosleep(256);
+        } while (v < a.flag_target);
+    }
+    if (a.trace && tid == 0) {
+        long long t1; asm volatile("mov.u64 %0, %%globaltimer;\n" : "=l"(t1));
+        const int cta = blockIdx.y * gridDim.x + blockIdx.x;
+        a.trace[3 * cta] = t_start; a.trace[3 * cta + 1] = t1;
+    }
+    __syncthreads();                                           // barriers exist (and the frame is staged) before the first bulk copy is issued
     if (tid == DX_EPI_WARPS * 32 && nt > 0) {                  // the first coefficient tile streams in while the right-hand side is staged
         mbar_expect_tx(&bars[BF], I * 16384); bulk_g2s(ct, coef_f, I * 16384, &bars[BF]);
     }
-    for (int i = tid; i < 128; i += DX_THREADS) gam[i] = a.gamma[i];
     // right-hand side rows: iteration i -> rows [64 i, 64 i + 64): qk_i (32 rows, zero beyond K) then dUx_i; MN-major, two 64-column blocks
 #pragma unroll 4
     for (int idx = tid; idx < KT * 16; idx += DX_THREADS) {
@@ -217,11 +236,15 @@ __global__ void __launch_bounds__(DX_THREADS, 1) dx_umma_kernel(const __grid_con
     }
     fence_before_sync();
     __syncthreads();
+    if (a.trace && tid == 0) {
+        long long t2; asm volatile("mov.u64 %0, %%globaltimer;\n" : "=l"(t2));
+        a.trace[3 * (blockIdx.y * gridDim.x + blockIdx.x) + 2] = t2;
+    }
     if (warp == DX_EPI_WARPS) tmem_dealloc(tb, TD_COLS);
 }
 }  // namespace
 
-cudaError_t savi_launch_dx_umma(const BwdArgs& a, const void* inputs, void* grad_inputs, cudaStream_t st) {
+cudaError_t savi_launch_dx_umma(const BwdArgs& a, const void* inputs, void* grad_inputs, bool overlap, cudaStream_t st) {
     const Dims& d = a.d;
     DxUArgs x;
     x.x = reinterpret_cast<const bf16*>(inputs);
@@ -238,8 +261,18 @@ cudaError_t savi_launch_dx_umma(const BwdArgs& a, const void* inputs, void* grad
     const int smem = dx_smem_total(d.I);
     cudaError_t e = cudaFuncSetAttribute(dx_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) return e;
-    dim3 grid((d.NTILE + x.tiles_per_cta - 1) / x.tiles_per_cta, d.B * d.T);
-    dx_umma_kernel<<<grid, DX_THREADS, smem, st>>>(x);
-    return cudaGetLastError();
+    x.flags = overlap ? reinterpret_cast<const int*>(reinterpret_cast<const unsigned char*>(a.ws) + a.wl.flags) : nullptr;
+    x.flag_target = d.CN;
+    x.trace = (a.dbg && getenv("SAVI_DX_TRACE")) ? a.dbg + 64 : nullptr;    // the debug buffer then holds 64 + 3 * grid + 2 entries
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((d.NTILE + x.tiles_per_cta - 1) / x.tiles_per_cta, d.B * d.T);
+    cfg.blockDim = dim3(DX_THREADS);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;       // may start while the preceding clip kernel still runs
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = overlap ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, dx_umma_kernel, x);
 }
 int savi_dx_umma_smem_bytes(int I) { return dx_smem_total(I); }

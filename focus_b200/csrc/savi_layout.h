@@ -228,6 +228,7 @@ struct BwdWsLayout {         // float offsets unless noted
     int64_t dq, st, dqk, du, dgi, dgh;           // S steps: widths Ds, Ds, D, Ds, 3Ds, 3Ds
     int64_t duxs;            // S steps, width D: d(Ux) of every step (right-hand side of the d_inputs kernel, mma mode)
     int64_t coef;            // BYTE offset: [B*T][I][2][KC][N] bf16 staged dL^T, W^T (mma mode)
+    int64_t flags;           // BYTE offset (tcgen05 path): int [B*T] "frame staged" counters, the clip kernel -> the overlapped d_inputs kernel
     int64_t dhm, da, m;                          // Sm steps: widths Ds, M, Ds
     int64_t pdq, pdk, pdv, pdx1, pdx2, pdf;      // Sp: widths Ds x5, 4Ds
     int64_t part;            // [B][2][CN][K*D]  partial d(qk) per cluster rank
@@ -275,4 +276,6 @@ static inline void savi_bwd_ws_layout(const Dims& d, BwdWsLayout& L) {
     if (d.umma) L.total_bytes = (g * 4 + 1023) / 1024 * 1024 + (int64_t)d.B * d.T * d.NTILE * d.I * 16384;
     else L.total_bytes = g * 4 + (d.mma ? (int64_t)d.B * d.T * d.I * 2 * d.KC * d.N * 2 : 0);
     if (d.umma) L.coef = (g * 4 + 1023) / 1024 * 1024;
+    L.flags = L.total_bytes;
+    if (d.umma) L.total_bytes += ((int64_t)d.B * d.T * 4 + 255) / 256 * 256;
 }

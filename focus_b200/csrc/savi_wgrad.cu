@@ -81,8 +81,13 @@ cudaError_t savi_launch_backward(const BwdArgs& a, const void* inputs, void* gra
     const Dims& d = a.d;
     cudaError_t e = cudaMemsetAsync(a.grad_params, 0, (size_t)a.po.total * sizeof(float), st);
     if (e != cudaSuccess) return e;
-    savi_prof_begin(3, st);
     const bool umma_bwd = d.umma && !getenv("SAVI_UMMA_FWD_ONLY");
+    const bool overlap_dx = umma_bwd && !getenv("SAVI_NO_OVERLAP");
+    if (umma_bwd) {
+        e = cudaMemsetAsync(reinterpret_cast<unsigned char*>(a.ws) + a.wl.flags, 0, (size_t)d.B * d.T * sizeof(int), st);
+        if (e != cudaSuccess) return e;
+    }
+    savi_prof_begin(3, st);
     if (umma_bwd) {
         WImg wi;
         savi_wimg_layout(d.D, d.Ds, d.M, d.blocks, wi);
@@ -91,6 +96,15 @@ cudaError_t savi_launch_backward(const BwdArgs& a, const void* inputs, void* gra
     savi_prof_end(3, st);
     if (e != cudaSuccess) return e;
     *launches += 1;
+    if (umma_bwd) {
+        // d_inputs directly behind the clip kernel as its programmatic dependent: its CTAs start on the SMs the clip grid
+        // leaves idle (148 - B*CN) and on every SM a finished clip CTA frees, gated per (clip, frame) by the staging flags
+        savi_prof_begin(5, st);
+        e = savi_launch_dx_umma(a, inputs, grad_inputs, overlap_dx, st);
+        savi_prof_end(5, st);
+        if (e != cudaSuccess) return e;
+        *launches += 1;
+    }
 
     const float* fb = reinterpret_cast<const float*>(a.saved + a.sl.fbase);
     const float* W = a.ws;
@@ -141,9 +155,9 @@ cudaError_t savi_launch_backward(const BwdArgs& a, const void* inputs, void* gra
         if (e != cudaSuccess) return e;
         *launches += 1;
     }
+    if (umma_bwd) return cudaSuccess;
     savi_prof_begin(5, st);
-    if (umma_bwd) e = savi_launch_dx_umma(a, inputs, grad_inputs, st);
-    else if (d.mma) e = savi_launch_dx_mma(a, inputs, grad_inputs, st);
+    if (d.mma) e = savi_launch_dx_mma(a, inputs, grad_inputs, st);
     else if (d.tok_bytes == 4) e = savi_launch_ln_bwd_f32(a, inputs, grad_inputs, st);
     else e = savi_launch_ln_bwd_bf16(a, inputs, grad_inputs, st);
     savi_prof_end(5, st);

@@ -13,6 +13,7 @@ SAVI_DTYPE_F32 = 0
 SAVI_DTYPE_BF16 = 1
 SAVI_MAX_BLOCKS = 4
 SAVI_MAX_SLOTS = 64
+PATH_NAMES = {0: "simt-fp32", 1: "mma.sync-bf16", 2: "tcgen05-bf16"}
 
 EXPORTS = ["savi_version", "savi_last_error", "savi_query", "savi_param_layout", "savi_pack_params",
            "savi_forward", "savi_backward", "savi_last_launch_count", "savi_profile_enable", "savi_profile_read", "savi_debug_set_phase_buffer"]
@@ -27,7 +28,7 @@ class SaviShape(ctypes.Structure):
 class SaviSizes(ctypes.Structure):
     _fields_ = [(n, ctypes.c_int64) for n in
                 ("n_params", "param_floats", "packed_bytes", "saved_bytes", "fwd_ws_bytes", "bwd_ws_bytes")] + \
-               [("cluster", ctypes.c_int32), ("reserved", ctypes.c_int32)]
+               [("cluster", ctypes.c_int32), ("path", ctypes.c_int32)]
 
 
 def _load():

@@ -189,7 +189,7 @@ extern "C" int savi_query(const SaviShape* shape, SaviSizes* sizes) {
     sizes->fwd_ws_bytes = fl.total_bytes;
     sizes->bwd_ws_bytes = bl.total_bytes;
     sizes->cluster = d.CN;
-    sizes->reserved = 0;
+    sizes->path = d.umma ? SAVI_PATH_TCGEN05 : d.mma ? SAVI_PATH_MMA_SYNC : SAVI_PATH_SIMT;
     return SAVI_OK;
 }
 

@@ -44,6 +44,11 @@ extern "C" {
 
 /* Problem description.  Mirrors the constructor arguments of the reference
  * module (steve.py:13-18) plus the call-time sizes of `inputs` [B,T,N,D]. */
+/* Kernel family chosen for a shape (SaviSizes.path); every family is hand-written sm_100a CUDA, there is no fallback. */
+#define SAVI_PATH_SIMT     0   /* fp32 tokens, or shapes outside the tensor-core tiles: fp32 FMA clip kernels      */
+#define SAVI_PATH_MMA_SYNC 1   /* bf16 tokens, general D/Ds/M/K: warp-level mma.sync clip kernels                  */
+#define SAVI_PATH_TCGEN05  2   /* bf16 tokens, D = Ds = M = 128, K <= 24: tcgen05 / TMEM clip kernels                */
+
 typedef struct {
     int32_t B;        /* clips in this call (per GPU)                               */
     int32_t T;        /* frames per clip                                            */
@@ -70,7 +75,7 @@ typedef struct {
     int64_t fwd_ws_bytes;    /* forward scratch (contents dead after forward)         */
     int64_t bwd_ws_bytes;    /* backward scratch                                      */
     int32_t cluster;         /* cluster size that will be used                        */
-    int32_t reserved;
+    int32_t path;            /* SAVI_PATH_*: which kernel family this shape runs on   */
 } SaviSizes;
 
 int savi_version(void);

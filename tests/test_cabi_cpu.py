@@ -49,6 +49,17 @@ def test_query_sizes_and_validation():
         assert L.query(s).cluster == want, (B, N)
 
 
+def test_query_reports_the_kernel_family():
+    L = _lib()
+    mk = lambda **kw: L.SaviShape(**{**dict(B=64, T=6, N=1024, D=128, Ds=128, M=128, K=24, I=3, blocks=1, heads=4, dtype=1,
+                                          cluster=0, eps=1e-8, ln_eps=1e-5), **kw})
+    assert L.PATH_NAMES[L.query(mk()).path] == "tcgen05-bf16"                       # C2
+    assert L.PATH_NAMES[L.query(mk(K=11, I=2, T=24)).path] == "tcgen05-bf16"        # C4
+    assert L.PATH_NAMES[L.query(mk(N=4096, D=192, Ds=192, M=192)).path] == "mma.sync-bf16"   # C3
+    assert L.PATH_NAMES[L.query(mk(K=32)).path] == "mma.sync-bf16"
+    assert L.PATH_NAMES[L.query(mk(B=2, dtype=0)).path] == "simt-fp32"              # C1
+
+
 @pytest.mark.parametrize("cfg", [(3, 24, 128, 128, 128, 1, 4), (2, 15, 192, 192, 192, 1, 4), (3, 7, 64, 32, 1024, 4, 8), (1, 3, 16, 16, 16, 0, 1)])
 def test_module_mirrors_reference_contract(cfg):
     from focus_b200 import SlotAttentionVideo

@@ -119,6 +119,50 @@ def test_shape_sweep_against_oracle(shape, dtype):
         _check((s, a, dx, G), _oracle(fx, x64, ga64, token_dtype="bf16"), TOL_BF16)
 
 
+# the tcgen05 clip kernels (bf16 tokens, D = Ds = M = 128, K <= 24): slot counts, ragged / sub-tile N, predictor variants
+UMMA_SHAPES = [
+    (3, 2, 200, 128, 128, 128, 7, 2, 1, 4),      # K=7, N not a multiple of the 128-token tile
+    (2, 3, 1032, 128, 128, 128, 11, 2, 2, 8),    # BASELINE configs[3]-like: K=11, 2 iterations; 2 blocks x 8 heads; 8 tiles + 8 tokens
+    (1, 1, 136, 128, 128, 128, 2, 1, 0, 1),      # K=2, I=1 (no MLP), T=1, no predictor block
+    (5, 2, 384, 128, 128, 128, 24, 3, 1, 2),     # odd clip count, K=24
+    (2, 2, 64, 128, 128, 128, 15, 2, 1, 4),      # fewer tokens than one tile (single CTA per clip)
+]
+
+
+@pytest.mark.parametrize("shape", UMMA_SHAPES)
+@pytest.mark.parametrize("cluster", [0, 1])
+def test_tcgen05_path_shape_sweep(shape, cluster):
+    from focus_b200 import SlotAttentionVideo, _lib
+    from oracle import savi_numpy as O
+    B, T, N, D, Ds, M, K, I, blocks, heads = shape
+    probe = SlotAttentionVideo(I, K, D, Ds, M, blocks, heads, 0.0)
+    probe.cluster = cluster
+    assert _lib.query(probe.make_shape(B, T, N, torch.bfloat16)).path == 2, "shape does not reach the tcgen05 kernels"
+    rng = np.random.default_rng(hash(shape) % 2 ** 31)
+    fx = dict(B=B, T=T, N=N, D=D, Ds=Ds, M=M, K=K, I=I, blocks=blocks, heads=heads, sub=1,
+              params={k: v.astype(np.float32) for k, v in O.random_params(K, D, Ds, M, blocks, seed=4).items()},
+              x=rng.standard_normal((B, T, N, D)).astype(np.float32) * 1.5 + 0.3,
+              noise=rng.standard_normal((B, K, Ds)).astype(np.float32),
+              g_slots=rng.standard_normal((B, T, K, Ds)).astype(np.float32),
+              g_attn=rng.standard_normal((B, T, N, K)).astype(np.float32))
+    s, a, dx, G, x64, ga64 = _run_cuda(fx, torch.bfloat16, cluster=cluster)
+    _check((s, a, dx, G), _oracle(fx, x64, ga64, token_dtype="bf16"), TOL_BF16)
+
+
+def test_overlapped_d_inputs_equals_serial(monkeypatch):
+    """The d_inputs kernel normally runs as a programmatic dependent of the backward clip kernel (gated by per-frame
+    flags); with SAVI_NO_OVERLAP it runs after it.  d_inputs must be bit-identical either way."""
+    fx = load_fixture("c1")
+    monkeypatch.delenv("SAVI_NO_OVERLAP", raising=False)
+    a1 = _run_cuda(fx, torch.bfloat16)
+    monkeypatch.setenv("SAVI_NO_OVERLAP", "1")
+    a2 = _run_cuda(fx, torch.bfloat16)
+    assert np.array_equal(a1[2], a2[2])
+    assert np.array_equal(a1[0], a2[0]) and np.array_equal(a1[1], a2[1])
+    gs = grad_scale(a2[3])
+    assert all(float(np.abs(a1[3][k] - a2[3][k]).max()) <= 1e-6 * gs for k in a2[3])      # atomics may reorder the LN sums
+
+
 def test_grad_attn_none_is_the_trainer_case():
     """steve_train_net.py never back-propagates through attns: grad_attn = None."""
     fx = load_fixture("tiny_a")

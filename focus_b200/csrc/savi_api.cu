@@ -6,6 +6,7 @@
 #include <cstdlib>
 #include "savi_dx_mma.cuh"
 #include "savi_args.h"
+#include "savi_smallgemm.cuh"
 
 static thread_local char g_err[512] = "";
 static thread_local int g_launches = 0;
@@ -230,7 +231,7 @@ extern "C" int savi_param_layout(const SaviShape* shape, int64_t* offsets_host, 
 constexpr int MAXP = 21 + 12 * SAVI_MAX_BLOCKS;
 struct PackArgs { const float* src[MAXP]; int off[MAXP]; int num[MAXP]; int count; };
 struct TrJob { int src, dst, rows, cols; };
-constexpr int MAXTR = 7 + 6 * SAVI_MAX_BLOCKS;
+constexpr int MAXTR = 9 + 6 * SAVI_MAX_BLOCKS;
 struct TrArgs { TrJob job[MAXTR]; int count; };
 
 __global__ void pack_copy_kernel(const __grid_constant__ PackArgs pa, float* __restrict__ packed) {
@@ -260,18 +261,29 @@ __global__ void pack_split_kernel(const float* __restrict__ packed, bf16* __rest
     }
 }
 
-// fp32 matrix A[R][C] (row-major at packed + src, leading dimension ld) -> blocked SWIZZLE_128B bf16 hi / lo image
-struct ImgJob { int src, R, C, ld; long long dst; };
+// fp32 matrix A[R][C] -> blocked SWIZZLE_128B bf16 hi / lo image.  tr = 0: A is row-major at packed + src (leading dimension
+// ld); tr = 1: A is the TRANSPOSE of the row-major [C][R] matrix stored there (the backward-orientation images are read
+// straight from the original weights: no transposed fp32 copy is needed on the tcgen05 path).
+struct ImgJob { int src, R, C, ld, tr; long long dst; };
 constexpr int MAXIMG = 2 * (7 + 6 * SAVI_MAX_BLOCKS);
 struct ImgArgs { ImgJob job[MAXIMG]; int count; };
 __global__ void pack_image_kernel(const __grid_constant__ ImgArgs ia, const float* __restrict__ packed, unsigned char* __restrict__ img) {
     const ImgJob j = ia.job[blockIdx.y];
     const int c8n = j.C >> 3;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < j.R * c8n; i += gridDim.x * blockDim.x) {
-        const int r = i / c8n, c0 = (i - r * c8n) * 8;
-        const float* src = packed + j.src + (size_t)r * j.ld + c0;
-        const float4 v0 = *reinterpret_cast<const float4*>(src), v1 = *reinterpret_cast<const float4*>(src + 4);
-        const float v[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
+        int r, c0;
+        float v[8];
+        if (!j.tr) {
+            r = i / c8n; c0 = (i - r * c8n) * 8;
+            const float* src = packed + j.src + (size_t)r * j.ld + c0;
+            const float4 v0 = *reinterpret_cast<const float4*>(src), v1 = *reinterpret_cast<const float4*>(src + 4);
+            v[0] = v0.x; v[1] = v0.y; v[2] = v0.z; v[3] = v0.w; v[4] = v1.x; v[5] = v1.y; v[6] = v1.z; v[7] = v1.w;
+        } else {
+            c0 = (i / j.R) * 8; r = i - (i / j.R) * j.R;            // consecutive threads read consecutive r: coalesced
+            const float* src = packed + j.src + (size_t)c0 * j.ld + r;
+#pragma unroll
+            for (int e = 0; e < 8; ++e) v[e] = src[(size_t)e * j.ld];
+        }
         bf16 h[8], l[8];
 #pragma unroll
         for (int e = 0; e < 8; ++e) split_bf16(v[e], h[e], l[e]);
@@ -317,49 +329,62 @@ extern "C" int savi_pack_params(const SaviShape* shape, const void* const* param
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return cuda_fail(e, "pack_copy_kernel");
     const int D = shape->D, Ds = shape->Ds, M = shape->M;
-    TrArgs ta; ta.count = 0;
-    auto tr = [&](int src, int dst, int rows, int cols) { ta.job[ta.count++] = TrJob{src, dst, rows, cols}; };
-    tr(po.wq, po.wq_t, Ds, Ds); tr(po.wk, po.wk_t, Ds, D); tr(po.wv, po.wv_t, Ds, D);
-    tr(po.wih, po.wih_t, 3 * Ds, Ds); tr(po.whh, po.whh_t, 3 * Ds, Ds);
-    tr(po.w1, po.w1_t, M, Ds); tr(po.w2, po.w2_t, Ds, M);
-    for (int j = 0; j < shape->blocks; ++j) {
-        const BlockOff& b = po.blk[j]; const BlockOffT& t = po.blkt[j];
-        tr(b.pq, t.pq_t, Ds, Ds); tr(b.pk, t.pk_t, Ds, Ds); tr(b.pv, t.pv_t, Ds, Ds); tr(b.po, t.po_t, Ds, Ds);
-        tr(b.f1, t.f1_t, 4 * Ds, Ds); tr(b.f2, t.f2_t, Ds, 4 * Ds);
+    g_launches = 1;                                          // pack_copy_kernel
+    if (d.umma) {
+        // folded weights of the tcgen05 path (ParamOff::wqk, wg), fp32, from the packed originals
+        float* Pk = reinterpret_cast<float*>(packed);
+        SmallGemmArgs ga; ga.count = 2;
+        ga.g[0] = SmallGemm{Pk + po.wk, Pk + po.wq, Pk + po.wqk, D, Ds, Ds, 1, D, Ds, 1, d.qscale};       // wqk[d][c] = s sum_a Wk[a][d] Wq[a][c]
+        ga.g[1] = SmallGemm{Pk + po.wih, Pk + po.wv, Pk + po.wg, 3 * Ds, D, Ds, Ds, 1, D, 1, 1.0f};        // wg[g][d] = sum_a Wih[g][a] Wv[a][d]
+        e = launch_small_gemms(ga, st);
+        if (e != cudaSuccess) return cuda_fail(e, "small_gemm_kernel (weight folds)");
+        g_launches += 1;
     }
-    pack_transpose_kernel<<<dim3(64, ta.count), 256, 0, st>>>(ta, reinterpret_cast<float*>(packed));
-    e = cudaGetLastError();
-    if (e != cudaSuccess) return cuda_fail(e, "pack_transpose_kernel");
-    {
+    if (!d.umma) {
+        // transposed fp32 copies + bf16 hi / lo copies: operands of the SIMT and mma.sync clip kernels
+        TrArgs ta; ta.count = 0;
+        auto tr = [&](int src, int dst, int rows, int cols) { ta.job[ta.count++] = TrJob{src, dst, rows, cols}; };
+        tr(po.wq, po.wq_t, Ds, Ds); tr(po.wk, po.wk_t, Ds, D); tr(po.wv, po.wv_t, Ds, D);
+        tr(po.wih, po.wih_t, 3 * Ds, Ds); tr(po.whh, po.whh_t, 3 * Ds, Ds);
+        tr(po.w1, po.w1_t, M, Ds); tr(po.w2, po.w2_t, Ds, M);
+        for (int j = 0; j < shape->blocks; ++j) {
+            const BlockOff& b = po.blk[j]; const BlockOffT& t = po.blkt[j];
+            tr(b.pq, t.pq_t, Ds, Ds); tr(b.pk, t.pk_t, Ds, Ds); tr(b.pv, t.pv_t, Ds, Ds); tr(b.po, t.po_t, Ds, Ds);
+            tr(b.f1, t.f1_t, 4 * Ds, Ds); tr(b.f2, t.f2_t, Ds, 4 * Ds);
+        }
+        pack_transpose_kernel<<<dim3(64, ta.count), 256, 0, st>>>(ta, reinterpret_cast<float*>(packed));
+        e = cudaGetLastError();
+        if (e != cudaSuccess) return cuda_fail(e, "pack_transpose_kernel");
         bf16* hi = reinterpret_cast<bf16*>(reinterpret_cast<float*>(packed) + po.packed_total);
         pack_split_kernel<<<148, 512, 0, st>>>(reinterpret_cast<const float*>(packed), hi, hi + po.packed_total, po.packed_total);
         e = cudaGetLastError();
         if (e != cudaSuccess) return cuda_fail(e, "pack_split_kernel");
-    }
-    g_launches = 3;
-    if (d.umma) {
+        g_launches += 2;
+    } else {
+        // tcgen05 path: every weight the clip kernels multiply by, as blocked SWIZZLE_128B bf16 hi / lo operand images
         WImg wi; savi_wimg_layout(D, Ds, M, shape->blocks, wi);
         ImgArgs ia; ia.count = 0;
-        auto im = [&](int src, int R, int C, int64_t dst) { ia.job[ia.count++] = ImgJob{src, R, C, C, (long long)dst}; };
-        // forward orientation: rows = output feature of the product (W itself; W_k enters transposed: qk = q W_k)
-        im(po.wq, Ds, Ds, wi.wq); im(po.wk_t, D, Ds, wi.wkT); im(po.wv, Ds, D, wi.wv);
-        im(po.wih, 3 * Ds, Ds, wi.wih); im(po.whh, 3 * Ds, Ds, wi.whh); im(po.w1, M, Ds, wi.w1); im(po.w2, Ds, M, wi.w2);
+        auto im = [&](int src, int R, int C, int64_t dst) { ia.job[ia.count++] = ImgJob{src, R, C, C, 0, (long long)dst}; };
+        auto imT = [&](int src, int R, int C, int64_t dst) { ia.job[ia.count++] = ImgJob{src, R, C, R, 1, (long long)dst}; };   // image of src^T, src = [C][R]
+        // forward orientation: rows = output feature of the product
+        im(po.wqk, D, Ds, wi.wqk); im(po.wg, 3 * Ds, D, wi.wg);
+        im(po.whh, 3 * Ds, Ds, wi.whh); im(po.w1, M, Ds, wi.w1); im(po.w2, Ds, M, wi.w2);
         // backward orientation: rows = input feature (dX = dY W)
-        im(po.wq_t, Ds, Ds, wi.wqT); im(po.wk, Ds, D, wi.wk); im(po.wv_t, D, Ds, wi.wvT);
-        im(po.wih_t, Ds, 3 * Ds, wi.wihT); im(po.whh_t, Ds, 3 * Ds, wi.whhT); im(po.w1_t, Ds, M, wi.w1T); im(po.w2_t, M, Ds, wi.w2T);
+        imT(po.wqk, Ds, D, wi.wqkT); imT(po.wg, D, 3 * Ds, wi.wgT);
+        imT(po.whh, Ds, 3 * Ds, wi.whhT); imT(po.w1, Ds, M, wi.w1T); imT(po.w2, M, Ds, wi.w2T);
         for (int j = 0; j < shape->blocks; ++j) {
-            const BlockOff& b = po.blk[j]; const BlockOffT& t = po.blkt[j];
+            const BlockOff& b = po.blk[j];
             const WImgBlock& f = wi.blk[j]; const WImgBlock& r = wi.blkT[j];
             im(b.pq, Ds, Ds, f.pq); im(b.pk, Ds, Ds, f.pk); im(b.pv, Ds, Ds, f.pv); im(b.po, Ds, Ds, f.po);
             im(b.f1, 4 * Ds, Ds, f.f1); im(b.f2, Ds, 4 * Ds, f.f2);
-            im(t.pq_t, Ds, Ds, r.pq); im(t.pk_t, Ds, Ds, r.pk); im(t.pv_t, Ds, Ds, r.pv); im(t.po_t, Ds, Ds, r.po);
-            im(t.f1_t, Ds, 4 * Ds, r.f1); im(t.f2_t, 4 * Ds, Ds, r.f2);
+            imT(b.pq, Ds, Ds, r.pq); imT(b.pk, Ds, Ds, r.pk); imT(b.pv, Ds, Ds, r.pv); imT(b.po, Ds, Ds, r.po);
+            imT(b.f1, Ds, 4 * Ds, r.f1); imT(b.f2, 4 * Ds, Ds, r.f2);
         }
         pack_image_kernel<<<dim3(16, ia.count), 256, 0, st>>>(ia, reinterpret_cast<const float*>(packed),
                                                               reinterpret_cast<unsigned char*>(packed) + savi_wimg_base(po.packed_total));
         e = cudaGetLastError();
         if (e != cudaSuccess) return cuda_fail(e, "pack_image_kernel");
-        g_launches = 4;
+        g_launches += 1;
     }
     savi_prof_end(0, st);
     return SAVI_OK;

@@ -417,12 +417,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) savi_bwd_umma_kernel(const __grid
                 const unsigned char* xf = ximg + ((size_t)(b * d.T + t) * d.NTILE + tile0) * 2 * BLK;
                 for (int it = d.I - 1; it >= 0; --it) {
                     if (it < d.I - 1) { prod_blocks(ring, Wi + wi.w2T, 4); prod_blocks(ring, Wi + wi.w1T, 4); }
-                    prod_blocks(ring, Wi + wi.wihT, 12);
+                    prod_blocks(ring, Wi + wi.wgT, 12);
                     prod_blocks(ring, Wi + wi.whhT, 12);
-                    prod_blocks(ring, Wi + wi.wvT, 4);
                     prod_blocks(ring, xf, 2 * ntile);
-                    prod_blocks(ring, Wi + wi.wk, 4);
-                    prod_blocks(ring, Wi + wi.wqT, 4);
+                    prod_blocks(ring, Wi + wi.wqkT, 4);
                 }
             }
         }
@@ -465,20 +463,16 @@ __global__ void __launch_bounds__(NTHREADS, 1) savi_bwd_umma_kernel(const __grid
                         issue_linear(ring, el, X1, tb + TB_B, 1, 2, false); if (el) mma_commit(&bars[B_ACC]);        // d m = mlp.0^T d a
                     }
                     wait_opnd();                                                           // dr, dz, dn, dn*r in X0..X3
-                    issue_linear(ring, el, X0, tb + TB_A, 1, 2, false);
-                    issue_linear(ring, el, X1, tb + TB_A, 1, 2, true);
-                    issue_linear(ring, el, X2, tb + TB_A, 1, 2, true); if (el) mma_commit(&bars[B_ACC]);             // dU = W_ih^T dgi
+                    issue_linear(ring, el, X0, tb + TB_B, 1, 2, false);
+                    issue_linear(ring, el, X1, tb + TB_B, 1, 2, true);
+                    issue_linear(ring, el, X2, tb + TB_B, 1, 2, true); if (el) mma_commit(&bars[B_ACC]);             // dUx = (W_ih W_v)^T dgi  (folded: dU is never formed)
                     issue_linear(ring, el, X0, tb + TB_HP, 1, 2, false);
                     issue_linear(ring, el, X1, tb + TB_HP, 1, 2, true);
                     issue_linear(ring, el, X3, tb + TB_HP, 1, 2, true); if (el) mma_commit(&bars[B_HP]);             // W_hh^T dgh (consumed at the end of the step)
-                    wait_opnd();                                                           // dU in X2
-                    issue_linear(ring, el, X2, tb + TB_B, 1, 2, false); if (el) mma_commit(&bars[B_ACC]);            // dUx = W_v^T dU
                     wait_opnd();                                                           // dUx in X0, qk in X1
                     issue_token_pass_bwd(ring, el, bars, tb, ntile, ts, X1, X0, X2, X3);
                     wait_opnd();                                                           // d qk in X0
-                    issue_linear(ring, el, X0, tb + TB_A, 1, 2, false); if (el) mma_commit(&bars[B_ACC]);            // dq = W_k d qk
-                    wait_opnd();                                                           // dq in X1
-                    issue_linear(ring, el, X1, tb + TB_B, 1, 2, false); if (el) mma_commit(&bars[B_ACC]);            // d s~ = W_q^T dq
+                    issue_linear(ring, el, X0, tb + TB_B, 1, 2, false); if (el) mma_commit(&bars[B_ACC]);            // d s~ = wqk^T d qk  (folded: dq is never formed)
                 }
             }
         }
@@ -708,13 +702,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) savi_bwd_umma_kernel(const __grid
                 load_field(c, frow(fbw, a.sl.qk, s, b, B, K, F), F, o, qk);
                 load_field(c, frow(fbw, a.sl.ux, s, b, B, K, F), F, o, ux);
                 const float ssv = (tid < K) ? fb[a.sl.ssum + (s * B + b) * KP + tid] : 1.f;
-                wait_acc(c); load_acc(c, TB_A, v);                                         // dU
-                UPH(28);
-                if (svA) save_field(c, frow(W, a.wl.du, s, b, B, K, F), F, o, v);
-                write_operand(c, xop(L, 2), v);
-                signal_operand(c);
                 if (tid < 32) cv[32 + tid] = (tid < K) ? 1.0f / ssv : 0.f;
-                wait_acc(c); load_acc(c, TB_B, dux);                                       // dUx
+                UPH(28);
+                wait_acc(c); load_acc(c, TB_B, dux);                                       // dUx = dgi (W_ih W_v)
                 UPH(29);
                 if (svB) save_field(c, frow(W, a.wl.duxs, s, b, B, K, F), F, o, dux);
                 // c[k] = <dUx[k,:], Ux[k,:]>: reduce over the 128 features through the scratch tile
@@ -764,13 +754,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) savi_bwd_umma_kernel(const __grid
                 if (svA) save_field(c, frow(W, a.wl.dqk, s, b, B, K, F), F, o, dqk);
                 write_operand(c, xop(L, 0), dqk);
                 signal_operand(c);
-                wait_acc(c); load_acc(c, TB_A, v);                                         // dq = Ds^-1/2 W_k d qk
-#pragma unroll
-                for (int kk = 0; kk < KH; ++kk) v[kk] *= d.qscale;
                 UPH(34);
-                if (svB) save_field(c, frow(W, a.wl.dq, s, b, B, K, F), F, o, v);
-                write_operand(c, xop(L, 1), v);
-                signal_operand(c);
                 float hp[KH], dst[KH], hpv[KH];
                 load_field(c, frow(fbw, a.sl.hp, s, b, B, K, F), F, o, hp);
                 load_acc(c, TB_HP, hpv);                                                   // W_hh^T dgh (B_HP was observed above)

@@ -292,12 +292,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) savi_fwd_umma_kernel(const __grid
             for (int t = 0; t < d.T; ++t) {
                 const unsigned char* xf = ximg + ((size_t)(b * d.T + t) * d.NTILE + tile0) * 2 * BLK;
                 for (int it = 0; it < d.I; ++it) {
-                    prod_blocks(ring, W + wi.wq, 4);
-                    prod_blocks(ring, W + wi.wkT, 4);
+                    prod_blocks(ring, W + wi.wqk, 4);
                     prod_blocks(ring, xf, 2 * ntile);
                     prod_blocks(ring, W + wi.whh, 12);
-                    prod_blocks(ring, W + wi.wv, 4);
-                    prod_blocks(ring, W + wi.wih, 12);
+                    prod_blocks(ring, W + wi.wg, 12);
                     if (it < d.I - 1) { prod_blocks(ring, W + wi.w1, 4); prod_blocks(ring, W + wi.w2, 4); }
                 }
                 if (t < d.T - 1) {
@@ -334,19 +332,15 @@ __global__ void __launch_bounds__(NTHREADS, 1) savi_fwd_umma_kernel(const __grid
             for (int t = 0; t < d.T; ++t) {
                 for (int it = 0; it < d.I; ++it) {
                     wait_opnd();                                                          // s~ in opA, h_prev in opC
-                    issue_linear(ring, el, opA, tb + TC_A, 1, 2, false); if (el) mma_commit(&bars[B_ACC]);          // q   (steve.py:75)
-                    wait_opnd();                                                          // q in opB
-                    issue_linear(ring, el, opB, tb + TC_B, 1, 2, false); if (el) mma_commit(&bars[B_ACC]);          // qk  (fold of :61,63,76)
+                    issue_linear(ring, el, opA, tb + TC_B, 1, 2, false); if (el) mma_commit(&bars[B_ACC]);          // qk = s~ . wqk^T  (steve.py:75 and the fold of :61,63,76 in one product)
                     wait_opnd();                                                          // qk in opA
                     { const long long t0 = clock64(); issue_token_pass(ring, el, sm, L, bars, tb, ntile, ts, opA); i_tok += clock64() - t0; }
                     // GRU hidden-side product, off the critical path: runs while the compute threads combine the partial sums.
                     // (It must not be streamed while token tiles are held in the ring: the ring is filled in order.)
                     issue_linear(ring, el, opC, tb + TC_R, 3, 2, false);                      // R, Z, HN = W_hh . h_prev
                     wait_opnd();                                                          // Ux in opB
-                    issue_linear(ring, el, opB, tb + TC_A, 1, 2, false); if (el) mma_commit(&bars[B_ACC]);          // updates (:83)
-                    wait_opnd();                                                          // U in opA
-                    issue_linear(ring, el, opA, tb + TC_R, 2, 2, true);                                      // R, Z += W_i{r,z} . U
-                    issue_linear(ring, el, opA, tb + TC_IN, 1, 2, false); if (el) mma_commit(&bars[B_ACC]);         // IN = W_in . U   (:87)
+                    issue_linear(ring, el, opB, tb + TC_R, 2, 2, true);                                      // R, Z += (W_i{r,z} W_v) . Ux   (updates :83 folded into :87)
+                    issue_linear(ring, el, opB, tb + TC_IN, 1, 2, false); if (el) mma_commit(&bars[B_ACC]);         // IN = (W_in W_v) . Ux
                     if (it < d.I - 1) {
                         wait_opnd();                                                      // LN_m(h') in opB
                         issue_linear(ring, el, opB, tb + TC_A, 1, 2, false); if (el) mma_commit(&bars[B_ACC]);      // mlp.0 (:92)
@@ -409,14 +403,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) savi_fwd_umma_kernel(const __grid
                 write_operand(c, L.opA, y);
                 signal_operand(c);
                 UPH(1);
-                wait_acc(c); UPH(2); load_acc(c, TC_A, y);                                  // q
-                if (svA) save_field(c, frow(fb, a.sl.q, s, b, B, K, F), F, o, y);
-                write_operand(c, L.opB, y);
-                signal_operand(c);
-                UPH(3);
-                wait_acc(c); UPH(4); load_acc(c, TC_B, y);                                  // qk = Ds^-1/2 q Wk
-#pragma unroll
-                for (int kk = 0; kk < KH; ++kk) y[kk] *= d.qscale;
+                wait_acc(c); UPH(4); load_acc(c, TC_B, y);                                  // qk = Ds^-1/2 (s~ Wq^T) Wk, the scale folded into wqk
                 if (svB) save_field(c, frow(fb, a.sl.qk, s, b, B, K, F), F, o, y);
                 write_operand(c, L.opA, y);
                 signal_operand(c);
@@ -471,11 +458,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) savi_fwd_umma_kernel(const __grid
                 write_operand(c, L.opB, y);
                 signal_operand(c);
                 UPH(10);
-                wait_acc(c); UPH(11); load_acc(c, TC_A, y);                                 // updates U (:83)
-                if (svB) save_field(c, frow(fb, a.sl.u, s, b, B, K, F), F, o, y);
-                write_operand(c, L.opA, y);
-                signal_operand(c);
-                // ---- GRUCell (:87-89) ----
+                // ---- GRUCell (:87-89): the input-side product takes Ux directly (updates = Ux Wv^T is never formed) ----
                 UPH(12);
                 wait_acc(c);
                 UPH(13);

@@ -33,6 +33,10 @@ struct ParamOff {
     // packed-only region: transposed weights
     int wq_t, wk_t, wv_t, wih_t, whh_t, w1_t, w2_t;
     BlockOffT blkt[SAVI_MAX_BLOCKS];
+    // packed-only region, tcgen05 path: products of weights that only ever act in sequence (built by pack_fold_kernel)
+    //   wqk[d][c] = Ds^-1/2 sum_a Wk[a][d] Wq[a][c]   (qk = s~ . wqk^T :  project_q then the folded project_k, steve.py:61-63,75-76)
+    //   wg[g][d]  = sum_a Wih[g][a] Wv[a][d]          (gi = Ux . wg^T  :  the folded project_v then gru.weight_ih, :83,87)
+    int wqk, wg, wqk_t, wg_t;
     int packed_total;        // floats in the packed buffer
 };
 
@@ -49,25 +53,25 @@ constexpr int64_t UMMA_BLK = 16384;
 static SAVI_HD int64_t wimg_bytes(int R, int C) { return (int64_t)(R / 128) * (C / 64) * 2 * UMMA_BLK; }
 struct WImgBlock { int64_t pq, pk, pv, po, f1, f2; };
 struct WImg {                // byte offsets from the image base
-    // forward orientation: rows = output feature
-    int64_t wq, wkT, wv, wih, whh, w1, w2;
+    // forward orientation: rows = output feature (wqk, wg: the folded products of ParamOff)
+    int64_t wqk, wg, whh, w1, w2;
     WImgBlock blk[SAVI_MAX_BLOCKS];
     // backward orientation: rows = input feature (dX = dY . W)
-    int64_t wqT, wk, wvT, wihT, whhT, w1T, w2T;
+    int64_t wqkT, wgT, whhT, w1T, w2T;
     WImgBlock blkT[SAVI_MAX_BLOCKS];
     int64_t total_bytes;
 };
 static inline void savi_wimg_layout(int D, int Ds, int M, int blocks, WImg& w) {
     int64_t p = 0;
     auto take = [&](int R, int C) { int64_t r = p; p += wimg_bytes(R, C); return r; };
-    w.wq = take(Ds, Ds); w.wkT = take(D, Ds); w.wv = take(Ds, D); w.wih = take(3 * Ds, Ds); w.whh = take(3 * Ds, Ds);
+    w.wqk = take(D, Ds); w.wg = take(3 * Ds, D); w.whh = take(3 * Ds, Ds);
     w.w1 = take(M, Ds); w.w2 = take(Ds, M);
     for (int j = 0; j < SAVI_MAX_BLOCKS; ++j) {
         WImgBlock& b = w.blk[j];
         if (j < blocks) { b.pq = take(Ds, Ds); b.pk = take(Ds, Ds); b.pv = take(Ds, Ds); b.po = take(Ds, Ds); b.f1 = take(4 * Ds, Ds); b.f2 = take(Ds, 4 * Ds); }
         else b = WImgBlock{0, 0, 0, 0, 0, 0};
     }
-    w.wqT = take(Ds, Ds); w.wk = take(Ds, D); w.wvT = take(D, Ds); w.wihT = take(Ds, 3 * Ds); w.whhT = take(Ds, 3 * Ds);
+    w.wqkT = take(Ds, D); w.wgT = take(D, 3 * Ds); w.whhT = take(Ds, 3 * Ds);
     w.w1T = take(Ds, M); w.w2T = take(M, Ds);
     for (int j = 0; j < SAVI_MAX_BLOCKS; ++j) {
         WImgBlock& b = w.blkT[j];
@@ -117,6 +121,7 @@ static inline void savi_param_offsets(const SaviShape& s, ParamOff& o) {
             b = BlockOffT{0, 0, 0, 0, 0, 0};
         }
     }
+    o.wqk = take(D * Ds); o.wg = take(3 * Ds * D); o.wqk_t = take(D * Ds); o.wg_t = take(3 * Ds * D);
     o.packed_total = p;
 }
 
@@ -228,6 +233,7 @@ struct BwdWsLayout {         // float offsets unless noted
     int64_t dq, st, dqk, du, dgi, dgh;           // S steps: widths Ds, Ds, D, Ds, 3Ds, 3Ds
     int64_t duxs;            // S steps, width D: d(Ux) of every step (right-hand side of the d_inputs kernel, mma mode)
     int64_t coef;            // BYTE offset: [B*T][I][2][KC][N] bf16 staged dL^T, W^T (mma mode)
+    int64_t dwqk, dwg;       // tcgen05 path: gradients of the folded weights wqk [D,Ds], wg [3Ds,D] (contiguous; zeroed per call)
     int64_t flags;           // BYTE offset (tcgen05 path): int [B*T] "frame staged" counters, the clip kernel -> the overlapped d_inputs kernel
     int64_t dhm, da, m;                          // Sm steps: widths Ds, M, Ds
     int64_t pdq, pdk, pdv, pdx1, pdx2, pdf;      // Sp: widths Ds x5, 4Ds
@@ -269,6 +275,7 @@ static inline void savi_bwd_ws_layout(const Dims& d, BwdWsLayout& L) {
     L.pdf = gt(Rp, 4 * d.Ds);
     L.duxs = gt(d.mma ? R : 0, d.D);
     L.part = gt((int64_t)d.B * 2 * d.CN, KD);
+    L.dwqk = gt(d.umma ? d.D : 0, d.Ds); L.dwg = gt(d.umma ? 3 * d.Ds : 0, d.D);
     L.cta = g; g += (int64_t)d.B * d.CN * L.cta_floats;
     g = (g + 63) / 64 * 64;
     L.coef = g * 4;

@@ -2,6 +2,7 @@
 #include "savi_dev.cuh"
 #include <cstdlib>
 #include "savi_args.h"
+#include "savi_smallgemm.cuh"
 
 // ---------------------------------------------------------------------------
 // K4: weight gradients.  dW[o][c] += alpha * sum_r dY[r][o] X[r][c] for every weight
@@ -67,6 +68,20 @@ __global__ void __launch_bounds__(256) wgrad_kernel(const __grid_constant__ Wgra
 }
 
 
+// Chain rule through the folded weights of the tcgen05 path (savi_layout.h: ParamOff::wqk, wg), s = Ds^-1/2:
+//   wqk[d][c] = s sum_a Wk[a][d] Wq[a][c]  =>  dWq[a][c] = s sum_d Wk[a][d] dwqk[d][c],   dWk[a][d] = s sum_c Wq[a][c] dwqk[d][c]
+//   wg[g][d]  =   sum_a Wih[g][a] Wv[a][d]  =>  dWih[g][a] = sum_d dwg[g][d] Wv[a][d],      dWv[a][d] = sum_g Wih[g][a] dwg[g][d]
+// (project_q / project_k / project_v / gru.weight_ih receive no other contribution on this path: plain stores.)
+static cudaError_t launch_fold_grads(const float* P, const float* dwqk, const float* dwg, float* G, const ParamOff& po,
+                                     int D, int Ds, float s, cudaStream_t st) {
+    SmallGemmArgs ga; ga.count = 4;
+    ga.g[0] = SmallGemm{P + po.wk, dwqk, G + po.wq, Ds, Ds, D, D, 1, Ds, 1, s};
+    ga.g[1] = SmallGemm{P + po.wq, dwqk, G + po.wk, Ds, D, Ds, Ds, 1, 1, Ds, s};
+    ga.g[2] = SmallGemm{dwg, P + po.wv, G + po.wih, 3 * Ds, Ds, D, D, 1, 1, D, 1.0f};
+    ga.g[3] = SmallGemm{P + po.wih, dwg, G + po.wv, Ds, D, 3 * Ds, 1, Ds, D, 1, 1.0f};
+    return launch_small_gemms(ga, st);
+}
+
 cudaError_t savi_launch_forward(const FwdArgs& a, const void* inputs, cudaStream_t st, int* launches) {
     return a.d.tok_bytes == 4 ? savi_launch_forward_f32(a, inputs, st, launches) : savi_launch_forward_bf16(a, inputs, st, launches);
 }
@@ -81,10 +96,12 @@ cudaError_t savi_launch_backward(const BwdArgs& a, const void* inputs, void* gra
     const Dims& d = a.d;
     cudaError_t e = cudaMemsetAsync(a.grad_params, 0, (size_t)a.po.total * sizeof(float), st);
     if (e != cudaSuccess) return e;
-    const bool umma_bwd = d.umma && !getenv("SAVI_UMMA_FWD_ONLY");
+    const bool umma_bwd = d.umma != 0;     // the tcgen05 forward saves only what the tcgen05 backward reads (no q, no U)
     const bool overlap_dx = umma_bwd && !getenv("SAVI_NO_OVERLAP");
     if (umma_bwd) {
         e = cudaMemsetAsync(reinterpret_cast<unsigned char*>(a.ws) + a.wl.flags, 0, (size_t)d.B * d.T * sizeof(int), st);
+        if (e != cudaSuccess) return e;
+        e = cudaMemsetAsync(a.ws + a.wl.dwqk, 0, (size_t)(a.wl.dwg - a.wl.dwqk + (int64_t)3 * d.Ds * d.D) * sizeof(float), st);
         if (e != cudaSuccess) return e;
     }
     savi_prof_begin(3, st);
@@ -115,10 +132,18 @@ cudaError_t savi_launch_backward(const BwdArgs& a, const void* inputs, void* gra
     // the tcgen05 forward saves s~ and LN_m(h'): its backward does not restage them
     const float* st_rows = umma_bwd ? fb + a.sl.st : W + a.wl.st;
     const float* m_rows = umma_bwd ? fb + a.sl.m : W + a.wl.m;
-    add_job(wa, W + a.wl.dq, Ds, st_rows, Ds, G + a.po.wq, R, Ds, Ds, 1.0f);
-    add_job(wa, fb + a.sl.q, Ds, W + a.wl.dqk, D, G + a.po.wk, R, Ds, D, d.qscale);
-    add_job(wa, W + a.wl.du, Ds, fb + a.sl.ux, D, G + a.po.wv, R, Ds, D, 1.0f);
-    add_job(wa, W + a.wl.dgi, 3 * Ds, fb + a.sl.u, Ds, G + a.po.wih, R, 3 * Ds, Ds, 1.0f);
+    if (umma_bwd) {
+        // the tcgen05 kernels multiply by the folded weights wqk = Ds^-1/2 Wk^T Wq and wg = Wih Wv (savi_layout.h): their
+        // gradients are reduced here into scratch and mapped back to the four parameters by fold_grads_kernel below
+        float* Wm = a.ws;
+        add_job(wa, W + a.wl.dqk, D, st_rows, Ds, Wm + a.wl.dwqk, R, D, Ds, 1.0f);
+        add_job(wa, W + a.wl.dgi, 3 * Ds, fb + a.sl.ux, D, Wm + a.wl.dwg, R, 3 * Ds, D, 1.0f);
+    } else {
+        add_job(wa, W + a.wl.dq, Ds, st_rows, Ds, G + a.po.wq, R, Ds, Ds, 1.0f);
+        add_job(wa, fb + a.sl.q, Ds, W + a.wl.dqk, D, G + a.po.wk, R, Ds, D, d.qscale);
+        add_job(wa, W + a.wl.du, Ds, fb + a.sl.ux, D, G + a.po.wv, R, Ds, D, 1.0f);
+        add_job(wa, W + a.wl.dgi, 3 * Ds, fb + a.sl.u, Ds, G + a.po.wih, R, 3 * Ds, Ds, 1.0f);
+    }
     add_job(wa, W + a.wl.dgh, 3 * Ds, fb + a.sl.hp, Ds, G + a.po.whh, R, 3 * Ds, Ds, 1.0f);
     add_job(wa, W + a.wl.da, M, m_rows, Ds, G + a.po.w1, Rm, M, Ds, 1.0f);
     add_job(wa, W + a.wl.dhm, Ds, fb + a.sl.a, M, G + a.po.w2, Rm, Ds, M, 1.0f);
@@ -135,9 +160,11 @@ cudaError_t savi_launch_backward(const BwdArgs& a, const void* inputs, void* gra
     if (wa.njobs > 0 && umma_bwd) {
         savi_prof_begin(4, st);
         e = savi_launch_wgrad_umma(wa, st);
+        if (e != cudaSuccess) return e;
+        e = launch_fold_grads(a.packed, a.ws + a.wl.dwqk, a.ws + a.wl.dwg, G, a.po, D, Ds, d.qscale, st);
         savi_prof_end(4, st);
         if (e != cudaSuccess) return e;
-        *launches += 1;
+        *launches += 2;
     } else if (wa.njobs > 0) {
         int maxR = 0, maxTiles = 0;
         for (int j = 0; j < wa.njobs; ++j) {

@@ -514,7 +514,7 @@ template <typename TokT>
 static cudaError_t launch_ln_fwd(const FwdArgs& a, const void* inputs, cudaStream_t st) {
     const int64_t rows = (int64_t)a.d.B * a.d.T * a.d.N;
     if constexpr (sizeof(TokT) == 2) {
-        if (a.d.umma && a.d.D == 128 && !getenv("SAVI_UMMA_FWD_ONLY")) {
+        if (a.d.umma && a.d.D == 128) {
             const int64_t npair = ((int64_t)a.d.B * a.d.T * a.d.NTILE * 128 + 1) / 2;
             int grid = (int)((npair + 7) / 8);
             if (grid > 148 * 16) grid = 148 * 16;
@@ -528,8 +528,7 @@ static cudaError_t launch_ln_fwd(const FwdArgs& a, const void* inputs, cudaStrea
     if (grid > 148 * 16) grid = 148 * 16;
     ln_tokens_fwd_kernel<TokT><<<grid, NT, 0, st>>>(
         reinterpret_cast<const TokT*>(inputs),
-        // the tcgen05 kernels read only the blocked image; the row-major copy is kept for the mma.sync backward (development toggle)
-        (a.d.umma && !getenv("SAVI_UMMA_FWD_ONLY")) ? nullptr : reinterpret_cast<TokT*>(a.saved + a.sl.xhat),
+        a.d.umma ? nullptr : reinterpret_cast<TokT*>(a.saved + a.sl.xhat),      // the tcgen05 kernels read only the blocked image
         reinterpret_cast<float2*>(a.saved + a.sl.stats), a.packed + a.po.ln_in_w, a.packed + a.po.ln_in_b, rows, a.d.D,
         a.d.ln_eps, a.d.umma ? a.saved + a.sl.ximg : nullptr, a.d.N, a.d.NTILE);
     return cudaGetLastError();

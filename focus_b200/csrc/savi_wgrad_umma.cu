@@ -13,8 +13,11 @@ typedef __nv_bfloat16 bf16;
 
 namespace {
 constexpr int WU_LOADERS = 256, WU_THREADS = 288;     // warps 0-7 load + convert, warp 8 issues
-constexpr int WU_CH = 64;                             // rows per chunk
-constexpr int WU_STAGE = 65536;                       // A hi | A lo | B hi | B lo, 16 KB each
+constexpr int WU_CH = 32;                             // rows per chunk (32: 32 KB stages, two CTAs per SM hide each other's load latency)
+constexpr int WU_CB = WU_CH * 128;                    // bytes of one 64-column block of a chunk
+constexpr int WU_SUB = 2 * WU_CB;                     // one operand: [WU_CH rows][2 x 64 columns] bf16
+constexpr int WU_STAGE = 4 * WU_SUB;                  // A hi | A lo | B hi | B lo
+constexpr int WU_LD = WU_CH * 16 / WU_LOADERS;        // 8-float groups per loader thread and operand
 constexpr uint32_t IDESC_MN_MN_128 = idesc_bf16(128, 128, true, true);
 
 struct WUArgs { WgradArgs wa; int chunks_per_cta; };
@@ -32,7 +35,7 @@ __device__ __forceinline__ void split8(const float4& p, const float4& q, uint4& 
     hi = make_uint4(h[0], h[1], h[2], h[3]); lo = make_uint4(l[0], l[1], l[2], l[3]);
 }
 
-__global__ void __launch_bounds__(WU_THREADS, 1) wgrad_umma_kernel(const __grid_constant__ WUArgs ua) {
+__global__ void __launch_bounds__(WU_THREADS, 2) wgrad_umma_kernel(const __grid_constant__ WUArgs ua) {
     extern __shared__ __align__(1024) unsigned char sm[];
     if ((smem_u32(sm) & 1023u) != 0u) __trap();
     const WgradArgs& wa = ua.wa;
@@ -73,9 +76,9 @@ __global__ void __launch_bounds__(WU_THREADS, 1) wgrad_umma_kernel(const __grid_
             const int st = ch & 1;
             unsigned char* base = sm + st * WU_STAGE;
             const int r0 = r_begin + ch * WU_CH;
-            float4 pa[4][2], pb[4][2];
+            float4 pa[WU_LD][2], pb[WU_LD][2];
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {                                 // all loads of the chunk are in flight before the stage wait
+            for (int i = 0; i < WU_LD; ++i) {                             // all loads of the chunk are in flight before the stage wait
                 const int u = tid + i * WU_LOADERS, r = u >> 4, cg = u & 15;
                 const bool ok = r0 + r < r_end;
                 const float* ya = jb.dY + (size_t)(r0 + r) * jb.ldy + o0 + cg * 8;
@@ -85,14 +88,14 @@ __global__ void __launch_bounds__(WU_THREADS, 1) wgrad_umma_kernel(const __grid_
             }
             mbar_wait(&bars[2 + st], ((ch >> 1) & 1u) ^ 1u);               // the MMAs that read this stage two chunks ago are done
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
+            for (int i = 0; i < WU_LD; ++i) {
                 const int u = tid + i * WU_LOADERS, r = u >> 4, cg = u & 15;
-                const uint32_t off = (uint32_t)(cg >> 3) * 8192u + (uint32_t)r * 128u + ((((uint32_t)cg & 7u) ^ ((uint32_t)r & 7u)) << 4);
+                const uint32_t off = (uint32_t)(cg >> 3) * (uint32_t)WU_CB + (uint32_t)r * 128u + ((((uint32_t)cg & 7u) ^ ((uint32_t)r & 7u)) << 4);
                 uint4 hi, lo;
                 split8(pa[i][0], pa[i][1], hi, lo);
-                *reinterpret_cast<uint4*>(base + off) = hi; *reinterpret_cast<uint4*>(base + 16384 + off) = lo;
+                *reinterpret_cast<uint4*>(base + off) = hi; *reinterpret_cast<uint4*>(base + WU_SUB + off) = lo;
                 split8(pb[i][0], pb[i][1], hi, lo);
-                *reinterpret_cast<uint4*>(base + 32768 + off) = hi; *reinterpret_cast<uint4*>(base + 49152 + off) = lo;
+                *reinterpret_cast<uint4*>(base + 2 * WU_SUB + off) = hi; *reinterpret_cast<uint4*>(base + 3 * WU_SUB + off) = lo;
             }
             fence_async_smem();
             __syncwarp();
@@ -119,10 +122,10 @@ __global__ void __launch_bounds__(WU_THREADS, 1) wgrad_umma_kernel(const __grid_
             const int st = ch & 1;
             mbar_wait(&bars[st], (ch >> 1) & 1u);
             fence_after_sync();
-            const uint32_t ah = dlo_mn(smem_u32(sm) + st * WU_STAGE, 8192), al = ah + 1024, bh = ah + 2048, bl = ah + 3072;
+            const uint32_t ah = dlo_mn(smem_u32(sm) + st * WU_STAGE, WU_CB), al = ah + (WU_SUB >> 4), bh = ah + 2 * (WU_SUB >> 4), bl = ah + 3 * (WU_SUB >> 4);
             if (el) {
 #pragma unroll
-                for (int ks = 0; ks < 4; ++ks) {
+                for (int ks = 0; ks < WU_CH / 16; ++ks) {
                     mma_lo(tb, ah + ks * 128, bh + ks * 128, IDESC_MN_MN_128, (ch > 0 || ks > 0) ? 1u : 0u);
                     mma_lo(tb, ah + ks * 128, bl + ks * 128, IDESC_MN_MN_128, 1u);
                     mma_lo(tb, al + ks * 128, bh + ks * 128, IDESC_MN_MN_128, 1u);

@@ -7,7 +7,7 @@ import ctypes
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libfocus_savi.so")
+LIB_PATH = os.environ.get("FOCUS_SAVI_LIB") or os.path.join(_HERE, "libfocus_savi.so")     # override: development A/B builds
 
 SAVI_DTYPE_F32 = 0
 SAVI_DTYPE_BF16 = 1

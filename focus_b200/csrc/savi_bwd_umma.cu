@@ -268,7 +268,8 @@ __device__ __forceinline__ void ln_bwd(const Ctx& c, const float (&dy)[KH], cons
 // Backward of the predictor's attention core in shared memory (transformer.py:34-47).  dQ is w.r.t. the UNSCALED projection.
 constexpr int ATT_PT = 8;     // attention-matrix elements per thread: heads * K * K <= 8 * 512
 __device__ __forceinline__ void mha_core_bwd(const Ctx& c, int H, float hscale, const float (&dO)[KH], const float (&Qv)[KH], const float (&Kv)[KH],
-                                             const float (&Vv)[KH], const float (&attv)[ATT_PT], float (&dQ)[KH], float (&dK)[KH], float (&dV)[KH]) {
+                                             const float (&Vv)[KH], const float (&attv)[ATT_PT], float (&dQ)[KH], float (&dK)[KH], float (&dV)[KH],
+                                             long long* dbg, long long& ph_last) {
     // layout as in the forward core (savi_fwd_umma.cu: mha_core): 16-byte aligned rows, attention rows padded to ka
     const int K = c.K, ld = MHA_LD, ka = mha_ka(K), dh = F / H;
     float* sO = reinterpret_cast<float*>(c.sm + c.L.opA);             // opA .. scratch are contiguous (5 x 16 KB + scratch)
@@ -284,25 +285,55 @@ __device__ __forceinline__ void mha_core_bwd(const Ctx& c, int H, float hscale, 
 #pragma unroll
     for (int e = 0; e < ATT_PT; ++e) { const int idx = c.tid + e * NCT; if (idx < H * K * K) sA[(idx / K) * ka + idx % K] = attv[e]; }
     bar_sync_compute();
-    for (int idx = c.tid; idx < H * K * K; idx += NCT) {              // d attention = dO_h . V_h^T
-        const int j = idx % K, i = (idx / K) % K, h = idx / (K * K);
-        const float4* a = reinterpret_cast<const float4*>(sO + i * ld + h * dh);
-        const float4* v = reinterpret_cast<const float4*>(sV + j * ld + h * dh);
-        float s = 0.f;
-        for (int e = 0; e < dh / 4; ++e) {
-            const float4 x = a[e], y = v[e];
-            s = fmaf(x.x, y.x, s); s = fmaf(x.y, y.y, s); s = fmaf(x.z, y.z, s); s = fmaf(x.w, y.w, s);
+    UPH(45);
+    // d attention = dO_h . V_h^T: 4 threads per (head, query) row, <= MHA_JP keys each with independent accumulators
+    for (int row = c.tid >> 2; row < H * K; row += NCT / 4) {
+        const int jq = c.tid & 3, JP = (K + 3) >> 2, j0 = jq * JP;
+        const int h = row / K, i = row - h * K;
+        const float* a = sO + i * ld + h * dh;
+        const float* b = sV + h * dh;
+        float acc[MHA_JP];
+#pragma unroll
+        for (int jj = 0; jj < MHA_JP; ++jj) acc[jj] = 0.f;
+        for (int e = 0; e < dh; e += 4) {
+            const float4 x = ld4(a + e);
+#pragma unroll
+            for (int jj = 0; jj < MHA_JP; ++jj) {
+                const float4 y = ld4(b + min(j0 + jj, K - 1) * ld + e);
+                acc[jj] = fmaf(x.x, y.x, acc[jj]); acc[jj] = fmaf(x.y, y.y, acc[jj]); acc[jj] = fmaf(x.z, y.z, acc[jj]); acc[jj] = fmaf(x.w, y.w, acc[jj]);
+            }
         }
-        sD[(h * K + i) * ka + j] = s;
+#pragma unroll
+        for (int jj = 0; jj < MHA_JP; ++jj) if (jj < JP && j0 + jj < K) sD[row * ka + j0 + jj] = acc[jj];
     }
     bar_sync_compute();
-    for (int row = c.warp; row < H * K; row += NCW) {                 // softmax backward: one warp per (head, query) row, lane = key
-        const bool on = c.lane < K;
-        const float a = on ? sA[row * ka + c.lane] : 0.f, da = on ? sD[row * ka + c.lane] : 0.f;
-        const float dl = a * (da - warp_sum(a * da));
-        if (on) { sD[row * ka + c.lane] = dl; sDT[((row / K) * K + c.lane) * ka + row % K] = dl; }
+    UPH(46);
+    // softmax backward: one warp per (head, query) row, lane = key; three rows in flight per warp
+    for (int row0 = c.warp; row0 < H * K; row0 += 3 * NCW) {
+        float av[3], dav[3], dot[3];
+#pragma unroll
+        for (int r = 0; r < 3; ++r) {
+            const int row = row0 + r * NCW;
+            const bool on = row < H * K && c.lane < K;
+            av[r] = on ? sA[row * ka + c.lane] : 0.f; dav[r] = on ? sD[row * ka + c.lane] : 0.f;
+            dot[r] = av[r] * dav[r];
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+            for (int r = 0; r < 3; ++r) dot[r] += __shfl_xor_sync(0xffffffffu, dot[r], o);
+        }
+#pragma unroll
+        for (int r = 0; r < 3; ++r) {
+            const int row = row0 + r * NCW;
+            if (row < H * K && c.lane < K) {
+                const float dl = av[r] * (dav[r] - dot[r]);
+                sD[row * ka + c.lane] = dl; sDT[((row / K) * K + c.lane) * ka + row % K] = dl;
+            }
+        }
     }
     bar_sync_compute();
+    UPH(47);
     const int hb = (c.o / dh) * K * ka + c.k0;
     const float* dlt = sDT + hb;                                      // row j: d logits [i][j] over this warpgroup's 8 slots i
     const float* dlg = sD + hb;                                       // row j: d logits [j][i]
@@ -311,6 +342,7 @@ __device__ __forceinline__ void mha_core_bwd(const Ctx& c, int H, float hscale, 
 #pragma unroll
     for (int kk = 0; kk < KH; ++kk) { sq[kk] = 0.f; sk[kk] = 0.f; sv[kk] = 0.f; }
     if (c.nk > 0) {
+#pragma unroll 2
         for (int j = 0; j < K; ++j) {
             const float kj = sK[j * ld + c.o], qj = sQ[j * ld + c.o], oj = sO[j * ld + c.o];
             float t[KH], u[KH], w[KH];                                // warp-uniform 16-byte reads
@@ -328,6 +360,7 @@ __device__ __forceinline__ void mha_core_bwd(const Ctx& c, int H, float hscale, 
 #pragma unroll
     for (int kk = 0; kk < KH; ++kk) { dQ[kk] = sq[kk] * hscale; dK[kk] = sk[kk]; dV[kk] = sv[kk]; }
     bar_sync_compute();
+    UPH(48);
 }
 
 __device__ __forceinline__ float sum8(const Ctx& c, const float (&v)[KH]) {
@@ -573,7 +606,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) savi_bwd_umma_kernel(const __grid
                         for (int e = 0; e < ATT_PT; ++e) { const int idx = tid + e * NCT; attv[e] = (idx < d.heads * K * K) ? p_att[idx] : 0.f; }
                         wait_acc(c); load_acc(c, TB_B, dO);
                         UPH(41);
-                        mha_core_bwd(c, d.heads, hscale, dO, qv, kv, vv, attv, dQ, dK, dV);
+                        mha_core_bwd(c, d.heads, hscale, dO, qv, kv, vv, attv, dQ, dK, dV, dbg, ph_last);
                         UPH(42);
                     }
                     if (svA) {
@@ -637,6 +670,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) savi_bwd_umma_kernel(const __grid
                             prefetch_l2(frow(fbw, a.sl.px2, f, b, B, K, F), rowb); prefetch_l2(frow(fbw, a.sl.px1, f, b, B, K, F), rowb);
                             prefetch_l2(frow(fbw, a.sl.pq, f, b, B, K, F), rowb); prefetch_l2(frow(fbw, a.sl.pk, f, b, B, K, F), rowb);
                             prefetch_l2(frow(fbw, a.sl.pv, f, b, B, K, F), rowb); prefetch_l2(frow(fbw, a.sl.pf, f, b, B, K, 4 * F), 4 * rowb);
+                            const int natt = d.heads * K * K;                               // saved attention matrices of the block
+                            if ((natt & 3) == 0) prefetch_l2(fb + a.sl.patt + (f * B + b) * (int64_t)natt, (uint32_t)natt * 4u);
                         }
                     }
                 }

@@ -189,29 +189,57 @@ __device__ __forceinline__ void mha_core(const Ctx& c, int H, const float (&q)[K
         if (kk < c.nk) { sQ[k * ld + c.o] = q[kk]; sK[k * ld + c.o] = kx[kk]; sV[k * ld + c.o] = v[kk]; }
     }
     bar_sync_compute();
-    for (int idx = c.tid; idx < H * K * K; idx += NCT) {
-        const int j = idx % K, i = (idx / K) % K, h = idx / (K * K);
-        const float4* a = reinterpret_cast<const float4*>(sQ + i * ld + h * dh);
-        const float4* b = reinterpret_cast<const float4*>(sK + j * ld + h * dh);
-        float s = 0.f;
-        for (int e = 0; e < dh / 4; ++e) {
-            const float4 x = a[e], y = b[e];
-            s = fmaf(x.x, y.x, s); s = fmaf(x.y, y.y, s); s = fmaf(x.z, y.z, s); s = fmaf(x.w, y.w, s);
+    // logits: 4 threads per (head, query) row, each a contiguous share of <= MHA_JP keys with independent accumulators
+    // (the query row chunk is loaded once and reused; 16-byte conflict-free reads)
+    for (int row = c.tid >> 2; row < H * K; row += NCT / 4) {
+        const int jq = c.tid & 3, JP = (K + 3) >> 2, j0 = jq * JP;
+        const int h = row / K, i = row - h * K;
+        const float* a = sQ + i * ld + h * dh;
+        const float* b = sK + h * dh;
+        float acc[MHA_JP];
+#pragma unroll
+        for (int jj = 0; jj < MHA_JP; ++jj) acc[jj] = 0.f;
+        for (int e = 0; e < dh; e += 4) {
+            const float4 x = ld4(a + e);
+#pragma unroll
+            for (int jj = 0; jj < MHA_JP; ++jj) {
+                const float4 y = ld4(b + min(j0 + jj, K - 1) * ld + e);
+                acc[jj] = fmaf(x.x, y.x, acc[jj]); acc[jj] = fmaf(x.y, y.y, acc[jj]); acc[jj] = fmaf(x.z, y.z, acc[jj]); acc[jj] = fmaf(x.w, y.w, acc[jj]);
+            }
         }
-        sA[(h * K + i) * ka + j] = s;
+#pragma unroll
+        for (int jj = 0; jj < MHA_JP; ++jj) if (jj < JP && j0 + jj < K) sA[row * ka + j0 + jj] = acc[jj];
     }
     bar_sync_compute();
-    for (int row = c.warp; row < H * K; row += NCW) {                // softmax over the keys: one warp per (head, query) row, lane = key
-        const bool on = c.lane < K;
-        const float x = on ? sA[row * ka + c.lane] : -INFINITY;
-        float mx = x;
+    // softmax over the keys: one warp per (head, query) row, lane = key; three rows in flight per warp
+    for (int row0 = c.warp; row0 < H * K; row0 += 3 * NCW) {
+        float x[3], e[3], mx[3], sm[3];
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
-        const float e = on ? expf(x - mx) : 0.f;
-        const float pr = e * (1.0f / warp_sum(e));
-        if (on) {
-            sAT[((row / K) * K + c.lane) * ka + row % K] = pr;
-            if (att_g) att_g[row * K + c.lane] = pr;
+        for (int r = 0; r < 3; ++r) {
+            const int row = row0 + r * NCW;
+            x[r] = (row < H * K && c.lane < K) ? sA[row * ka + c.lane] : -INFINITY;
+            mx[r] = x[r];
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+            for (int r = 0; r < 3; ++r) mx[r] = fmaxf(mx[r], __shfl_xor_sync(0xffffffffu, mx[r], o));
+        }
+#pragma unroll
+        for (int r = 0; r < 3; ++r) { e[r] = (c.lane < K && row0 + r * NCW < H * K) ? expf(x[r] - mx[r]) : 0.f; sm[r] = e[r]; }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+            for (int r = 0; r < 3; ++r) sm[r] += __shfl_xor_sync(0xffffffffu, sm[r], o);
+        }
+#pragma unroll
+        for (int r = 0; r < 3; ++r) {
+            const int row = row0 + r * NCW;
+            if (row < H * K && c.lane < K) {
+                const float pr = e[r] * (1.0f / sm[r]);
+                sAT[((row / K) * K + c.lane) * ka + row % K] = pr;
+                if (att_g) att_g[row * K + c.lane] = pr;
+            }
         }
     }
     bar_sync_compute();
@@ -219,6 +247,7 @@ __device__ __forceinline__ void mha_core(const Ctx& c, int H, const float (&q)[K
 #pragma unroll
     for (int kk = 0; kk < KH; ++kk) out[kk] = 0.f;
     if (c.nk > 0) {
+#pragma unroll 4
         for (int j = 0; j < K; ++j) {
             const float vj = sV[j * ld + c.o];
             const float4 p0 = ld4(at + j * ka), p1 = ld4(at + j * ka + 4);       // this warpgroup's 8 queries (warp-uniform address)
@@ -514,6 +543,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) savi_fwd_umma_kernel(const __grid
                 float x[KH];
 #pragma unroll
                 for (int kk = 0; kk < KH; ++kk) x[kk] = h[kk];
+                long long pp_last = clock64();
+#define PPH(id) do { if (dbg) { const long long t_ = clock64(); dbg[id] += t_ - pp_last; pp_last = t_; } } while (0)
                 for (int j = 0; j < d.blocks; ++j) {
                     const int64_t f = (int64_t)j * (d.T - 1) + t;
                     const BlockOff& bo = po.blk[j];
@@ -522,7 +553,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) savi_fwd_umma_kernel(const __grid
                     if (svB) save_field(c, frow(fb, a.sl.py, f, b, B, K, F), F, o, yv);
                     write_operand(c, L.opA, yv);
                     signal_operand(c);
+                    
                     wait_acc(c);
+                    PPH(21);
                     load_acc(c, TC_R, q); load_acc(c, TC_Z, kx); load_acc(c, TC_HN, v);
 #pragma unroll
                     for (int kk = 0; kk < KH; ++kk) q[kk] *= hscale;
@@ -536,7 +569,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) savi_fwd_umma_kernel(const __grid
                     if (svA) save_field(c, frow(fb, a.sl.po, f, b, B, K, F), F, o, ov);
                     write_operand(c, L.opB, ov);
                     signal_operand(c);
-                    wait_acc(c); load_acc(c, TC_A, x1);
+                    PPH(22);
+                    wait_acc(c);  load_acc(c, TC_A, x1);
                     // the first block adds the residual to the NORMALISED input (transformer.py:75-78)
 #pragma unroll
                     for (int kk = 0; kk < KH; ++kk) x1[kk] += (j == 0) ? yv[kk] : x[kk];
@@ -545,6 +579,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) savi_fwd_umma_kernel(const __grid
                     if (svA) save_field(c, frow(fb, a.sl.pl2, f, b, B, K, F), F, o, yv);
                     write_operand(c, L.opA, yv);
                     signal_operand(c);
+                    PPH(23);
 #pragma unroll
                     for (int ff = 0; ff < 4; ++ff) {
                         mbar_wait(&bars[B_FACC + ff], pcall & 1u); fence_after_sync();
@@ -557,13 +592,15 @@ __global__ void __launch_bounds__(NTHREADS, 1) savi_fwd_umma_kernel(const __grid
                         signal_operand(c, B_FOPND + ff);
                     }
                     ++pcall;
-                    wait_acc(c); load_acc(c, TC_B, yv);
+                    
+                    wait_acc(c);  load_acc(c, TC_B, yv);
                     const float bb2 = P[bo.f2b + o];
 #pragma unroll
                     for (int kk = 0; kk < KH; ++kk) x[kk] = x1[kk] + yv[kk] + bb2;
                     if (svB) save_field(c, frow(fb, a.sl.px2, f, b, B, K, F), F, o, x);
                 }
                 layer_norm(c, x, h, P[po.lnf_w + o], P[po.lnf_b + o], d.ln_eps);
+                PPH(24);
                 UPH(20);
             }
         }

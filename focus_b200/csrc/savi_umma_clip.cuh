@@ -38,6 +38,7 @@ constexpr uint32_t IDESC_MN_MN64 = idesc_bf16(128, 64, true, true);    // A MN-m
 
 // predictor attention core (shared-memory, SIMT): row stride of the q / k / v / dO tiles and of the attention matrices
 constexpr int MHA_LD = F + 4;
+constexpr int MHA_JP = 6;                     // keys per thread in the logits loops: ceil(K / 4) with K <= 24 on this path
 __host__ __device__ __forceinline__ constexpr int mha_ka(int K) { return (K + 3) & ~3; }
 // bytes the backward core needs from opA on (dO, q, k, v tiles + A, dL, dL^T); the forward needs less
 __host__ __device__ __forceinline__ constexpr int mha_bwd_bytes(int K, int H) { return (4 * K * MHA_LD + 3 * H * K * mha_ka(K)) * 4 + 64; }

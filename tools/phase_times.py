@@ -14,7 +14,7 @@ UN = {1: "u: save hp, LN_s, s~ operand", 2: "u: WAIT q", 3: "u: q epilogue", 4: 
       7: "u: WAIT token pass", 8: "u: ld numx + send", 9: "u: WAIT peer", 10: "u: Ux epilogue", 11: "u: WAIT U", 12: "u: U epilogue", 13: "u: WAIT gru",
       14: "u: gru math + saves", 15: "u: mlp LN + operand", 16: "u: WAIT a", 17: "u: a epilogue", 18: "u: WAIT h2", 19: "u: h2", 20: "u: predictor (total)",
       50: "  sm: WAIT logits", 51: "  sm: ld + softmax", 52: "  sm: WAIT aw free", 53: "  sm: write A + signal", 54: "  sm: attn out",
-      21: "  q: tmem ld", 22: "  q: save_field", 23: "  q: write_operand", 24: "  q: fence.proxy.async"}
+      21: "  p: LN1, WAIT q,k,v", 22: "  p: epilogue + attention core", 23: "  p: WAIT proj_o, residual, LN2", 24: "  p: ffn tiles, WAIT ffn.2, final LN"}
 cfg = sys.argv[1] if len(sys.argv) > 1 else "c2"
 c = dict(bench.CONFIGS[cfg])
 dt = torch.float32 if c["dtype"] == "fp32" else torch.bfloat16
@@ -34,7 +34,7 @@ step(); torch.cuda.synchronize()
 _lib.lib.savi_debug_set_phase_buffer(None)
 v = buf.cpu().tolist()
 if os.environ.get("SAVI_DISABLE_UMMA") is None and c["D"] == 128:
-    tot = sum(v[1:25])
+    tot = sum(v[1:21])
     print("UMMA forward, compute thread 0 of CTA 0: total %.1f us" % (tot / 1965.0))
     for i in sorted(UN):
         if v[i]: print("  %-34s %8.1f us  %5.1f%%" % (UN[i], v[i] / 1965.0, 100.0 * v[i] / tot))
@@ -42,9 +42,9 @@ if os.environ.get("SAVI_DISABLE_UMMA") is None and c["D"] == 128:
     for i in range(25): v[i] = 0
     for i in range(50, 55): v[i] = 0
     for i in range(60, 64): v[i] = 0
-    BN = {25: "b: predictor bwd + grad_slots (per frame)", 26: "b: mlp bwd", 27: "b: gru bwd + operands", 28: "b: WAIT dU", 29: "b: dU epi + loads + WAIT dUx",
-          30: "b: c vector + operands", 31: "b: softmax-bwd tiles (total)", 32: "b: WAIT token pass", 33: "b: dqk + exchange", 34: "b: dqk op + WAIT dq",
-          35: "b: dq op + WAIT ds~", 36: "b: LN_s bwd", 37: "  pb: LN_f / LN1 bwd (+ frame top)", 38: "  pb: dx2 operand, 4 ffn.2^T tiles, df chunks", 39: "  pb: WAIT d l2", 40: "  pb: LN2 bwd + dx1 operand", 41: "  pb: loads + WAIT dO", 42: "  pb: mha core bwd", 43: "  pb: saves + 3 operands", 44: "  pb: WAIT dy",
+    BN = {25: "b: predictor bwd + grad_slots (per frame)", 26: "b: mlp bwd", 27: "b: gru bwd + operands", 28: "b: loads, 1/S", 29: "b: WAIT dUx",
+          30: "b: c vector + operands", 31: "b: softmax-bwd tiles (total)", 32: "b: WAIT token pass", 33: "b: dqk + exchange", 34: "b: dqk operand",
+          35: "b: WAIT ds~", 36: "b: LN_s bwd", 37: "  pb: LN_f / LN1 bwd (+ frame top)", 38: "  pb: dx2 operand, 4 ffn.2^T tiles, df chunks", 39: "  pb: WAIT d l2", 40: "  pb: LN2 bwd + dx1 operand", 41: "  pb: loads + WAIT dO", 42: "  pb: mha core bwd", 43: "  pb: saves + 3 operands", 44: "  pb: WAIT dy", 45: "    core: stage tiles + barrier", 46: "    core: d attention", 47: "    core: softmax bwd", 48: "    core: dQ dK dV",
           55: "  sb: WAIT logits (incl. grad_attn load)", 56: "  sb: ld + softmax + dP + dot", 57: "  sb: WAIT dl free",
           58: "  sb: write dL + signal", 59: "  sb: coef stores"}
     tot = sum(v[25:37])

@@ -158,6 +158,12 @@ class SlotAttentionVideo(nn.Module):
         self.dropout = dropout
         self.cluster = 0               # CTAs per clip; 0 lets the library choose
         self.grad_sync = None          # focus_b200.distributed.attach_grad_sync: flat gradient all-reduce inside backward
+        # Cast policy (the reference follows `inputs` / autocast, steve_train_net.py:95).  None: compute in the dtype of
+        # `inputs` (fp32 -> fp32 kernels, 1e-5 parity; bf16 -> tensor-core kernels, 2e-2 parity; fp16, what autocast hands
+        # over, is computed as bf16).  torch.bfloat16: fp32 inputs are cast on entry and the outputs cast back, so the
+        # stock fp32 trainer (every FOCUS yaml has TRAIN.MIXED_PRECISION False) gets the tcgen05 kernels; opt-in because
+        # it trades the 1e-5 parity for the bf16 one.
+        self.compute_dtype = None
 
         # creation order == reference order, so torch.manual_seed(s) gives identical initial weights
         self.slot_mu = nn.Parameter(torch.Tensor(1, 1, slot_size))
@@ -206,8 +212,14 @@ class SlotAttentionVideo(nn.Module):
             raise ValueError("inputs must be [B, T, num_inputs, %d], got %s" % (self.input_size, tuple(inputs.shape)))
         if not inputs.is_cuda:
             raise RuntimeError("focus_b200.SlotAttentionVideo has no CPU path: inputs must live on a B200 (sm_100) device")
-        if inputs.dtype not in (torch.float32, torch.bfloat16):
-            raise TypeError("inputs must be float32 or bfloat16, got %s" % inputs.dtype)
+        if inputs.dtype not in (torch.float32, torch.bfloat16, torch.float16):
+            raise TypeError("inputs must be float32, bfloat16 or float16, got %s" % inputs.dtype)
+        out_dtype = inputs.dtype
+        cd = self.compute_dtype or (torch.bfloat16 if inputs.dtype == torch.float16 else inputs.dtype)
+        if cd not in (torch.float32, torch.bfloat16):
+            raise TypeError("compute_dtype must be None, torch.float32 or torch.bfloat16, got %s" % cd)
+        if inputs.dtype != cd:
+            inputs = inputs.to(cd)                 # differentiable: the gradient comes back in the caller's dtype
         if self.training and self.dropout > 0 and self.num_predictor_blocks > 0:
             raise NotImplementedError(
                 "predictor dropout > 0 in training mode is not supported (every FOCUS config uses "
@@ -218,6 +230,9 @@ class SlotAttentionVideo(nn.Module):
         noise = noise.to(device=inputs.device, dtype=torch.float32).contiguous()
         inputs = inputs.contiguous()
         shape = self.make_shape(B, T, N, inputs.dtype)
-        with torch.cuda.device(inputs.device):
-            return _SaviFunction.apply(shape, self.grad_sync if torch.is_grad_enabled() else None, inputs, noise,
-                                        *self._ordered_params())
+        with torch.cuda.device(inputs.device), torch.autocast("cuda", enabled=False):
+            slots, attns = _SaviFunction.apply(shape, self.grad_sync if torch.is_grad_enabled() else None, inputs, noise,
+                                               *self._ordered_params())
+        if out_dtype != cd:
+            slots, attns = slots.to(out_dtype), attns.to(out_dtype)
+        return slots, attns

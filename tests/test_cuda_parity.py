@@ -163,6 +163,30 @@ def test_overlapped_d_inputs_equals_serial(monkeypatch):
     assert all(float(np.abs(a1[3][k] - a2[3][k]).max()) <= 1e-6 * gs for k in a2[3])      # atomics may reorder the LN sums
 
 
+def test_cast_policy_fp32_trainer_and_autocast_half():
+    """fp32 inputs with compute_dtype=bfloat16 (the opt-in fast path for the stock fp32 trainer) and fp16 inputs (what
+    torch.autocast hands over): tensor-core kernels inside, the caller's dtype outside, gradients back in the caller's dtype."""
+    from focus_b200 import _lib
+    fx = load_fixture("c1")
+    m = _module(fx)
+    m.compute_dtype = torch.bfloat16
+    x = torch.from_numpy(fx["x"]).cuda().requires_grad_(True)                      # fp32
+    noise = torch.from_numpy(fx["noise"]).cuda()
+    assert _lib.query(m.make_shape(fx["B"], fx["T"], fx["N"], torch.bfloat16)).path == 2
+    s, a = m(x, noise=noise)
+    assert s.dtype == torch.float32 and a.dtype == torch.float32
+    (s * torch.from_numpy(fx["g_slots"]).cuda()).sum().backward()
+    assert x.grad is not None and x.grad.dtype == torch.float32 and torch.isfinite(x.grad).all()
+    x64 = x.detach().bfloat16().double().cpu().numpy()
+    rs, ra, _, _ = _oracle(fx, x64, None)
+    assert err(s.detach().cpu().numpy(), rs) < TOL_BF16 and err(a.detach().cpu().numpy(), ra) < TOL_BF16
+    m.compute_dtype = None
+    with torch.autocast("cuda", dtype=torch.float16):
+        s16, a16 = m(x.detach().half(), noise=noise)
+    assert s16.dtype == torch.float16 and a16.dtype == torch.float16
+    assert err(s16.float().cpu().numpy(), rs) < TOL_BF16 and err(a16.float().cpu().numpy(), ra) < TOL_BF16
+
+
 def test_grad_attn_none_is_the_trainer_case():
     """steve_train_net.py never back-propagates through attns: grad_attn = None."""
     fx = load_fixture("tiny_a")
@@ -213,7 +237,7 @@ def test_errors_are_loud():
     with pytest.raises(RuntimeError):
         m(torch.randn(1, 1, 8, 16))                              # CPU tensor: no fallback
     with pytest.raises(TypeError):
-        m(torch.randn(1, 1, 8, 16, device="cuda", dtype=torch.float16))
+        m(torch.randn(1, 1, 8, 16, device="cuda", dtype=torch.float64))
     with pytest.raises(ValueError):
         m(torch.randn(1, 1, 8, 12, device="cuda"))
     bad = SlotAttentionVideo(2, 4, 12, 16, 16, 1, 2, 0.0).cuda()   # D=12 is not a multiple of 8

@@ -11,6 +11,7 @@
 #include "savi_umma.cuh"
 #include "savi_dev.cuh"
 #include "savi_args.h"
+#include <cstdlib>
 
 using namespace umma;
 typedef __nv_bfloat16 bf16;
@@ -258,6 +259,10 @@ cudaError_t savi_launch_dx_umma(const BwdArgs& a, const void* inputs, void* grad
     x.B = d.B; x.T = d.T; x.N = d.N; x.K = d.K; x.I = d.I; x.NTILE = d.NTILE;
     // whole frames per CTA (one staging of the right-hand side) once there are >= 2 waves of frames; else >= 2 CTAs per frame
     x.tiles_per_cta = d.NTILE <= 8 ? ((d.B * d.T >= 2 * 148 || d.NTILE < 8) ? d.NTILE : 4) : 8;
+    // overlapped with the clip kernel, what remains when that kernel ends (about one frame of every clip) is the exposed
+    // tail: finer work items spread it over all SMs
+    if (overlap && x.tiles_per_cta > 4 && getenv("SAVI_DX_TPC") == nullptr) x.tiles_per_cta = 4;
+    if (getenv("SAVI_DX_TPC")) x.tiles_per_cta = atoi(getenv("SAVI_DX_TPC"));
     const int smem = dx_smem_total(d.I);
     cudaError_t e = cudaFuncSetAttribute(dx_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) return e;

@@ -99,50 +99,41 @@ static __global__ void __launch_bounds__(256) ln_tokens_fwd_img128_kernel(const 
 #pragma unroll
     for (int e = 0; e < 8; ++e) { gg[e] = __ldg(g + sub * 8 + e); bb[e] = __ldg(b + sub * 8 + e); }
     const int64_t npair = ((int64_t)(rows / N) * NTILE * 128 + 1) / 2;            // padded rows, two per warp
-    constexpr int U = 2;                                                          // consecutive row pairs in flight per warp
-    for (int64_t pr0 = ((int64_t)blockIdx.x * 8 + (threadIdx.x >> 5)) * U; pr0 < npair; pr0 += (int64_t)gridDim.x * 8 * U) {
-        float v[U][8];
-        int64_t frame[U]; int n[U]; bool real[U];
+    for (int64_t pr = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5); pr < npair; pr += (int64_t)gridDim.x * 8) {
+        const int64_t prow = pr * 2 + half;                                       // padded row index: frame * NTILE*128 + n
+        const int64_t frame = prow / (NTILE * 128);
+        const int n = (int)(prow - frame * (NTILE * 128));
+        const bool real = n < N;
+        float v[8];
+        if (real) Tok<__nv_bfloat16>::load(x + (frame * N + n) * 128 + sub * 8, v);
+        else {
 #pragma unroll
-        for (int u = 0; u < U; ++u) {
-            const int64_t prow = (pr0 + u) * 2 + half;                            // padded row index: frame * NTILE*128 + n
-            frame[u] = prow / (NTILE * 128);
-            n[u] = (int)(prow - frame[u] * (NTILE * 128));
-            real[u] = pr0 + u < npair && n[u] < N;
-            if (real[u]) Tok<__nv_bfloat16>::load(x + (frame[u] * N + n[u]) * 128 + sub * 8, v[u]);
-            else {
-#pragma unroll
-                for (int e = 0; e < 8; ++e) v[u][e] = 0.f;
-            }
+            for (int e = 0; e < 8; ++e) v[e] = 0.f;
         }
+        float s = 0.f;
 #pragma unroll
-        for (int u = 0; u < U; ++u) {
-            if (pr0 + u >= npair) break;                                          // warp-uniform
-            float s = 0.f;
+        for (int e = 0; e < 8; ++e) s += v[e];
 #pragma unroll
-            for (int e = 0; e < 8; ++e) s += v[u][e];
+        for (int o = 8; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+        const float mean = s * (1.0f / 128.0f);
+        float q = 0.f;
 #pragma unroll
-            for (int o = 8; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-            const float mean = s * (1.0f / 128.0f);
-            float q = 0.f;
+        for (int e = 0; e < 8; ++e) { const float t = v[e] - mean; q = fmaf(t, t, q); }
 #pragma unroll
-            for (int e = 0; e < 8; ++e) { const float t = v[u][e] - mean; q = fmaf(t, t, q); }
+        for (int o = 8; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
+        const float rstd = 1.0f / sqrtf(q * (1.0f / 128.0f) + eps);
+        uint4 out = make_uint4(0u, 0u, 0u, 0u);
+        if (real) {
+            if (sub == 0) stats[frame * N + n] = make_float2(mean, rstd);
+            float y[8];
 #pragma unroll
-            for (int o = 8; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
-            const float rstd = 1.0f / sqrtf(q * (1.0f / 128.0f) + eps);
-            uint4 out = make_uint4(0u, 0u, 0u, 0u);
-            if (real[u]) {
-                if (sub == 0) stats[frame[u] * N + n[u]] = make_float2(mean, rstd);
-                float y[8];
-#pragma unroll
-                for (int e = 0; e < 8; ++e) y[e] = (v[u][e] - mean) * rstd * gg[e] + bb[e];
-                __nv_bfloat162 p0 = __floats2bfloat162_rn(y[0], y[1]), p1 = __floats2bfloat162_rn(y[2], y[3]);
-                __nv_bfloat162 p2 = __floats2bfloat162_rn(y[4], y[5]), p3 = __floats2bfloat162_rn(y[6], y[7]);
-                out.x = *reinterpret_cast<unsigned*>(&p0); out.y = *reinterpret_cast<unsigned*>(&p1);
-                out.z = *reinterpret_cast<unsigned*>(&p2); out.w = *reinterpret_cast<unsigned*>(&p3);
-            }
-            *reinterpret_cast<uint4*>(ximg_chunk(ximg, frame[u], n[u], sub * 8, NTILE, 128)) = out;   // padding rows are zero-filled
+            for (int e = 0; e < 8; ++e) y[e] = (v[e] - mean) * rstd * gg[e] + bb[e];
+            __nv_bfloat162 p0 = __floats2bfloat162_rn(y[0], y[1]), p1 = __floats2bfloat162_rn(y[2], y[3]);
+            __nv_bfloat162 p2 = __floats2bfloat162_rn(y[4], y[5]), p3 = __floats2bfloat162_rn(y[6], y[7]);
+            out.x = *reinterpret_cast<unsigned*>(&p0); out.y = *reinterpret_cast<unsigned*>(&p1);
+            out.z = *reinterpret_cast<unsigned*>(&p2); out.w = *reinterpret_cast<unsigned*>(&p3);
         }
+        *reinterpret_cast<uint4*>(ximg_chunk(ximg, frame, n, sub * 8, NTILE, 128)) = out;   // padding rows are zero-filled
     }
 }
 
@@ -525,7 +516,7 @@ static cudaError_t launch_ln_fwd(const FwdArgs& a, const void* inputs, cudaStrea
     if constexpr (sizeof(TokT) == 2) {
         if (a.d.umma && a.d.D == 128) {
             const int64_t npair = ((int64_t)a.d.B * a.d.T * a.d.NTILE * 128 + 1) / 2;
-            int grid = (int)((npair + 15) / 16);                           // two row pairs per warp and iteration
+            int grid = (int)((npair + 7) / 8);
             if (grid > 148 * 16) grid = 148 * 16;
             ln_tokens_fwd_img128_kernel<<<grid, 256, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(inputs),
                 reinterpret_cast<float2*>(a.saved + a.sl.stats), a.packed + a.po.ln_in_w, a.packed + a.po.ln_in_b, rows, a.d.ln_eps,

@@ -184,7 +184,7 @@ def test_cast_policy_fp32_trainer_and_autocast_half():
     with torch.autocast("cuda", dtype=torch.float16):
         s16, a16 = m(x.detach().half(), noise=noise)
     assert s16.dtype == torch.float16 and a16.dtype == torch.float16
-    assert err(s16.float().cpu().numpy(), rs) < TOL_BF16 and err(a16.float().cpu().numpy(), ra) < TOL_BF16
+    assert err(s16.detach().float().cpu().numpy(), rs) < TOL_BF16 and err(a16.detach().float().cpu().numpy(), ra) < TOL_BF16
 
 
 def test_grad_attn_none_is_the_trainer_case():

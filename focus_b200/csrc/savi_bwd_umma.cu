@@ -25,7 +25,8 @@ struct BwdUArgs {
     WImg wi;
 };
 
-struct TokState { uint32_t cnt_s[2], cnt_a[2]; };
+struct TokState { uint32_t cnt_s[2], cnt_a[2];       // issuer: tiles issued (P1) / consumed (P2) per buffer = sequence numbers
+                  uint32_t nbase, own_s, own_a; };    // compute warpgroup: sequence number of its buffer's first tile of the step, own waits
 
 // operand buffers: X0..X3 = opA, opB, opC, aw0 of the shared plan; aw1 + scratch hold the float2 LayerNorm scratch
 __device__ __forceinline__ int xop(const Smem& L, int i) { return i == 0 ? L.opA : i == 1 ? L.opB : i == 2 ? L.opC : L.aw0; }
@@ -51,7 +52,7 @@ __device__ __forceinline__ void issue_token_pass_bwd(Ring& r, bool el, uint64_t*
             for (int kt = 1; kt < 8; ++kt) mma_lo(tb + TB_DQK, x0 + kt * 128, dl + kt * 128, IDESC_MN_MN64, 1u);
             mma_commit(&r.empty[ts0[g]]);
             mma_commit(&r.empty[ts0[g] + 1]);
-            mma_commit(&bars[B_AFREE + g]);
+            mma_commit(&bars[B_AFREE4 + tok_wg(ts.cnt_a[g] + 1u, g)]);        // the buffer's next writer may proceed
         }
         __syncwarp();
         ++ts.cnt_a[g];
@@ -79,7 +80,7 @@ __device__ __forceinline__ void issue_token_pass_bwd(Ring& r, bool el, uint64_t*
             __syncwarp();
             r.advance();
         }
-        if (el) mma_commit(&bars[B_SFULL + g]);
+        if (el) mma_commit(&bars[B_SFULL4 + tok_wg(ts.cnt_s[g], g)]);
         __syncwarp();
         ++ts.cnt_s[g];
         if (i >= 1) p2(i - 1);
@@ -90,146 +91,144 @@ __device__ __forceinline__ void issue_token_pass_bwd(Ring& r, bool el, uint64_t*
 }
 
 // ------------------------------------------------------------------------------------------------
-// compute threads: recompute P, form dL and W for this group's token tiles (thread = token, half of the slots)
+// compute threads: recompute P, form dL and W for this warpgroup's token tiles (thread = token, all K <= 24 slots of the
+// token in registers; tile ownership as in the forward, tok_wg())
 //   dP = (G - c)/S (+ grad_attn);  dL = P (dP - <P, dP>);  W = (P + eps)/S          
-// cv: shared [64] = c[32] | 1/S[32].  coef: first coefficient block of this (frame, iteration): tile j's block is j * I * 16 KB further.
+// cv: shared [64] floats: c[k] at [k], 1/S[k] at [32 + k].
 // ------------------------------------------------------------------------------------------------
 __device__ __forceinline__ void softmax_bwd_tiles(const Ctx& c, const Dims& d, int ntile, int tile0, const bf16* gattn_frame,
                                                   unsigned char* coef, const float* cv, int dl0_off, int dl1_off, TokState& ts, long long* dbg) {
     constexpr float LOG2E = 1.4426950408889634f;
     long long ph_last = clock64();
-    const int K = c.K, p = c.wg >> 1, h = c.wg & 1;
-    const int KHs = (((K + 1) >> 1) + 3) & ~3;
-    const int s0 = h * KHs, ns = min(max(K - s0, 0), KHs);
-    const uint32_t scol = c.tb + c.tlane + (p ? TB_S1 : TB_S0) + s0;
-    const uint32_t gcol = c.tb + c.tlane + (p ? TB_G1 : TB_G0) + s0;
-    unsigned char* dlrow = c.sm + (p ? dl1_off : dl0_off) + c.o * 128;
+    const int K = c.K, g = c.wg & 1;
+    const uint32_t hb = (uint32_t)(c.wg >> 1);
+    const uint32_t scol = c.tb + c.tlane + (g ? TB_S1 : TB_S0);
+    const uint32_t gcol = c.tb + c.tlane + (g ? TB_G1 : TB_G0);
+    unsigned char* dlrow = c.sm + (g ? dl1_off : dl0_off) + c.o * 128;
     const uint32_t sw = (uint32_t)(c.o & 7);
-    for (int i = p; i < ntile; i += 2) {
+    for (int i = g; i < ntile; i += 2) {
+        const uint32_t nseq = ts.nbase + (uint32_t)(i >> 1);
+        if ((nseq & 1u) != hb) continue;
         const int n = (tile0 + i) * 128 + c.o;
         const bool valid = n < d.N;
-        float ga[16];
+        // upstream gradient of the attention map (last iteration only), kept packed (bf16 pairs) until it is consumed;
+        // issued before the wait: latency hidden behind the MMAs
+        uint32_t gap[KTOK / 2];
 #pragma unroll
-        for (int s = 0; s < 16; ++s) ga[s] = 0.f;
-        if (gattn_frame && valid) {                              // issued before the wait: latency hidden behind the MMAs
-            const bf16* row = gattn_frame + (size_t)n * K + s0;
-            if ((K & 3) == 0) {
+        for (int j = 0; j < KTOK / 2; ++j) gap[j] = 0u;
+        if (gattn_frame && valid) {
+            const bf16* row = gattn_frame + (size_t)n * K;
+            if ((K & 7) == 0) {
 #pragma unroll
-                for (int s = 0; s < 16; s += 4) {
-                    if (s < ns) {
-                        const uint2 v = *reinterpret_cast<const uint2*>(row + s);
-                        const float2 a0 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&v.x));
-                        const float2 a1 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&v.y));
-                        ga[s] = a0.x; ga[s + 1] = a0.y; ga[s + 2] = a1.x; ga[s + 3] = a1.y;
+                for (int j = 0; j < KTOK / 8; ++j) {
+                    if (8 * j < K) {
+                        const uint4 v = *reinterpret_cast<const uint4*>(row + 8 * j);
+                        gap[4 * j] = v.x; gap[4 * j + 1] = v.y; gap[4 * j + 2] = v.z; gap[4 * j + 3] = v.w;
                     }
                 }
             } else {
 #pragma unroll
-                for (int s = 0; s < 16; ++s) if (s < ns) ga[s] = __bfloat162float(row[s]);
+                for (int j = 0; j < KTOK / 2; ++j) {
+                    const uint32_t lo = (2 * j < K) ? (uint32_t)__bfloat16_as_ushort(row[2 * j]) : 0u;
+                    const uint32_t hi = (2 * j + 1 < K) ? (uint32_t)__bfloat16_as_ushort(row[2 * j + 1]) : 0u;
+                    gap[j] = lo | (hi << 16);
+                }
             }
         }
-        mbar_wait(&c.bars[B_SFULL + p], ts.cnt_s[p] & 1u);
+        mbar_wait(&c.bars[B_SFULL4 + c.wg], ts.own_s & 1u);
+        ++ts.own_s;
         fence_after_sync();
         UPH(55);
-        float l[16], gq[16];
+        float l[KTOK], gq[KTOK];
         {
-            float t2[16];
-            tmem_ld16(scol, l); tmem_ld16(scol + 32, t2);
+            float t2[KTOK];
+            tmem_ld16(scol, l); tmem_ld8(scol + 16, l + 16);
+            tmem_ld16(scol + 32, t2); tmem_ld8(scol + 48, t2 + 16);
             tmem_wait_ld();
 #pragma unroll
-            for (int s = 0; s < 16; ++s) l[s] += t2[s];
-            tmem_ld16(gcol, gq); tmem_ld16(gcol + 32, t2);
+            for (int s = 0; s < KTOK; ++s) l[s] += t2[s];
+            tmem_ld16(gcol, gq); tmem_ld8(gcol + 16, gq + 16);
+            tmem_ld16(gcol + 32, t2); tmem_ld8(gcol + 48, t2 + 16);
             tmem_wait_ld();
 #pragma unroll
-            for (int s = 0; s < 16; ++s) gq[s] += t2[s];
+            for (int s = 0; s < KTOK; ++s) gq[s] += t2[s];
         }
         fence_before_sync();
         __syncwarp();
-        if (c.lane == 0) mbar_arrive(&c.bars[B_SFREE + p]);
+        if (c.lane == 0) mbar_arrive(&c.bars[B_SFREE + g]);
         float mx = -INFINITY;
 #pragma unroll
-        for (int s = 0; s < 16; ++s) if (s < ns) mx = fmaxf(mx, l[s]);
+        for (int s = 0; s < KTOK; ++s) if (s < K) mx = fmaxf(mx, l[s]);
         mx *= LOG2E;
         float sum = 0.f;
 #pragma unroll
-        for (int s = 0; s < 16; ++s) { l[s] = (s < ns) ? exp2f(fmaf(l[s], LOG2E, -mx)) : 0.f; sum += l[s]; }
-        float2* xch = reinterpret_cast<float2*>(c.sm + c.L.xch) + ((p * 2 + (ts.cnt_s[p] & 1u)) * 2) * 128;
-        xch[h * 128 + c.o] = make_float2(mx, sum);
-        bar_sync_n(2 + p, 256);
-        const float2 other = xch[(h ^ 1) * 128 + c.o];
-        const float M = fmaxf(mx, other.x);
-        const float wme = exp2f(mx - M);
-        const float scale = wme / (sum * wme + other.y * exp2f(other.x - M));
+        for (int s = 0; s < KTOK; ++s) { l[s] = (s < K) ? exp2f(fmaf(l[s], LOG2E, -mx)) : 0.f; sum += l[s]; }
+        const float scale = 1.0f / sum;
         float dot = 0.f;
 #pragma unroll
-        for (int s = 0; s < 16; ++s) {
-            if (s < ns) {
+        for (int s = 0; s < KTOK; ++s) {
+            if (s < K) {
                 l[s] *= scale;                                                           // P
-                const float dp = (gq[s] - cv[s0 + s]) * cv[32 + s0 + s] + ga[s];         // dP
+                const __nv_bfloat162 gp = *reinterpret_cast<const __nv_bfloat162*>(&gap[s >> 1]);
+                const float ga = (s & 1) ? __high2float(gp) : __low2float(gp);
+                const float dp = (gq[s] - cv[s]) * cv[32 + s] + ga;                      // dP
                 gq[s] = dp;
                 dot = fmaf(l[s], dp, dot);
             }
         }
-        // second exchange: the dot product over the whole slot axis (separate slots of the same buffer set)
-        float* xd = reinterpret_cast<float*>(c.sm + c.L.xch + 8192) + ((p * 2 + (ts.cnt_s[p] & 1u)) * 2) * 128;
-        xd[h * 128 + c.o] = dot;
-        bar_sync_n(2 + p, 256);
-        dot += xd[(h ^ 1) * 128 + c.o];
-        ++ts.cnt_s[p];
         UPH(56);
-        mbar_wait(&c.bars[B_AFREE + p], (ts.cnt_a[p] & 1u) ^ 1u);
+        if (nseq > 0u) { mbar_wait(&c.bars[B_AFREE4 + c.wg], ts.own_a & 1u); ++ts.own_a; }   // P2 of the buffer's previous tile is done
         UPH(57);
 #pragma unroll
-        for (int s = 0; s < 16; s += 4) {
-            if (s < KHs) {
-                float dl[4];
+        for (int s = 0; s < KTOK; s += 8) {
+            uint32_t hv[4], lv[4];
 #pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                    const bool ok = valid && s + e < ns;
-                    const float pv = l[s + e];
-                    dl[e] = ok ? pv * (gq[s + e] - dot) : 0.f;                                // dL
-                    l[s + e] = ok ? (pv + d.eps) * cv[32 + s0 + s + e] : 0.f;                 // W
-                    gq[s + e] = dl[e];
+            for (int e = 0; e < 4; ++e) {
+                float dl2[2];
+#pragma unroll
+                for (int q = 0; q < 2; ++q) {
+                    const int ss = s + 2 * e + q;
+                    const bool ok = valid && ss < K;
+                    const float pv = l[ss];
+                    dl2[q] = ok ? pv * (gq[ss] - dot) : 0.f;                                 // dL
+                    l[ss] = ok ? (pv + d.eps) * cv[32 + ss] : 0.f;                           // W
+                    gq[ss] = dl2[q];
                 }
-                const __nv_bfloat162 h0 = __floats2bfloat162_rn(dl[0], dl[1]), h1 = __floats2bfloat162_rn(dl[2], dl[3]);
-                const float2 f0 = __bfloat1622float2(h0), f1 = __bfloat1622float2(h1);
-                uint2 hv, lv;
-                hv.x = *reinterpret_cast<const uint32_t*>(&h0); hv.y = *reinterpret_cast<const uint32_t*>(&h1);
-                lv.x = pack_bf16x2(dl[0] - f0.x, dl[1] - f0.y); lv.y = pack_bf16x2(dl[2] - f1.x, dl[3] - f1.y);
-                const uint32_t bo = (uint32_t)(s0 + s) * 2u;
-                *reinterpret_cast<uint2*>(dlrow + ((((bo >> 4) ^ sw)) << 4) + (bo & 15u)) = hv;
-                *reinterpret_cast<uint2*>(dlrow + (((((bo + 64u) >> 4) ^ sw)) << 4) + (bo & 15u)) = lv;
+                const __nv_bfloat162 h2 = __floats2bfloat162_rn(dl2[0], dl2[1]);
+                const float2 f2 = __bfloat1622float2(h2);
+                hv[e] = *reinterpret_cast<const uint32_t*>(&h2);
+                lv[e] = pack_bf16x2(dl2[0] - f2.x, dl2[1] - f2.y);
             }
+            const uint32_t ch = (uint32_t)(s >> 3);
+            *reinterpret_cast<uint4*>(dlrow + ((ch ^ sw) << 4)) = make_uint4(hv[0], hv[1], hv[2], hv[3]);
+            *reinterpret_cast<uint4*>(dlrow + (((4u + ch) ^ sw) << 4)) = make_uint4(lv[0], lv[1], lv[2], lv[3]);
         }
         fence_async_smem();
         __syncwarp();
-        if (c.lane == 0) mbar_arrive(&c.bars[B_AREADY + p]);
-        ++ts.cnt_a[p];
+        if (c.lane == 0) mbar_arrive(&c.bars[B_AREADY + g]);
         UPH(58);
         if (valid) {
             // coefficients of the d_inputs kernel: this token's row of the iteration's K-major operand block,
-            // [128 tokens][32 dL | 32 W] bf16, SWIZZLE_128B (savi_dx_umma.cu fetches the block with one bulk copy)
+            // [128 tokens][32 dL | 32 W] bf16, SWIZZLE_128B (savi_dx_umma.cu fetches the block with one bulk copy);
+            // slots [24, 32) belong to nobody: written as zeros so the block stays finite
             unsigned char* row = coef + (size_t)(tile0 + i) * d.I * 16384 + (size_t)c.o * 128;
 #pragma unroll
-            for (int s = 0; s < 16; s += 4) {
-                if (s < KHs) {
-                    const uint32_t bo = (uint32_t)(s0 + s) * 2u;
-                    *reinterpret_cast<uint2*>(row + (((bo >> 4) ^ sw) << 4) + (bo & 15u)) =
-                        make_uint2(pack_bf16x2(gq[s], gq[s + 1]), pack_bf16x2(gq[s + 2], gq[s + 3]));
-                    *reinterpret_cast<uint2*>(row + ((((bo + 64u) >> 4) ^ sw) << 4) + (bo & 15u)) =
-                        make_uint2(pack_bf16x2(l[s], l[s + 1]), pack_bf16x2(l[s + 2], l[s + 3]));
-                }
+            for (int s = 0; s < KTOK; s += 8) {
+                const uint32_t ch = (uint32_t)(s >> 3);
+                *reinterpret_cast<uint4*>(row + ((ch ^ sw) << 4)) =
+                    make_uint4(pack_bf16x2(gq[s], gq[s + 1]), pack_bf16x2(gq[s + 2], gq[s + 3]), pack_bf16x2(gq[s + 4], gq[s + 5]), pack_bf16x2(gq[s + 6], gq[s + 7]));
+                *reinterpret_cast<uint4*>(row + (((4u + ch) ^ sw) << 4)) =
+                    make_uint4(pack_bf16x2(l[s], l[s + 1]), pack_bf16x2(l[s + 2], l[s + 3]), pack_bf16x2(l[s + 4], l[s + 5]), pack_bf16x2(l[s + 6], l[s + 7]));
             }
-            if (h == 1) {                                        // slots [2 KHs, 32) belong to nobody: keep them finite (zero)
-                for (int sp = 2 * KHs; sp < 32; sp += 4) {
-                    const uint32_t bo = (uint32_t)sp * 2u;
-                    *reinterpret_cast<uint2*>(row + (((bo >> 4) ^ sw) << 4) + (bo & 15u)) = make_uint2(0u, 0u);
-                    *reinterpret_cast<uint2*>(row + ((((bo + 64u) >> 4) ^ sw) << 4) + (bo & 15u)) = make_uint2(0u, 0u);
-                }
+#pragma unroll
+            for (uint32_t ch = KTOK / 8; ch < 4; ++ch) {
+                *reinterpret_cast<uint4*>(row + ((ch ^ sw) << 4)) = make_uint4(0u, 0u, 0u, 0u);
+                *reinterpret_cast<uint4*>(row + (((4u + ch) ^ sw) << 4)) = make_uint4(0u, 0u, 0u, 0u);
             }
         }
         UPH(59);
     }
+    ts.nbase += (uint32_t)((ntile + 1 - g) >> 1);
 }
 
 // LayerNorm backward in the feature-per-thread layout.  dy: gradient of the LN output; x: its input (this thread's column);
@@ -251,6 +250,7 @@ __device__ __forceinline__ void ln_bwd(const Ctx& c, const float (&dy)[KH], cons
         } else { xh[kk] = 0.f; dz[kk] = 0.f; s_[kk] = make_float2(0.f, 0.f); }
     }
     bar_sync_compute();
+#pragma unroll 1
     for (int k = c.warp; k < c.K; k += NCW) {
         const float4 a = *reinterpret_cast<const float4*>(scr + k * F + c.lane * 4);
         const float4 b = *reinterpret_cast<const float4*>(scr + k * F + c.lane * 4 + 2);
@@ -287,6 +287,7 @@ __device__ __forceinline__ void mha_core_bwd(const Ctx& c, int H, float hscale, 
     bar_sync_compute();
     UPH(45);
     // d attention = dO_h . V_h^T: 4 threads per (head, query) row, <= MHA_JP keys each with independent accumulators
+#pragma unroll 1
     for (int row = c.tid >> 2; row < H * K; row += NCT / 4) {
         const int jq = c.tid & 3, JP = (K + 3) >> 2, j0 = jq * JP;
         const int h = row / K, i = row - h * K;
@@ -295,6 +296,7 @@ __device__ __forceinline__ void mha_core_bwd(const Ctx& c, int H, float hscale, 
         float acc[MHA_JP];
 #pragma unroll
         for (int jj = 0; jj < MHA_JP; ++jj) acc[jj] = 0.f;
+#pragma unroll 1
         for (int e = 0; e < dh; e += 4) {
             const float4 x = ld4(a + e);
 #pragma unroll
@@ -309,6 +311,7 @@ __device__ __forceinline__ void mha_core_bwd(const Ctx& c, int H, float hscale, 
     bar_sync_compute();
     UPH(46);
     // softmax backward: one warp per (head, query) row, lane = key; three rows in flight per warp
+#pragma unroll 1
     for (int row0 = c.warp; row0 < H * K; row0 += 3 * NCW) {
         float av[3], dav[3], dot[3];
 #pragma unroll
@@ -407,11 +410,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) savi_bwd_umma_kernel(const __grid
         for (int s = 0; s < L.nst; ++s) { mbar_init(&bars[B_FULL + s], 1); mbar_init(&bars[B_EMPTY + s], 1); }
         mbar_init(&bars[B_OPND], NCW); mbar_init(&bars[B_ACC], 1); mbar_init(&bars[B_TOK], 1); mbar_init(&bars[B_HP], 1);
         for (int g = 0; g < 2; ++g) {
-            mbar_init(&bars[B_SFULL + g], 1); mbar_init(&bars[B_SFREE + g], 8);
-            mbar_init(&bars[B_AREADY + g], 8); mbar_init(&bars[B_AFREE + g], 1);
+            mbar_init(&bars[B_SFREE + g], 4); mbar_init(&bars[B_AREADY + g], 4);        // one warpgroup (4 warps) per tile
             mbar_init(&bars[B_INBOX + g], NCW);
         }
-        for (int f = 0; f < 4; ++f) { mbar_init(&bars[B_FACC + f], 1); mbar_init(&bars[B_FOPND + f], NCW); }
+        for (int f = 0; f < 4; ++f) { mbar_init(&bars[B_FACC + f], 1); mbar_init(&bars[B_FOPND + f], NCW); mbar_init(&bars[B_SFULL4 + f], 1); mbar_init(&bars[B_AFREE4 + f], 1); }
         mbar_init_fence();
     }
     if (warp == W_MMA) tmem_alloc(tmem_slot, TB_COLS);
@@ -464,7 +466,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) savi_bwd_umma_kernel(const __grid
         {
             const bool el = elect_one();
             uint32_t ph_opnd = 0, pcall = 0;
-            TokState ts = {{0, 0}, {0, 0}};
+            TokState ts = {{0, 0}, {0, 0}, 0, 0, 0};
             const uint32_t X0 = smem_u32(sm + L.opA), X1 = smem_u32(sm + L.opB), X2 = smem_u32(sm + L.opC), X3 = smem_u32(sm + L.aw0);
             auto wait_opnd = [&]() { mbar_wait(&bars[B_OPND], ph_opnd); ph_opnd ^= 1u; fence_after_sync(); };
             for (int t = d.T - 1; t >= 0; --t) {
@@ -516,7 +518,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) savi_bwd_umma_kernel(const __grid
         Ctx c;
         ctx_init(c, tid, K, sm, L, tb, bars);
         const int o = c.o;
-        TokState ts = {{0, 0}, {0, 0}};
+        TokState ts = {{0, 0}, {0, 0}, 0, 0, 0};
         long long* sdbg = reinterpret_cast<long long*>(sm + L.bars + NBAR * 8 + 16);
         if (a.dbg && blockIdx.x == 0 && tid == 0) for (int i = 0; i < 64; ++i) sdbg[i] = 0;
         long long* dbg = (a.dbg && blockIdx.x == 0 && tid == 0) ? sdbg : nullptr;
@@ -752,6 +754,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) savi_bwd_umma_kernel(const __grid
                     write_operand(c, xop(L, 0), dux);
                     write_operand(c, xop(L, 1), qk);
                     bar_sync_compute();
+#pragma unroll 1
                     for (int k = c.warp; k < K; k += NCW) {
                         const float4 x = ld4(scr + k * F + lane * 4);
                         const float sdot = warp_sum((x.x + x.y) + (x.z + x.w));

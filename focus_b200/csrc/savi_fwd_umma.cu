@@ -28,7 +28,8 @@ struct FwdUArgs {
 //   P2(i): NUMX   += xhat_i^T . [A_hi | A_lo]       (A = token tile, MN-major; B = attention-weight tile)
 //          SSUM   += 1 . [A_hi | A_lo]
 // ------------------------------------------------------------------------------------------------
-struct TokState { uint32_t cnt_s[2], cnt_a[2]; };
+struct TokState { uint32_t cnt_s[2], cnt_a[2];       // issuer: tiles issued (P1) / consumed (P2) per buffer = sequence numbers
+                  uint32_t nbase, own_s, own_a; };    // compute warpgroup: sequence number of its buffer's first tile of the step, own waits
 
 __device__ __forceinline__ void issue_token_pass(Ring& r, bool el, unsigned char* sm, const Smem& L, uint64_t* bars, uint32_t tb, int ntile,
                                                  TokState& ts, uint32_t qk_op) {
@@ -52,7 +53,7 @@ __device__ __forceinline__ void issue_token_pass(Ring& r, bool el, unsigned char
             }
             mma_commit(&r.empty[ts0[g]]);
             mma_commit(&r.empty[ts0[g] + 1]);
-            mma_commit(&bars[B_AFREE + g]);
+            mma_commit(&bars[B_AFREE4 + tok_wg(ts.cnt_a[g] + 1u, g)]);        // the buffer's next writer may proceed
         }
         __syncwarp();
         ++ts.cnt_a[g];
@@ -77,7 +78,7 @@ __device__ __forceinline__ void issue_token_pass(Ring& r, bool el, unsigned char
             __syncwarp();
             r.advance();
         }
-        if (el) mma_commit(&bars[B_SFULL + g]);
+        if (el) mma_commit(&bars[B_SFULL4 + tok_wg(ts.cnt_s[g], g)]);
         __syncwarp();
         ++ts.cnt_s[g];
         if (i >= 1) p2(i - 1);
@@ -88,85 +89,85 @@ __device__ __forceinline__ void issue_token_pass(Ring& r, bool el, unsigned char
 }
 
 // ------------------------------------------------------------------------------------------------
-// compute threads: softmax over the slot axis (thread = token).  Warpgroups 2p and 2p + 1 share the tiles with
-// tile % 2 == p; each takes one half of the slots and they exchange (max, sum) through shared memory.
+// compute threads: softmax over the slot axis, thread = token, all K <= 24 slots of the token in registers (steve.py:76-83).
+// Warpgroup w drains the tiles of buffer w & 1 whose sequence number is w >> 1 (mod 2): see tok_wg().
 // ------------------------------------------------------------------------------------------------
 __device__ __forceinline__ void softmax_tiles(const Ctx& c, const Dims& d, int ntile, int tile0, bf16* attn_frame, TokState& ts, long long* dbg) {
     constexpr float LOG2E = 1.4426950408889634f;
     long long ph_last = clock64();
-    const int K = c.K, p = c.wg >> 1, h = c.wg & 1;
-    const int KHs = (((K + 1) >> 1) + 3) & ~3;                       // slots per half, a multiple of 4 (8-byte store granules)
-    const int s0 = h * KHs, ns = min(max(K - s0, 0), KHs);
-    const uint32_t scol = c.tb + c.tlane + (p ? TC_S1 : TC_S0) + s0;
-    unsigned char* awrow = c.sm + (p ? c.L.aw1 : c.L.aw0) + c.o * 128;
+    const int K = c.K, g = c.wg & 1;
+    const uint32_t hb = (uint32_t)(c.wg >> 1);
+    const uint32_t scol = c.tb + c.tlane + (g ? TC_S1 : TC_S0);
+    unsigned char* awrow = c.sm + (g ? c.L.aw1 : c.L.aw0) + c.o * 128;
     const uint32_t sw = (uint32_t)(c.o & 7);
-    for (int i = p; i < ntile; i += 2) {
-        mbar_wait(&c.bars[B_SFULL + p], ts.cnt_s[p] & 1u);
+    for (int i = g; i < ntile; i += 2) {
+        const uint32_t nseq = ts.nbase + (uint32_t)(i >> 1);
+        if ((nseq & 1u) != hb) continue;
+        mbar_wait(&c.bars[B_SFULL4 + c.wg], ts.own_s & 1u);
+        ++ts.own_s;
         fence_after_sync();
         UPH(50);
-        float l[16], l2[16];
-        tmem_ld16(scol, l); tmem_ld16(scol + 32, l2);
-        tmem_wait_ld();
+        float l[KTOK];
+        {
+            float l2[KTOK];
+            tmem_ld16(scol, l); tmem_ld8(scol + 16, l + 16);
+            tmem_ld16(scol + 32, l2); tmem_ld8(scol + 48, l2 + 16);
+            tmem_wait_ld();
+#pragma unroll
+            for (int s = 0; s < KTOK; ++s) l[s] += l2[s];
+        }
         fence_before_sync();
         __syncwarp();
-        if (c.lane == 0) mbar_arrive(&c.bars[B_SFREE + p]);
+        if (c.lane == 0) mbar_arrive(&c.bars[B_SFREE + g]);
         float mx = -INFINITY;
 #pragma unroll
-        for (int s = 0; s < 16; ++s) { l[s] += l2[s]; if (s < ns) mx = fmaxf(mx, l[s]); }
+        for (int s = 0; s < KTOK; ++s) if (s < K) mx = fmaxf(mx, l[s]);
         mx *= LOG2E;
         float sum = 0.f;
 #pragma unroll
-        for (int s = 0; s < 16; ++s) { l[s] = (s < ns) ? exp2f(fmaf(l[s], LOG2E, -mx)) : 0.f; sum += l[s]; }
-        float2* xch = reinterpret_cast<float2*>(c.sm + c.L.xch) + ((p * 2 + (ts.cnt_s[p] & 1u)) * 2) * 128;
-        xch[h * 128 + c.o] = make_float2(mx, sum);
-        bar_sync_n(2 + p, 256);
-        const float2 other = xch[(h ^ 1) * 128 + c.o];
-        ++ts.cnt_s[p];
-        const float M = fmaxf(mx, other.x);
-        const float wme = exp2f(mx - M);
-        const float scale = wme / (sum * wme + other.y * exp2f(other.x - M));
+        for (int s = 0; s < KTOK; ++s) { l[s] = (s < K) ? exp2f(fmaf(l[s], LOG2E, -mx)) : 0.f; sum += l[s]; }
+        const float scale = 1.0f / sum;
         const int n = (tile0 + i) * 128 + c.o;                  // token index inside the frame
         const bool valid = n < d.N;
         UPH(51);
-        mbar_wait(&c.bars[B_AFREE + p], (ts.cnt_a[p] & 1u) ^ 1u);
+        if (nseq > 0u) { mbar_wait(&c.bars[B_AFREE4 + c.wg], ts.own_a & 1u); ++ts.own_a; }   // P2 of the buffer's previous tile is done
         UPH(52);
 #pragma unroll
-        for (int s = 0; s < 16; s += 4) {
-            if (s < KHs) {
-                float a[4];
+        for (int s = 0; s < KTOK; s += 8) {
+            uint32_t hv[4], lv[4];
 #pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                    l[s + e] *= scale;                                   // P (steve.py:77)
-                    a[e] = (valid && s + e < ns) ? l[s + e] + d.eps : 0.f;   // A = P + eps (:81); padded tokens carry no weight
-                }
-                const __nv_bfloat162 h0 = __floats2bfloat162_rn(a[0], a[1]), h1 = __floats2bfloat162_rn(a[2], a[3]);
-                const float2 f0 = __bfloat1622float2(h0), f1 = __bfloat1622float2(h1);
-                uint2 hv, lv;
-                hv.x = *reinterpret_cast<const uint32_t*>(&h0); hv.y = *reinterpret_cast<const uint32_t*>(&h1);
-                lv.x = pack_bf16x2(a[0] - f0.x, a[1] - f0.y); lv.y = pack_bf16x2(a[2] - f1.x, a[3] - f1.y);
-                const uint32_t bo = (uint32_t)(s0 + s) * 2u;             // byte offset of slot s0 + s in the hi half of the row
-                *reinterpret_cast<uint2*>(awrow + ((((bo >> 4) ^ sw)) << 4) + (bo & 15u)) = hv;
-                *reinterpret_cast<uint2*>(awrow + (((((bo + 64u) >> 4) ^ sw)) << 4) + (bo & 15u)) = lv;
+            for (int e = 0; e < 4; ++e) {
+                l[s + 2 * e] *= scale; l[s + 2 * e + 1] *= scale;                        // P (steve.py:77)
+                const float a0 = (valid && s + 2 * e < K) ? l[s + 2 * e] + d.eps : 0.f;  // A = P + eps (:81); padded tokens carry no weight
+                const float a1 = (valid && s + 2 * e + 1 < K) ? l[s + 2 * e + 1] + d.eps : 0.f;
+                const __nv_bfloat162 h2 = __floats2bfloat162_rn(a0, a1);
+                const float2 f2 = __bfloat1622float2(h2);
+                hv[e] = *reinterpret_cast<const uint32_t*>(&h2);
+                lv[e] = pack_bf16x2(a0 - f2.x, a1 - f2.y);
             }
+            const uint32_t ch = (uint32_t)(s >> 3);                                      // 16-byte chunk of the hi half; lo half: chunk 4 + ch
+            *reinterpret_cast<uint4*>(awrow + ((ch ^ sw) << 4)) = make_uint4(hv[0], hv[1], hv[2], hv[3]);
+            *reinterpret_cast<uint4*>(awrow + (((4u + ch) ^ sw) << 4)) = make_uint4(lv[0], lv[1], lv[2], lv[3]);
         }
         fence_async_smem();
         __syncwarp();
-        if (c.lane == 0) mbar_arrive(&c.bars[B_AREADY + p]);
-        ++ts.cnt_a[p];
+        if (c.lane == 0) mbar_arrive(&c.bars[B_AREADY + g]);
         UPH(53);
         if (attn_frame && valid) {                               // attns (:96): pre-epsilon softmax, [N][K]
-            bf16* row = attn_frame + (size_t)n * K + s0;
-            if ((K & 3) == 0) {
+            bf16* row = attn_frame + (size_t)n * K;
+            if ((K & 7) == 0) {
 #pragma unroll
-                for (int s = 0; s < 16; s += 4)
-                    if (s < ns) *reinterpret_cast<uint2*>(row + s) = make_uint2(pack_bf16x2(l[s], l[s + 1]), pack_bf16x2(l[s + 2], l[s + 3]));
+                for (int s = 0; s < KTOK; s += 8)
+                    if (s < K) *reinterpret_cast<uint4*>(row + s) = make_uint4(pack_bf16x2(l[s], l[s + 1]), pack_bf16x2(l[s + 2], l[s + 3]),
+                                                                               pack_bf16x2(l[s + 4], l[s + 5]), pack_bf16x2(l[s + 6], l[s + 7]));
             } else {
 #pragma unroll
-                for (int s = 0; s < 16; ++s) if (s < ns) row[s] = __float2bfloat16_rn(l[s]);
+                for (int s = 0; s < KTOK; ++s) if (s < K) row[s] = __float2bfloat16_rn(l[s]);
             }
         }
         UPH(54);
     }
+    ts.nbase += (uint32_t)((ntile + 1 - g) >> 1);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -191,6 +192,7 @@ __device__ __forceinline__ void mha_core(const Ctx& c, int H, const float (&q)[K
     bar_sync_compute();
     // logits: 4 threads per (head, query) row, each a contiguous share of <= MHA_JP keys with independent accumulators
     // (the query row chunk is loaded once and reused; 16-byte conflict-free reads)
+#pragma unroll 1
     for (int row = c.tid >> 2; row < H * K; row += NCT / 4) {
         const int jq = c.tid & 3, JP = (K + 3) >> 2, j0 = jq * JP;
         const int h = row / K, i = row - h * K;
@@ -199,6 +201,7 @@ __device__ __forceinline__ void mha_core(const Ctx& c, int H, const float (&q)[K
         float acc[MHA_JP];
 #pragma unroll
         for (int jj = 0; jj < MHA_JP; ++jj) acc[jj] = 0.f;
+#pragma unroll 1
         for (int e = 0; e < dh; e += 4) {
             const float4 x = ld4(a + e);
 #pragma unroll
@@ -212,6 +215,7 @@ __device__ __forceinline__ void mha_core(const Ctx& c, int H, const float (&q)[K
     }
     bar_sync_compute();
     // softmax over the keys: one warp per (head, query) row, lane = key; three rows in flight per warp
+#pragma unroll 1
     for (int row0 = c.warp; row0 < H * K; row0 += 3 * NCW) {
         float x[3], e[3], mx[3], sm[3];
 #pragma unroll
@@ -292,11 +296,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) savi_fwd_umma_kernel(const __grid
         for (int s = 0; s < L.nst; ++s) { mbar_init(&bars[B_FULL + s], 1); mbar_init(&bars[B_EMPTY + s], 1); }
         mbar_init(&bars[B_OPND], NCW); mbar_init(&bars[B_ACC], 1); mbar_init(&bars[B_TOK], 1);
         for (int g = 0; g < 2; ++g) {
-            mbar_init(&bars[B_SFULL + g], 1); mbar_init(&bars[B_SFREE + g], 8);
-            mbar_init(&bars[B_AREADY + g], 8); mbar_init(&bars[B_AFREE + g], 1);
+            mbar_init(&bars[B_SFREE + g], 4); mbar_init(&bars[B_AREADY + g], 4);        // one warpgroup (4 warps) per tile
             mbar_init(&bars[B_INBOX + g], NCW);
         }
-        for (int f = 0; f < 4; ++f) { mbar_init(&bars[B_FACC + f], 1); mbar_init(&bars[B_FOPND + f], NCW); }
+        for (int f = 0; f < 4; ++f) { mbar_init(&bars[B_FACC + f], 1); mbar_init(&bars[B_FOPND + f], NCW); mbar_init(&bars[B_SFULL4 + f], 1); mbar_init(&bars[B_AFREE4 + f], 1); }
         mbar_init_fence();
     }
     if (warp == W_MMA) tmem_alloc(tmem_slot, TC_COLS);
@@ -345,7 +348,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) savi_fwd_umma_kernel(const __grid
         {
             const bool el = elect_one();
             uint32_t ph_opnd = 0, pcall = 0;
-            TokState ts = {{0, 0}, {0, 0}};
+            TokState ts = {{0, 0}, {0, 0}, 0, 0, 0};
             const uint32_t opA = smem_u32(sm + L.opA), opB = smem_u32(sm + L.opB), opC = smem_u32(sm + L.opC);
             const uint32_t aw0 = smem_u32(sm + L.aw0), aw1 = smem_u32(sm + L.aw1);
             // development counters of the issuer (CTA 0): [60] waiting for operands, [61] waiting for ring blocks, [62] token pass, [63] total
@@ -403,7 +406,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) savi_fwd_umma_kernel(const __grid
         Ctx c;
         ctx_init(c, tid, K, sm, L, tb, bars);
         const int o = c.o;
-        TokState ts = {{0, 0}, {0, 0}};
+        TokState ts = {{0, 0}, {0, 0}, 0, 0, 0};
         // per-feature parameters of this thread
         const float g_s = P[po.ln_s_w + o], b_s = P[po.ln_s_b + o], g_m = P[po.ln_m_w + o], b_m = P[po.ln_m_b + o];
         const float b_r = P[po.bih + o] + P[po.bhh + o], b_z = P[po.bih + F + o] + P[po.bhh + F + o];

@@ -32,6 +32,7 @@ constexpr int BLK = 16384;                    // ring block: [128 rows][64] bf16
 constexpr int OPB = 16384;                    // activation operand: [128 rows][32 hi | 32 lo]
 constexpr int F = 128;                        // feature width handled by this path (D = Ds = M = 128)
 constexpr int KH = 8;                         // slots per compute thread
+constexpr int KTOK = 24;                      // slot columns a token thread handles in the token pass (K <= 24 on this path)
 constexpr uint32_t IDESC_K_MN64 = idesc_bf16(128, 64, false, true);    // A K-major,  B MN-major, N = 64
 constexpr uint32_t IDESC_K_MN32 = idesc_bf16(128, 32, false, true);    //                          N = 32 (hi half of B's rows)
 constexpr uint32_t IDESC_MN_MN64 = idesc_bf16(128, 64, true, true);    // A MN-major, B MN-major, N = 64
@@ -112,10 +113,19 @@ __host__ __device__ inline Smem plan_smem(int K, int CN, bool bwd) {
 // barrier indices inside Smem::bars
 enum { B_FULL = 0, B_EMPTY = 12, B_OPND = 24, B_ACC = 25, B_SFULL = 26, B_SFREE = 28, B_AREADY = 30, B_AFREE = 32, B_TOK = 34,
        B_INBOX = 35, B_OPND2 = 37, B_ACC2 = 38,
-       B_FACC = 40 /* x4: predictor FFN hidden tiles */, B_FOPND = 44 /* x4: their operand chunks */, B_END = 48 };
+       B_FACC = 40 /* x4: predictor FFN hidden tiles */, B_FOPND = 44 /* x4: their operand chunks */,
+       B_SFULL4 = 48 /* x4: logits of a tile ready, one barrier per compute warpgroup */,
+       B_AFREE4 = 52 /* x4: the weight / dL tile buffer this warpgroup writes next has been consumed */, B_END = 56 };
 // An mbarrier only distinguishes the parity of its phase: a barrier must never complete two phases before its
 // waiter has observed the first.  Strictly alternating producer / consumer pairs share B_OPND / B_ACC; anything
 // that is signalled several times in a row (FFN tiles and chunks, token tiles) has its own barrier per item.
+
+// Token pass: tile buffers (logits accumulator + weight / dL tile) alternate, g = tile & 1.  The tiles on buffer g carry a
+// running sequence number n over the whole kernel; tile n is handled by compute warpgroup 2 (n & 1) + g, so the two
+// warpgroups of a buffer alternate and every warpgroup processes a whole tile (all slots of a token in one thread: the
+// softmax needs no exchange).  Each warpgroup has private barriers (B_SFULL4 / B_AFREE4 + wg): an mbarrier only
+// distinguishes the parity of its phase, and a warpgroup would otherwise wait two phases ahead of a shared one.
+__device__ __forceinline__ int tok_wg(uint32_t n, int g) { return (int)(2u * (n & 1u)) + g; }
 
 struct Ring {
     unsigned char* base; uint64_t* full; uint64_t* empty; int nst; int stage; uint32_t phase;
@@ -125,6 +135,7 @@ struct Ring {
 
 // ---- producer ----------------------------------------------------------------------------------
 __device__ __forceinline__ void prod_blocks(Ring& r, const unsigned char* src, int nblk) {
+#pragma unroll 1                 // one thread, always ahead of its consumers: keep its code small (the SM's instruction cache is shared)
     for (int i = 0; i < nblk; ++i) {
         mbar_wait(&r.empty[r.stage], r.phase ^ 1u);
         mbar_expect_tx(&r.full[r.stage], BLK);
@@ -140,36 +151,55 @@ __device__ __forceinline__ void prod_blocks(Ring& r, const unsigned char* src, i
 // The WHOLE issuer warp runs this code with warp-uniform values and only the tcgen05 instructions are predicated
 // on one elected lane `el`: the descriptors then live in uniform registers.  (Issued from single-lane divergent
 // code, every tcgen05.mma is wrapped in a register-to-uniform "waterfall" loop of ~100 cycles.)
-__device__ __forceinline__ void issue_linear(Ring& r, bool el, uint32_t xop, uint32_t tacc, int ntile, int ncb, bool accumulate) {
+// The body is ONE real function (the kernels call it from 15-25 sites; inlined copies were ~15 % of the SASS, and the
+// clip kernels are sensitive to instruction-cache misses).  All state travels by value in registers: ring position in,
+// ring position out (a reference to the Ring would force it into local memory).
+__device__ __forceinline__ bool mbar_try_wait_a(uint32_t bar_addr, uint32_t parity) {
+    uint32_t ok;
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}\n"
+                 : "=r"(ok) : "r"(bar_addr), "r"(parity) : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void mma_commit_a(uint32_t bar_addr) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n" :: "r"(bar_addr) : "memory");
+}
+static __device__ __noinline__ uint32_t issue_linear_core(uint32_t rs /* stage | phase << 8 */, uint32_t el, uint32_t xop, uint32_t tacc,
+                                                          int ntile, int ncb, uint32_t accumulate,
+                                                          uint32_t ring_base, uint32_t full0, uint32_t empty0, int nst) {
+    uint32_t stage = rs & 0xffu, phase = rs >> 8;
     for (int rt = 0; rt < ntile; ++rt) {
         const uint32_t d = tacc + rt * 64;
         for (int cb = 0; cb < ncb; ++cb) {
             const uint32_t xb = dlo_mn(xop + cb * 8192, BLK);              // 64 rows x 128 B of the activation operand
-            if (r.wait_cycles) { const long long t0 = clock64(); mbar_wait(&r.full[r.stage], r.phase); if (el) *r.wait_cycles += clock64() - t0; }
-            else mbar_wait(&r.full[r.stage], r.phase);
+            while (!mbar_try_wait_a(full0 + stage * 8u, phase)) { }
             fence_after_sync();
-            uint32_t a = dlo_k(smem_u32(r.base) + r.stage * BLK);
+            uint32_t a = dlo_k(ring_base + stage * BLK);
             if (el) {
                 mma_lo(d, a, xb, IDESC_K_MN64, (accumulate || cb > 0) ? 1u : 0u);
 #pragma unroll
                 for (int k4 = 1; k4 < 4; ++k4) mma_lo(d, a + k4 * 2, xb + k4 * 128, IDESC_K_MN64, 1u);
-                mma_commit(&r.empty[r.stage]);
+                mma_commit_a(empty0 + stage * 8u);
             }
             __syncwarp();
-            r.advance();
-            if (r.wait_cycles) { const long long t0 = clock64(); mbar_wait(&r.full[r.stage], r.phase); if (el) *r.wait_cycles += clock64() - t0; }
-            else mbar_wait(&r.full[r.stage], r.phase);
+            if (++stage == (uint32_t)nst) { stage = 0; phase ^= 1u; }
+            while (!mbar_try_wait_a(full0 + stage * 8u, phase)) { }
             fence_after_sync();
-            a = dlo_k(smem_u32(r.base) + r.stage * BLK);
+            a = dlo_k(ring_base + stage * BLK);
             if (el) {
 #pragma unroll
                 for (int k4 = 0; k4 < 4; ++k4) mma_lo(d, a + k4 * 2, xb + k4 * 128, IDESC_K_MN32, 1u);
-                mma_commit(&r.empty[r.stage]);
+                mma_commit_a(empty0 + stage * 8u);
             }
             __syncwarp();
-            r.advance();
+            if (++stage == (uint32_t)nst) { stage = 0; phase ^= 1u; }
         }
     }
+    return stage | (phase << 8);
+}
+__device__ __forceinline__ void issue_linear(Ring& r, bool el, uint32_t xop, uint32_t tacc, int ntile, int ncb, bool accumulate) {
+    const uint32_t rs = issue_linear_core((uint32_t)r.stage | (r.phase << 8), el ? 1u : 0u, xop, tacc, ntile, ncb, accumulate ? 1u : 0u,
+                                          smem_u32(r.base), smem_u32(r.full), smem_u32(r.empty), r.nst);
+    r.stage = (int)(rs & 0xffu); r.phase = rs >> 8;
 }
 
 // ---- compute-thread helpers ----------------------------------------------------------------------
@@ -251,6 +281,7 @@ __device__ __forceinline__ void slot_stats(const Ctx& c, const float (&v)[KH], f
 #pragma unroll
     for (int kk = 0; kk < KH; ++kk) if (kk < c.nk) p[kk * F] = v[kk];
     bar_sync_compute();
+#pragma unroll 1
     for (int k = c.warp; k < c.K; k += NCW) {
         const float4 x = ld4(scr + k * F + c.lane * 4);
         const float mean = warp_sum((x.x + x.y) + (x.z + x.w)) * (1.0f / F);

@@ -282,8 +282,16 @@ __device__ __forceinline__ void mha_core_bwd(const Ctx& c, int H, float hscale, 
         const int k = c.k0 + kk;
         if (kk < c.nk) { sO[k * ld + c.o] = dO[kk]; sQ[k * ld + c.o] = Qv[kk]; sK[k * ld + c.o] = Kv[kk]; sV[k * ld + c.o] = Vv[kk]; }
     }
+    {   // element idx = tid + e * NCT of the [H*K][K] matrices -> padded row / column, without a division per element
+        int q = c.tid / K, r = c.tid - q * K;
+        const int dq = NCT / K, dr = NCT - dq * K;
 #pragma unroll
-    for (int e = 0; e < ATT_PT; ++e) { const int idx = c.tid + e * NCT; if (idx < H * K * K) sA[(idx / K) * ka + idx % K] = attv[e]; }
+        for (int e = 0; e < ATT_PT; ++e) {
+            if (q < H * K) sA[q * ka + r] = attv[e];
+            q += dq; r += dr;
+            if (r >= K) { r -= K; ++q; }
+        }
+    }
     bar_sync_compute();
     UPH(45);
     // d attention = dO_h . V_h^T: 4 threads per (head, query) row, <= MHA_JP keys each with independent accumulators
@@ -451,6 +459,35 @@ __global__ void __launch_bounds__(NTHREADS, 1) savi_bwd_umma_kernel(const __grid
                 }
                 const unsigned char* xf = ximg + ((size_t)(b * d.T + t) * d.NTILE + tile0) * 2 * BLK;
                 for (int it = d.I - 1; it >= 0; --it) {
+                    // (this otherwise idle thread also warms L2: kept out of the compute warps' instruction stream)
+                    const int64_t s = (int64_t)t * d.I + it;
+                    float* fbw = const_cast<float*>(fb);
+                    if (s > 0) {
+                        // The saved records are read in reverse order of their creation and do not fit L2 as a whole:
+                        // pull the previous step's rows (the next ones this kernel needs) into L2 while this step runs.
+                        const int64_t sp = s - 1;
+                        const uint32_t rowb = (uint32_t)K * F * 4u;
+                        prefetch_l2(frow(fbw, a.sl.r, sp, b, B, K, F), rowb); prefetch_l2(frow(fbw, a.sl.z, sp, b, B, K, F), rowb);
+                        prefetch_l2(frow(fbw, a.sl.n, sp, b, B, K, F), rowb); prefetch_l2(frow(fbw, a.sl.ghn, sp, b, B, K, F), rowb);
+                        prefetch_l2(frow(fbw, a.sl.hp, sp, b, B, K, F), rowb); prefetch_l2(frow(fbw, a.sl.qk, sp, b, B, K, F), rowb);
+                        prefetch_l2(frow(fbw, a.sl.ux, sp, b, B, K, F), rowb);
+                        const int itp = (it > 0) ? it - 1 : d.I - 1, tp = (it > 0) ? t : t - 1;
+                        if (itp < d.I - 1) {
+                            const int64_t smp = (int64_t)tp * (d.I - 1) + itp;
+                            prefetch_l2(frow(fbw, a.sl.a, smp, b, B, K, F), rowb); prefetch_l2(frow(fbw, a.sl.hg, smp, b, B, K, F), rowb);
+                        }
+                        if (it == 0 && t > 0) {                                                // the predictor link of frame t-1 comes next
+                            prefetch_l2(fb + a.sl.px0 + ((size_t)(t - 1) * B + b) * K * F, rowb);
+                            for (int j = 0; j < d.blocks; ++j) {
+                                const int64_t f = (int64_t)j * (d.T - 1) + (t - 1);
+                                prefetch_l2(frow(fbw, a.sl.px2, f, b, B, K, F), rowb); prefetch_l2(frow(fbw, a.sl.px1, f, b, B, K, F), rowb);
+                                prefetch_l2(frow(fbw, a.sl.pq, f, b, B, K, F), rowb); prefetch_l2(frow(fbw, a.sl.pk, f, b, B, K, F), rowb);
+                                prefetch_l2(frow(fbw, a.sl.pv, f, b, B, K, F), rowb); prefetch_l2(frow(fbw, a.sl.pf, f, b, B, K, 4 * F), 4 * rowb);
+                                const int natt = d.heads * K * K;                               // saved attention matrices of the block
+                                if ((natt & 3) == 0) prefetch_l2(fb + a.sl.patt + (f * B + b) * (int64_t)natt, (uint32_t)natt * 4u);
+                            }
+                        }
+                    }
                     if (it < d.I - 1) { prod_blocks(ring, Wi + wi.w2T, 4); prod_blocks(ring, Wi + wi.w1T, 4); }
                     prod_blocks(ring, Wi + wi.wgT, 12);
                     prod_blocks(ring, Wi + wi.whhT, 12);
@@ -651,32 +688,6 @@ __global__ void __launch_bounds__(NTHREADS, 1) savi_bwd_umma_kernel(const __grid
                 const int64_t s = (int64_t)t * d.I + it;
                 float* fbw = const_cast<float*>(fb);
                 UPH(25);
-                if (tid == 32 && s > 0) {
-                    // The saved records are read in reverse order of their creation and do not fit L2 as a whole:
-                    // pull the previous step's rows (the next ones this kernel needs) into L2 while this step runs.
-                    const int64_t sp = s - 1;
-                    const uint32_t rowb = (uint32_t)K * F * 4u;
-                    prefetch_l2(frow(fbw, a.sl.r, sp, b, B, K, F), rowb); prefetch_l2(frow(fbw, a.sl.z, sp, b, B, K, F), rowb);
-                    prefetch_l2(frow(fbw, a.sl.n, sp, b, B, K, F), rowb); prefetch_l2(frow(fbw, a.sl.ghn, sp, b, B, K, F), rowb);
-                    prefetch_l2(frow(fbw, a.sl.hp, sp, b, B, K, F), rowb); prefetch_l2(frow(fbw, a.sl.qk, sp, b, B, K, F), rowb);
-                    prefetch_l2(frow(fbw, a.sl.ux, sp, b, B, K, F), rowb);
-                    const int itp = (it > 0) ? it - 1 : d.I - 1, tp = (it > 0) ? t : t - 1;
-                    if (itp < d.I - 1) {
-                        const int64_t smp = (int64_t)tp * (d.I - 1) + itp;
-                        prefetch_l2(frow(fbw, a.sl.a, smp, b, B, K, F), rowb); prefetch_l2(frow(fbw, a.sl.hg, smp, b, B, K, F), rowb);
-                    }
-                    if (it == 0 && t > 0) {                                                // the predictor link of frame t-1 comes next
-                        prefetch_l2(fb + a.sl.px0 + ((size_t)(t - 1) * B + b) * K * F, rowb);
-                        for (int j = 0; j < d.blocks; ++j) {
-                            const int64_t f = (int64_t)j * (d.T - 1) + (t - 1);
-                            prefetch_l2(frow(fbw, a.sl.px2, f, b, B, K, F), rowb); prefetch_l2(frow(fbw, a.sl.px1, f, b, B, K, F), rowb);
-                            prefetch_l2(frow(fbw, a.sl.pq, f, b, B, K, F), rowb); prefetch_l2(frow(fbw, a.sl.pk, f, b, B, K, F), rowb);
-                            prefetch_l2(frow(fbw, a.sl.pv, f, b, B, K, F), rowb); prefetch_l2(frow(fbw, a.sl.pf, f, b, B, K, 4 * F), 4 * rowb);
-                            const int natt = d.heads * K * K;                               // saved attention matrices of the block
-                            if ((natt & 3) == 0) prefetch_l2(fb + a.sl.patt + (f * B + b) * (int64_t)natt, (uint32_t)natt * 4u);
-                        }
-                    }
-                }
                 if (it < d.I - 1) {
                     // ---- residual MLP backward (steve.py:92-93) ----
                     const int64_t smi = (int64_t)t * (d.I - 1) + it;

@@ -231,6 +231,17 @@ __device__ __forceinline__ void softmax_bwd_tiles(const Ctx& c, const Dims& d, i
     ts.nbase += (uint32_t)((ntile + 1 - g) >> 1);
 }
 
+static __device__ __noinline__ void ln_bwd_reduce(const float2* scr, float2* red, int warp, int lane, int K) {
+    bar_sync_compute();
+#pragma unroll 1
+    for (int k = warp; k < K; k += NCW) {
+        const float4 a = *reinterpret_cast<const float4*>(scr + k * F + lane * 4);
+        const float4 b = *reinterpret_cast<const float4*>(scr + k * F + lane * 4 + 2);
+        const float s1 = warp_sum((a.x + a.z) + (b.x + b.z)), s2 = warp_sum((a.y + a.w) + (b.y + b.w));
+        if (lane == 0) red[k] = make_float2(s1 * (1.0f / F), s2 * (1.0f / F));
+    }
+    bar_sync_compute();
+}
 // LayerNorm backward in the feature-per-thread layout.  dy: gradient of the LN output; x: its input (this thread's column);
 // st: (mean, rstd) of each slot row.  Accumulates d gamma / d beta of this feature; returns dx.
 __device__ __forceinline__ void ln_bwd(const Ctx& c, const float (&dy)[KH], const float (&x)[KH], const float2* st, float gamma,
@@ -249,15 +260,7 @@ __device__ __forceinline__ void ln_bwd(const Ctx& c, const float (&dy)[KH], cons
             scr[(c.k0 + kk) * F + c.o] = make_float2(dz[kk], dz[kk] * xh[kk]);
         } else { xh[kk] = 0.f; dz[kk] = 0.f; s_[kk] = make_float2(0.f, 0.f); }
     }
-    bar_sync_compute();
-#pragma unroll 1
-    for (int k = c.warp; k < c.K; k += NCW) {
-        const float4 a = *reinterpret_cast<const float4*>(scr + k * F + c.lane * 4);
-        const float4 b = *reinterpret_cast<const float4*>(scr + k * F + c.lane * 4 + 2);
-        const float s1 = warp_sum((a.x + a.z) + (b.x + b.z)), s2 = warp_sum((a.y + a.w) + (b.y + b.w));
-        if (c.lane == 0) red[k] = make_float2(s1 * (1.0f / F), s2 * (1.0f / F));
-    }
-    bar_sync_compute();
+    ln_bwd_reduce(scr, red, c.warp, c.lane, c.K);
 #pragma unroll
     for (int kk = 0; kk < KH; ++kk) {
         if (kk < c.nk) { const float2 r = red[c.k0 + kk]; dx[kk] = s_[kk].y * (dz[kk] - r.x - xh[kk] * r.y); }

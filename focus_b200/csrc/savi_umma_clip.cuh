@@ -273,6 +273,20 @@ __device__ __forceinline__ void load_field(const Ctx& c, const float* src, int l
     for (int kk = 0; kk < KH; ++kk) v[kk] = (kk < c.nk) ? p[kk * ld] : 0.f;
 }
 
+// The barrier-to-barrier middle of the LayerNorm helpers takes no register arrays: ONE real function each instead of an
+// inlined copy per call site (instruction-cache diet, see issue_linear_core).
+static __device__ __noinline__ void slot_stats_reduce(const float* scr, float2* st, int warp, int lane, int K, float eps) {
+    bar_sync_compute();
+#pragma unroll 1
+    for (int k = warp; k < K; k += NCW) {
+        const float4 x = ld4(scr + k * F + lane * 4);
+        const float mean = warp_sum((x.x + x.y) + (x.z + x.w)) * (1.0f / F);
+        const float a = x.x - mean, b = x.y - mean, e = x.z - mean, f = x.w - mean;
+        const float var = warp_sum((a * a + b * b) + (e * e + f * f)) * (1.0f / F);
+        if (lane == 0) st[k] = make_float2(mean, 1.0f / sqrtf(var + eps));
+    }
+    bar_sync_compute();
+}
 // per-slot mean / rstd over the 128 features (torch LayerNorm: biased variance, two-pass), via the scratch tile
 __device__ __forceinline__ void slot_stats(const Ctx& c, const float (&v)[KH], float eps) {
     float* scr = reinterpret_cast<float*>(c.sm + c.L.scratch);
@@ -280,16 +294,7 @@ __device__ __forceinline__ void slot_stats(const Ctx& c, const float (&v)[KH], f
     float* p = scr + c.k0 * F + c.o;
 #pragma unroll
     for (int kk = 0; kk < KH; ++kk) if (kk < c.nk) p[kk * F] = v[kk];
-    bar_sync_compute();
-#pragma unroll 1
-    for (int k = c.warp; k < c.K; k += NCW) {
-        const float4 x = ld4(scr + k * F + c.lane * 4);
-        const float mean = warp_sum((x.x + x.y) + (x.z + x.w)) * (1.0f / F);
-        const float a = x.x - mean, b = x.y - mean, e = x.z - mean, f = x.w - mean;
-        const float var = warp_sum((a * a + b * b) + (e * e + f * f)) * (1.0f / F);
-        if (c.lane == 0) st[k] = make_float2(mean, 1.0f / sqrtf(var + eps));
-    }
-    bar_sync_compute();
+    slot_stats_reduce(scr, st, c.warp, c.lane, c.K, eps);
 }
 // stats_out (nullable): global [K][2] record of (mean, rstd), written by one thread per warpgroup
 __device__ __forceinline__ void layer_norm(const Ctx& c, const float (&v)[KH], float (&y)[KH], float gamma, float beta, float eps,

@@ -91,7 +91,7 @@ __global__ void __launch_bounds__(NT) ln_tokens_fwd_kernel(const TokT* __restric
 
 // tcgen05 path, D = 128 bf16: 16 lanes per token (one 16-byte chunk each), two tokens per warp, output written
 // only as SWIZZLE_128B operand blocks.  Reads 256 B and writes 256 B per token with full 16-byte accesses.
-static __global__ void __launch_bounds__(256) ln_tokens_fwd_img128_kernel(const __nv_bfloat16* __restrict__ x, float2* __restrict__ stats,
+static __global__ void __launch_bounds__(256, 6) ln_tokens_fwd_img128_kernel(const __nv_bfloat16* __restrict__ x, float2* __restrict__ stats,
                                                                    const float* __restrict__ g, const float* __restrict__ b, int64_t rows,
                                                                    float eps, unsigned char* __restrict__ ximg, int N, int NTILE) {
     const int lane = threadIdx.x & 31, sub = lane & 15, half = lane >> 4;

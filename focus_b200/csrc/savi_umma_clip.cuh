@@ -3,8 +3,8 @@
 // Execution model.  One CTA (or a cluster of 2) owns one clip for the whole recurrence.
 //   * 16 compute warps (512 threads): thread (wg, o), wg = warp / 4, o = (warp % 4) * 32 + lane.  For slot-side
 //     tensors the thread owns FEATURE o of the 8 slots [8 wg, 8 wg + 8); the fp32 slot state lives in its
-//     registers for the whole kernel.  In the token pass it owns TOKEN o of a tile (two warpgroups share a
-//     tile, each takes half of the slot axis).
+//     registers for the whole kernel.  In the token pass it owns TOKEN o of a tile with all K <= 24 slots of
+//     that token (one whole tile per warpgroup, see tok_wg()).
 //   * warp 16, one lane: producer.  Streams the static schedule of 16 KB operand blocks (weight images and
 //     token tiles, all pre-swizzled in global memory) into a shared-memory ring with 1-D bulk copies.
 //   * warp 17, one lane: tcgen05.mma issuer.  Every product is computed TRANSPOSED, Y^T = W . X^T, so the
@@ -75,7 +75,6 @@ struct Smem {
     int aw0, aw1;                  // token pass: attention-weight tiles [128 tokens][32 hi | 32 lo]
     int scratch;                   // fp32 [KR][128] transposition scratch (LayerNorm statistics); follows aw1 (predictor q/k/v alias aw0..scratch)
     int stats;                     // float2 [32]
-    int xch;                       // token pass: softmax (max, sum) exchange between the two halves of the slot axis: float2 [2][2][2][128]
     int ones;                      // MN-major ones operand [16][128] bf16
     int inbox;                     // CN = 2: two buffers of [KR][128] + [32] fp32 written by the peer CTA
     int inbox_stride;
@@ -93,7 +92,6 @@ __host__ __device__ inline Smem plan_smem(int K, int CN, bool bwd) {
     s.aw0 = p; p += OPB; s.aw1 = p; p += OPB;
     s.scratch = p; p += KR * F * 4;
     s.stats = p; p += 512;                         // float2 [32] LayerNorm statistics | float [64] c, 1/S (backward)
-    s.xch = p; p += bwd ? 12288 : 8192;            // float2 [pair][tile parity][half][token] (+ float [..] for the backward's dot product)
     p = (p + 1023) & ~1023;
     s.ones = p; p += bwd ? 0 : 4096;
     s.inbox_stride = (KR * F * 4 + (bwd ? 0 : 32 * 4) + 127) & ~127;

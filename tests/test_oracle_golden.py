@@ -61,3 +61,37 @@ def test_c1_reference_fp32_noise_floor():
 def test_norm_slots_bias_grad_is_structurally_zero():
     fx = load_fixture("tiny_a")
     assert np.abs(fx["grads"]["norm_slots.bias"]).max() < 1e-12 * grad_scale(fx["grads"]) + 1e-13
+
+
+def test_weight_fold_algebra_and_chain_rule():
+    """The tcgen05 kernels multiply by the folded weights wqk = Ds^-1/2 Wk^T Wq and wg = Wih Wv and map the
+    gradients of the folded weights back to the four parameters (savi_wgrad.cu: launch_fold_grads).  fp64 check of both
+    identities against the two-step products and their autograd-free closed form."""
+    rng = np.random.default_rng(11)
+    R, D, Ds = 40, 12, 8
+    s = Ds ** -0.5
+    Wq, Wk, Wv = rng.standard_normal((Ds, Ds)), rng.standard_normal((Ds, D)), rng.standard_normal((Ds, D))
+    Wih = rng.standard_normal((3 * Ds, Ds))
+    st, ux = rng.standard_normal((R, Ds)), rng.standard_normal((R, D))          # s~ rows, Ux rows (all steps and clips stacked)
+    dqk, dgi = rng.standard_normal((R, D)), rng.standard_normal((R, 3 * Ds))    # upstream gradients of qk and gi
+    # forward: two-step (reference order) vs folded
+    wqk = s * Wk.T @ Wq                     # [D, Ds]
+    wg = Wih @ Wv                           # [3Ds, D]
+    np.testing.assert_allclose(s * (st @ Wq.T) @ Wk, st @ wqk.T, rtol=1e-12, atol=1e-12)
+    np.testing.assert_allclose((ux @ Wv.T) @ Wih.T, ux @ wg.T, rtol=1e-12, atol=1e-12)
+    # backward of the two-step form
+    q = st @ Wq.T
+    dq = s * dqk @ Wk.T
+    dWq_ref, dWk_ref = dq.T @ st, s * q.T @ dqk
+    U = ux @ Wv.T
+    dU = dgi @ Wih
+    dWih_ref, dWv_ref = dgi.T @ U, dU.T @ ux
+    # backward through the folded weights + chain rule (what the CUDA path computes)
+    dwqk, dwg = dqk.T @ st, dgi.T @ ux
+    np.testing.assert_allclose(s * Wk @ dwqk, dWq_ref, rtol=1e-11, atol=1e-11)
+    np.testing.assert_allclose(s * Wq @ dwqk.T, dWk_ref, rtol=1e-11, atol=1e-11)
+    np.testing.assert_allclose(dwg @ Wv.T, dWih_ref, rtol=1e-11, atol=1e-11)
+    np.testing.assert_allclose(Wih.T @ dwg, dWv_ref, rtol=1e-11, atol=1e-11)
+    # and the activations' gradients
+    np.testing.assert_allclose(dqk @ wqk, dq @ Wq, rtol=1e-11, atol=1e-11)      # d s~
+    np.testing.assert_allclose(dgi @ wg, dU @ Wv, rtol=1e-11, atol=1e-11)       # d Ux

@@ -98,7 +98,7 @@ static int validate(const SaviShape* s, Dims& d) {
     const int MT = d.KC / 16 == 3 ? 4 : d.KC / 16;
     d.mma = (s->dtype == SAVI_DTYPE_BF16 && s->D % 16 == 0 && s->D <= 256 && s->Ds % 8 == 0 && s->M % 8 == 0 &&
              s->N % 8 == 0 && !getenv("SAVI_DISABLE_MMA") &&
-             dx_smem_bytes(s->I, d.KC, s->D) <= (size_t)kMaxSmem &&
+             dx_pick_ig(s->I, d.KC, s->D, (size_t)kMaxSmem) >= 1 &&
              tmma_smem_bytes(MT, s->D, s->K, 1, true) <= (size_t)kMaxSmem) ? 1 : 0;
     if (d.mma) d.KC = MT * 16;
     // tcgen05 clip kernels: bf16 tokens, 128-wide features (one M tile per product), slots and scratch that fit shared memory

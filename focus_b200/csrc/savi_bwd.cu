@@ -603,7 +603,7 @@ cudaError_t SAVI_CAT(savi_launch_ln_bwd_, SAVI_SUFFIX)(const BwdArgs& a, const v
 }
 
 #if defined(SAVI_IS_BF16)
-size_t savi_dx_smem_bytes(const Dims& d) { return dx_smem_bytes(d.I, d.KC, d.D); }
+size_t savi_dx_smem_bytes(const Dims& d) { return dx_smem_bytes(dx_pick_ig(d.I, d.KC, d.D, 227 * 1024), d.KC, d.D); }
 
 cudaError_t savi_launch_dx_mma(const BwdArgs& a, const void* inputs, void* grad_inputs, cudaStream_t st) {
     const Dims& d = a.d;
@@ -617,9 +617,11 @@ cudaError_t savi_launch_dx_mma(const BwdArgs& a, const void* inputs, void* grad_
     x.dx = reinterpret_cast<bf16*>(grad_inputs);
     x.dgamma = a.grad_params + a.po.ln_in_w; x.dbeta = a.grad_params + a.po.ln_in_b;
     x.B = d.B; x.T = d.T; x.N = d.N; x.D = d.D; x.K = d.K; x.I = d.I; x.KC = d.KC; x.tiles_per_cta = 4;
+    x.IG = dx_pick_ig(d.I, d.KC, d.D, 227 * 1024);
+    if (x.IG < 1) return cudaErrorInvalidValue;
     const int tiles = (d.N + TMMA_TN - 1) / TMMA_TN;
     dim3 grid((tiles + x.tiles_per_cta - 1) / x.tiles_per_cta, d.B * d.T);
-    const int smem = (int)dx_smem_bytes(d.I, d.KC, d.D);
+    const int smem = (int)dx_smem_bytes(x.IG, d.KC, d.D);
     cudaError_t e;
 #define DX_LAUNCH(ND_) \
     e = cudaFuncSetAttribute(dx_finalize_kernel<ND_>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); \

@@ -18,11 +18,19 @@ struct DxArgs {
     bf16* dx;                 // d_inputs [B*T, N, D]
     float* dgamma; float* dbeta;
     int B, T, N, D, K, I, KC, tiles_per_cta;
+    int IG;                   // iterations staged in shared memory at a time (== I unless the operands of all I do not fit)
 };
 
-__host__ __device__ __forceinline__ size_t dx_smem_bytes(int I, int KC, int D) {
-    const size_t rows = (size_t)I * 2 * KC;
+// shared memory with IG iterations' right-hand side rows and coefficient rows staged at a time
+__host__ __device__ __forceinline__ size_t dx_smem_bytes(int IG, int KC, int D) {
+    const size_t rows = (size_t)IG * 2 * KC;
     return rows * tmma_xs(D) + rows * TMMA_ATS + (size_t)TMMA_TN * tmma_xs(D) + 2 * (size_t)D * 4 + 16;
+}
+// the largest group of iterations whose operands fit `max_bytes` (0: not even one iteration fits)
+__host__ __device__ __forceinline__ int dx_pick_ig(int I, int KC, int D, size_t max_bytes) {
+    int ig = I;
+    while (ig > 0 && dx_smem_bytes(ig, KC, D) > max_bytes) --ig;
+    return ig;
 }
 
 constexpr int DX_NT = 256;      // 8 warps x 16 tokens = one 128-token tile
@@ -33,62 +41,68 @@ __global__ void __launch_bounds__(DX_NT, 1) dx_finalize_kernel(const __grid_cons
     unsigned char* smem = reinterpret_cast<unsigned char*>(smem4);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, q = lane & 3, mi = lane >> 3, rr = lane & 7;
     const int D = a.D, N = a.N, K = a.K, KC = a.KC, I = a.I, xs = tmma_xs(D);
-    const int rows = I * 2 * KC, nd = D >> 3;
+    const int IG = a.IG, rows = IG * 2 * KC, nd = D >> 3;          // rows staged at a time
     unsigned char* rs = smem;                                       // R  [rows][D+8] bf16
     unsigned char* cs = rs + (size_t)rows * xs;                     // coef tile [rows][TN+8] bf16
     unsigned char* xo = cs + (size_t)rows * TMMA_ATS;               // x tile, later the d_inputs tile [TN][D+8]
     float* red = reinterpret_cast<float*>(xo + (size_t)TMMA_TN * xs);   // [2][D] d gamma, d beta
     const int f = blockIdx.y, b = f / a.T, t = f - b * a.T;
     for (int i = tid; i < 2 * D; i += DX_NT) red[i] = 0.f;
-    // right-hand side rows: for each iteration i: qk_i (KC rows, zero beyond K) then dUx_i
-    {
+    // right-hand side rows of iterations [i0, i0 + ig): for each iteration qk_i (KC rows, zero beyond K) then dUx_i
+    auto stage_rhs = [&](int i0, int ig) {
         const int d4 = D >> 2;
-        for (int idx = tid; idx < rows * d4; idx += DX_NT) {
+        for (int idx = tid; idx < ig * 2 * KC * d4; idx += DX_NT) {
             const int r = idx / d4, c = (idx - r * d4) * 4;
             const int i = r / (2 * KC), rem = r - i * 2 * KC, which = rem / KC, k = rem - which * KC;
             float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
             if (k < K) {
-                const float* src = (which == 0 ? a.qk : a.dux) + ((((size_t)t * I + i) * a.B + b) * K + k) * D + c;
+                const float* src = (which == 0 ? a.qk : a.dux) + ((((size_t)t * I + i0 + i) * a.B + b) * K + k) * D + c;
                 v = ld4(src);
             }
             uint2 p; p.x = pack_bf16(v.x, v.y); p.y = pack_bf16(v.z, v.w);
             *reinterpret_cast<uint2*>(rs + (size_t)r * xs + c * 2) = p;
         }
-    }
+    };
+    if (IG == I) stage_rhs(0, I);                                   // everything fits: staged once per CTA
     const bf16* coef_f = a.coef + (size_t)f * I * 2 * KC * N;
     const int tile0 = blockIdx.x * a.tiles_per_cta;
     for (int tt = 0; tt < a.tiles_per_cta; ++tt) {
         const int n0 = (tile0 + tt) * TMMA_TN;
         if (n0 >= N) break;
         const int tn = min(TMMA_TN, N - n0);
-        __syncthreads();                                            // previous tile's staging buffers are free
-        {   // coefficient rows (contiguous 256 B per row) and the x tile
-            const int cpr = TMMA_TN / 8;
-            for (int idx = tid; idx < rows * cpr; idx += DX_NT) {
-                const int r = idx / cpr, c = idx - r * cpr;
-                unsigned char* dst = cs + (size_t)r * TMMA_ATS + c * 16;
-                if (c * 8 < tn) cp_async16(dst, coef_f + (size_t)r * N + n0 + c * 8);     // N % 8 == 0: whole chunks valid
-                else *reinterpret_cast<uint4*>(dst) = make_uint4(0u, 0u, 0u, 0u);
-            }
-            tmma_issue_tile<DX_NT>(xo, a.x + (size_t)f * N * D, n0, tn, D);
-            cp_async_wait_all();
-        }
-        __syncthreads();
         float acc[ND][4];
 #pragma unroll
         for (int n = 0; n < ND; ++n)
 #pragma unroll
             for (int e = 0; e < 4; ++e) acc[n][e] = 0.f;
-        for (int k0 = 0; k0 < rows; k0 += 16) {
-            uint32_t af[4];
-            ldsm_x4_t(af, cs + (size_t)(k0 + (mi >> 1) * 8 + rr) * TMMA_ATS + (warp * 16 + (mi & 1) * 8) * 2);
+        for (int i0 = 0; i0 < I; i0 += IG) {                        // one pass per group of iterations (a single pass when IG == I)
+            const int ig = min(IG, I - i0), rows_g = ig * 2 * KC;
+            __syncthreads();                                        // the previous pass / tile no longer reads the staging buffers
+            if (IG != I) stage_rhs(i0, ig);
+            {   // coefficient rows (contiguous 256 B per row) and, in the first pass, the x tile
+                const int cpr = TMMA_TN / 8;
+                const bf16* coef_g = coef_f + (size_t)i0 * 2 * KC * N;
+                for (int idx = tid; idx < rows_g * cpr; idx += DX_NT) {
+                    const int r = idx / cpr, c = idx - r * cpr;
+                    unsigned char* dst = cs + (size_t)r * TMMA_ATS + c * 16;
+                    if (c * 8 < tn) cp_async16(dst, coef_g + (size_t)r * N + n0 + c * 8);     // N % 8 == 0: whole chunks valid
+                    else *reinterpret_cast<uint4*>(dst) = make_uint4(0u, 0u, 0u, 0u);
+                }
+                if (i0 == 0) tmma_issue_tile<DX_NT>(xo, a.x + (size_t)f * N * D, n0, tn, D);
+                cp_async_wait_all();
+            }
+            __syncthreads();
+            for (int k0 = 0; k0 < rows_g; k0 += 16) {
+                uint32_t af[4];
+                ldsm_x4_t(af, cs + (size_t)(k0 + (mi >> 1) * 8 + rr) * TMMA_ATS + (warp * 16 + (mi & 1) * 8) * 2);
 #pragma unroll
-            for (int n2 = 0; n2 < ND / 2; ++n2) {
-                if (n2 * 2 < nd) {
-                    uint32_t bf[4];
-                    ldsm_x4_t(bf, rs + (size_t)(k0 + (mi & 1) * 8 + rr) * xs + (n2 * 16 + (mi >> 1) * 8) * 2);
-                    mma16816(acc[n2 * 2], af[0], af[1], af[2], af[3], bf[0], bf[1]);
-                    mma16816(acc[n2 * 2 + 1], af[0], af[1], af[2], af[3], bf[2], bf[3]);
+                for (int n2 = 0; n2 < ND / 2; ++n2) {
+                    if (n2 * 2 < nd) {
+                        uint32_t bf[4];
+                        ldsm_x4_t(bf, rs + (size_t)(k0 + (mi & 1) * 8 + rr) * xs + (n2 * 16 + (mi >> 1) * 8) * 2);
+                        mma16816(acc[n2 * 2], af[0], af[1], af[2], af[3], bf[0], bf[1]);
+                        mma16816(acc[n2 * 2 + 1], af[0], af[1], af[2], af[3], bf[2], bf[3]);
+                    }
                 }
             }
         }

@@ -57,6 +57,7 @@ def test_query_reports_the_kernel_family():
     assert L.PATH_NAMES[L.query(mk(K=11, I=2, T=24)).path] == "tcgen05-bf16"        # C4
     assert L.PATH_NAMES[L.query(mk(N=4096, D=192, Ds=192, M=192)).path] == "mma.sync-bf16"   # C3
     assert L.PATH_NAMES[L.query(mk(K=32)).path] == "mma.sync-bf16"
+    assert L.PATH_NAMES[L.query(mk(K=64)).path] == "mma.sync-bf16"                  # d_inputs operands staged in iteration groups
     assert L.PATH_NAMES[L.query(mk(B=2, dtype=0)).path] == "simt-fp32"              # C1
 
 

@@ -97,6 +97,8 @@ SHAPES = [
     (2, 1, 96, 256, 128, 64, 64, 2, 0, 1),       # K=64 (max), D != Ds, T=1, no predictor blocks
     (5, 2, 64, 32, 32, 32, 11, 1, 2, 2),         # I=1 (no MLP), K=11
     (1, 2, 1, 8, 8, 4, 3, 2, 1, 1),              # N=1 (a single token), smallest dims
+    (2, 2, 136, 128, 128, 128, 64, 3, 1, 4),     # K=64 with 3 iterations: mma.sync path, d_inputs kernel in iteration groups
+    (2, 2, 264, 64, 64, 64, 40, 3, 1, 2),        # K=40 (3 slot m-tiles), D=64
 ]
 
 

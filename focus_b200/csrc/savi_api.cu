@@ -104,9 +104,12 @@ static int validate(const SaviShape* s, Dims& d) {
     // tcgen05 clip kernels: bf16 tokens, 128-wide features (one M tile per product), slots and scratch that fit shared memory
     d.NTILE = (s->N + 127) / 128;
     d.umma = 0;
-    if (d.mma && s->D == 128 && s->Ds == 128 && s->M == 128 && s->K <= 24 && (s->cluster == 0 || s->cluster <= 2) &&
-        savi_umma_mha_fits(s->K, s->heads) && savi_dx_umma_smem_bytes(s->I) <= kMaxSmem && !getenv("SAVI_DISABLE_UMMA")) {
+    // (any N: ragged and odd token counts are handled by the 128-token tiles; the mma.sync path needs N % 8 == 0)
+    if (s->dtype == SAVI_DTYPE_BF16 && s->D == 128 && s->Ds == 128 && s->M == 128 && s->K <= 24 && (s->cluster == 0 || s->cluster <= 2) &&
+        savi_umma_mha_fits(s->K, s->heads) && savi_dx_umma_smem_bytes(s->I) <= kMaxSmem && !getenv("SAVI_DISABLE_UMMA") &&
+        !getenv("SAVI_DISABLE_MMA")) {
         d.umma = 1;
+        d.mma = 1;                       // shares the tensor-core workspace layout (staged d(Ux) rows, no fp32 d xhat accumulator)
         d.CN = s->cluster ? s->cluster : ((int64_t)s->B * 2 <= 148 ? 2 : 1);
         if (d.NTILE < d.CN) d.CN = 1;
     }

@@ -81,6 +81,6 @@ int savi_bwd_umma_smem_bytes(const Dims& d);
 cudaError_t savi_launch_dx_umma(const BwdArgs& a, const void* inputs, void* grad_inputs, bool overlap, cudaStream_t st);
 bool savi_prof_enabled();
 int savi_dx_umma_smem_bytes(int I);
-cudaError_t savi_launch_wgrad_umma(const WgradArgs& wa, cudaStream_t st);
+cudaError_t savi_launch_wgrad_umma(const WgradArgs& wa, const int* done, int done_target, cudaStream_t st);
 size_t savi_fwd_smem_bytes(const Dims& d, int TN);
 size_t savi_bwd_smem_bytes(const Dims& d, int TN);

@@ -853,6 +853,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) savi_bwd_umma_kernel(const __grid
     __syncwarp();
     fence_before_sync();
     __syncthreads();
+    if (tid == 0) {     // every record of this CTA is written: count it for the weight-gradient kernel (a programmatic dependent too)
+        __threadfence();
+        atomicAdd(reinterpret_cast<int*>(reinterpret_cast<unsigned char*>(a.ws) + a.wl.flags) + d.B * d.T, 1);
+    }
     if (ua.trace && tid == 0) { long long t_; asm volatile("mov.u64 %0, %%globaltimer;\n" : "=l"(t_)); atomicMax(ua.trace + 1, t_); }
     if (CN > 1) { cluster_arrive(); cluster_wait(); }
     if (warp == W_MMA) tmem_dealloc(tb, TB_COLS);

@@ -95,6 +95,7 @@ __global__ void __launch_bounds__(DX_THREADS, 1) dx_umma_kernel(const __grid_con
     }
     if (warp == DX_EPI_WARPS) tmem_alloc(tmem_slot, TD_COLS);
     for (int i = tid; i < 128; i += DX_THREADS) gam[i] = a.gamma[i];
+    asm volatile("griddepcontrol.launch_dependents;\n" ::: "memory");      // the weight-gradient kernel may fill the SMs this grid's last wave leaves idle
     long long t_start = 0;
     if (a.trace && tid == 0) asm volatile("mov.u64 %0, %%globaltimer;\n" : "=l"(t_start));
     if (tid == 0 && a.flags) {

@@ -284,5 +284,5 @@ static inline void savi_bwd_ws_layout(const Dims& d, BwdWsLayout& L) {
     else L.total_bytes = g * 4 + (d.mma ? (int64_t)d.B * d.T * d.I * 2 * d.KC * d.N * 2 : 0);
     if (d.umma) L.coef = (g * 4 + 1023) / 1024 * 1024;
     L.flags = L.total_bytes;
-    if (d.umma) L.total_bytes += ((int64_t)d.B * d.T * 4 + 255) / 256 * 256;
+    if (d.umma) L.total_bytes += (((int64_t)d.B * d.T + 1) * 4 + 255) / 256 * 256;     // + 1: "clip kernel finished" CTA counter
 }

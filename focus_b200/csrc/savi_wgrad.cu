@@ -99,7 +99,7 @@ cudaError_t savi_launch_backward(const BwdArgs& a, const void* inputs, void* gra
     const bool umma_bwd = d.umma != 0;     // the tcgen05 forward saves only what the tcgen05 backward reads (no q, no U)
     const bool overlap_dx = umma_bwd && !getenv("SAVI_NO_OVERLAP");
     if (umma_bwd) {
-        e = cudaMemsetAsync(reinterpret_cast<unsigned char*>(a.ws) + a.wl.flags, 0, (size_t)d.B * d.T * sizeof(int), st);
+        e = cudaMemsetAsync(reinterpret_cast<unsigned char*>(a.ws) + a.wl.flags, 0, ((size_t)d.B * d.T + 1) * sizeof(int), st);
         if (e != cudaSuccess) return e;
         e = cudaMemsetAsync(a.ws + a.wl.dwqk, 0, (size_t)(a.wl.dwg - a.wl.dwqk + (int64_t)3 * d.Ds * d.D) * sizeof(float), st);
         if (e != cudaSuccess) return e;
@@ -159,7 +159,10 @@ cudaError_t savi_launch_backward(const BwdArgs& a, const void* inputs, void* gra
     }
     if (wa.njobs > 0 && umma_bwd) {
         savi_prof_begin(4, st);
-        e = savi_launch_wgrad_umma(wa, st);
+        // behind d_inputs as ITS programmatic dependent: starts once every d_inputs CTA is resident, waits for the clip kernel's
+        // CTA counter, then fills the SMs the last d_inputs wave leaves idle
+        const int* done = overlap_dx ? reinterpret_cast<const int*>(reinterpret_cast<const unsigned char*>(a.ws) + a.wl.flags) + d.B * d.T : nullptr;
+        e = savi_launch_wgrad_umma(wa, done, d.B * d.CN, st);
         if (e != cudaSuccess) return e;
         e = launch_fold_grads(a.packed, a.ws + a.wl.dwqk, a.ws + a.wl.dwg, G, a.po, D, Ds, d.qscale, st);
         savi_prof_end(4, st);

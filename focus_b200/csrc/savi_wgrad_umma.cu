@@ -20,7 +20,8 @@ constexpr int WU_STAGE = 4 * WU_SUB;                  // A hi | A lo | B hi | B 
 constexpr int WU_LD = WU_CH * 16 / WU_LOADERS;        // 8-float groups per loader thread and operand
 constexpr uint32_t IDESC_MN_MN_128 = idesc_bf16(128, 128, true, true);
 
-struct WUArgs { WgradArgs wa; int chunks_per_cta; };
+struct WUArgs { WgradArgs wa; int chunks_per_cta;
+                const int* done; int done_target; };      // overlapped launch: CTA counter of the backward clip kernel to wait for
 
 __device__ __forceinline__ void split8(const float4& p, const float4& q, uint4& hi, uint4& lo) {
     const float v[8] = {p.x, p.y, p.z, p.w, q.x, q.y, q.z, q.w};
@@ -53,6 +54,13 @@ __global__ void __launch_bounds__(WU_THREADS, 2) wgrad_umma_kernel(const __grid_
         }
     }
     if (job < 0) return;
+    if (ua.done && tid == 0) {          // launched early (programmatic dependent of d_inputs): the clip kernel's records must be complete
+        int v;
+        do {
+            asm volatile("ld.acquire.gpu.global.s32 %0, [%1];\n" : "=r"(v) : "l"(ua.done) : "memory");
+            if (v < ua.done_target) __nanosleep(256);
+        } while (v < ua.done_target);
+    }
     const WgradJob& jb = wa.job[job];
     const int tc = jb.C >> 7, o0 = (tile / tc) * 128, c0 = (tile % tc) * 128;
     const int r_begin = slice * ua.chunks_per_cta * WU_CH, r_end = min(jb.R, r_begin + ua.chunks_per_cta * WU_CH);
@@ -142,9 +150,9 @@ __global__ void __launch_bounds__(WU_THREADS, 2) wgrad_umma_kernel(const __grid_
 }
 }  // namespace
 
-cudaError_t savi_launch_wgrad_umma(const WgradArgs& wa, cudaStream_t st) {
+cudaError_t savi_launch_wgrad_umma(const WgradArgs& wa, const int* done, int done_target, cudaStream_t st) {
     WUArgs ua;
-    ua.wa = wa;
+    ua.wa = wa; ua.done = done; ua.done_target = done_target;
     int64_t total = 0;
     for (int j = 0; j < wa.njobs; ++j) {
         if ((wa.job[j].O & 127) || (wa.job[j].C & 127)) return cudaErrorInvalidValue;
@@ -163,6 +171,11 @@ cudaError_t savi_launch_wgrad_umma(const WgradArgs& wa, cudaStream_t st) {
     const int smem = 2 * WU_STAGE + 128;
     cudaError_t e = cudaFuncSetAttribute(wgrad_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) return e;
-    wgrad_umma_kernel<<<grid, WU_THREADS, smem, st>>>(ua);
-    return cudaGetLastError();
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid); cfg.blockDim = dim3(WU_THREADS); cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = done ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, wgrad_umma_kernel, ua);
 }

@@ -129,6 +129,7 @@ UMMA_SHAPES = [
     (5, 2, 384, 128, 128, 128, 24, 3, 1, 2),     # odd clip count, K=24
     (2, 2, 64, 128, 128, 128, 15, 2, 1, 4),      # fewer tokens than one tile (single CTA per clip)
     (2, 2, 301, 128, 128, 128, 24, 2, 1, 4),     # odd token count (the mma.sync path would need N % 8 == 0)
+    (170, 2, 128, 128, 128, 128, 5, 2, 1, 4),    # more clips than SMs: two waves of clip CTAs under the overlapped dependent kernels
 ]
 
 

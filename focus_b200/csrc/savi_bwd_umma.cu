@@ -13,7 +13,7 @@ using namespace uc;
 #define UPH(id) do { if (dbg) { const long long t_ = clock64(); dbg[id] += t_ - ph_last; ph_last = t_; } } while (0)
 
 // TMEM columns (64 each)
-enum { TB_A = 0, TB_B = 64, TB_HP = 128, TB_DQK = 192, TB_S0 = 256, TB_G0 = 320, TB_S1 = 384, TB_G1 = 448,
+enum { TB_A = 0, TB_B = 64, TB_HP = 128, TB_DQK = 192, TB_S0 = 256 /* 4 x 32: logits per warpgroup */, TB_G0 = 384 /* 4 x 32 */,
        TB_F0 = TB_S0,                         // predictor: the four ffn.2^T tiles live where the token-pass accumulators are
        TB_COLS = 512 };
 enum { B_HP = B_OPND2 };                      // W_hh^T product complete (its operands may be overwritten)
@@ -25,8 +25,8 @@ struct BwdUArgs {
     WImg wi;
 };
 
-struct TokState { uint32_t cnt_s[2], cnt_a[2];       // issuer: tiles issued (P1) / consumed (P2) per buffer = sequence numbers
-                  uint32_t nbase, own_s, own_a; };    // compute warpgroup: sequence number of its buffer's first tile of the step, own waits
+struct TokState { uint32_t nseq;                      // issuer: sequence number of the next tile; compute: of the step's first tile
+                  uint32_t own_s, own_a; };           // compute warpgroup: its waits on B_SFULL4 / B_AFREE4 so far
 
 // operand buffers: X0..X3 = opA, opB, opC, aw0 of the shared plan; aw1 + scratch hold the float2 LayerNorm scratch
 __device__ __forceinline__ int xop(const Smem& L, int i) { return i == 0 ? L.opA : i == 1 ? L.opB : i == 2 ? L.opC : L.aw0; }
@@ -38,32 +38,35 @@ __device__ __forceinline__ int xop(const Smem& L, int i) { return i == 0 ? L.opA
 // ------------------------------------------------------------------------------------------------
 __device__ __forceinline__ void issue_token_pass_bwd(Ring& r, bool el, uint64_t* bars, uint32_t tb, int ntile, TokState& ts,
                                                      uint32_t qk_op, uint32_t dux_op, uint32_t dl0, uint32_t dl1) {
-    int ts0[2] = {0, 0};
+    int ts0[4] = {0, 0, 0, 0};                              // ring stage of the tile's first token block, per in-flight tile
     const uint32_t rb = smem_u32(r.base);
+    const uint32_t n0 = ts.nseq;
+    const int la = r.nst >= 6 ? TOK_LA : 1;                 // tiles whose token blocks the ring can hold besides the one being issued
     auto p2 = [&](int j) {
-        const int g = j & 1;
-        mbar_wait(&bars[B_AREADY + g], ts.cnt_a[g] & 1u);
+        const uint32_t n = n0 + (uint32_t)j;
+        const int g = (int)(n & 1u);
+        mbar_wait(&bars[B_AREADY + g], (n >> 1) & 1u);
         fence_after_sync();
-        const uint32_t x0 = dlo_mn(rb + ts0[g] * BLK, BLK);
+        const int st = ts0[n & 3u];
+        const uint32_t x0 = dlo_mn(rb + st * BLK, BLK);
         const uint32_t dl = dlo_mn(g ? dl1 : dl0, BLK);
         if (el) {
             mma_lo(tb + TB_DQK, x0, dl, IDESC_MN_MN64, j > 0 ? 1u : 0u);
 #pragma unroll
             for (int kt = 1; kt < 8; ++kt) mma_lo(tb + TB_DQK, x0 + kt * 128, dl + kt * 128, IDESC_MN_MN64, 1u);
-            mma_commit(&r.empty[ts0[g]]);
-            mma_commit(&r.empty[ts0[g] + 1]);
-            mma_commit(&bars[B_AFREE4 + tok_wg(ts.cnt_a[g] + 1u, g)]);        // the buffer's next writer may proceed
+            mma_commit(&r.empty[st]);
+            mma_commit(&r.empty[st + 1]);
+            mma_commit(&bars[B_AFREE4 + ((n + 2u) & 3u)]);                // the dL tile's next writer may proceed
         }
         __syncwarp();
-        ++ts.cnt_a[g];
     };
     const uint32_t qk0 = dlo_mn(qk_op, BLK), du0 = dlo_mn(dux_op, BLK);
     for (int i = 0; i < ntile; ++i) {
-        const int g = i & 1;
-        mbar_wait(&bars[B_SFREE + g], (ts.cnt_s[g] & 1u) ^ 1u);
+        const uint32_t n = n0 + (uint32_t)i, w = n & 3u;
+        mbar_wait(&bars[B_SFREE4 + w], ((n >> 2) & 1u) ^ 1u);           // warpgroup w has drained its previous logits
         fence_after_sync();
-        ts0[g] = r.stage;
-        const uint32_t acc_s = tb + (g ? TB_S1 : TB_S0), acc_g = tb + (g ? TB_G1 : TB_G0);
+        ts0[w] = r.stage;
+        const uint32_t acc_s = tb + TB_S0 + 32u * w, acc_g = tb + TB_G0 + 32u * w;
 #pragma unroll
         for (int db = 0; db < 2; ++db) {
             mbar_wait(&r.full[r.stage], r.phase);
@@ -71,28 +74,31 @@ __device__ __forceinline__ void issue_token_pass_bwd(Ring& r, bool el, uint64_t*
             const uint32_t a = dlo_k(rb + r.stage * BLK);
             if (el) {
 #pragma unroll
-                for (int k4 = 0; k4 < 4; ++k4) {
+                for (int k4 = 0; k4 < 4; ++k4) {          // hi and lo halves accumulate into the SAME 32 columns (lo: 64 B into the swizzled row)
                     const uint32_t acc = (db > 0 || k4 > 0) ? 1u : 0u;
-                    mma_lo(acc_s, a + k4 * 2, qk0 + (db * 4 + k4) * 128, IDESC_K_MN64, acc);
-                    mma_lo(acc_g, a + k4 * 2, du0 + (db * 4 + k4) * 128, IDESC_K_MN64, acc);
+                    const uint32_t ko = (uint32_t)(db * 4 + k4) * 128u;
+                    mma_lo(acc_s, a + k4 * 2, qk0 + ko, IDESC_K_MN32, acc);
+                    mma_lo(acc_s, a + k4 * 2, qk0 + 4 + ko, IDESC_K_MN32, 1u);
+                    mma_lo(acc_g, a + k4 * 2, du0 + ko, IDESC_K_MN32, acc);
+                    mma_lo(acc_g, a + k4 * 2, du0 + 4 + ko, IDESC_K_MN32, 1u);
                 }
             }
             __syncwarp();
             r.advance();
         }
-        if (el) mma_commit(&bars[B_SFULL4 + tok_wg(ts.cnt_s[g], g)]);
+        if (el) mma_commit(&bars[B_SFULL4 + w]);
         __syncwarp();
-        ++ts.cnt_s[g];
-        if (i >= 1) p2(i - 1);
+        if (i >= la) p2(i - la);
     }
-    p2(ntile - 1);
+    for (int j = ntile > la ? ntile - la : 0; j < ntile; ++j) p2(j);
+    ts.nseq = n0 + (uint32_t)ntile;
     if (el) mma_commit(&bars[B_TOK]);
     __syncwarp();
 }
 
 // ------------------------------------------------------------------------------------------------
 // compute threads: recompute P, form dL and W for this warpgroup's token tiles (thread = token, all K <= 24 slots of the
-// token in registers; tile ownership as in the forward, tok_wg())
+// token in registers; tile ownership as in the forward: savi_umma_clip.cuh, "Token pass")
 //   dP = (G - c)/S (+ grad_attn);  dL = P (dP - <P, dP>);  W = (P + eps)/S          
 // cv: shared [64] floats: c[k] at [k], 1/S[k] at [32 + k].
 // ------------------------------------------------------------------------------------------------
@@ -100,15 +106,15 @@ __device__ __forceinline__ void softmax_bwd_tiles(const Ctx& c, const Dims& d, i
                                                   unsigned char* coef, const float* cv, int dl0_off, int dl1_off, TokState& ts, long long* dbg) {
     constexpr float LOG2E = 1.4426950408889634f;
     long long ph_last = clock64();
-    const int K = c.K, g = c.wg & 1;
-    const uint32_t hb = (uint32_t)(c.wg >> 1);
-    const uint32_t scol = c.tb + c.tlane + (g ? TB_S1 : TB_S0);
-    const uint32_t gcol = c.tb + c.tlane + (g ? TB_G1 : TB_G0);
-    unsigned char* dlrow = c.sm + (g ? dl1_off : dl0_off) + c.o * 128;
+    const int K = c.K;
+    const uint32_t scol = c.tb + c.tlane + TB_S0 + 32u * (uint32_t)c.wg;
+    const uint32_t gcol = c.tb + c.tlane + TB_G0 + 32u * (uint32_t)c.wg;
     const uint32_t sw = (uint32_t)(c.o & 7);
-    for (int i = g; i < ntile; i += 2) {
-        const uint32_t nseq = ts.nbase + (uint32_t)(i >> 1);
-        if ((nseq & 1u) != hb) continue;
+    for (int i = 0; i < ntile; ++i) {
+        const uint32_t nseq = ts.nseq + (uint32_t)i;
+        if ((nseq & 3u) != (uint32_t)c.wg) continue;
+        const int g = (int)(nseq & 1u);
+        unsigned char* dlrow = c.sm + (g ? dl1_off : dl0_off) + c.o * 128;
         const int n = (tile0 + i) * 128 + c.o;
         const bool valid = n < d.N;
         // upstream gradient of the attention map (last iteration only), kept packed (bf16 pairs) until it is consumed;
@@ -140,22 +146,12 @@ __device__ __forceinline__ void softmax_bwd_tiles(const Ctx& c, const Dims& d, i
         fence_after_sync();
         UPH(55);
         float l[KTOK], gq[KTOK];
-        {
-            float t2[KTOK];
-            tmem_ld16(scol, l); tmem_ld8(scol + 16, l + 16);
-            tmem_ld16(scol + 32, t2); tmem_ld8(scol + 48, t2 + 16);
-            tmem_wait_ld();
-#pragma unroll
-            for (int s = 0; s < KTOK; ++s) l[s] += t2[s];
-            tmem_ld16(gcol, gq); tmem_ld8(gcol + 16, gq + 16);
-            tmem_ld16(gcol + 32, t2); tmem_ld8(gcol + 48, t2 + 16);
-            tmem_wait_ld();
-#pragma unroll
-            for (int s = 0; s < KTOK; ++s) gq[s] += t2[s];
-        }
+        tmem_ld16(scol, l); tmem_ld8(scol + 16, l + 16);
+        tmem_ld16(gcol, gq); tmem_ld8(gcol + 16, gq + 16);
+        tmem_wait_ld();
         fence_before_sync();
         __syncwarp();
-        if (c.lane == 0) mbar_arrive(&c.bars[B_SFREE + g]);
+        if (c.lane == 0) mbar_arrive(&c.bars[B_SFREE4 + c.wg]);
         float mx = -INFINITY;
 #pragma unroll
         for (int s = 0; s < KTOK; ++s) if (s < K) mx = fmaxf(mx, l[s]);
@@ -177,7 +173,7 @@ __device__ __forceinline__ void softmax_bwd_tiles(const Ctx& c, const Dims& d, i
             }
         }
         UPH(56);
-        if (nseq > 0u) { mbar_wait(&c.bars[B_AFREE4 + c.wg], ts.own_a & 1u); ++ts.own_a; }   // P2 of the buffer's previous tile is done
+        if (nseq > 1u) { mbar_wait(&c.bars[B_AFREE4 + c.wg], ts.own_a & 1u); ++ts.own_a; }   // the second product of tile n - 2 has read this dL tile
         UPH(57);
 #pragma unroll
         for (int s = 0; s < KTOK; s += 8) {
@@ -228,7 +224,7 @@ __device__ __forceinline__ void softmax_bwd_tiles(const Ctx& c, const Dims& d, i
         }
         UPH(59);
     }
-    ts.nbase += (uint32_t)((ntile + 1 - g) >> 1);
+    ts.nseq += (uint32_t)ntile;
 }
 
 static __device__ __noinline__ void ln_bwd_reduce(const float2* scr, float2* red, int warp, int lane, int K) {
@@ -421,10 +417,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) savi_bwd_umma_kernel(const __grid
         for (int s = 0; s < L.nst; ++s) { mbar_init(&bars[B_FULL + s], 1); mbar_init(&bars[B_EMPTY + s], 1); }
         mbar_init(&bars[B_OPND], NCW); mbar_init(&bars[B_ACC], 1); mbar_init(&bars[B_TOK], 1); mbar_init(&bars[B_HP], 1);
         for (int g = 0; g < 2; ++g) {
-            mbar_init(&bars[B_SFREE + g], 4); mbar_init(&bars[B_AREADY + g], 4);        // one warpgroup (4 warps) per tile
+            mbar_init(&bars[B_AREADY + g], 4);                                         // one warpgroup (4 warps) per tile
             mbar_init(&bars[B_INBOX + g], NCW);
         }
-        for (int f = 0; f < 4; ++f) { mbar_init(&bars[B_FACC + f], 1); mbar_init(&bars[B_FOPND + f], NCW); mbar_init(&bars[B_SFULL4 + f], 1); mbar_init(&bars[B_AFREE4 + f], 1); }
+        for (int f = 0; f < 4; ++f) { mbar_init(&bars[B_FACC + f], 1); mbar_init(&bars[B_FOPND + f], NCW); mbar_init(&bars[B_SFULL4 + f], 1); mbar_init(&bars[B_AFREE4 + f], 1); mbar_init(&bars[B_SFREE4 + f], 4); }
         mbar_init_fence();
     }
     if (warp == W_MMA) tmem_alloc(tmem_slot, TB_COLS);
@@ -506,7 +502,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) savi_bwd_umma_kernel(const __grid
         {
             const bool el = elect_one();
             uint32_t ph_opnd = 0, pcall = 0;
-            TokState ts = {{0, 0}, {0, 0}, 0, 0, 0};
+            TokState ts = {0, 0, 0};
             const uint32_t X0 = smem_u32(sm + L.opA), X1 = smem_u32(sm + L.opB), X2 = smem_u32(sm + L.opC), X3 = smem_u32(sm + L.aw0);
             auto wait_opnd = [&]() { mbar_wait(&bars[B_OPND], ph_opnd); ph_opnd ^= 1u; fence_after_sync(); };
             for (int t = d.T - 1; t >= 0; --t) {
@@ -558,7 +554,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) savi_bwd_umma_kernel(const __grid
         Ctx c;
         ctx_init(c, tid, K, sm, L, tb, bars);
         const int o = c.o;
-        TokState ts = {{0, 0}, {0, 0}, 0, 0, 0};
+        TokState ts = {0, 0, 0};
         long long* sdbg = reinterpret_cast<long long*>(sm + L.bars + NBAR * 8 + 16);
         if (a.dbg && blockIdx.x == 0 && tid == 0) for (int i = 0; i < 64; ++i) sdbg[i] = 0;
         long long* dbg = (a.dbg && blockIdx.x == 0 && tid == 0) ? sdbg : nullptr;

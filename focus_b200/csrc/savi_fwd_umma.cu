@@ -28,19 +28,23 @@ struct FwdUArgs {
 //   P2(i): NUMX   += xhat_i^T . [A_hi | A_lo]       (A = token tile, MN-major; B = attention-weight tile)
 //          SSUM   += 1 . [A_hi | A_lo]
 // ------------------------------------------------------------------------------------------------
-struct TokState { uint32_t cnt_s[2], cnt_a[2];       // issuer: tiles issued (P1) / consumed (P2) per buffer = sequence numbers
-                  uint32_t nbase, own_s, own_a; };    // compute warpgroup: sequence number of its buffer's first tile of the step, own waits
+struct TokState { uint32_t nseq;                      // issuer: sequence number of the next tile; compute: of the step's first tile
+                  uint32_t own_s, own_a; };           // compute warpgroup: its waits on B_SFULL4 / B_AFREE4 so far
 
 __device__ __forceinline__ void issue_token_pass(Ring& r, bool el, unsigned char* sm, const Smem& L, uint64_t* bars, uint32_t tb, int ntile,
                                                  TokState& ts, uint32_t qk_op) {
-    int ts0[2] = {0, 0};
+    int ts0[4] = {0, 0, 0, 0};                              // ring stage of the tile's first token block, per in-flight tile
     const uint32_t ones = dlo_mn(smem_u32(sm + L.ones), 2048);
     const uint32_t rb = smem_u32(r.base);
+    const uint32_t n0 = ts.nseq;
+    const int la = r.nst >= 6 ? TOK_LA : 1;                 // tiles whose token blocks the ring can hold besides the one being issued
     auto p2 = [&](int j) {
-        const int g = j & 1;
-        mbar_wait(&bars[B_AREADY + g], ts.cnt_a[g] & 1u);
+        const uint32_t n = n0 + (uint32_t)j;
+        const int g = (int)(n & 1u);
+        mbar_wait(&bars[B_AREADY + g], (n >> 1) & 1u);
         fence_after_sync();
-        const uint32_t x0 = dlo_mn(rb + ts0[g] * BLK, BLK);
+        const int st = ts0[n & 3u];
+        const uint32_t x0 = dlo_mn(rb + st * BLK, BLK);
         const uint32_t aw = dlo_mn(smem_u32(sm + (g ? L.aw1 : L.aw0)), BLK);
         const uint32_t acc0 = j > 0 ? 1u : 0u;
         if (el) {
@@ -51,20 +55,19 @@ __device__ __forceinline__ void issue_token_pass(Ring& r, bool el, unsigned char
                 mma_lo(tb + TC_NUMX, x0 + kt * 128, aw + kt * 128, IDESC_MN_MN64, 1u);
                 mma_lo(tb + TC_SSUM, ones, aw + kt * 128, IDESC_MN_MN64, 1u);
             }
-            mma_commit(&r.empty[ts0[g]]);
-            mma_commit(&r.empty[ts0[g] + 1]);
-            mma_commit(&bars[B_AFREE4 + tok_wg(ts.cnt_a[g] + 1u, g)]);        // the buffer's next writer may proceed
+            mma_commit(&r.empty[st]);
+            mma_commit(&r.empty[st + 1]);
+            mma_commit(&bars[B_AFREE4 + ((n + 2u) & 3u)]);                // the weight tile's next writer may proceed
         }
         __syncwarp();
-        ++ts.cnt_a[g];
     };
     const uint32_t qk0 = dlo_mn(qk_op, BLK);
     for (int i = 0; i < ntile; ++i) {
-        const int g = i & 1;
-        mbar_wait(&bars[B_SFREE + g], (ts.cnt_s[g] & 1u) ^ 1u);
+        const uint32_t n = n0 + (uint32_t)i, w = n & 3u;
+        mbar_wait(&bars[B_SFREE4 + w], ((n >> 2) & 1u) ^ 1u);           // warpgroup w has drained its previous logits
         fence_after_sync();
-        ts0[g] = r.stage;                                   // the ring has an even number of stages: the pair never wraps
-        const uint32_t acc_s = tb + (g ? TC_S1 : TC_S0);
+        ts0[w] = r.stage;                                   // the ring has an even number of stages: the pair never wraps
+        const uint32_t acc_s = tb + TC_S0 + 32u * w;
 #pragma unroll
         for (int db = 0; db < 2; ++db) {
             mbar_wait(&r.full[r.stage], r.phase);
@@ -72,53 +75,49 @@ __device__ __forceinline__ void issue_token_pass(Ring& r, bool el, unsigned char
             const uint32_t a = dlo_k(rb + r.stage * BLK);
             if (el) {
 #pragma unroll
-                for (int k4 = 0; k4 < 4; ++k4)
-                    mma_lo(acc_s, a + k4 * 2, qk0 + (db * 4 + k4) * 128, IDESC_K_MN64, (db > 0 || k4 > 0) ? 1u : 0u);
+                for (int k4 = 0; k4 < 4; ++k4) {          // hi and lo halves of qk accumulate into the SAME 32 columns (lo: 64 B into the swizzled row)
+                    mma_lo(acc_s, a + k4 * 2, qk0 + (db * 4 + k4) * 128, IDESC_K_MN32, (db > 0 || k4 > 0) ? 1u : 0u);
+                    mma_lo(acc_s, a + k4 * 2, qk0 + 4 + (db * 4 + k4) * 128, IDESC_K_MN32, 1u);
+                }
             }
             __syncwarp();
             r.advance();
         }
-        if (el) mma_commit(&bars[B_SFULL4 + tok_wg(ts.cnt_s[g], g)]);
+        if (el) mma_commit(&bars[B_SFULL4 + w]);
         __syncwarp();
-        ++ts.cnt_s[g];
-        if (i >= 1) p2(i - 1);
+        if (i >= la) p2(i - la);
     }
-    p2(ntile - 1);
+    for (int j = ntile > la ? ntile - la : 0; j < ntile; ++j) p2(j);
+    ts.nseq = n0 + (uint32_t)ntile;
     if (el) mma_commit(&bars[B_TOK]);
     __syncwarp();
 }
 
 // ------------------------------------------------------------------------------------------------
 // compute threads: softmax over the slot axis, thread = token, all K <= 24 slots of the token in registers (steve.py:76-83).
-// Warpgroup w drains the tiles of buffer w & 1 whose sequence number is w >> 1 (mod 2): see tok_wg().
+// Warpgroup w drains the tiles with sequence number n & 3 == w (savi_umma_clip.cuh, "Token pass").
 // ------------------------------------------------------------------------------------------------
 __device__ __forceinline__ void softmax_tiles(const Ctx& c, const Dims& d, int ntile, int tile0, bf16* attn_frame, TokState& ts, long long* dbg) {
     constexpr float LOG2E = 1.4426950408889634f;
     long long ph_last = clock64();
-    const int K = c.K, g = c.wg & 1;
-    const uint32_t hb = (uint32_t)(c.wg >> 1);
-    const uint32_t scol = c.tb + c.tlane + (g ? TC_S1 : TC_S0);
-    unsigned char* awrow = c.sm + (g ? c.L.aw1 : c.L.aw0) + c.o * 128;
+    const int K = c.K;
+    const uint32_t scol = c.tb + c.tlane + TC_S0 + 32u * (uint32_t)c.wg;
     const uint32_t sw = (uint32_t)(c.o & 7);
-    for (int i = g; i < ntile; i += 2) {
-        const uint32_t nseq = ts.nbase + (uint32_t)(i >> 1);
-        if ((nseq & 1u) != hb) continue;
+    for (int i = 0; i < ntile; ++i) {
+        const uint32_t nseq = ts.nseq + (uint32_t)i;
+        if ((nseq & 3u) != (uint32_t)c.wg) continue;
+        const int g = (int)(nseq & 1u);
+        unsigned char* awrow = c.sm + (g ? c.L.aw1 : c.L.aw0) + c.o * 128;
         mbar_wait(&c.bars[B_SFULL4 + c.wg], ts.own_s & 1u);
         ++ts.own_s;
         fence_after_sync();
         UPH(50);
         float l[KTOK];
-        {
-            float l2[KTOK];
-            tmem_ld16(scol, l); tmem_ld8(scol + 16, l + 16);
-            tmem_ld16(scol + 32, l2); tmem_ld8(scol + 48, l2 + 16);
-            tmem_wait_ld();
-#pragma unroll
-            for (int s = 0; s < KTOK; ++s) l[s] += l2[s];
-        }
+        tmem_ld16(scol, l); tmem_ld8(scol + 16, l + 16);
+        tmem_wait_ld();
         fence_before_sync();
         __syncwarp();
-        if (c.lane == 0) mbar_arrive(&c.bars[B_SFREE + g]);
+        if (c.lane == 0) mbar_arrive(&c.bars[B_SFREE4 + c.wg]);
         float mx = -INFINITY;
 #pragma unroll
         for (int s = 0; s < KTOK; ++s) if (s < K) mx = fmaxf(mx, l[s]);
@@ -130,7 +129,7 @@ __device__ __forceinline__ void softmax_tiles(const Ctx& c, const Dims& d, int n
         const int n = (tile0 + i) * 128 + c.o;                  // token index inside the frame
         const bool valid = n < d.N;
         UPH(51);
-        if (nseq > 0u) { mbar_wait(&c.bars[B_AFREE4 + c.wg], ts.own_a & 1u); ++ts.own_a; }   // P2 of the buffer's previous tile is done
+        if (nseq > 1u) { mbar_wait(&c.bars[B_AFREE4 + c.wg], ts.own_a & 1u); ++ts.own_a; }   // the second product of tile n - 2 has read this weight tile
         UPH(52);
 #pragma unroll
         for (int s = 0; s < KTOK; s += 8) {
@@ -167,7 +166,7 @@ __device__ __forceinline__ void softmax_tiles(const Ctx& c, const Dims& d, int n
         }
         UPH(54);
     }
-    ts.nbase += (uint32_t)((ntile + 1 - g) >> 1);
+    ts.nseq += (uint32_t)ntile;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -296,10 +295,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) savi_fwd_umma_kernel(const __grid
         for (int s = 0; s < L.nst; ++s) { mbar_init(&bars[B_FULL + s], 1); mbar_init(&bars[B_EMPTY + s], 1); }
         mbar_init(&bars[B_OPND], NCW); mbar_init(&bars[B_ACC], 1); mbar_init(&bars[B_TOK], 1);
         for (int g = 0; g < 2; ++g) {
-            mbar_init(&bars[B_SFREE + g], 4); mbar_init(&bars[B_AREADY + g], 4);        // one warpgroup (4 warps) per tile
+            mbar_init(&bars[B_AREADY + g], 4);                                         // one warpgroup (4 warps) per tile
             mbar_init(&bars[B_INBOX + g], NCW);
         }
-        for (int f = 0; f < 4; ++f) { mbar_init(&bars[B_FACC + f], 1); mbar_init(&bars[B_FOPND + f], NCW); mbar_init(&bars[B_SFULL4 + f], 1); mbar_init(&bars[B_AFREE4 + f], 1); }
+        for (int f = 0; f < 4; ++f) { mbar_init(&bars[B_FACC + f], 1); mbar_init(&bars[B_FOPND + f], NCW); mbar_init(&bars[B_SFULL4 + f], 1); mbar_init(&bars[B_AFREE4 + f], 1); mbar_init(&bars[B_SFREE4 + f], 4); }
         mbar_init_fence();
     }
     if (warp == W_MMA) tmem_alloc(tmem_slot, TC_COLS);
@@ -348,7 +347,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) savi_fwd_umma_kernel(const __grid
         {
             const bool el = elect_one();
             uint32_t ph_opnd = 0, pcall = 0;
-            TokState ts = {{0, 0}, {0, 0}, 0, 0, 0};
+            TokState ts = {0, 0, 0};
             const uint32_t opA = smem_u32(sm + L.opA), opB = smem_u32(sm + L.opB), opC = smem_u32(sm + L.opC);
             const uint32_t aw0 = smem_u32(sm + L.aw0), aw1 = smem_u32(sm + L.aw1);
             // development counters of the issuer (CTA 0): [60] waiting for operands, [61] waiting for ring blocks, [62] token pass, [63] total
@@ -406,7 +405,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) savi_fwd_umma_kernel(const __grid
         Ctx c;
         ctx_init(c, tid, K, sm, L, tb, bars);
         const int o = c.o;
-        TokState ts = {{0, 0}, {0, 0}, 0, 0, 0};
+        TokState ts = {0, 0, 0};
         // per-feature parameters of this thread
         const float g_s = P[po.ln_s_w + o], b_s = P[po.ln_s_b + o], g_m = P[po.ln_m_w + o], b_m = P[po.ln_m_b + o];
         const float b_r = P[po.bih + o] + P[po.bhh + o], b_z = P[po.bih + F + o] + P[po.bhh + F + o];

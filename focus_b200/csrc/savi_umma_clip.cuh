@@ -4,7 +4,7 @@
 //   * 16 compute warps (512 threads): thread (wg, o), wg = warp / 4, o = (warp % 4) * 32 + lane.  For slot-side
 //     tensors the thread owns FEATURE o of the 8 slots [8 wg, 8 wg + 8); the fp32 slot state lives in its
 //     registers for the whole kernel.  In the token pass it owns TOKEN o of a tile with all K <= 24 slots of
-//     that token (one whole tile per warpgroup, see tok_wg()).
+//     that token (one whole tile per warpgroup, see "Token pass" below).
 //   * warp 16, one lane: producer.  Streams the static schedule of 16 KB operand blocks (weight images and
 //     token tiles, all pre-swizzled in global memory) into a shared-memory ring with 1-D bulk copies.
 //   * warp 17, one lane: tcgen05.mma issuer.  Every product is computed TRANSPOSED, Y^T = W . X^T, so the
@@ -109,7 +109,8 @@ __host__ __device__ inline Smem plan_smem(int K, int CN, bool bwd) {
 }
 
 // barrier indices inside Smem::bars
-enum { B_FULL = 0, B_EMPTY = 12, B_OPND = 24, B_ACC = 25, B_SFULL = 26, B_SFREE = 28, B_AREADY = 30, B_AFREE = 32, B_TOK = 34,
+enum { B_FULL = 0, B_EMPTY = 12, B_OPND = 24, B_ACC = 25, B_SFREE4 = 26 /* x4: logits accumulator of a warpgroup drained */,
+       B_AREADY = 30 /* x2: weight / dL tile written */, B_TOK = 34,
        B_INBOX = 35, B_OPND2 = 37, B_ACC2 = 38,
        B_FACC = 40 /* x4: predictor FFN hidden tiles */, B_FOPND = 44 /* x4: their operand chunks */,
        B_SFULL4 = 48 /* x4: logits of a tile ready, one barrier per compute warpgroup */,
@@ -118,12 +119,13 @@ enum { B_FULL = 0, B_EMPTY = 12, B_OPND = 24, B_ACC = 25, B_SFULL = 26, B_SFREE 
 // waiter has observed the first.  Strictly alternating producer / consumer pairs share B_OPND / B_ACC; anything
 // that is signalled several times in a row (FFN tiles and chunks, token tiles) has its own barrier per item.
 
-// Token pass: tile buffers (logits accumulator + weight / dL tile) alternate, g = tile & 1.  The tiles on buffer g carry a
-// running sequence number n over the whole kernel; tile n is handled by compute warpgroup 2 (n & 1) + g, so the two
-// warpgroups of a buffer alternate and every warpgroup processes a whole tile (all slots of a token in one thread: the
-// softmax needs no exchange).  Each warpgroup has private barriers (B_SFULL4 / B_AFREE4 + wg): an mbarrier only
-// distinguishes the parity of its phase, and a warpgroup would otherwise wait two phases ahead of a shared one.
-__device__ __forceinline__ int tok_wg(uint32_t n, int g) { return (int)(2u * (n & 1u)) + g; }
+// Token pass.  Tiles carry a running sequence number n over the whole kernel.  Tile n is handled by compute warpgroup n & 3,
+// which owns logits accumulator n & 3 (32 TMEM columns: the hi and lo halves of the slot-side operand accumulate into the
+// same columns) and processes a whole tile (all slots of a token in one thread: the softmax needs no exchange); the
+// weight / dL tile it writes for the second product is buffer n & 1, shared with warpgroup (n + 2) & 3.  Barriers that a
+// warpgroup WAITS on are private to it (B_SFULL4 / B_AFREE4 + wg): an mbarrier only distinguishes the parity of its phase,
+// and a warpgroup would otherwise wait two phases ahead of a barrier shared with its partner.
+constexpr int TOK_LA = 2;        // first products issued ahead of the second ones (the ring holds the token blocks of 3 tiles)
 
 struct Ring {
     unsigned char* base; uint64_t* full; uint64_t* empty; int nst; int stage; uint32_t phase;

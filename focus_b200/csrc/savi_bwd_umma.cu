@@ -41,7 +41,7 @@ __device__ __forceinline__ void issue_token_pass_bwd(Ring& r, bool el, uint64_t*
     int ts0[4] = {0, 0, 0, 0};                              // ring stage of the tile's first token block, per in-flight tile
     const uint32_t rb = smem_u32(r.base);
     const uint32_t n0 = ts.nseq;
-    const int la = r.nst >= 6 ? TOK_LA : 1;                 // tiles whose token blocks the ring can hold besides the one being issued
+    const int la = tok_lookahead(r.nst);                    // tiles whose token blocks the ring can hold besides the one being issued
     auto p2 = [&](int j) {
         const uint32_t n = n0 + (uint32_t)j;
         const int g = (int)(n & 1u);
@@ -407,7 +407,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) savi_bwd_umma_kernel(const __grid
     const unsigned char* ximg = a.saved + a.sl.ximg;
     float* W = a.ws;
     unsigned char* coef_base = reinterpret_cast<unsigned char*>(W) + a.wl.coef;
-    const int scr2 = L.aw1;                                   // float2 [K][128] LayerNorm-backward scratch: aw1 + scratch (contiguous, 16 KB + K*512 B)
+    const int scr2 = L.opC;                                   // float2 [K][128] LayerNorm-backward scratch: opC | aw0 (= X2 | X3, idle at every ln_bwd call)
     float* cv = reinterpret_cast<float*>(sm + L.stats + 256);  // [64]: c | 1/S
 
     // ---- one-time setup ----
@@ -785,18 +785,21 @@ __global__ void __launch_bounds__(NTHREADS, 1) savi_bwd_umma_kernel(const __grid
                 float dqk[KH];
                 load_acc(c, TB_DQK, dqk);
                 if (CN > 1) {
-                    const int buf = step & 1;
-                    float* ib = reinterpret_cast<float*>(sm + L.inbox + buf * L.inbox_stride);
+                    float* ib = reinterpret_cast<float*>(sm + L.inbox);
                     const uint32_t peer = rank ^ 1u;
+                    // single inbox: the peer must have consumed what this CTA sent in the previous step (it says so on OUR barrier)
+                    if (step > 0) mbar_wait_cluster(&bars[B_INBOX + 1], (step - 1) & 1u);
                     const uint32_t rb = map_to_rank(ib, peer) + (uint32_t)(c.k0 * F + o) * 4u;
 #pragma unroll
                     for (int kk = 0; kk < KH; ++kk) if (kk < c.nk) st_cluster_f1(rb + (uint32_t)(kk * F) * 4u, dqk[kk]);
                     __syncwarp();
-                    if (lane == 0) mbar_arrive_remote(map_to_rank(&bars[B_INBOX + buf], peer));
-                    mbar_wait_cluster(&bars[B_INBOX + buf], (step >> 1) & 1u);
+                    if (lane == 0) mbar_arrive_remote(map_to_rank(&bars[B_INBOX], peer));
+                    mbar_wait_cluster(&bars[B_INBOX], step & 1u);
                     const float* pn = ib + c.k0 * F + o;
 #pragma unroll
                     for (int kk = 0; kk < KH; ++kk) if (kk < c.nk) dqk[kk] = lead ? dqk[kk] + pn[kk * F] : pn[kk * F] + dqk[kk];
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive_remote(map_to_rank(&bars[B_INBOX + 1], peer));     // consumed: the peer may send again
                 }
                 UPH(33);
                 if (svA) save_field(c, frow(W, a.wl.dqk, s, b, B, K, F), F, o, dqk);

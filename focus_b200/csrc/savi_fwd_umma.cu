@@ -37,7 +37,7 @@ __device__ __forceinline__ void issue_token_pass(Ring& r, bool el, unsigned char
     const uint32_t ones = dlo_mn(smem_u32(sm + L.ones), 2048);
     const uint32_t rb = smem_u32(r.base);
     const uint32_t n0 = ts.nseq;
-    const int la = r.nst >= 6 ? TOK_LA : 1;                 // tiles whose token blocks the ring can hold besides the one being issued
+    const int la = tok_lookahead(r.nst);                    // tiles whose token blocks the ring can hold besides the one being issued
     auto p2 = [&](int j) {
         const uint32_t n = n0 + (uint32_t)j;
         const int g = (int)(n & 1u);
@@ -622,7 +622,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) savi_fwd_umma_kernel(const __grid
 int savi_umma_mha_fits(int K, int heads) {
     if (heads < 1 || F % heads || (F / heads) % 4) return 0;
     const int KR = (K + 3) & ~3, ka = mha_ka(K);
-    const int win_bwd = 5 * OPB + KR * F * 4;                 // opA .. scratch
+    const int win_bwd = 5 * OPB;                              // opA .. aw1
     const int win_fwd = 2 * OPB + KR * F * 4;                 // aw0 .. scratch (q, k, v tiles); the attention matrices take opB | opC
     return heads * K * K <= 8 * NCT && mha_bwd_bytes(K, heads) <= win_bwd &&
            3 * K * MHA_LD * 4 <= win_fwd && 2 * heads * K * ka * 4 <= 2 * OPB;

@@ -73,10 +73,10 @@ struct Smem {
     int ring, nst;                 // ring of nst blocks
     int opA, opB, opC;             // slot-side activation operands
     int aw0, aw1;                  // token pass: attention-weight tiles [128 tokens][32 hi | 32 lo]
-    int scratch;                   // fp32 [KR][128] transposition scratch (LayerNorm statistics); follows aw1 (predictor q/k/v alias aw0..scratch)
+    int scratch;                   // fp32 [KR][128] transposition scratch (LayerNorm statistics); forward: follows aw1 (predictor q/k/v alias aw0..scratch), backward: aliases aw1
     int stats;                     // float2 [32]
     int ones;                      // MN-major ones operand [16][128] bf16
-    int inbox;                     // CN = 2: two buffers of [KR][128] + [32] fp32 written by the peer CTA
+    int inbox;                     // CN = 2: [KR][128] (+ [32]) fp32 written by the peer CTA; forward: two buffers, backward: one + handshake
     int inbox_stride;
     int aux;                       // backward: extra region (see savi_bwd_umma.cu)
     int bars;                      // mbarriers + tmem base
@@ -90,12 +90,16 @@ __host__ __device__ inline Smem plan_smem(int K, int CN, bool bwd) {
     int p = 0;
     s.opA = p; p += OPB; s.opB = p; p += OPB; s.opC = p; p += OPB;
     s.aw0 = p; p += OPB; s.aw1 = p; p += OPB;
-    s.scratch = p; p += KR * F * 4;
+    // backward: its token tiles take ~6 us each, so all four of a CTA must be in flight: that needs 8 ring stages (two per
+    // tile).  The fp32 LayerNorm / c-vector scratch therefore lives in aw1 (not an operand buffer in the backward), the
+    // float2 LayerNorm-backward scratch in opC | aw0 (idle at every call site: the products that read them have completed),
+    // and the cluster inbox is single-buffered behind a "consumed" handshake.  (Measured in the forward: no gain, not done.)
+    if (bwd) s.scratch = s.aw1; else { s.scratch = p; p += KR * F * 4; }
     s.stats = p; p += 512;                         // float2 [32] LayerNorm statistics | float [64] c, 1/S (backward)
     p = (p + 1023) & ~1023;
     s.ones = p; p += bwd ? 0 : 4096;
     s.inbox_stride = (KR * F * 4 + (bwd ? 0 : 32 * 4) + 127) & ~127;
-    s.inbox = p; p += (CN > 1) ? 2 * s.inbox_stride : 0;
+    s.inbox = p; p += (CN > 1) ? (bwd ? 1 : 2) * s.inbox_stride : 0;
     s.aux = p;
     p = (p + 15) & ~15;
     s.bars = p; p += NBAR * 8 + 16 + 512;          // mbarriers, TMEM base, development counters
@@ -125,7 +129,8 @@ enum { B_FULL = 0, B_EMPTY = 12, B_OPND = 24, B_ACC = 25, B_SFREE4 = 26 /* x4: l
 // weight / dL tile it writes for the second product is buffer n & 1, shared with warpgroup (n + 2) & 3.  Barriers that a
 // warpgroup WAITS on are private to it (B_SFULL4 / B_AFREE4 + wg): an mbarrier only distinguishes the parity of its phase,
 // and a warpgroup would otherwise wait two phases ahead of a barrier shared with its partner.
-constexpr int TOK_LA = 2;        // first products issued ahead of the second ones (the ring holds the token blocks of 3 tiles)
+// first products issued ahead of the second ones: the ring must hold the token blocks (2 per tile) of LA + 1 tiles
+__host__ __device__ __forceinline__ constexpr int tok_lookahead(int nst) { return nst >= 8 ? 3 : nst >= 6 ? 2 : 1; }
 
 struct Ring {
     unsigned char* base; uint64_t* full; uint64_t* empty; int nst; int stage; uint32_t phase;

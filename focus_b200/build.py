@@ -31,14 +31,18 @@ def _newest_source_mtime():
     return m
 
 
-def build(force=False, verbose=False):
-    """Compile the CUDA library if it is missing or older than its sources. Returns the .so path."""
+def build(force=False, verbose=False, out=None, extra_flags=()):
+    """Compile the CUDA library if it is missing or older than its sources. Returns the .so path.
+    `out` / `extra_flags`: development A/B builds (e.g. focus_b200/variants/x.so with -DSAVI_WIMG_SPLIT=1), loaded through
+    the FOCUS_SAVI_LIB override of focus_b200/_lib.py."""
+    OUT = out or globals()["OUT"]
     if not force and os.path.exists(OUT) and os.path.getmtime(OUT) >= _newest_source_mtime():
         return OUT
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
-    objdir = os.path.join(HERE, "build")
+    objdir = os.path.join(HERE, "build") if out is None else os.path.join(HERE, "build", os.path.basename(OUT) + ".d")
     os.makedirs(objdir, exist_ok=True)
-    extra = (["-Xptxas", "-v"] if verbose else []) + os.environ.get("SAVI_NVCC_EXTRA", "").split()
+    extra = (["-Xptxas", "-v"] if verbose else []) + os.environ.get("SAVI_NVCC_EXTRA", "").split() + list(extra_flags)
+    os.makedirs(os.path.dirname(OUT), exist_ok=True)
 
     def cc(unit):
         src, oname, defs = unit
@@ -61,4 +65,8 @@ def build(force=False, verbose=False):
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    args = [a for a in sys.argv[1:] if a not in ("--force", "-v")]
+    if args:        # python -m focus_b200.build [--force] [-v] OUT.so [nvcc flags ...]
+        print(build(force=True, verbose="-v" in sys.argv, out=os.path.abspath(args[0]), extra_flags=args[1:]))
+    else:
+        print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))

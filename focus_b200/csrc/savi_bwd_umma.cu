@@ -158,8 +158,8 @@ __device__ __forceinline__ void softmax_bwd_tiles(const Ctx& c, const Dims& d, i
         mx *= LOG2E;
         float sum = 0.f;
 #pragma unroll
-        for (int s = 0; s < KTOK; ++s) { l[s] = (s < K) ? exp2f(fmaf(l[s], LOG2E, -mx)) : 0.f; sum += l[s]; }
-        const float scale = 1.0f / sum;
+        for (int s = 0; s < KTOK; ++s) { l[s] = (s < K) ? ex2_fast(fmaf(l[s], LOG2E, -mx)) : 0.f; sum += l[s]; }
+        const float scale = rcp_fast(sum);
         float dot = 0.f;
 #pragma unroll
         for (int s = 0; s < KTOK; ++s) {
@@ -449,11 +449,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) savi_bwd_umma_kernel(const __grid
                 if (t < d.T - 1) {
                     for (int j = d.blocks - 1; j >= 0; --j) {
                         const WImgBlock& wb = wi.blkT[j];
-                        prod_blocks(ring, Wi + wb.f2, 16);                       // ffn.2^T: 4 row tiles x K = 128
-                        prod_blocks(ring, Wi + wb.f1 + 4 * BLK, 12);             // ffn.0^T: contraction chunks 1, 2, 3, then 0
-                        prod_blocks(ring, Wi + wb.f1, 4);
-                        prod_blocks(ring, Wi + wb.po, 4);
-                        prod_blocks(ring, Wi + wb.pq, 4); prod_blocks(ring, Wi + wb.pk, 4); prod_blocks(ring, Wi + wb.pv, 4);
+                        prod_blocks(ring, Wi + wb.f2, 8 * NBW);                       // ffn.2^T: 4 row tiles x K = 128
+                        prod_blocks(ring, Wi + wb.f1 + 2 * NBW * BLK, 6 * NBW);             // ffn.0^T: contraction chunks 1, 2, 3, then 0
+                        prod_blocks(ring, Wi + wb.f1, 2 * NBW);
+                        prod_blocks(ring, Wi + wb.po, 2 * NBW);
+                        prod_blocks(ring, Wi + wb.pq, 2 * NBW); prod_blocks(ring, Wi + wb.pk, 2 * NBW); prod_blocks(ring, Wi + wb.pv, 2 * NBW);
                     }
                 }
                 const unsigned char* xf = ximg + ((size_t)(b * d.T + t) * d.NTILE + tile0) * 2 * BLK;
@@ -487,11 +487,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) savi_bwd_umma_kernel(const __grid
                             }
                         }
                     }
-                    if (it < d.I - 1) { prod_blocks(ring, Wi + wi.w2T, 4); prod_blocks(ring, Wi + wi.w1T, 4); }
-                    prod_blocks(ring, Wi + wi.wgT, 12);
-                    prod_blocks(ring, Wi + wi.whhT, 12);
+                    if (it < d.I - 1) { prod_blocks(ring, Wi + wi.w2T, 2 * NBW); prod_blocks(ring, Wi + wi.w1T, 2 * NBW); }
+                    prod_blocks(ring, Wi + wi.wgT, 6 * NBW);
+                    prod_blocks(ring, Wi + wi.whhT, 6 * NBW);
                     prod_blocks(ring, xf, 2 * ntile);
-                    prod_blocks(ring, Wi + wi.wqkT, 4);
+                    prod_blocks(ring, Wi + wi.wqkT, 2 * NBW);
                 }
             }
         }
@@ -693,17 +693,18 @@ __global__ void __launch_bounds__(NTHREADS, 1) savi_bwd_umma_kernel(const __grid
                     float am[KH], hg[KH], v[KH];
                     load_field(c, frow(fbw, a.sl.a, smi, b, B, K, F), F, o, am);
                     load_field(c, frow(fbw, a.sl.hg, smi, b, B, K, F), F, o, hg);
-                    if (svA) save_field(c, frow(W, a.wl.dhm, smi, b, B, K, F), F, o, dh);
-                    a_b2 += sum8(c, dh);
+                    // (staged records are stored after the operand hand-over of their phase, off the serial chain)
                     write_operand(c, xop(L, 0), dh);
                     signal_operand(c);
+                    if (svA) save_field(c, frow(W, a.wl.dhm, smi, b, B, K, F), F, o, dh);
+                    a_b2 += sum8(c, dh);
                     wait_acc(c); load_acc(c, TB_A, v);
 #pragma unroll
                     for (int kk = 0; kk < KH; ++kk) v[kk] = (am[kk] > 0.f) ? v[kk] : 0.f;    // d a
-                    if (svB) save_field(c, frow(W, a.wl.da, smi, b, B, K, F), F, o, v);
-                    a_b1 += sum8(c, v);
                     write_operand(c, xop(L, 1), v);
                     signal_operand(c);
+                    if (svB) save_field(c, frow(W, a.wl.da, smi, b, B, K, F), F, o, v);
+                    a_b1 += sum8(c, v);
                     wait_acc(c); load_acc(c, TB_B, v);                                     // d m
                     float dxm[KH];
                     ln_bwd(c, v, hg, reinterpret_cast<const float2*>(fb + a.sl.lnm) + (smi * B + b) * K, g_m, a_gm, a_bm, dxm, scr2);
@@ -729,6 +730,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) savi_bwd_umma_kernel(const __grid
                         dnr[kk] = dn[kk] * r_[kk];
                         dh[kk] = g * z_[kk];
                     }
+                    write_operand(c, xop(L, 0), dr); write_operand(c, xop(L, 1), dz);
+                    write_operand(c, xop(L, 2), dn); write_operand(c, xop(L, 3), dnr);
+                    signal_operand(c);
                     if (svA) {
                         float* gi = frow(W, a.wl.dgi, s, b, B, K, 3 * F);
                         save_field(c, gi, 3 * F, o, dr); save_field(c, gi, 3 * F, F + o, dz); save_field(c, gi, 3 * F, 2 * F + o, dn);
@@ -738,9 +742,6 @@ __global__ void __launch_bounds__(NTHREADS, 1) savi_bwd_umma_kernel(const __grid
                         save_field(c, gh, 3 * F, o, dr); save_field(c, gh, 3 * F, F + o, dz); save_field(c, gh, 3 * F, 2 * F + o, dnr);
                     }
                     a_dr += sum8(c, dr); a_dz += sum8(c, dz); a_dn += sum8(c, dn); a_dnr += sum8(c, dnr);
-                    write_operand(c, xop(L, 0), dr); write_operand(c, xop(L, 1), dz);
-                    write_operand(c, xop(L, 2), dn); write_operand(c, xop(L, 3), dnr);
-                    signal_operand(c);
                 }
                 UPH(27);
                 float v[KH], dux[KH];
@@ -753,7 +754,6 @@ __global__ void __launch_bounds__(NTHREADS, 1) savi_bwd_umma_kernel(const __grid
                 UPH(28);
                 wait_acc(c); load_acc(c, TB_B, dux);                                       // dUx = dgi (W_ih W_v)
                 UPH(29);
-                if (svB) save_field(c, frow(W, a.wl.duxs, s, b, B, K, F), F, o, dux);
                 // c[k] = <dUx[k,:], Ux[k,:]>: reduce over the 128 features through the scratch tile
                 {
                     float* scr = reinterpret_cast<float*>(sm + L.scratch);
@@ -773,6 +773,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) savi_bwd_umma_kernel(const __grid
                     bar_sync_compute();
                 }
                 signal_operand(c);
+                if (svB) save_field(c, frow(W, a.wl.duxs, s, b, B, K, F), F, o, dux);
                 UPH(30);
                 // ---- attention step backward over the token tiles ----
                 const bf16* ga = (a.grad_attn && it == d.I - 1) ? reinterpret_cast<const bf16*>(a.grad_attn) + ((size_t)b * d.T + t) * d.N * K : nullptr;
@@ -785,26 +786,33 @@ __global__ void __launch_bounds__(NTHREADS, 1) savi_bwd_umma_kernel(const __grid
                 float dqk[KH];
                 load_acc(c, TB_DQK, dqk);
                 if (CN > 1) {
+                    // inbox layout [feature o][KR8 slots]: two 16-byte remote stores per thread (as in the forward)
                     float* ib = reinterpret_cast<float*>(sm + L.inbox);
+                    const int KR8 = (K + 7) & ~7;
                     const uint32_t peer = rank ^ 1u;
                     // single inbox: the peer must have consumed what this CTA sent in the previous step (it says so on OUR barrier)
                     if (step > 0) mbar_wait_cluster(&bars[B_INBOX + 1], (step - 1) & 1u);
-                    const uint32_t rb = map_to_rank(ib, peer) + (uint32_t)(c.k0 * F + o) * 4u;
-#pragma unroll
-                    for (int kk = 0; kk < KH; ++kk) if (kk < c.nk) st_cluster_f1(rb + (uint32_t)(kk * F) * 4u, dqk[kk]);
+                    if (c.nk > 0) {
+                        const uint32_t rb = map_to_rank(ib, peer) + (uint32_t)(o * KR8 + c.k0) * 4u;
+                        st_cluster_f4(rb, make_float4(dqk[0], dqk[1], dqk[2], dqk[3]));
+                        st_cluster_f4(rb + 16u, make_float4(dqk[4], dqk[5], dqk[6], dqk[7]));
+                    }
                     __syncwarp();
                     if (lane == 0) mbar_arrive_remote(map_to_rank(&bars[B_INBOX], peer));
                     mbar_wait_cluster(&bars[B_INBOX], step & 1u);
-                    const float* pn = ib + c.k0 * F + o;
+                    if (c.nk > 0) {
+                        float pn[KH];
+                        *reinterpret_cast<float4*>(pn) = ld4(ib + o * KR8 + c.k0); *reinterpret_cast<float4*>(pn + 4) = ld4(ib + o * KR8 + c.k0 + 4);
 #pragma unroll
-                    for (int kk = 0; kk < KH; ++kk) if (kk < c.nk) dqk[kk] = lead ? dqk[kk] + pn[kk * F] : pn[kk * F] + dqk[kk];
+                        for (int kk = 0; kk < KH; ++kk) dqk[kk] = lead ? dqk[kk] + pn[kk] : pn[kk] + dqk[kk];
+                    }
                     __syncwarp();
                     if (lane == 0) mbar_arrive_remote(map_to_rank(&bars[B_INBOX + 1], peer));     // consumed: the peer may send again
                 }
                 UPH(33);
-                if (svA) save_field(c, frow(W, a.wl.dqk, s, b, B, K, F), F, o, dqk);
                 write_operand(c, xop(L, 0), dqk);
                 signal_operand(c);
+                if (svA) save_field(c, frow(W, a.wl.dqk, s, b, B, K, F), F, o, dqk);
                 UPH(34);
                 float hp[KH], dst[KH], hpv[KH];
                 load_field(c, frow(fbw, a.sl.hp, s, b, B, K, F), F, o, hp);

@@ -124,8 +124,8 @@ __device__ __forceinline__ void softmax_tiles(const Ctx& c, const Dims& d, int n
         mx *= LOG2E;
         float sum = 0.f;
 #pragma unroll
-        for (int s = 0; s < KTOK; ++s) { l[s] = (s < K) ? exp2f(fmaf(l[s], LOG2E, -mx)) : 0.f; sum += l[s]; }
-        const float scale = 1.0f / sum;
+        for (int s = 0; s < KTOK; ++s) { l[s] = (s < K) ? ex2_fast(fmaf(l[s], LOG2E, -mx)) : 0.f; sum += l[s]; }
+        const float scale = rcp_fast(sum);
         const int n = (tile0 + i) * 128 + c.o;                  // token index inside the frame
         const bool valid = n < d.N;
         UPH(51);
@@ -323,19 +323,19 @@ __global__ void __launch_bounds__(NTHREADS, 1) savi_fwd_umma_kernel(const __grid
             for (int t = 0; t < d.T; ++t) {
                 const unsigned char* xf = ximg + ((size_t)(b * d.T + t) * d.NTILE + tile0) * 2 * BLK;
                 for (int it = 0; it < d.I; ++it) {
-                    prod_blocks(ring, W + wi.wqk, 4);
+                    prod_blocks(ring, W + wi.wqk, 2 * NBW);
                     prod_blocks(ring, xf, 2 * ntile);
-                    prod_blocks(ring, W + wi.whh, 12);
-                    prod_blocks(ring, W + wi.wg, 12);
-                    if (it < d.I - 1) { prod_blocks(ring, W + wi.w1, 4); prod_blocks(ring, W + wi.w2, 4); }
+                    prod_blocks(ring, W + wi.whh, 6 * NBW);
+                    prod_blocks(ring, W + wi.wg, 6 * NBW);
+                    if (it < d.I - 1) { prod_blocks(ring, W + wi.w1, 2 * NBW); prod_blocks(ring, W + wi.w2, 2 * NBW); }
                 }
                 if (t < d.T - 1) {
                     for (int j = 0; j < d.blocks; ++j) {
                         const WImgBlock& wb = wi.blk[j];
-                        prod_blocks(ring, W + wb.pq, 4); prod_blocks(ring, W + wb.pk, 4); prod_blocks(ring, W + wb.pv, 4);
-                        prod_blocks(ring, W + wb.po, 4);
-                        prod_blocks(ring, W + wb.f1, 16);
-                        prod_blocks(ring, W + wb.f2, 16);
+                        prod_blocks(ring, W + wb.pq, 2 * NBW); prod_blocks(ring, W + wb.pk, 2 * NBW); prod_blocks(ring, W + wb.pv, 2 * NBW);
+                        prod_blocks(ring, W + wb.po, 2 * NBW);
+                        prod_blocks(ring, W + wb.f1, 8 * NBW);
+                        prod_blocks(ring, W + wb.f2, 8 * NBW);
                     }
                 }
             }
@@ -427,17 +427,19 @@ __global__ void __launch_bounds__(NTHREADS, 1) savi_fwd_umma_kernel(const __grid
             for (int it = 0; it < d.I; ++it, ++step) {
                 const int64_t s = (int64_t)t * d.I + it;
                 // ---- slots_prev, LayerNorm, q ----
-                if (svA) save_field(c, frow(fb, a.sl.hp, s, b, B, K, F), F, o, h);
+                // (the saved-for-backward records are stored AFTER the operand hand-over of their phase: the stores then overlap
+                // the tensor-core round trip instead of sitting in front of it on the serial chain)
                 write_operand(c, L.opC, h);
                 layer_norm(c, h, y, g_s, b_s, d.ln_eps, lead ? reinterpret_cast<float2*>(fb + a.sl.lns) + (s * B + b) * K : nullptr);   // :72
-                if (svB) save_field(c, frow(fb, a.sl.st, s, b, B, K, F), F, o, y);
                 write_operand(c, L.opA, y);
                 signal_operand(c);
+                if (svA) save_field(c, frow(fb, a.sl.hp, s, b, B, K, F), F, o, h);
+                if (svB) save_field(c, frow(fb, a.sl.st, s, b, B, K, F), F, o, y);
                 UPH(1);
                 wait_acc(c); UPH(4); load_acc(c, TC_B, y);                                  // qk = Ds^-1/2 (s~ Wq^T) Wk, the scale folded into wqk
-                if (svB) save_field(c, frow(fb, a.sl.qk, s, b, B, K, F), F, o, y);
                 write_operand(c, L.opA, y);
                 signal_operand(c);
+                if (svB) save_field(c, frow(fb, a.sl.qk, s, b, B, K, F), F, o, y);
                 // ---- attention step over the token tiles ----
                 bf16* attn_frame = (it == d.I - 1) ? reinterpret_cast<bf16*>(a.attn_out) + ((size_t)b * d.T + t) * d.N * K : nullptr;
                 UPH(5);
@@ -449,35 +451,43 @@ __global__ void __launch_bounds__(NTHREADS, 1) savi_fwd_umma_kernel(const __grid
                 float num[KH], den[KH];
                 load_acc(c, TC_NUMX, num); load_acc(c, TC_SSUM, den);
                 if (CN > 1) {                                                              // exchange the partial sums with the peer CTA
+                    // inbox layout [feature o][KR8 slots] (+ [KR8] sums): a thread's 8 slot values are 32 contiguous bytes, two
+                    // 16-byte remote stores instead of eight scalar ones
                     const int buf = step & 1;
+                    const int KR8 = (K + 7) & ~7;
                     float* ib = reinterpret_cast<float*>(sm + L.inbox + buf * L.inbox_stride);
                     const uint32_t peer = rank ^ 1u;
-                    const uint32_t rb = map_to_rank(ib, peer) + (uint32_t)(c.k0 * F + o) * 4u;
-#pragma unroll
-                    for (int kk = 0; kk < KH; ++kk) if (kk < c.nk) st_cluster_f1(rb + (uint32_t)(kk * F) * 4u, num[kk]);
-                    if (o == 0) {
-                        const uint32_t rd = map_to_rank(ib + KP * F + c.k0, peer);
-#pragma unroll
-                        for (int kk = 0; kk < KH; ++kk) if (kk < c.nk) st_cluster_f1(rd + kk * 4u, den[kk]);
+                    if (c.nk > 0) {
+                        const uint32_t rb = map_to_rank(ib, peer) + (uint32_t)(o * KR8 + c.k0) * 4u;
+                        st_cluster_f4(rb, make_float4(num[0], num[1], num[2], num[3]));
+                        st_cluster_f4(rb + 16u, make_float4(num[4], num[5], num[6], num[7]));
+                        if (o == 0) {
+                            const uint32_t rd = map_to_rank(ib + F * KR8 + c.k0, peer);
+                            st_cluster_f4(rd, make_float4(den[0], den[1], den[2], den[3]));
+                            st_cluster_f4(rd + 16u, make_float4(den[4], den[5], den[6], den[7]));
+                        }
                     }
                     __syncwarp();
                     if (lane == 0) mbar_arrive_remote(map_to_rank(&bars[B_INBOX + buf], peer));
                     UPH(8);
                     mbar_wait_cluster(&bars[B_INBOX + buf], (step >> 1) & 1u);
                     UPH(9);
-                    const float* pn = ib + c.k0 * F + o;
-                    const float* pd = ib + KP * F + c.k0;
+                    if (c.nk > 0) {
+                        float pn[KH], pd[KH];
+                        *reinterpret_cast<float4*>(pn) = ld4(ib + o * KR8 + c.k0); *reinterpret_cast<float4*>(pn + 4) = ld4(ib + o * KR8 + c.k0 + 4);
+                        *reinterpret_cast<float4*>(pd) = ld4(ib + F * KR8 + c.k0); *reinterpret_cast<float4*>(pd + 4) = ld4(ib + F * KR8 + c.k0 + 4);
 #pragma unroll
-                    for (int kk = 0; kk < KH; ++kk) {
-                        if (kk < c.nk) {
+                        for (int kk = 0; kk < KH; ++kk) {
                             // fixed order rank 0 + rank 1 on both CTAs: their slot states stay bit-identical
-                            num[kk] = lead ? num[kk] + pn[kk * F] : pn[kk * F] + num[kk];
+                            num[kk] = lead ? num[kk] + pn[kk] : pn[kk] + num[kk];
                             den[kk] = lead ? den[kk] + pd[kk] : pd[kk] + den[kk];
                         }
                     }
                 }
 #pragma unroll
-                for (int kk = 0; kk < KH; ++kk) y[kk] = (kk < c.nk) ? num[kk] / den[kk] : 0.f;      // Ux (:82-83)
+                for (int kk = 0; kk < KH; ++kk) y[kk] = (kk < c.nk) ? num[kk] * rcp_fast(den[kk]) : 0.f;      // Ux (:82-83)
+                write_operand(c, L.opB, y);
+                signal_operand(c);
                 if (lead) {
                     save_field(c, frow(fb, a.sl.ux, s, b, B, K, F), F, o, y);
                     if (o == 0) {
@@ -486,8 +496,6 @@ __global__ void __launch_bounds__(NTHREADS, 1) savi_fwd_umma_kernel(const __grid
                         for (int kk = 0; kk < KH; ++kk) if (kk < c.nk) r_ss[kk] = den[kk];
                     }
                 }
-                write_operand(c, L.opB, y);
-                signal_operand(c);
                 UPH(10);
                 // ---- GRUCell (:87-89): the input-side product takes Ux directly (updates = Ux Wv^T is never formed) ----
                 UPH(12);
@@ -500,39 +508,48 @@ __global__ void __launch_bounds__(NTHREADS, 1) savi_fwd_umma_kernel(const __grid
 #pragma unroll
                     for (int kk = 0; kk < KH; ++kk) {
                         const float hnb = hn[kk] + bhn;
-                        const float vr = sigmoidf_(r_[kk] + b_r);
-                        const float vz = sigmoidf_(z_[kk] + b_z);
-                        const float vn = tanhf(n_[kk] + bin + vr * hnb);
+                        const float vr = sigmoid_fast(r_[kk] + b_r);
+                        const float vz = sigmoid_fast(z_[kk] + b_z);
+                        const float vn = tanh_fast(n_[kk] + bin + vr * hnb);
                         r_[kk] = vr; z_[kk] = vz; n_[kk] = vn; hn[kk] = hnb;
-                        h[kk] = (1.0f - vz) * vn + vz * h[kk];
-                    }
-                    if (svA) {
-                        save_field(c, frow(fb, a.sl.r, s, b, B, K, F), F, o, r_);
-                        save_field(c, frow(fb, a.sl.n, s, b, B, K, F), F, o, n_);
-                    }
-                    if (svB) {
-                        save_field(c, frow(fb, a.sl.z, s, b, B, K, F), F, o, z_);
-                        save_field(c, frow(fb, a.sl.ghn, s, b, B, K, F), F, o, hn);
+                        h[kk] = fmaf(vz, h[kk] - vn, vn);                                  // (1 - z) n + z h
                     }
                     if (mlp) {                                                             // residual MLP (:92-93)
                         const int64_t smi = (int64_t)t * (d.I - 1) + it;
-                        if (svA) save_field(c, frow(fb, a.sl.hg, smi, b, B, K, F), F, o, h);
                         UPH(14);
                         layer_norm(c, h, y, g_m, b_m, d.ln_eps, svB ? reinterpret_cast<float2*>(fb + a.sl.lnm) + (smi * B + b) * K : nullptr);
-                        if (svB) save_field(c, frow(fb, a.sl.m, smi, b, B, K, F), F, o, y);
                         write_operand(c, L.opB, y);
                         signal_operand(c);
+                        if (svA) {
+                            save_field(c, frow(fb, a.sl.r, s, b, B, K, F), F, o, r_);
+                            save_field(c, frow(fb, a.sl.n, s, b, B, K, F), F, o, n_);
+                            save_field(c, frow(fb, a.sl.hg, smi, b, B, K, F), F, o, h);
+                        }
+                        if (svB) {
+                            save_field(c, frow(fb, a.sl.z, s, b, B, K, F), F, o, z_);
+                            save_field(c, frow(fb, a.sl.ghn, s, b, B, K, F), F, o, hn);
+                            save_field(c, frow(fb, a.sl.m, smi, b, B, K, F), F, o, y);
+                        }
                         UPH(15);
                         wait_acc(c); UPH(16); load_acc(c, TC_A, y);
 #pragma unroll
                         for (int kk = 0; kk < KH; ++kk) y[kk] = fmaxf(y[kk] + b1, 0.f);
-                        if (svA) save_field(c, frow(fb, a.sl.a, smi, b, B, K, F), F, o, y);
                         write_operand(c, L.opA, y);
                         signal_operand(c);
+                        if (svA) save_field(c, frow(fb, a.sl.a, smi, b, B, K, F), F, o, y);
                         UPH(17);
                         wait_acc(c); UPH(18); load_acc(c, TC_B, y);
 #pragma unroll
                         for (int kk = 0; kk < KH; ++kk) h[kk] += y[kk] + b2;
+                    } else {
+                        if (svA) {
+                            save_field(c, frow(fb, a.sl.r, s, b, B, K, F), F, o, r_);
+                            save_field(c, frow(fb, a.sl.n, s, b, B, K, F), F, o, n_);
+                        }
+                        if (svB) {
+                            save_field(c, frow(fb, a.sl.z, s, b, B, K, F), F, o, z_);
+                            save_field(c, frow(fb, a.sl.ghn, s, b, B, K, F), F, o, hn);
+                        }
                     }
                     UPH(19);
                 }

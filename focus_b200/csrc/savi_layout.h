@@ -45,12 +45,19 @@ static SAVI_HD int savi_align(int64_t x, int a) { return (int)((x + a - 1) / a *
 // ---------------------------------------------------------------------------
 // tcgen05 path: every weight the clip kernels multiply by is also kept as a "blocked image": the
 // matrix A[R][C] (R = the 128-row M dimension of the MMA, C = contraction) is cut into [128 x 64]
-// blocks, each stored as a 16 KB SWIZZLE_128B K-major operand block, bf16 hi then bf16 lo, in the
-// order the kernels consume them: for rt in R/128: for cb in C/64: hi block, lo block.
-// One 1-D bulk copy moves a block from L2 into the shared-memory ring, ready for tcgen05.mma.
+// blocks, each stored as ONE 16 KB SWIZZLE_128B K-major operand block of fp16 values, in the order the
+// kernels consume them: for rt in R/128: for cb in C/64.  One 1-D bulk copy moves a block from L2 into the
+// shared-memory ring, ready for tcgen05.mma (kind::f16 with A = fp16 weights, B = bf16 hi | lo activations).
+// fp16 keeps 11 significand bits: 8x finer than one bf16 image and half the bytes of a bf16 hi + lo pair, which
+// is what every CTA re-streams from L2 on every step of the recurrence.  (SAVI_WIMG_SPLIT = 1 restores the
+// bf16 hi block + lo block pair of round 1 for A/B measurements.)
 // ---------------------------------------------------------------------------
+#ifndef SAVI_WIMG_SPLIT
+#define SAVI_WIMG_SPLIT 0
+#endif
 constexpr int64_t UMMA_BLK = 16384;
-static SAVI_HD int64_t wimg_bytes(int R, int C) { return (int64_t)(R / 128) * (C / 64) * 2 * UMMA_BLK; }
+constexpr int WIMG_NB = SAVI_WIMG_SPLIT ? 2 : 1;            // 16 KB blocks per [128 x 64] weight panel
+static SAVI_HD int64_t wimg_bytes(int R, int C) { return (int64_t)(R / 128) * (C / 64) * WIMG_NB * UMMA_BLK; }
 struct WImgBlock { int64_t pq, pk, pv, po, f1, f2; };
 struct WImg {                // byte offsets from the image base
     // forward orientation: rows = output feature (wqk, wg: the folded products of ParamOff)

@@ -11,11 +11,11 @@
 //     128 output features are the M dimension of the tensor core and the (<= 32) slots are N: accumulator
 //     row = TMEM lane = feature = the compute thread that post-processes it (32x32b tcgen05.ld, no shuffles).
 //
-// fp32 operands are split x = hi + lo (two bf16).  An activation operand is ONE MN-major B matrix
+// fp32 activations are split x = hi + lo (two bf16).  An activation operand is ONE MN-major B matrix
 // [128 rows = contraction index][64 = 32 slots hi | 32 slots lo] (SWIZZLE_128B, 128 B per row): the thread that
-// owns feature / token `o` writes row `o` with two 16-byte stores.  Per 16-wide k-step a product is two MMAs,
-//     W_hi . [X_hi | X_lo]  (N = 64)   and   W_lo . X_hi  (N = 32),
-// and the epilogue adds accumulator columns s and 32 + s.
+// owns feature / token `o` writes row `o` with two 16-byte stores.  Weights are fp16 images (11 significand bits,
+// savi_layout.h): per 16-wide k-step a product is ONE MMA,  W_f16 . [X_hi | X_lo]  (N = 64, kind::f16 with
+// A = fp16, B = bf16), and the epilogue adds accumulator columns s and 32 + s.
 #pragma once
 #include "savi_umma.cuh"
 #include "savi_dev.cuh"
@@ -36,6 +36,8 @@ constexpr int KTOK = 24;                      // slot columns a token thread han
 constexpr uint32_t IDESC_K_MN64 = idesc_bf16(128, 64, false, true);    // A K-major,  B MN-major, N = 64
 constexpr uint32_t IDESC_K_MN32 = idesc_bf16(128, 32, false, true);    //                          N = 32 (hi half of B's rows)
 constexpr uint32_t IDESC_MN_MN64 = idesc_bf16(128, 64, true, true);    // A MN-major, B MN-major, N = 64
+constexpr uint32_t IDESC_W16_K_MN64 = idesc_f16a_bf16b(128, 64, false, true);   // A = fp16 weight block (K-major), B = bf16 hi | lo activations
+constexpr int NBW = WIMG_NB;                  // ring blocks per [128 x 64] weight panel (savi_layout.h)
 
 // predictor attention core (shared-memory, SIMT): row stride of the q / k / v / dO tiles and of the attention matrices
 constexpr int MHA_LD = F + 4;
@@ -48,6 +50,14 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
     __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
     return *reinterpret_cast<uint32_t*>(&v);
 }
+// Fast transcendental forms for the bf16-mode clip kernels (2e-2 parity class; relative error ~2^-22, one MUFU each):
+// the 512 compute threads of a CTA share four issue ports, and the IEEE-exact expf / division / tanhf sequences were
+// ~40 % of the instructions of the GRU phase, which sits on the serial chain of every step.
+__device__ __forceinline__ float ex2_fast(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float rcp_fast(float x) { float y; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float sigmoid_fast(float x) { return rcp_fast(1.0f + ex2_fast(-1.4426950408889634f * x)); }
+__device__ __forceinline__ float tanh_fast(float x) { return fmaf(2.0f, rcp_fast(1.0f + ex2_fast(-2.8853900817779268f * x)), -1.0f); }
+
 __device__ __forceinline__ void bar_sync_n(int id, int nthreads) { asm volatile("bar.sync %0, %1;\n" :: "r"(id), "r"(nthreads) : "memory"); }
 __device__ __forceinline__ void bar_sync_compute() { bar_sync_n(1, NCT); }
 
@@ -98,7 +108,8 @@ __host__ __device__ inline Smem plan_smem(int K, int CN, bool bwd) {
     s.stats = p; p += 512;                         // float2 [32] LayerNorm statistics | float [64] c, 1/S (backward)
     p = (p + 1023) & ~1023;
     s.ones = p; p += bwd ? 0 : 4096;
-    s.inbox_stride = (KR * F * 4 + (bwd ? 0 : 32 * 4) + 127) & ~127;
+    const int KR8 = (K + 7) & ~7;                 // inbox layout [128 features][KR8 slots] (+ [KR8] sums in the forward)
+    s.inbox_stride = (KR8 * F * 4 + (bwd ? 0 : 32 * 4) + 127) & ~127;
     s.inbox = p; p += (CN > 1) ? (bwd ? 1 : 2) * s.inbox_stride : 0;
     s.aux = p;
     p = (p + 15) & ~15;
@@ -179,6 +190,16 @@ static __device__ __noinline__ uint32_t issue_linear_core(uint32_t rs /* stage |
             while (!mbar_try_wait_a(full0 + stage * 8u, phase)) { }
             fence_after_sync();
             uint32_t a = dlo_k(ring_base + stage * BLK);
+#if !SAVI_WIMG_SPLIT
+            if (el) {                                                     // W_f16 . [X_hi | X_lo]: one fp16 block per panel
+                mma_lo(d, a, xb, IDESC_W16_K_MN64, (accumulate || cb > 0) ? 1u : 0u);
+#pragma unroll
+                for (int k4 = 1; k4 < 4; ++k4) mma_lo(d, a + k4 * 2, xb + k4 * 128, IDESC_W16_K_MN64, 1u);
+                mma_commit_a(empty0 + stage * 8u);
+            }
+            __syncwarp();
+            if (++stage == (uint32_t)nst) { stage = 0; phase ^= 1u; }
+#else
             if (el) {
                 mma_lo(d, a, xb, IDESC_K_MN64, (accumulate || cb > 0) ? 1u : 0u);
 #pragma unroll
@@ -197,6 +218,7 @@ static __device__ __noinline__ uint32_t issue_linear_core(uint32_t rs /* stage |
             }
             __syncwarp();
             if (++stage == (uint32_t)nst) { stage = 0; phase ^= 1u; }
+#endif
         }
     }
     return stage | (phase << 8);

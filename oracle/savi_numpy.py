@@ -201,7 +201,12 @@ def _predictor_bwd(P, sv, dout, blocks, heads, G):
 # ----------------------------------------------------------------------------
 # forward
 # ----------------------------------------------------------------------------
-def forward(P, x, noise, num_iterations, heads, eps=1e-8, folded=True, keep=False, token_dtype=None):
+def round_f16(a):
+    """Round-to-nearest-even to IEEE half precision (returned in a's dtype)."""
+    return np.asarray(a).astype(np.float16).astype(np.asarray(a).dtype)
+
+
+def forward(P, x, noise, num_iterations, heads, eps=1e-8, folded=True, keep=False, token_dtype=None, weight_dtype=None):
     """x [B,T,N,D], noise [B,K,Ds] -> slots [B,T,K,Ds], attn [B,T,N,K] (pre-eps softmax).
 
     dtype follows x (run float64 for the oracle, float32 to measure rounding).
@@ -210,6 +215,11 @@ def forward(P, x, noise, num_iterations, heads, eps=1e-8, folded=True, keep=Fals
     LayerNorm'd token stream xhat is stored in bfloat16 (everything on the slot side
     stays fp32 there, fp64 here); backward() then differentiates that same function
     (rounding treated as identity), which is what the kernels compute.
+    weight_dtype="f16" additionally models the tcgen05 clip kernels' weight operands
+    (focus_b200/csrc/savi_layout.h: WImg): every matrix a slot-side product multiplies by is
+    an fp16 image — the folded products wqk = Ds^-1/2 Wk^T Wq and wg = W_ih W_v (formed in
+    full precision, then rounded), W_hh, the MLP and the predictor matrices; biases,
+    LayerNorm affines and all activations stay full precision.  (folded form only.)
     """
     dt = x.dtype
     P = {k: np.asarray(v, dtype=dt) for k, v in P.items()}
@@ -220,6 +230,18 @@ def forward(P, x, noise, num_iterations, heads, eps=1e-8, folded=True, keep=Fals
     sc = dt.type(Ds ** -0.5)
     eps = dt.type(eps)
 
+    w16 = weight_dtype == "f16"
+    if weight_dtype not in (None, "f16"):
+        raise ValueError("weight_dtype must be None or 'f16'")
+    if w16:
+        assert folded, "weight_dtype models the folded (CUDA) operation order"
+        wqk16 = round_f16(sc * (P["project_k.weight"].T @ P["project_q.weight"]))   # [D,Ds]: qk = s~ wqk^T
+        wg16 = round_f16(P["gru.weight_ih"] @ P["project_v.weight"])                 # [3Ds,D]: gi = Ux wg^T + b_ih
+        whh16 = round_f16(P["gru.weight_hh"])
+        w1_16, w2_16 = round_f16(P["mlp.0.weight"]), round_f16(P["mlp.2.weight"])
+        Ppred = {k: (round_f16(v) if (k.startswith("predictor.blocks.") and v.ndim == 2) else v) for k, v in P.items()}
+    else:
+        Ppred = P
     h = P["slot_mu"] + np.exp(P["slot_log_sigma"]) * noise.astype(dt)       # steve.py:56-57
     xhat, zx, rx = _ln(x, P["norm_inputs.weight"], P["norm_inputs.bias"])   # steve.py:60
     if token_dtype == "bf16":
@@ -236,7 +258,7 @@ def forward(P, x, noise, num_iterations, heads, eps=1e-8, folded=True, keep=Fals
             st, zs, rs = _ln(hp, P["norm_slots.weight"], P["norm_slots.bias"])      # :72
             q = st @ P["project_q.weight"].T                                         # :75
             if folded:
-                qk = (q * sc) @ P["project_k.weight"]                                # [B,K,D]
+                qk = st @ wqk16.T if w16 else (q * sc) @ P["project_k.weight"]       # [B,K,D]
                 L = xhat[:, t] @ qk.transpose(0, 2, 1)
             else:
                 qk = None
@@ -250,8 +272,12 @@ def forward(P, x, noise, num_iterations, heads, eps=1e-8, folded=True, keep=Fals
             else:
                 Ux = None
                 U = np.einsum("bnk,bnd->bkd", A / S[:, None, :], v[:, t])            # :82-83
-            gi = U @ P["gru.weight_ih"].T + P["gru.bias_ih"]                         # :87-89
-            gh = hp @ P["gru.weight_hh"].T + P["gru.bias_hh"]
+            if w16:
+                gi = Ux @ wg16.T + P["gru.bias_ih"]
+                gh = hp @ whh16.T + P["gru.bias_hh"]
+            else:
+                gi = U @ P["gru.weight_ih"].T + P["gru.bias_ih"]                     # :87-89
+                gh = hp @ P["gru.weight_hh"].T + P["gru.bias_hh"]
             r = _sigmoid(gi[..., :Ds] + gh[..., :Ds])
             z = _sigmoid(gi[..., Ds:2 * Ds] + gh[..., Ds:2 * Ds])
             ghn = gh[..., 2 * Ds:]
@@ -260,8 +286,8 @@ def forward(P, x, noise, num_iterations, heads, eps=1e-8, folded=True, keep=Fals
             rec = dict(hp=hp, zs=zs, rs=rs, st=st, q=q, qk=qk, S=S, Ux=Ux, U=U, r=r, z=z, n=n, ghn=ghn, hg=hg, t=t)
             if i < I - 1:                                                            # :92-93
                 m, zm, rm = _ln(hg, P["norm_mlp.weight"], P["norm_mlp.bias"])
-                a = np.maximum(m @ P["mlp.0.weight"].T + P["mlp.0.bias"], 0)
-                h = hg + a @ P["mlp.2.weight"].T + P["mlp.2.bias"]
+                a = np.maximum(m @ (w1_16 if w16 else P["mlp.0.weight"]).T + P["mlp.0.bias"], 0)
+                h = hg + a @ (w2_16 if w16 else P["mlp.2.weight"]).T + P["mlp.2.bias"]
                 rec.update(m=m, zm=zm, rm=rm, a=a)
             else:
                 h = hg
@@ -269,7 +295,7 @@ def forward(P, x, noise, num_iterations, heads, eps=1e-8, folded=True, keep=Fals
         slots_out[:, t] = h                                                          # :96-97
         attn_out[:, t] = Pm
         if t < T - 1:     # the reference also runs it after the last frame and discards it (:100)
-            h, psv = _predictor_fwd(P, h, blocks, heads)
+            h, psv = _predictor_fwd(Ppred, h, blocks, heads)
             preds.append(psv)
     if not keep:
         return slots_out, attn_out

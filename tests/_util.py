@@ -44,3 +44,23 @@ def load_fixture(name):
 
 def grad_scale(grads):
     return max(float(np.abs(g).max()) for g in grads.values())
+
+
+def grad_errs(G, RG):
+    """Per-TENSOR max-normalised error of every parameter gradient: max|g - ref| / max|ref_k|  (SURVEY.md §8c).
+    A tensor whose reference gradient is structurally zero (norm_slots.bias: the softmax over slots is invariant to a
+    per-feature shift of the queries; unused parameters when I == 1 / T == 1) has nothing to normalise by: it is
+    reported relative to the largest gradient of the whole set instead (an absolute bound), flagged by `zero`."""
+    gs = grad_scale(RG)
+    out = {}
+    for k, g in RG.items():
+        m = float(np.abs(g).max())
+        zero = m <= 1e-9 * gs
+        out[k] = (float(np.abs(np.asarray(G[k], np.float64) - g).max() / (gs if zero else m)), zero)
+    return out
+
+
+def load_ref_bf16(name):
+    """{tag/tensor: error} of the reference's own bf16 runs against its fp64 run (tests/golden/make_golden.py --bf16-reference)."""
+    z = np.load(os.path.join(GOLDEN, name + "_refbf16.npz"))
+    return {k: float(z[k]) for k in z.files}

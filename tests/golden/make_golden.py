@@ -91,7 +91,43 @@ def _fwd_only(ref, x, noise):
         torch.Tensor.normal_ = orig
 
 
+def make_bf16_reference(name, out_name):
+    """The reference's OWN bf16 accuracy on fixture `name`: the unmodified module run (a) under
+    torch.autocast(bfloat16) with fp32 parameters (the AMP flavour of tools/steve_train_net.py:95, in bf16) and
+    (b) converted with .bfloat16(), each compared with the same module in fp64 on the same bf16-rounded inputs.
+    Stored: the max-normalised error of every output / gradient tensor (`autocast/<tensor>`, `bf16/<tensor>`), which is
+    what tests/test_cuda_parity.py bounds the CUDA bf16 path by (the BPTT gradient of this module amplifies any
+    2^-9 rounding ~100x, so "within the reference's own bf16 error" is the meaningful gradient bar)."""
+    import copy
+    sys.path.insert(0, os.path.join(HERE, ".."))
+    from _util import load_fixture, err
+    fx = load_fixture(name)
+    ref = reference_slot_attention_video(fx["I"], fx["K"], fx["D"], fx["Ds"], fx["M"], fx["blocks"], fx["heads"], 0.0)
+    ref.load_state_dict({k: torch.from_numpy(np.asarray(v, np.float32)) for k, v in fx["params"].items()})
+    t = torch.from_numpy
+    xb, noise, gs = t(fx["x"]).bfloat16(), t(fx["noise"]), t(fx["g_slots"])
+    gab = t(fx["g_attn"]).bfloat16() if fx["g_attn"] is not None else None
+    truth = run_reference(copy.deepcopy(ref).double(), xb.double(), noise.double(), gs.double(), None if gab is None else gab.double())
+    with torch.autocast("cpu", dtype=torch.bfloat16):
+        auto = run_reference(copy.deepcopy(ref), xb, noise, gs, gab)
+    half = run_reference(copy.deepcopy(ref).bfloat16(), xb, noise.bfloat16(), gs.bfloat16(), gab)
+    out = {}
+    for tag, r in (("autocast", auto), ("bf16", half)):
+        out[tag + "/slots"] = err(r[0].float().numpy(), truth[0].numpy())
+        out[tag + "/attn"] = err(r[1].float().numpy(), truth[1].numpy())
+        out[tag + "/d_inputs"] = err(r[2].float().numpy(), truth[2].numpy())
+        for k in truth[3]:
+            out[tag + "/grad/" + k] = err(r[3][k].float().numpy(), truth[3][k].numpy())
+    path = os.path.join(HERE, out_name + ".npz")
+    np.savez_compressed(path, **{k: np.float64(v) for k, v in out.items()})
+    print(out_name, {k: "%.2e" % v for k, v in out.items() if "grad" not in k})
+
+
 if __name__ == "__main__":
+    if "--bf16-reference" in sys.argv:          # only the reference-bf16 accuracy record (the fixtures above stay as committed)
+        make_bf16_reference("c1", "c1_refbf16")
+        make_bf16_reference("tiny_a", "tiny_a_refbf16")
+        sys.exit(0)
     #            B  T  N    D    Ds   M    K   I  blocks heads seed
     make("tiny_a", 2, 3, 64, 32, 32, 48, 5, 3, 1, 4, 11)
     make("tiny_b", 1, 2, 50, 24, 16, 20, 7, 2, 2, 2, 12)                       # D != Ds, 2 predictor blocks, ragged N

@@ -1,18 +1,25 @@
 """GPU parity tests (run with `-m gpu` on a B200): the CUDA path, called through the module ->
 autograd.Function -> C ABI, against the oracle on the same seeded inputs.
 
-Error metric: max|a-b| / max|b| per tensor.  Tolerances (BASELINE.json north_star):
-fp32 1e-5, bf16 2e-2.  In bf16 mode the one quantisation point of the design is the LayerNorm'd token
-stream (stored in bf16); gradients are compared with the oracle evaluated at that same quantisation
-point (`token_dtype="bf16"`), because the BPTT gradient of this module amplifies ANY token rounding by
-~50x (measured on the oracle itself: 9e-2 on d_inputs at C1; the reference's own bf16 is 1.2e-1,
-BASELINE.md §5) — see DESIGN.md "bf16 parity".
+Error metric: max|a-b| / max|b| PER TENSOR (every parameter gradient is normalised by its own
+largest reference entry; structurally-zero gradients by the largest gradient of the set).  Tolerances
+(BASELINE.json north_star): fp32 1e-5, bf16 2e-2.
+
+bf16 mode has two tiers, because the BPTT gradient of this module amplifies ANY 2^-9 .. 2^-11 rounding by ~100x
+(measured on the fp64 oracle at C1: rounding only the LayerNorm'd tokens to bf16 moves d_inputs by 8.8e-2, the
+reference's own bf16 runs are off by 1.8e-1; tests/golden/c1_refbf16.npz):
+  * accuracy tier  — against the UNQUANTISED fp64 oracle: forward (slots, attn) within 2e-2; every gradient tensor
+    within the reference's own bf16 error on the same inputs (autocast and .bfloat16(), whichever is larger), both
+    numbers printed (`test_bf16_gradients_within_the_reference_bf16_error`);
+  * implementation tier — against the oracle evaluated at the design's quantisation points (LayerNorm'd tokens
+    stored in bf16; on the tcgen05 path the weight operands are fp16 images), within 2e-2 per tensor: this is the
+    tier that catches kernel bugs.
 """
 import numpy as np
 import pytest
 import torch
 
-from tests._util import FIXTURES, TOL_BF16, TOL_FP32, err, grad_scale, load_fixture
+from tests._util import FIXTURES, TOL_BF16, TOL_FP32, err, grad_errs, grad_scale, load_fixture, load_ref_bf16
 
 pytestmark = pytest.mark.gpu
 
@@ -42,12 +49,25 @@ def _run_cuda(fx, dtype, cluster=0, with_g_attn=True):
             None if ga is None else ga.float().cpu().numpy().astype(np.float64))
 
 
-def _oracle(fx, x64, ga64, token_dtype=None):
+def _oracle(fx, x64, ga64, token_dtype=None, weight_dtype=None):
     from oracle import savi_numpy as O
     s, a, sv = O.forward(fx["params"], x64, fx["noise"].astype(np.float64), fx["I"], fx["heads"], keep=True,
-                         token_dtype=token_dtype)
+                         token_dtype=token_dtype, weight_dtype=weight_dtype)
     dx, G, _ = O.backward(fx["params"], sv, fx["g_slots"].astype(np.float64), ga64)
     return s, a, dx, G
+
+
+def _path(fx, dtype, cluster=0):
+    """Kernel family the library dispatches this problem to (0 SIMT fp32, 1 mma.sync, 2 tcgen05)."""
+    from focus_b200 import SlotAttentionVideo, _lib
+    probe = SlotAttentionVideo(fx["I"], fx["K"], fx["D"], fx["Ds"], fx["M"], fx["blocks"], fx["heads"], 0.0)
+    probe.cluster = cluster
+    return _lib.query(probe.make_shape(fx["B"], fx["T"], fx["N"], dtype)).path
+
+
+def _oracle_at_quantisation_points(fx, x64, ga64, path):
+    """bf16 mode, implementation tier: xhat stored in bf16; the tcgen05 kernels multiply by fp16 weight images."""
+    return _oracle(fx, x64, ga64, token_dtype="bf16", weight_dtype="f16" if path == 2 else None)
 
 
 def _check(got, ref, tol):
@@ -56,10 +76,9 @@ def _check(got, ref, tol):
     assert err(s, rs) < tol, "slots %g" % err(s, rs)
     assert err(a, ra) < tol, "attn %g" % err(a, ra)
     assert err(dx, rdx) < tol, "d_inputs %g" % err(dx, rdx)
-    gs = grad_scale(RG)
-    for k, g in RG.items():      # norm_slots.bias has a structurally zero gradient -> absolute (max-normalised) check
-        e = float(np.abs(G[k] - g).max() / gs)
-        assert e < tol, "grad %s %g" % (k, e)
+    ge = grad_errs(G, RG)       # per tensor; structurally-zero gradients against the largest gradient of the set
+    bad = {k: "%.2e%s" % (e, " (zero-gradient tensor)" if z else "") for k, (e, z) in ge.items() if not e < tol}
+    assert not bad, "parameter gradients off (per-tensor max-normalised, tol %g): %s" % (tol, bad)
 
 
 @pytest.mark.parametrize("name", FIXTURES)
@@ -73,20 +92,48 @@ def test_fp32_matches_oracle_and_reference_fixture(name, cluster):
     assert err(s, fx["slots_f64"]) < TOL_FP32
     assert err(a[:, :, ::sub], fx["attn_f64"]) < TOL_FP32
     assert err(dx[:, :, ::sub], fx["dx_f64"]) < TOL_FP32
-    gs = grad_scale(fx["grads"])
-    for k, g in fx["grads"].items():
-        assert np.abs(G[k] - g).max() / gs < TOL_FP32, k
+    bad = {k: e for k, (e, z) in grad_errs(G, fx["grads"]).items() if not e < TOL_FP32}
+    assert not bad, bad
 
 
 @pytest.mark.parametrize("name", FIXTURES)
 def test_bf16_matches_oracle(name):
     fx = load_fixture(name)
     s, a, dx, G, x64, ga64 = _run_cuda(fx, torch.bfloat16)
-    # forward against the UNQUANTISED fp64 oracle (bf16-rounded inputs, exact math)
+    # accuracy tier, forward: against the UNQUANTISED fp64 oracle (bf16-rounded inputs, exact math)
     rs, ra, _, _ = _oracle(fx, x64, ga64)
-    assert err(s, rs) < TOL_BF16 and err(a, ra) < TOL_BF16
-    # forward + gradients against the oracle at the design's quantisation point (xhat stored in bf16)
-    _check((s, a, dx, G), _oracle(fx, x64, ga64, token_dtype="bf16"), TOL_BF16)
+    assert err(s, rs) < TOL_BF16 and err(a, ra) < TOL_BF16, (err(s, rs), err(a, ra))
+    # implementation tier: forward + every gradient against the oracle at the design's quantisation points
+    _check((s, a, dx, G), _oracle_at_quantisation_points(fx, x64, ga64, _path(fx, torch.bfloat16)), TOL_BF16)
+
+
+@pytest.mark.parametrize("name", ["c1", "tiny_a"])
+def test_bf16_gradients_within_the_reference_bf16_error(name, capsys):
+    """Accuracy tier, gradients: against the UNQUANTISED fp64 oracle every tensor must be at least as accurate as the
+    reference's own bf16 execution of the same problem (autocast / .bfloat16(), tests/golden/*_refbf16.npz, generated
+    from the unmodified reference).  Prints both numbers per tensor."""
+    fx = load_fixture(name)
+    ref = load_ref_bf16(name)
+    s, a, dx, G, x64, ga64 = _run_cuda(fx, torch.bfloat16)
+    rs, ra, rdx, RG = _oracle(fx, x64, ga64)
+    ours = {"slots": err(s, rs), "attn": err(a, ra), "d_inputs": err(dx, rdx)}
+    zero = set()
+    for k, (e, z) in grad_errs(G, RG).items():
+        ours["grad/" + k] = e
+        if z:
+            zero.add("grad/" + k)
+    rows, worse = [], []
+    for k, e in ours.items():
+        bound = TOL_BF16 if k in zero else max(ref["autocast/" + k], ref["bf16/" + k])
+        rows.append("%-52s ours %.2e | reference autocast-bf16 %.2e  .bfloat16() %.2e" % (k, e, ref["autocast/" + k], ref["bf16/" + k]))
+        if not e <= bound:
+            worse.append(k)
+    with capsys.disabled():
+        print("\n[%s, bf16 vs the unquantised fp64 oracle, per-tensor max-normalised error]\n" % name + "\n".join(rows))
+    assert ours["slots"] < TOL_BF16 and ours["attn"] < TOL_BF16
+    assert not worse, "less accurate than the reference's own bf16 run: %s" % worse
+    med = lambda tag: float(np.median([v for k, v in ref.items() if k.startswith(tag + "/grad/")]))
+    assert float(np.median([v for k, v in ours.items() if k.startswith("grad/") and k not in zero])) <= min(med("autocast"), med("bf16"))
 
 
 SHAPES = [
@@ -118,7 +165,7 @@ def test_shape_sweep_against_oracle(shape, dtype):
     if dtype == torch.float32:
         _check((s, a, dx, G), _oracle(fx, x64, ga64), TOL_FP32)
     else:
-        _check((s, a, dx, G), _oracle(fx, x64, ga64, token_dtype="bf16"), TOL_BF16)
+        _check((s, a, dx, G), _oracle_at_quantisation_points(fx, x64, ga64, _path(fx, dtype)), TOL_BF16)
 
 
 # the tcgen05 clip kernels (bf16 tokens, D = Ds = M = 128, K <= 24): slot counts, ragged / sub-tile N, predictor variants
@@ -150,7 +197,7 @@ def test_tcgen05_path_shape_sweep(shape, cluster):
               g_slots=rng.standard_normal((B, T, K, Ds)).astype(np.float32),
               g_attn=rng.standard_normal((B, T, N, K)).astype(np.float32))
     s, a, dx, G, x64, ga64 = _run_cuda(fx, torch.bfloat16, cluster=cluster)
-    _check((s, a, dx, G), _oracle(fx, x64, ga64, token_dtype="bf16"), TOL_BF16)
+    _check((s, a, dx, G), _oracle_at_quantisation_points(fx, x64, ga64, 2), TOL_BF16)
 
 
 def test_overlapped_d_inputs_equals_serial(monkeypatch):
@@ -250,6 +297,93 @@ def test_errors_are_loud():
     drop = SlotAttentionVideo(2, 4, 16, 16, 16, 1, 2, 0.1).cuda().train()
     with pytest.raises(NotImplementedError):
         drop(torch.randn(1, 1, 8, 16, device="cuda"))
+
+
+# ---- BASELINE.json configs at FULL size against the oracle ---------------------------------------
+# The CUDA path runs the benchmarked problem (all 64 clips: the benchmark's grid, cluster size and dependent-launch
+# overlap); every clip is independent, so the oracle re-computes a few of them (first, middle, last) and their slots,
+# attention maps and d_inputs are compared directly.  Parameter gradients sum over clips: they are compared on the
+# same sub-batch run by itself.
+def _full_size_case(cfg_name, clips, B=None):
+    import bench
+    from oracle import savi_numpy as O
+    c = dict(bench.CONFIGS[cfg_name])
+    if B:
+        c["B"] = B
+    dt = torch.float32 if c["dtype"] == "fp32" else torch.bfloat16
+    m = bench.make_params_like(c).cuda()
+    with torch.no_grad():                                   # non-trivial biases / LayerNorm affines
+        gp = torch.Generator().manual_seed(5)
+        for p_ in m.parameters():
+            if p_.ndim == 1:
+                p_.add_(0.2 * torch.randn(p_.shape, generator=gp).to(p_.device))
+    g = torch.Generator().manual_seed(11)
+    Bc, T, N, D, K, Ds = c["B"], c["T"], c["N"], c["D"], c["K"], c["Ds"]
+    x = torch.randn(Bc, T, N, D, generator=g).to(dt)
+    noise = torch.randn(Bc, K, Ds, generator=g)
+    gs = torch.randn(Bc, T, K, Ds, generator=g)
+    ga = torch.randn(Bc, T, N, K, generator=g).to(dt)
+    P = {k: v.detach().cpu().numpy() for k, v in m.state_dict().items()}
+
+    def run(sel):
+        xx = x[sel].cuda().requires_grad_(True)
+        for p_ in m.parameters():
+            p_.grad = None
+        s_, a_ = m(xx, noise=noise[sel].cuda())
+        torch.autograd.backward([s_, a_], [gs[sel].cuda().to(s_.dtype), ga[sel].cuda()])
+        torch.cuda.synchronize()
+        G = {n: p_.grad.detach().cpu().numpy() for n, p_ in m.named_parameters()}
+        return s_.detach().float().cpu().numpy(), a_.detach().float().cpu().numpy(), xx.grad.float().cpu().numpy(), G
+
+    idx = torch.tensor(clips)
+    full = run(torch.arange(Bc))
+    sub = run(idx)
+    fx = dict(B=len(clips), T=T, N=N, D=D, Ds=Ds, M=c["M"], K=K, I=c["I"], blocks=c["blocks"], heads=c["heads"], params=P,
+              noise=noise[idx].numpy(), g_slots=gs[idx].numpy())
+    path = _path(dict(fx, B=Bc), dt)
+    x64, ga64 = x[idx].double().numpy(), ga[idx].double().numpy()
+    ref = _oracle(fx, x64, ga64) if dt == torch.float32 else _oracle_at_quantisation_points(fx, x64, ga64, path)
+    return c, path, full, sub, ref, idx.numpy()
+
+
+@pytest.mark.parametrize("cfg_name,clips,B,expect_path", [
+    ("c2", [0, 31, 63], None, 2),      # BASELINE configs[1]: the benchmarked problem, 64 clips
+    ("c4", [0, 63], None, 2),          # configs[3]: T = 24 frames x 2 iterations = 48 sequential steps per clip
+    ("c3", [0, 15], 16, None),         # configs[2]: N = 4096, D = 192 (16 clips: 6 GB of fp64 oracle state otherwise)
+])
+def test_baseline_configs_full_size_against_oracle(cfg_name, clips, B, expect_path, capsys):
+    c, path, full, sub, ref, idx = _full_size_case(cfg_name, clips, B)
+    if expect_path is not None:
+        assert path == expect_path
+    tol = TOL_FP32 if c["dtype"] == "fp32" else TOL_BF16
+    rs, ra, rdx, RG = ref
+    e = {"slots": err(full[0][idx], rs), "attn": err(full[1][idx], ra), "d_inputs": err(full[2][idx], rdx)}
+    ge = grad_errs(sub[3], RG)
+    with capsys.disabled():
+        print("\n[%s full size, path %d] %s | worst gradient tensor %.2e" %
+              (cfg_name, path, {k: "%.2e" % v for k, v in e.items()}, max(v for v, _ in ge.values())))
+    assert max(e.values()) < tol, e
+    _check(sub, ref, tol)
+
+
+# BASELINE configs[4] sweep corners (K in {32, 64} x D in {64, 256}): the shapes tools/sweep.py times
+@pytest.mark.parametrize("K,D", [(32, 64), (32, 256), (64, 64), (64, 256)])
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_sweep_corners_against_oracle(K, D, dtype):
+    from oracle import savi_numpy as O
+    B, T, N, I, blocks, heads = 2, 2, 1024, 3, 1, 4
+    rng = np.random.default_rng(K * 1000 + D)
+    fx = dict(B=B, T=T, N=N, D=D, Ds=D, M=D, K=K, I=I, blocks=blocks, heads=heads, sub=1,
+              params={k: v.astype(np.float32) for k, v in O.random_params(K, D, D, D, blocks, seed=6).items()},
+              x=rng.standard_normal((B, T, N, D)).astype(np.float32),
+              noise=rng.standard_normal((B, K, D)).astype(np.float32),
+              g_slots=rng.standard_normal((B, T, K, D)).astype(np.float32),
+              g_attn=rng.standard_normal((B, T, N, K)).astype(np.float32))
+    s, a, dx, G, x64, ga64 = _run_cuda(fx, dtype)
+    if dtype == torch.float32:
+        _check((s, a, dx, G), _oracle(fx, x64, ga64), TOL_FP32)
+    else:
+        _check((s, a, dx, G), _oracle_at_quantisation_points(fx, x64, ga64, _path(fx, dtype)), TOL_BF16)
 
 
 # ---- BASELINE.json full sizes: size-independent properties ---------------------------------------

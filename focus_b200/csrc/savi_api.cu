@@ -265,7 +265,7 @@ __global__ void pack_split_kernel(const float* __restrict__ packed, bf16* __rest
     }
 }
 
-// fp32 matrix A[R][C] -> blocked SWIZZLE_128B fp16 image (savi_layout.h: WImg).  tr = 0: A is row-major at packed + src (leading dimension
+// fp32 matrix A[R][C] -> blocked SWIZZLE_128B 16-bit image (savi_layout.h: WImg): fp16 forward orientation, bf16 backward.  tr = 0: A is row-major at packed + src (leading dimension
 // ld); tr = 1: A is the TRANSPOSE of the row-major [C][R] matrix stored there (the backward-orientation images are read
 // straight from the original weights: no transposed fp32 copy is needed on the tcgen05 path).
 struct ImgJob { int src, R, C, ld, tr; long long dst; };
@@ -290,18 +290,19 @@ __global__ void pack_image_kernel(const __grid_constant__ ImgArgs ia, const floa
         }
         unsigned char* blk = img + j.dst + ((size_t)((r >> 7) * (j.C >> 6) + (c0 >> 6)) * WIMG_NB) * UMMA_BLK;
         const unsigned off = (unsigned)(r & 127) * 128u + (((unsigned)((c0 & 63) >> 3) ^ (unsigned)(r & 7)) << 4);
-#if SAVI_WIMG_SPLIT
-        bf16 h[8], l[8];
+        uint4 out;
+        if (j.tr) {                                  // backward orientation: bf16 (savi_layout.h)
+            __nv_bfloat162 b2[4];
 #pragma unroll
-        for (int e = 0; e < 8; ++e) split_bf16(v[e], h[e], l[e]);
-        *reinterpret_cast<uint4*>(blk + off) = *reinterpret_cast<const uint4*>(h);
-        *reinterpret_cast<uint4*>(blk + UMMA_BLK + off) = *reinterpret_cast<const uint4*>(l);
-#else
-        __half2 h2[4];
+            for (int e = 0; e < 4; ++e) b2[e] = __floats2bfloat162_rn(v[2 * e], v[2 * e + 1]);
+            out = *reinterpret_cast<const uint4*>(b2);
+        } else {                                     // forward orientation: fp16
+            __half2 h2[4];
 #pragma unroll
-        for (int e = 0; e < 4; ++e) h2[e] = __floats2half2_rn(v[2 * e], v[2 * e + 1]);
-        *reinterpret_cast<uint4*>(blk + off) = *reinterpret_cast<const uint4*>(h2);
-#endif
+            for (int e = 0; e < 4; ++e) h2[e] = __floats2half2_rn(v[2 * e], v[2 * e + 1]);
+            out = *reinterpret_cast<const uint4*>(h2);
+        }
+        *reinterpret_cast<uint4*>(blk + off) = out;
     }
 }
 

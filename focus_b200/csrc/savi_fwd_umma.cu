@@ -3,6 +3,7 @@
 // Reference semantics: /root/reference/slowfast/models/STEVE/steve.py:52-105 (SlotAttentionVideo.forward),
 // transformer.py:22-49, 70-86, 106-114 (predictor).  Execution model: savi_umma_clip.cuh.
 // Writes exactly the saved-for-backward records of the mma.sync kernel (savi_layout.h: SavedLayout).
+#define SAVI_CLIP_F16_LINEAR 1      // slot-side linears: fp16 weight images x fp16 hi | lo activations (savi_layout.h)
 #include "savi_umma_clip.cuh"
 
 using namespace uc;
@@ -429,15 +430,15 @@ __global__ void __launch_bounds__(NTHREADS, 1) savi_fwd_umma_kernel(const __grid
                 // ---- slots_prev, LayerNorm, q ----
                 // (the saved-for-backward records are stored AFTER the operand hand-over of their phase: the stores then overlap
                 // the tensor-core round trip instead of sitting in front of it on the serial chain)
-                write_operand(c, L.opC, h);
+                write_operand_f16(c, L.opC, h);
                 layer_norm(c, h, y, g_s, b_s, d.ln_eps, lead ? reinterpret_cast<float2*>(fb + a.sl.lns) + (s * B + b) * K : nullptr);   // :72
-                write_operand(c, L.opA, y);
+                write_operand_f16(c, L.opA, y);
                 signal_operand(c);
                 if (svA) save_field(c, frow(fb, a.sl.hp, s, b, B, K, F), F, o, h);
                 if (svB) save_field(c, frow(fb, a.sl.st, s, b, B, K, F), F, o, y);
                 UPH(1);
                 wait_acc(c); UPH(4); load_acc(c, TC_B, y);                                  // qk = Ds^-1/2 (s~ Wq^T) Wk, the scale folded into wqk
-                write_operand(c, L.opA, y);
+                write_operand(c, L.opA, y);                                                 // bf16 hi | lo: multiplied by the bf16 token tiles
                 signal_operand(c);
                 if (svB) save_field(c, frow(fb, a.sl.qk, s, b, B, K, F), F, o, y);
                 // ---- attention step over the token tiles ----
@@ -486,7 +487,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) savi_fwd_umma_kernel(const __grid
                 }
 #pragma unroll
                 for (int kk = 0; kk < KH; ++kk) y[kk] = (kk < c.nk) ? num[kk] * rcp_fast(den[kk]) : 0.f;      // Ux (:82-83)
-                write_operand(c, L.opB, y);
+                write_operand_f16(c, L.opB, y);
                 signal_operand(c);
                 if (lead) {
                     save_field(c, frow(fb, a.sl.ux, s, b, B, K, F), F, o, y);
@@ -518,7 +519,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) savi_fwd_umma_kernel(const __grid
                         const int64_t smi = (int64_t)t * (d.I - 1) + it;
                         UPH(14);
                         layer_norm(c, h, y, g_m, b_m, d.ln_eps, svB ? reinterpret_cast<float2*>(fb + a.sl.lnm) + (smi * B + b) * K : nullptr);
-                        write_operand(c, L.opB, y);
+                        write_operand_f16(c, L.opB, y);
                         signal_operand(c);
                         if (svA) {
                             save_field(c, frow(fb, a.sl.r, s, b, B, K, F), F, o, r_);
@@ -534,7 +535,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) savi_fwd_umma_kernel(const __grid
                         wait_acc(c); UPH(16); load_acc(c, TC_A, y);
 #pragma unroll
                         for (int kk = 0; kk < KH; ++kk) y[kk] = fmaxf(y[kk] + b1, 0.f);
-                        write_operand(c, L.opA, y);
+                        write_operand_f16(c, L.opA, y);
                         signal_operand(c);
                         if (svA) save_field(c, frow(fb, a.sl.a, smi, b, B, K, F), F, o, y);
                         UPH(17);
@@ -570,7 +571,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) savi_fwd_umma_kernel(const __grid
                     float yv[KH], q[KH], kx[KH], v[KH], x1[KH];
                     layer_norm(c, x, yv, P[bo.ln1_w + o], P[bo.ln1_b + o], d.ln_eps);
                     if (svB) save_field(c, frow(fb, a.sl.py, f, b, B, K, F), F, o, yv);
-                    write_operand(c, L.opA, yv);
+                    write_operand_f16(c, L.opA, yv);
                     signal_operand(c);
                     
                     wait_acc(c);
@@ -586,7 +587,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) savi_fwd_umma_kernel(const __grid
                     float ov[KH];
                     mha_core(c, d.heads, q, kx, v, ov, svB ? fb + a.sl.patt + (f * B + b) * ((int64_t)d.heads * K * K) : nullptr);
                     if (svA) save_field(c, frow(fb, a.sl.po, f, b, B, K, F), F, o, ov);
-                    write_operand(c, L.opB, ov);
+                    write_operand_f16(c, L.opB, ov);
                     signal_operand(c);
                     PPH(22);
                     wait_acc(c);  load_acc(c, TC_A, x1);
@@ -596,7 +597,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) savi_fwd_umma_kernel(const __grid
                     if (svB) save_field(c, frow(fb, a.sl.px1, f, b, B, K, F), F, o, x1);
                     layer_norm(c, x1, yv, P[bo.ln2_w + o], P[bo.ln2_b + o], d.ln_eps);
                     if (svA) save_field(c, frow(fb, a.sl.pl2, f, b, B, K, F), F, o, yv);
-                    write_operand(c, L.opA, yv);
+                    write_operand_f16(c, L.opA, yv);
                     signal_operand(c);
                     PPH(23);
 #pragma unroll
@@ -607,7 +608,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) savi_fwd_umma_kernel(const __grid
 #pragma unroll
                         for (int kk = 0; kk < KH; ++kk) yv[kk] = fmaxf(yv[kk] + bb, 0.f);
                         if ((ff & 1) ? svB : svA) save_field(c, frow(fb, a.sl.pf, f, b, B, K, 4 * F), 4 * F, ff * F + o, yv);
-                        write_operand(c, ff == 0 ? L.opB : ff == 1 ? L.opC : ff == 2 ? L.aw0 : L.aw1, yv);
+                        write_operand_f16(c, ff == 0 ? L.opB : ff == 1 ? L.opC : ff == 2 ? L.aw0 : L.aw1, yv);
                         signal_operand(c, B_FOPND + ff);
                     }
                     ++pcall;

@@ -45,9 +45,10 @@ __host__ __device__ constexpr uint32_t idesc_bf16(int M, int N, bool a_mn_major,
     return (1u << 4) | (1u << 7) | (1u << 10) | ((a_mn_major ? 1u : 0u) << 15) | ((b_mn_major ? 1u : 0u) << 16) |
            ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
-// same, A = fp16 (format 0), B = bf16: the weight images are fp16, the activation operands bf16 hi | lo
-__host__ __device__ constexpr uint32_t idesc_f16a_bf16b(int M, int N, bool a_mn_major, bool b_mn_major) {
-    return (1u << 4) | (0u << 7) | (1u << 10) | ((a_mn_major ? 1u : 0u) << 15) | ((b_mn_major ? 1u : 0u) << 16) |
+// same with fp16 x fp16 operands (format 0).  A and B must share the format: a mixed fp16 x bf16 kind::f16 MMA is an
+// illegal instruction on sm_100a (measured, round 2)
+__host__ __device__ constexpr uint32_t idesc_f16(int M, int N, bool a_mn_major, bool b_mn_major) {
+    return (1u << 4) | (0u << 7) | (0u << 10) | ((a_mn_major ? 1u : 0u) << 15) | ((b_mn_major ? 1u : 0u) << 16) |
            ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 

@@ -13,10 +13,11 @@
 //
 // fp32 activations are split x = hi + lo (two bf16).  An activation operand is ONE MN-major B matrix
 // [128 rows = contraction index][64 = 32 slots hi | 32 slots lo] (SWIZZLE_128B, 128 B per row): the thread that
-// owns feature / token `o` writes row `o` with two 16-byte stores.  Weights are fp16 images (11 significand bits,
-// savi_layout.h): per 16-wide k-step a product is ONE MMA,  W_f16 . [X_hi | X_lo]  (N = 64, kind::f16 with
-// A = fp16, B = bf16), and the epilogue adds accumulator columns s and 32 + s.
+// owns feature / token `o` writes row `o` with two 16-byte stores.  Weights are single 16-bit images (savi_layout.h:
+// fp16 in the forward, where the activation operands are fp16 hi | lo too; bf16 in the backward): per 16-wide k-step a
+// product is ONE MMA,  W . [X_hi | X_lo]  (N = 64), and the epilogue adds accumulator columns s and 32 + s.
 #pragma once
+#include <cuda_fp16.h>
 #include "savi_umma.cuh"
 #include "savi_dev.cuh"
 #include "savi_args.h"
@@ -36,7 +37,13 @@ constexpr int KTOK = 24;                      // slot columns a token thread han
 constexpr uint32_t IDESC_K_MN64 = idesc_bf16(128, 64, false, true);    // A K-major,  B MN-major, N = 64
 constexpr uint32_t IDESC_K_MN32 = idesc_bf16(128, 32, false, true);    //                          N = 32 (hi half of B's rows)
 constexpr uint32_t IDESC_MN_MN64 = idesc_bf16(128, 64, true, true);    // A MN-major, B MN-major, N = 64
-constexpr uint32_t IDESC_W16_K_MN64 = idesc_f16a_bf16b(128, 64, false, true);   // A = fp16 weight block (K-major), B = bf16 hi | lo activations
+// slot-side linears: ONE 16-bit weight block per panel (savi_layout.h).  The forward kernel defines SAVI_CLIP_F16_LINEAR:
+// fp16 weights x fp16 hi | lo activations; the backward multiplies bf16 weights by bf16 hi | lo gradient operands.
+#ifdef SAVI_CLIP_F16_LINEAR
+constexpr uint32_t IDESC_LIN = idesc_f16(128, 64, false, true);
+#else
+constexpr uint32_t IDESC_LIN = IDESC_K_MN64;
+#endif
 constexpr int NBW = WIMG_NB;                  // ring blocks per [128 x 64] weight panel (savi_layout.h)
 
 // predictor attention core (shared-memory, SIMT): row stride of the q / k / v / dO tiles and of the attention matrices
@@ -190,35 +197,14 @@ static __device__ __noinline__ uint32_t issue_linear_core(uint32_t rs /* stage |
             while (!mbar_try_wait_a(full0 + stage * 8u, phase)) { }
             fence_after_sync();
             uint32_t a = dlo_k(ring_base + stage * BLK);
-#if !SAVI_WIMG_SPLIT
-            if (el) {                                                     // W_f16 . [X_hi | X_lo]: one fp16 block per panel
-                mma_lo(d, a, xb, IDESC_W16_K_MN64, (accumulate || cb > 0) ? 1u : 0u);
+            if (el) {                                                     // W . [X_hi | X_lo]: one 16-bit weight block per panel
+                mma_lo(d, a, xb, IDESC_LIN, (accumulate || cb > 0) ? 1u : 0u);
 #pragma unroll
-                for (int k4 = 1; k4 < 4; ++k4) mma_lo(d, a + k4 * 2, xb + k4 * 128, IDESC_W16_K_MN64, 1u);
+                for (int k4 = 1; k4 < 4; ++k4) mma_lo(d, a + k4 * 2, xb + k4 * 128, IDESC_LIN, 1u);
                 mma_commit_a(empty0 + stage * 8u);
             }
             __syncwarp();
             if (++stage == (uint32_t)nst) { stage = 0; phase ^= 1u; }
-#else
-            if (el) {
-                mma_lo(d, a, xb, IDESC_K_MN64, (accumulate || cb > 0) ? 1u : 0u);
-#pragma unroll
-                for (int k4 = 1; k4 < 4; ++k4) mma_lo(d, a + k4 * 2, xb + k4 * 128, IDESC_K_MN64, 1u);
-                mma_commit_a(empty0 + stage * 8u);
-            }
-            __syncwarp();
-            if (++stage == (uint32_t)nst) { stage = 0; phase ^= 1u; }
-            while (!mbar_try_wait_a(full0 + stage * 8u, phase)) { }
-            fence_after_sync();
-            a = dlo_k(ring_base + stage * BLK);
-            if (el) {
-#pragma unroll
-                for (int k4 = 0; k4 < 4; ++k4) mma_lo(d, a + k4 * 2, xb + k4 * 128, IDESC_K_MN32, 1u);
-                mma_commit_a(empty0 + stage * 8u);
-            }
-            __syncwarp();
-            if (++stage == (uint32_t)nst) { stage = 0; phase ^= 1u; }
-#endif
         }
     }
     return stage | (phase << 8);
@@ -263,6 +249,25 @@ __device__ __forceinline__ void write_operand(const Ctx& c, int op_off, const fl
         const float2 hf = __bfloat1622float2(hh);
         h[j] = *reinterpret_cast<const uint32_t*>(&hh);
         l[j] = pack_bf16x2(a - hf.x, b - hf.y);
+    }
+    *reinterpret_cast<uint4*>(c.sm + op_off + c.row_hi) = make_uint4(h[0], h[1], h[2], h[3]);
+    *reinterpret_cast<uint4*>(c.sm + op_off + c.row_lo) = make_uint4(l[0], l[1], l[2], l[3]);
+}
+// same as fp16 hi | lo (operands of the forward's slot-side linears, whose weight images are fp16).  The conversion
+// saturates: a slot state beyond fp16's range (65504) would otherwise turn into inf - inf = NaN in the lo half.
+__device__ __forceinline__ uint32_t pack_f16x2_sat(float lo, float hi) {
+    uint32_t r;
+    asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+    return r;
+}
+__device__ __forceinline__ void write_operand_f16(const Ctx& c, int op_off, const float (&v)[KH]) {
+    uint32_t h[4], l[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const float a = (2 * j < c.nk) ? v[2 * j] : 0.f, b = (2 * j + 1 < c.nk) ? v[2 * j + 1] : 0.f;
+        h[j] = pack_f16x2_sat(a, b);
+        const float2 hf = __half22float2(*reinterpret_cast<const __half2*>(&h[j]));
+        l[j] = pack_f16x2_sat(a - hf.x, b - hf.y);
     }
     *reinterpret_cast<uint4*>(c.sm + op_off + c.row_hi) = make_uint4(h[0], h[1], h[2], h[3]);
     *reinterpret_cast<uint4*>(c.sm + op_off + c.row_lo) = make_uint4(l[0], l[1], l[2], l[3]);

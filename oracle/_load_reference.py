@@ -1,10 +1,11 @@
 """Import the UNMODIFIED reference SlotAttentionVideo from /root/reference.
 
-TEST INFRASTRUCTURE ONLY (see oracle/README.md).  Works only in the build
-container where /root/reference is mounted; the GPU box has no such path, so
-nothing on the product path, in `-m gpu` tests, smoke() or bench.py imports
-this file.  It is used by tests/golden/make_golden.py (fixture generation) and
-by CPU tests that are skipped when the reference tree is absent.
+TEST INFRASTRUCTURE ONLY.  In the build container the package is imported from
+/root/reference; on the GPU box (no such path) from oracle/_ref/, the byte-identical
+copies oracle/make_ref.py makes (git-ignored, shipped with the gpurun snapshot).
+Nothing under focus_b200/ imports this file.  Users: tests/golden/make_golden.py
+(fixture generation), tests/test_reference_integration.py, bench.py's reference arm
+and its gpu_eager_baseline leg.
 
 The reference package cannot be imported normally: slowfast/__init__.py pulls
 iopath and slowfast/models/__init__.py pulls fvcore (neither installed).  The
@@ -18,11 +19,21 @@ import os
 import sys
 import types
 
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_TRAVEL_ROOT = os.path.join(_HERE, "_ref")      # byte-identical copies made by oracle/make_ref.py (git-ignored; ships to the GPU box)
+
+
+def _has_steve(root):
+    return os.path.isfile(os.path.join(root, "slowfast", "models", "STEVE", "steve.py"))
+
+
 REFERENCE_ROOT = os.environ.get("FOCUS_REFERENCE_ROOT", "/root/reference")
+if not _has_steve(REFERENCE_ROOT) and _has_steve(_TRAVEL_ROOT):
+    REFERENCE_ROOT = _TRAVEL_ROOT
 
 
 def reference_available() -> bool:
-    return os.path.isfile(os.path.join(REFERENCE_ROOT, "slowfast", "models", "STEVE", "steve.py"))
+    return _has_steve(REFERENCE_ROOT)
 
 
 def load_reference_steve():
@@ -67,3 +78,14 @@ def load_reference_steve():
 
 def reference_slot_attention_video(*args, **kwargs):
     return load_reference_steve().SlotAttentionVideo(*args, **kwargs)
+
+
+def steve_config(img_size=32, dim=128, slot_size=128, mlp_hidden=128, num_slots=7, num_iters=2, blocks=1, heads=4,
+                 vocab=64, cnn_hidden=32, dec_blocks=1, dec_heads=4, dropout=0.0):
+    """A cfg object with the fields STEVE.__init__ reads (steve.py:160-275; yaml names of configs/movi_e/base.yaml)."""
+    ns = types.SimpleNamespace
+    return ns(MODEL=ns(CNN_NAME="base"),
+              SLOTS=ns(NUM_ITERS=num_iters, NUM_SLOTS=num_slots, CNN_HID_SIZE=cnn_hidden, SIZE=slot_size, MLP_HID_SIZE=mlp_hidden,
+                       IMG_CHANNELS=3, IMG_SIZE=img_size, VOCAB_SIZE=vocab, DIM=dim, NUM_PREDICTOR_BLOCKS=blocks,
+                       NUM_PREDICTOR_HEADS=heads, PREDICTOR_DROPOUT=dropout,
+                       DECODER=ns(DIM=dim, NUM_BLOCKS=dec_blocks, NUM_HEADS=dec_heads, DROPOUT=dropout)))

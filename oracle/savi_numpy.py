@@ -307,8 +307,12 @@ def forward(P, x, noise, num_iterations, heads, eps=1e-8, folded=True, keep=Fals
 # ----------------------------------------------------------------------------
 # backward (folded form; what the CUDA backward kernels implement)
 # ----------------------------------------------------------------------------
-def backward(P, saved, g_slots, g_attn=None):
-    """Returns (d_inputs [B,T,N,D], {param name: grad}, d_noise [B,K,Ds])."""
+def backward(P, saved, g_slots, g_attn=None, bwd_weight_dtype=None):
+    """Returns (d_inputs [B,T,N,D], {param name: grad}, d_noise [B,K,Ds]).
+
+    bwd_weight_dtype="bf16" models the tcgen05 backward kernel's weight operands (savi_layout.h: WImg, backward
+    orientation): every dX = dY . W product multiplies by a bf16 image of W (the folded wg = W_ih W_v and
+    wqk = Ds^-1/2 Wk^T Wq are rounded after folding); the weight GRADIENTS dW = dY^T X use no weights and stay exact."""
     B, T, N, D, K, Ds = saved["shape"]
     dt = saved["xhat"].dtype
     P = {k: np.asarray(v, dtype=dt) for k, v in P.items()}
@@ -319,9 +323,17 @@ def backward(P, saved, g_slots, g_attn=None):
     dxhat = np.zeros_like(xhat)
     dh = np.zeros((B, K, Ds), dt)
     Wq, Wk, Wv = P["project_q.weight"], P["project_k.weight"], P["project_v.weight"]
+    if bwd_weight_dtype not in (None, "bf16"):
+        raise ValueError("bwd_weight_dtype must be None or 'bf16'")
+    wb = bwd_weight_dtype == "bf16"
+    rb = round_bf16 if wb else (lambda a: a)
+    W2b, W1b, Whhb = rb(P["mlp.2.weight"]) if "mlp.2.weight" in P else None, rb(P["mlp.0.weight"]), rb(P["gru.weight_hh"])
+    wgb = rb(P["gru.weight_ih"] @ Wv)                    # [3Ds, D]
+    wqkb = rb(sc * (Wk.T @ Wq))                          # [D, Ds]
+    Pp = {k: (rb(v) if (wb and k.startswith("predictor.blocks.") and v.ndim == 2) else v) for k, v in P.items()}
     for t in reversed(range(T)):
         if t < T - 1:
-            dh = _predictor_bwd(P, saved["preds"][t], dh, blocks, heads, G)
+            dh = _predictor_bwd(Pp, saved["preds"][t], dh, blocks, heads, G)
         dh = dh + g_slots[:, t].astype(dt)
         for i in reversed(range(I)):
             s = saved["steps"][t * I + i]
@@ -329,10 +341,10 @@ def backward(P, saved, g_slots, g_attn=None):
             if i < I - 1:
                 _acc(G, "mlp.2.bias", dh.sum((0, 1)))
                 _acc(G, "mlp.2.weight", np.einsum("bko,bkc->oc", dh, s["a"]))
-                da = (dh @ P["mlp.2.weight"]) * (s["a"] > 0)
+                da = (dh @ W2b) * (s["a"] > 0)
                 _acc(G, "mlp.0.bias", da.sum((0, 1)))
                 _acc(G, "mlp.0.weight", np.einsum("bko,bkc->oc", da, s["m"]))
-                d, dg, db = _ln_bwd(da @ P["mlp.0.weight"], s["zm"], s["rm"], P["norm_mlp.weight"])
+                d, dg, db = _ln_bwd(da @ W1b, s["zm"], s["rm"], P["norm_mlp.weight"])
                 _acc(G, "norm_mlp.weight", dg)
                 _acc(G, "norm_mlp.bias", db)
                 dhg = dh + d
@@ -344,7 +356,7 @@ def backward(P, saved, g_slots, g_attn=None):
             dr_pre = dn_pre * ghn * r * (1 - r)
             dgi = np.concatenate([dr_pre, dz_pre, dn_pre], -1)
             dgh = np.concatenate([dr_pre, dz_pre, dn_pre * r], -1)
-            dhp = dhg * z + dgh @ P["gru.weight_hh"]
+            dhp = dhg * z + dgh @ Whhb
             _acc(G, "gru.weight_ih", np.einsum("bko,bkc->oc", dgi, s["U"]))
             _acc(G, "gru.weight_hh", np.einsum("bko,bkc->oc", dgh, hp))
             _acc(G, "gru.bias_ih", dgi.sum((0, 1)))
@@ -352,7 +364,7 @@ def backward(P, saved, g_slots, g_attn=None):
             dU = dgi @ P["gru.weight_ih"]
             # ---- attention step backward (token pass) ----
             _acc(G, "project_v.weight", np.einsum("bko,bkc->oc", dU, s["Ux"]))
-            dUx = dU @ Wv                                                   # [B,K,D]
+            dUx = dgi @ wgb if wb else dU @ Wv                              # [B,K,D]
             c = (dUx * s["Ux"]).sum(-1)                                     # [B,K]
             xt = xhat[:, t]
             L = xt @ s["qk"].transpose(0, 2, 1)
@@ -371,7 +383,7 @@ def backward(P, saved, g_slots, g_attn=None):
             _acc(G, "project_k.weight", np.einsum("bko,bkc->oc", qs, dqk))
             dq = (dqk @ Wk.T) * sc
             _acc(G, "project_q.weight", np.einsum("bko,bkc->oc", dq, s["st"]))
-            d, dg, db = _ln_bwd(dq @ Wq, s["zs"], s["rs"], P["norm_slots.weight"])
+            d, dg, db = _ln_bwd(dqk @ wqkb if wb else dq @ Wq, s["zs"], s["rs"], P["norm_slots.weight"])
             _acc(G, "norm_slots.weight", dg)
             _acc(G, "norm_slots.bias", db)
             dh = dhp + d

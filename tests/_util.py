@@ -64,3 +64,20 @@ def load_ref_bf16(name):
     """{tag/tensor: error} of the reference's own bf16 runs against its fp64 run (tests/golden/make_golden.py --bf16-reference)."""
     z = np.load(os.path.join(GOLDEN, name + "_refbf16.npz"))
     return {k: float(z[k]) for k in z.files}
+
+
+def relu_fed(name):
+    """Weight / bias gradients whose reduction is gated by a ReLU mask taken from the forward pass (mlp.0, predictor ffn.0).
+    A pre-activation within the forward error of zero flips its mask, and ONE flipped (unit, row) pair moves that unit's
+    gradient row by a whole sample's contribution, ~ (rows/2)^-1/2 of the row in max-norm however small the forward error
+    is.  In bf16 mode (forward error ~1e-3) a few hundred such flips per tensor are certain, so for these tensors the
+    implementation-tier metric is the relative L2 (Frobenius) error, with the max-norm bound relaxed to 3x; fp32 mode
+    (flip probability ~1e-7 per unit) keeps the plain max-norm metric."""
+    return name.endswith("mlp.0.weight") or name.endswith("mlp.0.bias") or name.endswith("ffn.0.weight") or name.endswith("ffn.0.bias")
+
+
+def l2_err(a, b):
+    a = np.asarray(a, np.float64)
+    b = np.asarray(b, np.float64)
+    den = np.sqrt((b * b).sum())
+    return float(np.sqrt(((a - b) ** 2).sum()) / (den if den > 0 else 1.0))

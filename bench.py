@@ -2,7 +2,7 @@
 """bench.py — slot-attention fwd+bwd frames/sec on B200 (BASELINE.json metric).
 
     python bench.py --gpus N --steps K --warmup W            # our arm (CUDA library)
-    python bench.py --impl reference --gpus N --steps K ...  # reference CPU arm (oracle port, host cores)
+    python bench.py --impl reference --gpus N --steps K ...  # reference CPU arm (the unmodified reference module, host cores)
 
 One "step" = one SlotAttentionVideo forward + backward over one batch of synthetic
 MOVi-E-shaped clips (BASELINE.json configs[1], "C2": bf16, 64 clips/GPU, T=6, N=1024,
@@ -12,7 +12,7 @@ both outputs, plus (N>1) the DDP gradient all-reduce.  One frame = one (clip, t)
 Prints ONE JSON line (rank 0).  Keys beyond the base contract:
   roofline     the dominant kernel against the measured HBM peak (MEASURED_PEAKS.json)
   step_roofline  whole-step k/v-bytes-x-iterations roofline of BASELINE.md §3
-  cpu_baseline the oracle's torch port timed on this box's host cores (N=1 only)
+  cpu_baseline the unmodified reference module (oracle/_ref) timed on this box's host cores (N=1 only)
   kernels_ms   per-kernel CUDA-event times of the last timed step
 """
 import argparse
@@ -104,44 +104,116 @@ def make_params_like(model_cfg, seed=0):
 
 
 # ---------------------------------------------------------------------------------------------
-# reference arm / cpu_baseline: oracle torch port on the host cores (bounded sample of the workload)
+# reference arm / cpu_baseline: the UNMODIFIED reference module (oracle/_ref, made by oracle/make_ref.py from
+# /root/reference; see oracle/_load_reference.py) on the host cores.  Nothing of focus_b200 is imported on this path:
+# parameters come from the reference constructor under torch.manual_seed(0) (the same values make_params_like gives
+# our module: the constructors are RNG-identical, tests/test_cabi_cpu.py).
 # ---------------------------------------------------------------------------------------------
-def time_cpu_port(cfg, sample_clips, steps, warmup):
-    from oracle import savi_torch as OT
+def _reference_module(c):
+    from oracle import _load_reference as LR
+    if not LR.reference_available():
+        return None
+    torch.manual_seed(0)
+    return LR.reference_slot_attention_video(c["I"], c["K"], c["D"], c["Ds"], c["M"], c["blocks"], c["heads"], 0.0)
+
+
+def _ref_step(ref, x, noise, gs, ga):
+    """One forward + backward of the reference module with the slot noise injected (its single RNG draw, steve.py:56)."""
+    x = x.detach().requires_grad_(True)
+    orig = torch.Tensor.normal_
+    torch.Tensor.normal_ = lambda self, *a, **k: self.copy_(noise)
+    try:
+        slots, attn = ref(x)
+    finally:
+        torch.Tensor.normal_ = orig
+    for p in ref.parameters():
+        p.grad = None
+    torch.autograd.backward([slots, attn], [gs.to(slots.dtype), ga.to(attn.dtype)])
+    return slots
+
+
+def _ref_inputs(c, clips, device="cpu", dtype=torch.float32):
+    g = torch.Generator().manual_seed(1)
+    x = torch.randn(clips, c["T"], c["N"], c["D"], generator=g).to(dtype).to(device)
+    noise = torch.randn(clips, c["K"], c["Ds"], generator=g).to(device)
+    gs = torch.randn(clips, c["T"], c["K"], c["Ds"], generator=g).to(device)
+    ga = torch.randn(clips, c["T"], c["N"], c["K"], generator=g).to(dtype).to(device)
+    return x, noise, gs, ga
+
+
+def time_cpu_reference(cfg, sample_clips, steps, warmup):
+    """frames/s of the reference's own CPU path (fp32, all host threads) on `sample_clips` clips of the workload."""
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
     c = cfg
-    module = make_params_like(c)
-    P = {k: v.detach().float() for k, v in module.state_dict().items()}
-    g = torch.Generator().manual_seed(1)
-    x = torch.randn(sample_clips, c["T"], c["N"], c["D"], generator=g)
-    noise = torch.randn(sample_clips, c["K"], c["Ds"], generator=g)
-    gs = torch.randn(sample_clips, c["T"], c["K"], c["Ds"], generator=g)
-    ga = torch.randn(sample_clips, c["T"], c["N"], c["K"], generator=g)
+    ref = _reference_module(c)
+    x, noise, gs, ga = _ref_inputs(c, sample_clips)
+    if ref is None:
+        raise SystemExit("bench.py: neither /root/reference nor oracle/_ref is present; run `python oracle/make_ref.py` "
+                         "(or __graft_entry__.build()) in the build container")
+    kind, what = "reference", "the unmodified reference module slowfast/models/STEVE/steve.py:SlotAttentionVideo (oracle/_ref)"
+    run = lambda: _ref_step(ref, x, noise, gs, ga)
     times = []
     for i in range(warmup + steps):
         t0 = time.perf_counter()
-        OT.forward_backward(P, x, noise, c["I"], c["heads"], gs, ga)
+        run()
         dt = time.perf_counter() - t0
         if i >= warmup:
             times.append(dt)
     t = statistics.median(times)
-    return dict(value=sample_clips * c["T"] / t, unit=UNIT, cores=cores, kind="port",
-                sample="%d of %d clips/step, fp32, oracle/savi_torch.py (torch CPU ops in the reference's operation "
-                       "order; the Python reference itself cannot travel to the GPU box), median of %d steps" %
-                       (sample_clips, c["B"], steps)), t
+    return dict(value=sample_clips * c["T"] / t, unit=UNIT, cores=cores, kind=kind,
+                sample="%d of %d clips/step, fp32 forward + backward (both upstream gradients), %s; median of %d steps after %d warm-up" %
+                       (sample_clips, c["B"], what, steps, warmup)), t
+
+
+def time_gpu_eager_reference(cfg, steps=10, warmup=3):
+    """The reference module through PyTorch eager on the B200 (what FOCUS runs today): fp32 with TF32 off, and bf16 autocast.
+    A reported baseline (SURVEY.md §8d "the real beat-this number"); never part of the product path."""
+    out = {}
+    dev = torch.device("cuda", 0)
+    c = cfg
+    for tag in ("fp32_tf32_off", "bf16_autocast"):
+        ref = _reference_module(c)
+        if ref is None:
+            return None
+        ref = ref.to(dev)
+        x, noise, gs, ga = _ref_inputs(c, c["B"], dev)
+        torch.backends.cuda.matmul.allow_tf32 = False
+        torch.backends.cudnn.allow_tf32 = False
+        ctx = torch.autocast("cuda", dtype=torch.bfloat16) if tag == "bf16_autocast" else torch.autocast("cuda", enabled=False)
+        flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+        evs = []
+        for i in range(warmup + steps):
+            flush.fill_(i & 0xFF)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            with ctx:
+                _ref_step(ref, x, noise, gs, ga)
+            e1.record()
+            if i >= warmup:
+                evs.append((e0, e1))
+        torch.cuda.synchronize(dev)
+        ms = statistics.median(a.elapsed_time(b) for a, b in evs)
+        out[tag] = {"ms_per_step": ms, "value": c["B"] * c["T"] / (ms * 1e-3), "unit": UNIT}
+        del ref, x, noise, gs, ga, flush
+        torch.cuda.empty_cache()
+    out["what"] = ("unmodified reference module (oracle/_ref) via PyTorch eager on cuda:0, %d clips, forward + backward, CUDA events, "
+                   "median of %d steps after %d warm-up, L2 flushed between steps" % (c["B"], steps, warmup))
+    return out
 
 
 def run_reference(args, cfg, rank):
     if rank != 0:
         return
-    sample = min(cfg["B"], 4)
-    cb, t = time_cpu_port(cfg, sample, max(1, args.steps), max(0, min(args.warmup, 2)))
+    warm = max(0, args.warmup)
+    cb, t = time_cpu_reference(cfg, cfg["B"], max(1, args.steps), warm)
     line = {"impl": "reference", "metric": METRIC, "value": cb["value"], "unit": UNIT, "n_gpus": args.gpus,
-            "steps": args.steps, "warmup": min(args.warmup, 2), "ms_per_step": t * 1e3, "higher_is_better": True,
+            "steps": args.steps, "warmup": warm, "ms_per_step": t * 1e3, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": config_dict(args, cfg, args.gpus), "cpu_baseline": cb,
             "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    if args.gpu_eager and torch.cuda.is_available():
+        line["gpu_eager_baseline"] = time_gpu_eager_reference(cfg)
     print(json.dumps(line), flush=True)
 
 
@@ -221,6 +293,42 @@ def run_ours(args, cfg, rank, world, local_rank):
         evs[i][1].record()
         x.grad = None
     sync_all()
+    eager_ms = sum(a.elapsed_time(b) for a, b in evs)
+    # ---- the same K steps replayed as ONE CUDA graph per step (stream capture of the module's forward + autograd backward,
+    # incl. zero_grad and, for N > 1, the NCCL gradient all-reduce): same kernels, same work, no host launch gaps.
+    graph_ms = None
+    graph_err = None
+    if not args.no_graph:
+        try:
+            cs = torch.cuda.Stream(dev)
+            cs.wait_stream(torch.cuda.current_stream(dev))
+            with torch.cuda.stream(cs):
+                for _ in range(3):
+                    step(x); x.grad = None
+            torch.cuda.current_stream(dev).wait_stream(cs)
+            sync_all()
+            eager_slots = step(x).detach().clone(); x.grad = None
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph, stream=cs):
+                g_slots = step(x)
+            for _ in range(3):
+                graph.replay()
+            sync_all()
+            if not torch.equal(g_slots, eager_slots):
+                raise RuntimeError("graph replay does not reproduce the eager forward bit for bit")
+            gevs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+            for i in range(args.steps):
+                flush.fill_(i & 0xFF)
+                gevs[i][0].record()
+                graph.replay()
+                gevs[i][1].record()
+            sync_all()
+            graph_ms = sum(a.elapsed_time(b) for a, b in gevs)
+            x.grad = None
+        except Exception as e:       # reported, never silent: the eager number stands
+            graph_err = "%s: %s" % (type(e).__name__, str(e)[:200])
+            graph_ms = None
+            sync_all()
     clocks = sampler.stop()
     # ---- per-kernel CUDA-event times: the same step, 5 more times, with the library's event pairs around every launch
     # (on the launch stream).  A separate pass because an event record between two launches serialises them, and the
@@ -235,11 +343,13 @@ def run_ours(args, cfg, rank, world, local_rank):
     sync_all()
     _lib.profile_enable(False)
     launches_per_step = None
-    total_ms = sum(a.elapsed_time(b) for a, b in evs)
-    t_local = torch.tensor([total_ms], dtype=torch.float64, device=dev)
+    # max over ranks; the graph number is used only when EVERY rank captured successfully
+    t_local = torch.tensor([eager_ms, graph_ms if graph_ms is not None else float("inf")], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t_local, op=dist.ReduceOp.MAX)
-    total_ms = float(t_local.item())
+    eager_ms, graph_ms = float(t_local[0].item()), float(t_local[1].item())
+    use_graph = graph_ms != float("inf") and graph_ms < eager_ms
+    total_ms = graph_ms if use_graph else eager_ms
     ms_per_step = total_ms / args.steps
     frames = B * T * world
     value = frames / (ms_per_step * 1e-3)
@@ -336,6 +446,9 @@ def run_ours(args, cfg, rank, world, local_rank):
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "bf16" if c["dtype"] == "bf16" else "f32", "data": "synthetic", "config": config_dict(args, cfg, world),
             "clocks": clocks,
+            "launch": {"mode": "cuda-graph replay (one graph = one step)" if use_graph else "eager (one Python call per step)",
+                       "ms_per_step_eager": eager_ms / args.steps,
+                       "ms_per_step_graph": None if graph_ms == float("inf") else graph_ms / args.steps, "graph_error": graph_err},
             "e2e": {"value": frames / (e2e_ms * 1e-3), "unit": UNIT, "ms_per_step": e2e_ms,
                     "h2d_bytes_per_step": x_host.numel() * x_host.element_size(), "d2h_bytes_per_step": 4},
             "gpu_launches": launches_per_step * args.steps,
@@ -343,7 +456,7 @@ def run_ours(args, cfg, rank, world, local_rank):
             "kernels_ms_note": "CUDA events around each launch in a separate 5-step pass right after the timed region (serialised: "
                                "in the timed steps d_inputs overlaps the backward clip kernel on the SMs it leaves idle)"}
     if world == 1 and not args.no_cpu_baseline:
-        cb, _ = time_cpu_port(cfg, min(cfg["B"], 4), 3, 1)
+        cb, _ = time_cpu_reference(cfg, min(cfg["B"], 16), 5, 1)      # bounded sample: ~10-20 s of host time
         line["cpu_baseline"] = cb
     sys.stdout.flush()
     os.dup2(saved_stdout, 1)
@@ -362,6 +475,8 @@ def main():
     ap.add_argument("--clips", type=int, default=0, help="override clips per GPU")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--ddp", action="store_true", help="N>1: wrap the module in torch DDP instead of the fused flat all-reduce")
+    ap.add_argument("--no-graph", action="store_true", help="do not try the CUDA-graph replay of the step")
+    ap.add_argument("--gpu-eager", action="store_true", help="--impl reference only: also time the reference module through PyTorch eager on cuda:0")
     args = ap.parse_args()
     cfg = dict(CONFIGS[args.config])
     if args.clips:

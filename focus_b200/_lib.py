@@ -16,7 +16,7 @@ SAVI_MAX_SLOTS = 64
 PATH_NAMES = {0: "simt-fp32", 1: "mma.sync-bf16", 2: "tcgen05-bf16"}
 
 EXPORTS = ["savi_version", "savi_last_error", "savi_query", "savi_param_layout", "savi_pack_params",
-           "savi_forward", "savi_backward", "savi_last_launch_count", "savi_profile_enable", "savi_profile_read", "savi_debug_set_phase_buffer"]
+           "savi_forward", "savi_backward", "savi_last_launch_count", "savi_profile_enable", "savi_profile_read", "savi_debug_set_phase_buffer", "savi_set_option"]
 
 
 class SaviShape(ctypes.Structure):
@@ -57,6 +57,8 @@ def _load():
     lib.savi_profile_read.restype = ip
     lib.savi_debug_set_phase_buffer.argtypes = [vp]
     lib.savi_debug_set_phase_buffer.restype = ip
+    lib.savi_set_option.argtypes = [ctypes.c_char_p, ip]
+    lib.savi_set_option.restype = ip
     return lib
 
 
@@ -66,6 +68,11 @@ lib = _load()
 def check(rc, what):
     if rc != 0:
         raise RuntimeError("focus_b200 %s failed (code %d): %s" % (what, rc, lib.savi_last_error().decode()))
+
+
+def set_option(name, value):
+    """Process-wide development option of the library (include/focus_savi.h: savi_set_option)."""
+    check(lib.savi_set_option(name.encode(), int(value)), "savi_set_option")
 
 
 def query(shape):

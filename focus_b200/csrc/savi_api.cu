@@ -28,6 +28,29 @@ extern "C" const char* savi_last_error(void) { return g_err; }
 extern "C" int savi_last_launch_count(void) { return g_launches; }
 
 static const int kMaxSmem = 227 * 1024;
+
+// ---- process-wide options ---------------------------------------------------------------------
+static SaviOptions options_from_env() {
+    SaviOptions o;
+    o.disable_umma = getenv("SAVI_DISABLE_UMMA") ? 1 : 0;
+    o.disable_mma = getenv("SAVI_DISABLE_MMA") ? 1 : 0;
+    o.no_opstage = getenv("SAVI_NO_OPSTAGE") ? 1 : 0;
+    o.no_overlap = getenv("SAVI_NO_OVERLAP") ? 1 : 0;
+    o.dx_trace = getenv("SAVI_DX_TRACE") ? 1 : 0;
+    o.dx_tpc = getenv("SAVI_DX_TPC") ? atoi(getenv("SAVI_DX_TPC")) : 0;
+    o.dx_gate_last = getenv("SAVI_DX_GATE_LAST") ? 1 : 0;
+    return o;
+}
+static SaviOptions g_opt = options_from_env();          // environment read once, at library load
+const SaviOptions& savi_options() { return g_opt; }
+extern "C" int savi_set_option(const char* name, int value) {
+    if (!name) return fail(SAVI_EINVAL, "null option name");
+    struct { const char* n; int* v; } tab[] = {{"disable_umma", &g_opt.disable_umma}, {"disable_mma", &g_opt.disable_mma},
+        {"no_opstage", &g_opt.no_opstage}, {"no_overlap", &g_opt.no_overlap}, {"dx_trace", &g_opt.dx_trace},
+        {"dx_tpc", &g_opt.dx_tpc}, {"dx_gate_last", &g_opt.dx_gate_last}};
+    for (auto& t : tab) if (!strcmp(name, t.n)) { *t.v = value; return SAVI_OK; }
+    return fail(SAVI_EINVAL, "unknown option '%s'", name);
+}
 static long long* g_dbg = nullptr;     // device buffer of 64 phase counters (development aid)
 extern "C" int savi_debug_set_phase_buffer(void* dev_ptr) { g_dbg = reinterpret_cast<long long*>(dev_ptr); return SAVI_OK; }
 
@@ -83,12 +106,14 @@ static int validate(const SaviShape* s, Dims& d) {
     if (s->Ds < 4 || s->Ds > 512 || s->Ds % 4) return fail(SAVI_EINVAL, "slot_size Ds=%d must be a multiple of 4 in [4,512]", s->Ds);
     if (s->M < 4 || s->M % 4 || s->M > 4096) return fail(SAVI_EINVAL, "mlp_hidden_size M=%d must be a multiple of 4 in [4,4096]", s->M);
     if (s->blocks < 0 || s->blocks > SAVI_MAX_BLOCKS) return fail(SAVI_EINVAL, "num_predictor_blocks=%d outside [0,%d]", s->blocks, SAVI_MAX_BLOCKS);
-    if (s->heads < 1 || s->Ds % s->heads) return fail(SAVI_EINVAL, "slot_size %d not divisible by num_predictor_heads %d", s->Ds, s->heads);
+    // (the reference only builds the multi-head attention when there are predictor blocks: transformer.py:94-101)
+    if (s->blocks > 0 && (s->heads < 1 || s->Ds % s->heads)) return fail(SAVI_EINVAL, "slot_size %d not divisible by num_predictor_heads %d", s->Ds, s->heads);
+    if ((int64_t)s->B * s->T > 65535) return fail(SAVI_EINVAL, "B*T = %lld frames per call exceed the 65535 limit of the token-parallel kernels' grid (split the batch)", (long long)s->B * s->T);
     if (s->dtype != SAVI_DTYPE_F32 && s->dtype != SAVI_DTYPE_BF16) return fail(SAVI_EINVAL, "unknown dtype %d", s->dtype);
     if (s->cluster != 0 && s->cluster != 1 && s->cluster != 2 && s->cluster != 4 && s->cluster != 8)
         return fail(SAVI_EINVAL, "cluster must be 0,1,2,4 or 8");
     d.B = s->B; d.T = s->T; d.N = s->N; d.D = s->D; d.Ds = s->Ds; d.M = s->M; d.K = s->K; d.I = s->I;
-    d.blocks = s->blocks; d.heads = s->heads;
+    d.blocks = s->blocks; d.heads = s->blocks > 0 ? s->heads : 1;
     d.KP = (s->K + 3) & ~3;
     d.CN = choose_cluster(*s);
     d.S = s->T * s->I; d.Sm = s->T * (s->I - 1); d.Sp = (s->T - 1) * s->blocks;
@@ -98,7 +123,7 @@ static int validate(const SaviShape* s, Dims& d) {
     // tensor-core path: bf16 token stream and shapes the mma.sync tiles cover; everything else takes the SIMT path
     const int MT = d.KC / 16 == 3 ? 4 : d.KC / 16;
     d.mma = (s->dtype == SAVI_DTYPE_BF16 && s->D % 16 == 0 && s->D <= 256 && s->Ds % 8 == 0 && s->M % 8 == 0 &&
-             s->N % 8 == 0 && !getenv("SAVI_DISABLE_MMA") &&
+             s->N % 8 == 0 && !g_opt.disable_mma &&
              dx_pick_ig(s->I, d.KC, s->D, (size_t)kMaxSmem) >= 1 &&
              tmma_smem_bytes(MT, s->D, s->K, 1, true) <= (size_t)kMaxSmem) ? 1 : 0;
     if (d.mma) d.KC = MT * 16;
@@ -107,8 +132,7 @@ static int validate(const SaviShape* s, Dims& d) {
     d.umma = 0;
     // (any N: ragged and odd token counts are handled by the 128-token tiles; the mma.sync path needs N % 8 == 0)
     if (s->dtype == SAVI_DTYPE_BF16 && s->D == 128 && s->Ds == 128 && s->M == 128 && s->K <= 24 && (s->cluster == 0 || s->cluster <= 2) &&
-        savi_umma_mha_fits(s->K, s->heads) && savi_dx_umma_smem_bytes(s->I) <= kMaxSmem && !getenv("SAVI_DISABLE_UMMA") &&
-        !getenv("SAVI_DISABLE_MMA")) {
+        savi_umma_mha_fits(s->K, d.heads) && savi_dx_umma_smem_bytes(s->I) <= kMaxSmem && !g_opt.disable_umma && !g_opt.disable_mma) {
         d.umma = 1;
         d.mma = 1;                       // shares the tensor-core workspace layout (staged d(Ux) rows, no fp32 d xhat accumulator)
         d.CN = s->cluster ? s->cluster : ((int64_t)s->B * 2 <= 148 ? 2 : 1);
@@ -144,8 +168,8 @@ static int plan_smem(const Dims& d, bool bwd, int* TN, int* arena_floats, int* s
         // two operand buffers in front of the arena let consecutive linears hand their A operand over in shared memory
         const int cop = d.D > d.Ds ? d.D : d.Ds;
         size_t opb = (lin_mma_smem(MT, cop) + 15) / 16 * 16;
-        if (cop % 32 != 0 || bytes + 2 * opb > (size_t)kMaxSmem || bwd || getenv("SAVI_NO_OPSTAGE")) opb = 0;   // backward does not use them (yet)
-        if (opb == 0 && *stages == 2 && cop % 32 == 0 && !bwd && !getenv("SAVI_NO_OPSTAGE")) {      // prefer the hand-over buffers to the second token tile
+        if (cop % 32 != 0 || bytes + 2 * opb > (size_t)kMaxSmem || bwd || g_opt.no_opstage) opb = 0;   // backward does not use them (yet)
+        if (opb == 0 && *stages == 2 && cop % 32 == 0 && !bwd && !g_opt.no_opstage) {      // prefer the hand-over buffers to the second token tile
             const size_t tok1 = tmma_smem_bytes(MT, d.D, d.K, 1, bwd);
             size_t b1 = tok1 > want ? tok1 : want; b1 = (b1 + 15) / 16 * 16;
             const size_t o1 = (lin_mma_smem(MT, cop) + 15) / 16 * 16;

@@ -58,6 +58,19 @@ struct WgradJob {               // dW[o][c] (+)= alpha * sum_r dY[r][o] * X[r][c
 constexpr int WGRAD_MAX_JOBS = 7 + 6 * SAVI_MAX_BLOCKS;
 struct WgradArgs { WgradJob job[WGRAD_MAX_JOBS]; int njobs; int rows_per_split; };
 
+// Process-wide development options (include/focus_savi.h: savi_set_option).  Read-only on the forward / backward path; their
+// initial values come from the SAVI_* environment variables, read ONCE when the library is loaded.
+struct SaviOptions {
+    int disable_umma;      // "disable_umma"  (SAVI_DISABLE_UMMA): never dispatch to the tcgen05 clip kernels
+    int disable_mma;       // "disable_mma"   (SAVI_DISABLE_MMA):  never dispatch to any tensor-core family
+    int no_opstage;        // "no_opstage"    (SAVI_NO_OPSTAGE):   mma.sync family: no operand hand-over buffers
+    int no_overlap;        // "no_overlap"    (SAVI_NO_OVERLAP):   d_inputs / weight-gradient kernels after the clip kernel, not overlapped
+    int dx_trace;          // "dx_trace"      (SAVI_DX_TRACE):     globaltimer trace of the overlapped kernels (tools/dx_trace.py)
+    int dx_tpc;            // "dx_tpc"        (SAVI_DX_TPC):       tiles per d_inputs CTA (0 = automatic)
+    int dx_gate_last;      // "dx_gate_last"  (SAVI_DX_GATE_LAST)
+};
+const SaviOptions& savi_options();
+
 // per-kernel timing hooks (savi_api.cu); no-ops unless savi_profile_enable(1)
 void savi_prof_begin(int slot, cudaStream_t st);
 void savi_prof_end(int slot, cudaStream_t st);

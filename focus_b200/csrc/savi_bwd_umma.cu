@@ -879,7 +879,7 @@ int savi_bwd_umma_smem_bytes(const Dims& d) {
 cudaError_t savi_launch_bwd_umma(const BwdArgs& a, const unsigned char* wimg, const WImg& wi, cudaStream_t st) {
     BwdUArgs ua;
     ua.a = a; ua.wimg = wimg; ua.wi = wi;
-    ua.trace = (a.dbg && getenv("SAVI_DX_TRACE")) ? a.dbg + 64 + 3 * 4096 : nullptr;      // [0] = min start (preset to LLONG_MAX), [1] = max end
+    ua.trace = (a.dbg && savi_options().dx_trace) ? a.dbg + 64 + 3 * 4096 : nullptr;      // [0] = min start (preset to LLONG_MAX), [1] = max end
     if (ua.trace) ua.a.dbg = nullptr;                                                         // no phase counters in a trace run
     ua.a.smem_bytes = savi_bwd_umma_smem_bytes(a.d);
     cudaError_t e = cudaFuncSetAttribute(savi_bwd_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ua.a.smem_bytes);

@@ -113,6 +113,9 @@ __global__ void __launch_bounds__(DX_THREADS, 1) dx_umma_kernel(const __grid_con
     }
     __syncthreads();                                           // barriers exist (and the frame is staged) before the first bulk copy is issued
     if (tid == DX_EPI_WARPS * 32 && nt > 0) {                  // the first coefficient tile streams in while the right-hand side is staged
+        // the coefficient blocks were written by the (possibly still running) clip kernel with generic-proxy stores and are
+        // read here through the async proxy (bulk copy): order the two proxies after the acquire above
+        asm volatile("fence.proxy.async.global;\n" ::: "memory");
         mbar_expect_tx(&bars[BF], I * 16384); bulk_g2s(ct, coef_f, I * 16384, &bars[BF]);
     }
     // right-hand side rows: iteration i -> rows [64 i, 64 i + 64): qk_i (32 rows, zero beyond K) then dUx_i; MN-major, two 64-column blocks
@@ -262,14 +265,14 @@ cudaError_t savi_launch_dx_umma(const BwdArgs& a, const void* inputs, void* grad
     // whole frames per CTA (one staging of the right-hand side) once there are >= 2 waves of frames; else >= 2 CTAs per frame
     x.tiles_per_cta = d.NTILE <= 8 ? ((d.B * d.T >= 2 * 148 || d.NTILE < 8) ? d.NTILE : 4) : 8;
     // (finer work items would shorten the tail left when the overlapped clip kernel ends, but measured slower: 1.724 vs 1.701 ms/step)
-    if (getenv("SAVI_DX_TPC")) x.tiles_per_cta = atoi(getenv("SAVI_DX_TPC"));             // development knob
+    if (savi_options().dx_tpc > 0) x.tiles_per_cta = savi_options().dx_tpc;                // development knob
     const int smem = dx_smem_total(d.I);
     cudaError_t e = cudaFuncSetAttribute(dx_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) return e;
     x.flags = overlap ? reinterpret_cast<const int*>(reinterpret_cast<const unsigned char*>(a.ws) + a.wl.flags) : nullptr;
     x.flag_target = d.CN;
-    x.gate_last = getenv("SAVI_DX_GATE_LAST") ? 1 : 0;
-    x.trace = (a.dbg && getenv("SAVI_DX_TRACE")) ? a.dbg + 64 : nullptr;    // the debug buffer then holds 64 + 3 * grid + 2 entries
+    x.gate_last = savi_options().dx_gate_last;
+    x.trace = (a.dbg && savi_options().dx_trace) ? a.dbg + 64 : nullptr;    // the debug buffer then holds 64 + 3 * grid + 2 entries
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3((d.NTILE + x.tiles_per_cta - 1) / x.tiles_per_cta, d.B * d.T);
     cfg.blockDim = dim3(DX_THREADS);

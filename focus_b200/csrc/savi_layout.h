@@ -176,13 +176,15 @@ struct SavedLayout {
 
 static inline void savi_saved_layout(const Dims& d, SavedLayout& L) {
     int64_t b = 0;
-    L.xhat = b;  b += (int64_t)d.B * d.T * d.N * d.D * d.tok_bytes; b = (b + 255) / 256 * 256;
+    // (the tcgen05 kernels read the LayerNorm'd tokens from the swizzled token image `ximg` only: no row-major copy is kept)
+    L.xhat = b;  b += d.umma ? 0 : (int64_t)d.B * d.T * d.N * d.D * d.tok_bytes; b = (b + 255) / 256 * 256;
     L.stats = b; b += (int64_t)d.B * d.T * d.N * 2 * 4;             b = (b + 255) / 256 * 256;
     L.fbase = b;
     int64_t f = 0;
     auto take = [&](int64_t rows, int64_t w) { int64_t r = f; f += rows * w; f = (f + 3) / 4 * 4; return r; };
     const int64_t R = (int64_t)d.S * d.B * d.K, Rm = (int64_t)d.Sm * d.B * d.K, Rp = (int64_t)d.Sp * d.B * d.K;
-    L.hp = take(R, d.Ds); L.q = take(R, d.Ds); L.qk = take(R, d.D); L.ux = take(R, d.D); L.u = take(R, d.Ds);
+    // (q and U are never formed on the tcgen05 path: project_q / project_k and project_v / gru.weight_ih are folded)
+    L.hp = take(R, d.Ds); L.q = take(d.umma ? 0 : R, d.Ds); L.qk = take(R, d.D); L.ux = take(R, d.D); L.u = take(d.umma ? 0 : R, d.Ds);
     L.r = take(R, d.Ds); L.z = take(R, d.Ds); L.n = take(R, d.Ds); L.ghn = take(R, d.Ds);
     L.ssum = take((int64_t)d.S * d.B, d.KP);
     L.hg = take(Rm, d.Ds); L.a = take(Rm, d.M);

@@ -97,7 +97,7 @@ cudaError_t savi_launch_backward(const BwdArgs& a, const void* inputs, void* gra
     cudaError_t e = cudaMemsetAsync(a.grad_params, 0, (size_t)a.po.total * sizeof(float), st);
     if (e != cudaSuccess) return e;
     const bool umma_bwd = d.umma != 0;     // the tcgen05 forward saves only what the tcgen05 backward reads (no q, no U)
-    const bool overlap_dx = umma_bwd && !getenv("SAVI_NO_OVERLAP");
+    const bool overlap_dx = umma_bwd && !savi_options().no_overlap;
     if (umma_bwd) {
         e = cudaMemsetAsync(reinterpret_cast<unsigned char*>(a.ws) + a.wl.flags, 0, ((size_t)d.B * d.T + 1) * sizeof(int), st);
         if (e != cudaSuccess) return e;

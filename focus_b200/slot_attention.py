@@ -235,4 +235,9 @@ class SlotAttentionVideo(nn.Module):
                                                *self._ordered_params())
         if out_dtype != cd:
             slots, attns = slots.to(out_dtype), attns.to(out_dtype)
+        if torch.is_autocast_enabled("cuda"):
+            # Output dtypes of the reference under torch.autocast("cuda") (tools/steve_train_net.py:95; probed on a B200,
+            # tests/test_reference_integration.py): `slots` leave nn.GRUCell / nn.Linear, which autocast runs in the
+            # autocast dtype, `attns` leave F.softmax, which autocast runs in float32 — whatever dtype `inputs` had.
+            slots, attns = slots.to(torch.get_autocast_dtype("cuda")), attns.float()
         return slots, attns

@@ -13,9 +13,15 @@
  *  - plain pointers and sizes only; no torch / C++ types cross this boundary;
  *  - every pointer is a DEVICE pointer unless the name ends in _host;
  *  - the caller owns all memory (outputs, saved-for-backward, workspaces); the
- *    library allocates nothing and keeps no mutable global state;
+ *    library allocates no device memory.  Its only mutable global state is opt-in
+ *    and process-wide: the development options of savi_set_option(), the event
+ *    pairs of savi_profile_enable() and the savi_debug_set_phase_buffer() pointer.
+ *    With none of them touched (the default) savi_query / savi_pack_params /
+ *    savi_forward / savi_backward read nothing but their arguments;
  *  - all work is enqueued on `stream` (a cudaStream_t passed as void*); no host
- *    synchronisation inside, safe for CUDA-graph capture and one-process-per-GPU;
+ *    synchronisation inside; the launch sequence is shape-static, so a stream
+ *    capture of pack + forward + backward replays as a CUDA graph
+ *    (tests/test_cabi_gpu.py) and one process per GPU needs no coordination;
  *  - every entry point returns 0 or a negative SAVI_E* code; savi_last_error()
  *    returns a thread-local message.  Nothing aborts, throws or falls back to a
  *    CPU / library path.
@@ -131,6 +137,14 @@ int savi_last_launch_count(void);
 #define SAVI_PROFILE_SLOTS 6
 int savi_profile_enable(int on);
 int savi_profile_read(float* ms_host, int n);
+
+/* Process-wide development options (A/B measurements, tests).  Initial values come from the SAVI_<NAME> environment
+ * variables, read once when the library is loaded; nothing on the forward / backward path reads the environment.
+ *   "disable_umma"  never dispatch to the tcgen05 clip kernels      "disable_mma"  never use a tensor-core family
+ *   "no_overlap"    run d_inputs / weight gradients after the backward clip kernel instead of overlapped with it
+ *   "no_opstage", "dx_trace", "dx_tpc", "dx_gate_last"  kernel-tuning knobs (focus_b200/csrc/savi_args.h)
+ * Returns SAVI_EINVAL for an unknown name.  Not thread-safe against concurrent forward / backward calls. */
+int savi_set_option(const char* name, int value);
 
 /* Development aid: when set to a device buffer of 64 int64 counters, CTA 0 of the clip kernels
  * accumulates the SM cycles spent in each phase of the recurrence (tools/phase_times.py).

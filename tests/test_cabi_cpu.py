@@ -36,7 +36,16 @@ def test_query_sizes_and_validation():
     ok = L.SaviShape(B=64, T=6, N=1024, D=128, Ds=128, M=128, K=24, I=3, blocks=1, heads=4, dtype=1, cluster=0, eps=1e-8, ln_eps=1e-5)
     sz = L.query(ok)
     assert sz.n_params == 33 and sz.param_floats == 380288 and sz.cluster == 2
-    assert sz.saved_bytes > 64 * 6 * 1024 * 128 * 2
+    tokens = 64 * 6 * 1024 * 128 * 2
+    # tcgen05 path: ONE copy of the LayerNorm'd tokens (the swizzled image, 100 MB) + ~200 MB of fp32 slot-side records
+    assert 2 * tokens < sz.saved_bytes < 3 * tokens, sz.saved_bytes
+    # heads only matter when there are predictor blocks (the reference builds no attention otherwise: transformer.py:94-101)
+    L.query(L.SaviShape(B=1, T=2, N=8, D=16, Ds=16, M=16, K=4, I=1, blocks=0, heads=3, dtype=0, cluster=0, eps=1e-8, ln_eps=1e-5))
+    with pytest.raises(RuntimeError, match="65535"):  # grid limit of the token-parallel kernels
+        L.query(L.SaviShape(B=11000, T=6, N=8, D=16, Ds=16, M=16, K=4, I=1, blocks=0, heads=1, dtype=0, cluster=0, eps=1e-8, ln_eps=1e-5))
+    with pytest.raises(RuntimeError, match="unknown option"):
+        L.set_option("no_such_option", 1)
+    L.set_option("no_overlap", 0)
     for field, bad in (("K", 65), ("K", 0), ("D", 12), ("Ds", 130), ("heads", 3), ("blocks", 5), ("dtype", 7), ("cluster", 3), ("I", 0)):
         s = L.SaviShape(B=1, T=1, N=8, D=16, Ds=16, M=16, K=4, I=1, blocks=1, heads=2, dtype=0, cluster=0, eps=1e-8, ln_eps=1e-5)
         setattr(s, field, bad)

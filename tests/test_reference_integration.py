@@ -93,16 +93,21 @@ def test_steve_training_step_with_swapped_savi_fp32():
     assert err(o[3].detach().cpu().numpy(), r[3].detach().cpu().numpy()) < 1e-4            # attention overlays
     assert abs(o[4] - r[4]) <= 1e-3 * r[4]                                                   # global gradient norm
     gr = dict(ref.named_parameters())
-    worst = 0.0
+    gmax = max(float(p.grad.abs().max()) for p in ref.parameters() if p.grad is not None)
+    worst, worst_name = 0.0, None
     for n, p in ours.named_parameters():
         if not p.requires_grad:                                                               # steve_encoder.pos.pe is a frozen grid
             continue
         assert p.grad is not None, n                                                          # clip_grad_norm_ needs every .grad
         g = gr[n].grad
         den = float(g.abs().max())
-        if den > 0:
-            worst = max(worst, float((p.grad - g).abs().max()) / den)
-    assert worst < 2e-3, worst        # whole-model gradients (cuDNN convolutions, fp32 eager elsewhere) incl. every .savi tensor
+        if den <= 1e-6 * gmax:                      # structurally zero (savi.norm_slots.bias): absolute bound instead
+            den = gmax
+        e = float((p.grad - g).abs().max()) / den
+        if e > worst:
+            worst, worst_name = e, n
+    # whole-model gradients through the swapped module (cuDNN convolutions and fp32 eager everywhere else), every tensor by its own max
+    assert worst < 2e-3, (worst_name, worst)
 
 
 @needs_ref

@@ -17,6 +17,7 @@ PATH_NAMES = {0: "simt-fp32", 1: "mma.sync-bf16", 2: "tcgen05-bf16"}
 
 EXPORTS = ["savi_version", "savi_last_error", "savi_query", "savi_param_layout", "savi_pack_params",
            "savi_forward", "savi_backward", "savi_last_launch_count", "savi_profile_enable", "savi_profile_read", "savi_debug_set_phase_buffer", "savi_set_option"]
+EXPORTS_STEVE = ["steve_attention_overlay", "steve_ari_tables"]            # include/focus_steve.h
 
 
 class SaviShape(ctypes.Structure):
@@ -59,6 +60,11 @@ def _load():
     lib.savi_debug_set_phase_buffer.restype = ip
     lib.savi_set_option.argtypes = [ctypes.c_char_p, ip]
     lib.savi_set_option.restype = ip
+    i64 = ctypes.c_int64
+    lib.steve_attention_overlay.argtypes = [vp, ip, vp, vp, vp, i64, ip, ip, ip, ip, ip, ip, vp]
+    lib.steve_attention_overlay.restype = ip
+    lib.steve_ari_tables.argtypes = [vp, vp, vp, ip, ip, ip, i64, vp]
+    lib.steve_ari_tables.restype = ip
     return lib
 
 

@@ -19,6 +19,14 @@ static int fail(int code, const char* fmt, ...) {
     va_end(ap);
     return code;
 }
+// same, for the other translation units of the library (steve_neighbors.cu)
+int savi_set_error(int code, const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
 static int cuda_fail(cudaError_t e, const char* what) {
     return fail(SAVI_ECUDA, "%s: %s (%s)", what, cudaGetErrorName(e), cudaGetErrorString(e));
 }

@@ -89,3 +89,16 @@ def steve_config(img_size=32, dim=128, slot_size=128, mlp_hidden=128, num_slots=
                        IMG_CHANNELS=3, IMG_SIZE=img_size, VOCAB_SIZE=vocab, DIM=dim, NUM_PREDICTOR_BLOCKS=blocks,
                        NUM_PREDICTOR_HEADS=heads, PREDICTOR_DROPOUT=dropout,
                        DECODER=ns(DIM=dim, NUM_BLOCKS=dec_blocks, NUM_HEADS=dec_heads, DROPOUT=dropout)))
+
+
+def load_reference_metrics():
+    """The reference's slowfast/utils/metrics.py (evaluate_ari, compute_mask_ari, compute_ari), loaded by file path: the
+    slowfast.utils package itself pulls iopath / fvcore."""
+    import importlib.util
+    path = os.path.join(REFERENCE_ROOT, "slowfast", "utils", "metrics.py")
+    if not os.path.isfile(path):
+        raise RuntimeError("reference metrics.py not present under %s" % REFERENCE_ROOT)
+    spec = importlib.util.spec_from_file_location("_focus_reference_metrics", path)
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod

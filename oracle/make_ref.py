@@ -5,6 +5,7 @@ TEST INFRASTRUCTURE ONLY.  `/root/reference` exists only in the build container;
 snapshot.  It copies, byte for byte, the four source files of the reference's STEVE package
 
     slowfast/models/STEVE/{steve.py, transformer.py, utils.py, dvae.py}   (+ the empty __init__.py)
+    slowfast/utils/metrics.py                                             (FG-ARI, for the §8f N4 parity tests)
 
 into `oracle/_ref/slowfast/models/STEVE/` and writes `oracle/_ref/slowfast/models/build.py`, a stand-in of our own for
 the only symbol steve.py takes from the rest of PySlowFast (`MODEL_REGISTRY`, reference slowfast/models/build.py:7-9;
@@ -28,7 +29,8 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 REF_ROOT = os.environ.get("FOCUS_REFERENCE_ROOT", "/root/reference")
 OUT = os.path.join(HERE, "_ref")
 FILES = ["slowfast/models/STEVE/__init__.py", "slowfast/models/STEVE/steve.py", "slowfast/models/STEVE/transformer.py",
-         "slowfast/models/STEVE/utils.py", "slowfast/models/STEVE/dvae.py"]
+         "slowfast/models/STEVE/utils.py", "slowfast/models/STEVE/dvae.py",
+         "slowfast/utils/metrics.py"]                 # FG-ARI; loaded by path, never through slowfast.utils
 BUILD_STUB = '''"""Stand-in (ours, not reference code) for slowfast/models/build.py: only MODEL_REGISTRY is needed by STEVE/steve.py."""
 from fvcore.common.registry import Registry
 

@@ -298,6 +298,7 @@ def run_ours(args, cfg, rank, world, local_rank):
     # incl. zero_grad and, for N > 1, the NCCL gradient all-reduce): same kernels, same work, no host launch gaps.
     graph_ms = None
     graph_err = None
+    graph = None
     if not args.no_graph:
         try:
             cs = torch.cuda.Stream(dev)
@@ -420,9 +421,27 @@ def run_ours(args, cfg, rank, world, local_rank):
     # token LayerNorm + forward clip kernel, then backward clip kernel + weight gradients + d_inputs
     launches_per_step = fwd_launches + bwd_launches
 
-    if rank != 0:
+    def shutdown():
+        """Release the captured graph (it holds NCCL kernels when N > 1) BEFORE the process group goes away, and never let a
+        stuck communicator teardown keep the job alive: the JSON line is already out, so a watchdog ends the process."""
+        nonlocal graph
+        if graph is not None:
+            graph.reset()
+            graph = None
+        torch.cuda.synchronize(dev)
         if world > 1:
-            dist.destroy_process_group()
+            sys.stdout.flush(); sys.stderr.flush()
+            wd = threading.Timer(20.0, lambda: os._exit(0))
+            wd.daemon = True
+            wd.start()
+            try:
+                dist.barrier()
+                dist.destroy_process_group()
+            finally:
+                wd.cancel()
+
+    if rank != 0:
+        shutdown()
         return
     # ---- roofline of the dominant kernel ----
     peak, peak_src = measured_peaks()
@@ -461,8 +480,7 @@ def run_ours(args, cfg, rank, world, local_rank):
     sys.stdout.flush()
     os.dup2(saved_stdout, 1)
     print(json.dumps(line), flush=True)
-    if world > 1:
-        dist.destroy_process_group()
+    shutdown()
 
 
 def main():

@@ -17,7 +17,7 @@ PATH_NAMES = {0: "simt-fp32", 1: "mma.sync-bf16", 2: "tcgen05-bf16"}
 
 EXPORTS = ["savi_version", "savi_last_error", "savi_query", "savi_param_layout", "savi_pack_params",
            "savi_forward", "savi_backward", "savi_last_launch_count", "savi_profile_enable", "savi_profile_read", "savi_debug_set_phase_buffer", "savi_set_option"]
-EXPORTS_STEVE = ["steve_attention_overlay", "steve_ari_tables"]            # include/focus_steve.h
+EXPORTS_STEVE = ["steve_attention_overlay", "steve_ari_tables", "steve_token_mlp", "steve_token_mlp_ws_bytes"]            # include/focus_steve.h
 
 
 class SaviShape(ctypes.Structure):
@@ -65,6 +65,10 @@ def _load():
     lib.steve_attention_overlay.restype = ip
     lib.steve_ari_tables.argtypes = [vp, vp, vp, ip, ip, ip, i64, vp]
     lib.steve_ari_tables.restype = ip
+    lib.steve_token_mlp_ws_bytes.argtypes = [ip]
+    lib.steve_token_mlp_ws_bytes.restype = i64
+    lib.steve_token_mlp.argtypes = [vp] * 8 + [ip, i64, ip, ip, ctypes.c_float, vp, vp]
+    lib.steve_token_mlp.restype = ip
     return lib
 
 

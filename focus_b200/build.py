@@ -16,6 +16,7 @@ UNITS = [("savi_api.cu", "savi_api.o", []),
          ("savi_dx_umma.cu", "savi_dx_umma.o", []),
          ("savi_wgrad_umma.cu", "savi_wgrad_umma.o", []),
          ("steve_neighbors.cu", "steve_neighbors.o", []),
+         ("steve_token_mlp.cu", "steve_token_mlp.o", []),
          ("savi_fwd.cu", "savi_fwd_f32.o", ["-DSAVI_TOK=float", "-DSAVI_SUFFIX=f32"]),
          ("savi_fwd.cu", "savi_fwd_bf16.o", ["-DSAVI_TOK=__nv_bfloat16", "-DSAVI_SUFFIX=bf16"]),
          ("savi_bwd.cu", "savi_bwd_f32.o", ["-DSAVI_TOK=float", "-DSAVI_SUFFIX=f32"]),

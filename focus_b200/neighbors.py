@@ -1,6 +1,8 @@
-"""B200-native versions of the two consumers next to the slot-attention path, with the
+"""B200-native versions of the components next to the slot-attention path, with the
 reference's own call signatures.  CUDA only (include/focus_steve.h); no CPU / PyTorch fallback.
 
+  token_mlp(emb, layer_norm, mlp)                 reference slowfast/models/STEVE/steve.py:307-309 / :342-344: the encoder tail
+                                                  that turns the CNN map into the slot-attention module's `inputs`
   attention_overlay(video, attns, H_enc, W_enc)   reference slowfast/models/STEVE/steve.py:314-319 (STEVE.forward) and
                                                   :349-355 (STEVE.encode): the per-slot attention overlays
   evaluate_ari(true_mask, pred_mask)              reference slowfast/utils/metrics.py:58-83, the FG-ARI of
@@ -20,6 +22,35 @@ def _stream(dev):
 
 def _p(t):
     return ctypes.c_void_p(t.data_ptr()) if t is not None else ctypes.c_void_p(0)
+
+
+def token_mlp(emb, layer_norm, mlp, out_dtype=torch.bfloat16):
+    """emb [BT, C, H, W] fp32 (CNN + positional embedding, channels first), `layer_norm` = steve_encoder.layer_norm,
+    `mlp` = steve_encoder.mlp (Sequential(Linear, ReLU, Linear)) -> emb_set [BT, H*W, C] =
+        mlp(layer_norm(emb.permute(0, 2, 3, 1).flatten(start_dim=1, end_dim=2)))
+    in one kernel.  Forward only: use it under torch.no_grad() (STEVE.encode, evaluation); training keeps the reference's
+    own modules, whose backward autograd provides."""
+    if not emb.is_cuda:
+        raise RuntimeError("focus_b200.neighbors.token_mlp has no CPU path")
+    if torch.is_grad_enabled() and (emb.requires_grad or any(p.requires_grad for p in list(layer_norm.parameters()) + list(mlp.parameters()))):
+        raise RuntimeError("focus_b200.neighbors.token_mlp is forward-only: call it under torch.no_grad() (evaluation / STEVE.encode)")
+    BT, C, H, W = emb.shape
+    lin1, lin2 = mlp[0], mlp[2]
+    if tuple(lin1.weight.shape) != (C, C) or tuple(lin2.weight.shape) != (C, C) or tuple(layer_norm.normalized_shape) != (C,):
+        raise ValueError("token_mlp expects LayerNorm(C) -> Linear(C, C) -> ReLU -> Linear(C, C) with C = emb.shape[1] = %d" % C)
+    if out_dtype not in (torch.float32, torch.bfloat16):
+        raise TypeError("out_dtype must be torch.float32 or torch.bfloat16")
+    dev = emb.device
+    f = lambda t: t.detach().float().contiguous()
+    emb = f(emb)
+    out = torch.empty(BT, H * W, C, dtype=out_dtype, device=dev)
+    ws = torch.empty(int(_lib.lib.steve_token_mlp_ws_bytes(C)), dtype=torch.uint8, device=dev)
+    args = [f(layer_norm.weight), f(layer_norm.bias), f(lin1.weight), f(lin1.bias), f(lin2.weight), f(lin2.bias)]
+    with torch.cuda.device(dev):
+        _lib.check(_lib.lib.steve_token_mlp(_p(emb), *[_p(t) for t in args], _p(out),
+                                            _lib.SAVI_DTYPE_F32 if out_dtype == torch.float32 else _lib.SAVI_DTYPE_BF16,
+                                            BT, H * W, C, float(layer_norm.eps), _p(ws), _stream(dev)), "steve_token_mlp")
+    return out
 
 
 def attention_overlay(video, attns, H_enc, W_enc, want_overlay=True, want_up=True):

@@ -182,6 +182,24 @@ class SlotAttentionVideo(nn.Module):
         if num_predictor_blocks > 0:
             assert slot_size % num_predictor_heads == 0, "d_model must be divisible by num_heads"
         self.predictor = _Predictor(num_predictor_blocks, slot_size)
+        if self._dropout_active():
+            import warnings
+            warnings.warn("focus_b200.SlotAttentionVideo: predictor dropout=%g is accepted for evaluation only; .train() will raise "
+                          "(every FOCUS config sets SLOTS.PREDICTOR_DROPOUT = 0.0; construct with dropout=0.0 to train: the "
+                          "parameters and the state_dict do not depend on it)" % dropout, stacklevel=2)
+
+    def _dropout_active(self):
+        return self.dropout > 0 and self.num_predictor_blocks > 0
+
+    def train(self, mode=True):
+        """Training-mode predictor dropout (reference transformer.py:12-13,44,48,68; constructor default 0.1, steve.py:16) is
+        not implemented by the CUDA kernels: fail when training is switched ON (the first thing a trainer does,
+        tools/steve_train_net.py:88), not in the middle of an epoch.  Evaluation (dropout is the identity) is unaffected."""
+        if mode and getattr(self, "predictor", None) is not None and self._dropout_active():
+            raise NotImplementedError(
+                "predictor dropout > 0 in training mode is not supported (every FOCUS config uses SLOTS.PREDICTOR_DROPOUT = 0.0); "
+                "construct with dropout=0.0 (same parameters / state_dict) or keep the module in .eval()")
+        return super().train(mode)
 
     def _ordered_params(self):
         """Parameters in the order of the flat buffer (include/focus_savi.h: savi_param_layout)."""
@@ -220,7 +238,7 @@ class SlotAttentionVideo(nn.Module):
             raise TypeError("compute_dtype must be None, torch.float32 or torch.bfloat16, got %s" % cd)
         if inputs.dtype != cd:
             inputs = inputs.to(cd)                 # differentiable: the gradient comes back in the caller's dtype
-        if self.training and self.dropout > 0 and self.num_predictor_blocks > 0:
+        if self.training and self._dropout_active():     # a freshly constructed module is in training mode: see train()
             raise NotImplementedError(
                 "predictor dropout > 0 in training mode is not supported (every FOCUS config uses "
                 "SLOTS.PREDICTOR_DROPOUT = 0.0); construct with dropout=0.0 or call .eval()")

@@ -1,7 +1,8 @@
-"""numpy restatement of the two consumers next to the slot-attention path.
+"""numpy restatement of the components next to the slot-attention path.
 
 TEST INFRASTRUCTURE ONLY (same rules as oracle/savi_numpy.py): nothing under focus_b200/ imports this file.
 
+  token_mlp         : /root/reference/slowfast/models/STEVE/steve.py:307-309 (STEVE.forward), :342-344 (STEVE.encode)
   attention_overlay : /root/reference/slowfast/models/STEVE/steve.py:314-319 (STEVE.forward), :349-355 (STEVE.encode)
   ari_tables / evaluate_ari : /root/reference/slowfast/utils/metrics.py:10-36 (compute_ari), :40-57 (compute_mask_ari),
                               :58-83 (evaluate_ari)
@@ -9,6 +10,28 @@ Pinned in tests/test_neighbors.py against the reference functions themselves (im
 oracle/_ref copies on the GPU box) on seeded inputs, ties and degenerate tables included.
 """
 import numpy as np
+
+
+def _round_bf16(a):
+    f = np.ascontiguousarray(a, dtype=np.float32)
+    u = f.view(np.uint32).astype(np.uint64)
+    u = ((u + 0x7FFF + ((u >> 16) & 1)) >> 16) << 16
+    return u.astype(np.uint32).view(np.float32).astype(np.asarray(a).dtype).reshape(np.shape(a))
+
+
+def token_mlp(emb, ln_w, ln_b, w1, b1, w2, b2, eps=1e-5, operand_dtype=None):
+    """emb [BT,C,H,W] -> emb_set [BT,H*W,C] = mlp(layer_norm(emb.permute(0,2,3,1).flatten(1,2)))  (steve.py:307-308), float64.
+    operand_dtype="bf16" models the CUDA kernel's tensor-core operands: the LayerNorm output, both weight matrices and the
+    hidden activations are rounded to bfloat16 before each product (accumulation and biases stay full precision)."""
+    r = _round_bf16 if operand_dtype == "bf16" else (lambda a: a)
+    x = np.asarray(emb, np.float64)
+    BT, C, H, W = x.shape
+    x = x.transpose(0, 2, 3, 1).reshape(BT, H * W, C)
+    mu = x.mean(-1, keepdims=True)
+    xc = x - mu
+    xn = xc / np.sqrt((xc * xc).mean(-1, keepdims=True) + eps) * np.asarray(ln_w, np.float64) + np.asarray(ln_b, np.float64)
+    h = np.maximum(r(xn) @ r(np.asarray(w1, np.float64)).T + np.asarray(b1, np.float64), 0.0)
+    return r(h) @ r(np.asarray(w2, np.float64)).T + np.asarray(b2, np.float64)
 
 
 def attention_overlay(video, attns, H_enc, W_enc):

@@ -72,6 +72,22 @@ def test_oracle_overlay_equals_reference_encode_cpu():
     assert np.array_equal(o_up, up.numpy()) and np.array_equal(o_vis, vis.numpy())
 
 
+@needs_ref
+def test_oracle_token_mlp_equals_reference_modules_cpu():
+    """steve.py:307-308 executed with the reference's own STEVEEncoder modules against the oracle (fp64)."""
+    steve = LR.load_reference_steve()
+    torch.manual_seed(0)
+    enc = steve.STEVE(LR.steve_config()).steve_encoder.double()
+    with torch.no_grad():
+        for p_ in list(enc.layer_norm.parameters()) + [enc.mlp[0].bias, enc.mlp[2].bias]:
+            p_.add_(0.3 * torch.randn_like(p_))
+        emb = torch.randn(3, 128, 16, 16, dtype=torch.float64)
+        want = enc.mlp(enc.layer_norm(emb.permute(0, 2, 3, 1).flatten(start_dim=1, end_dim=2)))
+    got = ON.token_mlp(emb.numpy(), *[t.detach().numpy() for t in (enc.layer_norm.weight, enc.layer_norm.bias, enc.mlp[0].weight, enc.mlp[0].bias,
+                                                                    enc.mlp[2].weight, enc.mlp[2].bias)])
+    assert np.abs(got - want.numpy()).max() <= 1e-12 * np.abs(want.numpy()).max()
+
+
 def test_library_exports_the_neighbour_symbols():
     import ctypes
     import re
@@ -153,3 +169,54 @@ def test_cuda_overlay_equals_reference_encode_on_gpu():
     h.remove()
     o_vis, o_up = neighbors.attention_overlay(video, grabbed["attn"], 16, 16)
     assert torch.equal(o_up, up) and torch.equal(o_vis, vis)
+
+
+def _encoder_tail(C, seed):
+    from focus_b200.slot_attention import _linear
+    torch.manual_seed(seed)
+    ln = torch.nn.LayerNorm(C)
+    mlp = torch.nn.Sequential(_linear(C, C, weight_init="kaiming"), torch.nn.ReLU(), _linear(C, C))     # steve.py:224-227
+    with torch.no_grad():
+        for p_ in list(ln.parameters()) + [mlp[0].bias, mlp[2].bias]:
+            p_.add_(0.3 * torch.randn_like(p_))
+    return ln, mlp
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("case", [(6, 128, 32, 32, torch.bfloat16), (2, 128, 32, 32, torch.float32), (3, 64, 16, 16, torch.bfloat16),
+                                  (2, 192, 64, 64, torch.bfloat16), (5, 128, 9, 7, torch.bfloat16), (1, 64, 4, 5, torch.float32)])
+def test_cuda_token_mlp_against_oracle(case):
+    from focus_b200 import neighbors
+    from tests._util import err
+    BT, C, H, W, odt = case
+    ln, mlp = _encoder_tail(C, seed=C + H)
+    emb = torch.randn(BT, C, H, W, generator=torch.Generator().manual_seed(BT)) * 1.5 + 0.2
+    with torch.no_grad():
+        got = neighbors.token_mlp(emb.cuda(), ln.cuda(), mlp.cuda(), out_dtype=odt)
+    assert got.shape == (BT, H * W, C) and got.dtype == odt
+    prm = [t.detach().cpu().numpy() for t in (ln.weight, ln.bias, mlp[0].weight, mlp[0].bias, mlp[2].weight, mlp[2].bias)]
+    exact = ON.token_mlp(emb.numpy(), *prm)
+    quant = ON.token_mlp(emb.numpy(), *prm, operand_dtype="bf16")
+    g = got.float().cpu().numpy()
+    assert err(g, exact) < 2e-2                                           # accuracy tier: the bf16 bar against the unquantised oracle
+    assert err(g, quant) < (6e-3 if odt == torch.bfloat16 else 2e-4)      # implementation tier: operands rounded as the kernel rounds them
+
+
+@needs_ref
+@pytest.mark.gpu
+def test_cuda_token_mlp_in_the_reference_encode_path():
+    """The reference's STEVE.encode up to `emb_set` (steve.py:336-344) against the fused kernel fed with the same CNN map."""
+    from focus_b200 import neighbors
+    from tests._util import err
+    steve = LR.load_reference_steve()
+    torch.manual_seed(0)
+    dev = torch.device("cuda", 0)
+    model = steve.STEVE(LR.steve_config()).to(dev).eval()
+    video = torch.rand(2, 3, 3, 32, 32, device=dev)
+    with torch.no_grad():
+        emb = model.steve_encoder.pos(model.steve_encoder.cnn(video.flatten(end_dim=1)))
+        want = model.steve_encoder.mlp(model.steve_encoder.layer_norm(emb.permute(0, 2, 3, 1).flatten(start_dim=1, end_dim=2)))
+        got = neighbors.token_mlp(emb, model.steve_encoder.layer_norm, model.steve_encoder.mlp, out_dtype=torch.float32)
+    assert err(got.cpu().numpy(), want.cpu().numpy()) < 2e-2
+    with pytest.raises(RuntimeError, match="forward-only"):
+        neighbors.token_mlp(emb, model.steve_encoder.layer_norm, model.steve_encoder.mlp)

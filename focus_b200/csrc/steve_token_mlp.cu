@@ -69,8 +69,11 @@ __global__ void __launch_bounds__(NTHR) token_mlp_kernel(const __grid_constant__
     extern __shared__ __align__(1024) unsigned char sm[];
     unsigned char* sW = sm;                                  // W1 | W2 images
     unsigned char* sA = sm + 2 * WB;                         // A tile (LayerNorm'd tokens, then the hidden activations)
-    unsigned char* sO = sA + AB;                             // staged output rows
-    float* sP = reinterpret_cast<float*>(sO + OB);           // ln_w | ln_b | b1 | b2
+    // staged output rows: a bf16 tile is exactly as large as the A tile and is written only after the second product has
+    // consumed it, so it aliases the A buffer (the next tile waits for the bulk store's reads before it writes A again)
+    constexpr bool ALIAS_O = sizeof(OutT) == 2;
+    unsigned char* sO = ALIAS_O ? sA : sA + AB;
+    float* sP = reinterpret_cast<float*>(sA + AB + (ALIAS_O ? 0 : OB));   // ln_w | ln_b | b1 | b2
     uint64_t* bars = reinterpret_cast<uint64_t*>(sP + 4 * C);
     uint32_t* tslot = reinterpret_cast<uint32_t*>(bars + 2);
     const int tid = threadIdx.x, warp = tid >> 5;
@@ -247,7 +250,7 @@ __global__ void __launch_bounds__(NTHR) token_mlp_kernel(const __grid_constant__
 }
 
 template <int C, typename OutT> static size_t smem_bytes() {
-    return (size_t)2 * C * C * 2 + (size_t)TOK * C * 2 + (size_t)TOK * C * sizeof(OutT) + 4 * C * sizeof(float) + 64;
+    return (size_t)2 * C * C * 2 + (size_t)TOK * C * 2 + (sizeof(OutT) == 2 ? 0 : (size_t)TOK * C * sizeof(OutT)) + 4 * C * sizeof(float) + 64;
 }
 template <int C, typename OutT> static cudaError_t launch(const Args& a, cudaStream_t st) {
     const size_t smem = smem_bytes<C, OutT>();

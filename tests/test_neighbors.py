@@ -199,7 +199,9 @@ def test_cuda_token_mlp_against_oracle(case):
     quant = ON.token_mlp(emb.numpy(), *prm, operand_dtype="bf16")
     g = got.float().cpu().numpy()
     assert err(g, exact) < 2e-2                                           # accuracy tier: the bf16 bar against the unquantised oracle
-    assert err(g, quant) < (6e-3 if odt == torch.bfloat16 else 2e-4)      # implementation tier: operands rounded as the kernel rounds them
+    # implementation tier: operands rounded as the kernel rounds them (a LayerNorm output or hidden activation that sits on a
+    # bf16 rounding boundary may round the other way in fp32 than in fp64: a few 2^-9 operand flips, ~1e-3 on the output)
+    assert err(g, quant) < (6e-3 if odt == torch.bfloat16 else 2e-3)
 
 
 @needs_ref

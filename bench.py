@@ -34,6 +34,8 @@ CONFIGS = {
     "c2": dict(B=64, T=6, N=1024, D=128, Ds=128, M=128, K=24, I=3, blocks=1, heads=4, dtype="bf16"),
     "c3": dict(B=64, T=6, N=4096, D=192, Ds=192, M=192, K=24, I=3, blocks=1, heads=4, dtype="bf16"),
     "c4": dict(B=64, T=24, N=1024, D=128, Ds=128, M=128, K=11, I=2, blocks=1, heads=4, dtype="bf16"),
+    # BASELINE configs[4] sweep corner in the throughput regime (tools/sweep.py; phase breakdowns with tools/phase_times.py n16k)
+    "n16k": dict(B=64, T=2, N=16384, D=128, Ds=128, M=128, K=24, I=3, blocks=1, heads=4, dtype="bf16"),
 }
 METRIC = "slot-attn fwd+bwd frames/sec"
 UNIT = "frames/s"

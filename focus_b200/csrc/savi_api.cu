@@ -329,10 +329,11 @@ __global__ void pack_image_kernel(const __grid_constant__ ImgArgs ia, const floa
             for (int e = 0; e < 4; ++e) b2[e] = __floats2bfloat162_rn(v[2 * e], v[2 * e + 1]);
             out = *reinterpret_cast<const uint4*>(b2);
         } else {                                     // forward orientation: fp16
-            __half2 h2[4];
+            // saturating conversion: a weight beyond fp16's range (65504) stays finite instead of turning the product into inf / NaN
+            unsigned h2[4];
 #pragma unroll
-            for (int e = 0; e < 4; ++e) h2[e] = __floats2half2_rn(v[2 * e], v[2 * e + 1]);
-            out = *reinterpret_cast<const uint4*>(h2);
+            for (int e = 0; e < 4; ++e) asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(h2[e]) : "f"(v[2 * e + 1]), "f"(v[2 * e]));
+            out = make_uint4(h2[0], h2[1], h2[2], h2[3]);
         }
         *reinterpret_cast<uint4*>(blk + off) = out;
     }

@@ -89,27 +89,35 @@ __global__ void __launch_bounds__(NT) ln_tokens_fwd_kernel(const TokT* __restric
     }
 }
 
-// tcgen05 path, D = 128 bf16: 16 lanes per token (one 16-byte chunk each), two tokens per warp, output written
-// only as SWIZZLE_128B operand blocks.  Reads 256 B and writes 256 B per token with full 16-byte accesses.
-static __global__ void __launch_bounds__(256, 6) ln_tokens_fwd_img128_kernel(const __nv_bfloat16* __restrict__ x, float2* __restrict__ stats,
-                                                                   const float* __restrict__ g, const float* __restrict__ b, int64_t rows,
+// tcgen05 path, D = 128 bf16: one CTA per (frame, 128-token tile), 16 lanes per token (one 16-byte chunk each), two tokens per
+// warp and pass, four passes of a warp loaded up front (4 x 16 B in flight per thread at 64 registers -> 4 CTAs per SM; no index
+// divisions in the loop).
+// Output only as SWIZZLE_128B operand blocks: reads 256 B and writes 256 B per token with full 16-byte accesses.
+static __global__ void __launch_bounds__(256, 4) ln_tokens_fwd_img128_kernel(const __nv_bfloat16* __restrict__ x, float2* __restrict__ stats,
+                                                                   const float* __restrict__ g, const float* __restrict__ b,
                                                                    float eps, unsigned char* __restrict__ ximg, int N, int NTILE) {
-    const int lane = threadIdx.x & 31, sub = lane & 15, half = lane >> 4;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, sub = lane & 15, half = lane >> 4;
+    const int frame = blockIdx.x / NTILE, tile = blockIdx.x - frame * NTILE;
     float gg[8], bb[8];
 #pragma unroll
     for (int e = 0; e < 8; ++e) { gg[e] = __ldg(g + sub * 8 + e); bb[e] = __ldg(b + sub * 8 + e); }
-    const int64_t npair = ((int64_t)(rows / N) * NTILE * 128 + 1) / 2;            // padded rows, two per warp
-    for (int64_t pr = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5); pr < npair; pr += (int64_t)gridDim.x * 8) {
-        const int64_t prow = pr * 2 + half;                                       // padded row index: frame * NTILE*128 + n
-        const int64_t frame = prow / (NTILE * 128);
-        const int n = (int)(prow - frame * (NTILE * 128));
+    const __nv_bfloat16* xf = x + (size_t)frame * N * 128;
+#pragma unroll 1
+    for (int it0 = 0; it0 < 8; it0 += 4) {              // two batches of four rows: 4 x 16 B in flight per thread at 64 registers
+    uint4 raw[4];
+#pragma unroll
+    for (int it = 0; it < 4; ++it) {
+        const int n = tile * 128 + (it0 + it) * 16 + warp * 2 + half;
+        raw[it] = (n < N) ? __ldg(reinterpret_cast<const uint4*>(xf + (size_t)n * 128 + sub * 8)) : make_uint4(0u, 0u, 0u, 0u);
+    }
+#pragma unroll
+    for (int it = 0; it < 4; ++it) {
+        const int n = tile * 128 + (it0 + it) * 16 + warp * 2 + half;
         const bool real = n < N;
         float v[8];
-        if (real) Tok<__nv_bfloat16>::load(x + (frame * N + n) * 128 + sub * 8, v);
-        else {
+        const __nv_bfloat162* hp = reinterpret_cast<const __nv_bfloat162*>(&raw[it]);
 #pragma unroll
-            for (int e = 0; e < 8; ++e) v[e] = 0.f;
-        }
+        for (int e = 0; e < 4; ++e) { const float2 f = __bfloat1622float2(hp[e]); v[2 * e] = f.x; v[2 * e + 1] = f.y; }
         float s = 0.f;
 #pragma unroll
         for (int e = 0; e < 8; ++e) s += v[e];
@@ -124,7 +132,7 @@ static __global__ void __launch_bounds__(256, 6) ln_tokens_fwd_img128_kernel(con
         const float rstd = 1.0f / sqrtf(q * (1.0f / 128.0f) + eps);
         uint4 out = make_uint4(0u, 0u, 0u, 0u);
         if (real) {
-            if (sub == 0) stats[frame * N + n] = make_float2(mean, rstd);
+            if (sub == 0) stats[(size_t)frame * N + n] = make_float2(mean, rstd);
             float y[8];
 #pragma unroll
             for (int e = 0; e < 8; ++e) y[e] = (v[e] - mean) * rstd * gg[e] + bb[e];
@@ -134,6 +142,7 @@ static __global__ void __launch_bounds__(256, 6) ln_tokens_fwd_img128_kernel(con
             out.z = *reinterpret_cast<unsigned*>(&p2); out.w = *reinterpret_cast<unsigned*>(&p3);
         }
         *reinterpret_cast<uint4*>(ximg_chunk(ximg, frame, n, sub * 8, NTILE, 128)) = out;   // padding rows are zero-filled
+    }
     }
 }
 
@@ -515,11 +524,8 @@ static cudaError_t launch_ln_fwd(const FwdArgs& a, const void* inputs, cudaStrea
     const int64_t rows = (int64_t)a.d.B * a.d.T * a.d.N;
     if constexpr (sizeof(TokT) == 2) {
         if (a.d.umma && a.d.D == 128) {
-            const int64_t npair = ((int64_t)a.d.B * a.d.T * a.d.NTILE * 128 + 1) / 2;
-            int grid = (int)((npair + 7) / 8);
-            if (grid > 148 * 16) grid = 148 * 16;
-            ln_tokens_fwd_img128_kernel<<<grid, 256, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(inputs),
-                reinterpret_cast<float2*>(a.saved + a.sl.stats), a.packed + a.po.ln_in_w, a.packed + a.po.ln_in_b, rows, a.d.ln_eps,
+            ln_tokens_fwd_img128_kernel<<<(unsigned)(a.d.B * a.d.T * a.d.NTILE), 256, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(inputs),
+                reinterpret_cast<float2*>(a.saved + a.sl.stats), a.packed + a.po.ln_in_w, a.packed + a.po.ln_in_b, a.d.ln_eps,
                 a.saved + a.sl.ximg, a.d.N, a.d.NTILE);
             return cudaGetLastError();
         }

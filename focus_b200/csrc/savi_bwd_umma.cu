@@ -13,7 +13,7 @@ using namespace uc;
 #define UPH(id) do { if (dbg) { const long long t_ = clock64(); dbg[id] += t_ - ph_last; ph_last = t_; } } while (0)
 
 // TMEM columns (64 each)
-enum { TB_A = 0, TB_B = 64, TB_HP = 128, TB_DQK = 192, TB_S0 = 256 /* 4 x 32: logits per warpgroup */, TB_G0 = 384 /* 4 x 32 */,
+enum { TB_A = 0, TB_B = 64, TB_HP = 128, TB_DQK = 192, TB_S0 = 256 /* 4 x 64: [S logits 32 | G 32] per warpgroup */,
        TB_F0 = TB_S0,                         // predictor: the four ffn.2^T tiles live where the token-pass accumulators are
        TB_COLS = 512 };
 enum { B_HP = B_OPND2 };                      // W_hh^T product complete (its operands may be overwritten)
@@ -33,11 +33,15 @@ __device__ __forceinline__ int xop(const Smem& L, int i) { return i == 0 ? L.opA
 
 // ------------------------------------------------------------------------------------------------
 // issuer: attention-step backward products of this CTA's token tiles
-//   P1(i): S[i&1] = xhat_i . [qk_hi | qk_lo],  G[i&1] = xhat_i . [dUx_hi | dUx_lo]
+//   P1(i): [S | G] = xhat_i . [qk_hi | dUx_hi]  +  xhat_i . [qk_lo | dUx_lo]     (two N = 64 MMAs per k-step into one 64-column
+//          accumulator).  S and G share their A operand (the token tile), and one tcgen05.mma costs 45 / 51 / 65 cycles at
+//          N = 32 / 64 / 128 (tools/umma_rate.cu: a ~40-cycle floor per instruction, the 4 KB A read), so pairing them per
+//          precision half instead of four N = 32 MMAs takes the tile's first products from 1440 to 816 cycles; the four
+//          tiles' first products are issued back to back, so this is on the serial chain of every step.
 //   P2(i): DQK   += xhat_i^T . [dL_hi | dL_lo]
 // ------------------------------------------------------------------------------------------------
 __device__ __forceinline__ void issue_token_pass_bwd(Ring& r, bool el, uint64_t* bars, uint32_t tb, int ntile, TokState& ts,
-                                                     uint32_t qk_op, uint32_t dux_op, uint32_t dl0, uint32_t dl1) {
+                                                     uint32_t hi_op, uint32_t lo_op, uint32_t dl0, uint32_t dl1) {
     int ts0[4] = {0, 0, 0, 0};                              // ring stage of the tile's first token block, per in-flight tile
     const uint32_t rb = smem_u32(r.base);
     const uint32_t n0 = ts.nseq;
@@ -60,13 +64,13 @@ __device__ __forceinline__ void issue_token_pass_bwd(Ring& r, bool el, uint64_t*
         }
         __syncwarp();
     };
-    const uint32_t qk0 = dlo_mn(qk_op, BLK), du0 = dlo_mn(dux_op, BLK);
+    const uint32_t hi0 = dlo_mn(hi_op, BLK), lo0 = dlo_mn(lo_op, BLK);
     for (int i = 0; i < ntile; ++i) {
         const uint32_t n = n0 + (uint32_t)i, w = n & 3u;
         mbar_wait(&bars[B_SFREE4 + w], ((n >> 2) & 1u) ^ 1u);           // warpgroup w has drained its previous logits
         fence_after_sync();
         ts0[w] = r.stage;
-        const uint32_t acc_s = tb + TB_S0 + 32u * w, acc_g = tb + TB_G0 + 32u * w;
+        const uint32_t acc_sg = tb + TB_S0 + 64u * w;
 #pragma unroll
         for (int db = 0; db < 2; ++db) {
             mbar_wait(&r.full[r.stage], r.phase);
@@ -74,13 +78,11 @@ __device__ __forceinline__ void issue_token_pass_bwd(Ring& r, bool el, uint64_t*
             const uint32_t a = dlo_k(rb + r.stage * BLK);
             if (el) {
 #pragma unroll
-                for (int k4 = 0; k4 < 4; ++k4) {          // hi and lo halves accumulate into the SAME 32 columns (lo: 64 B into the swizzled row)
+                for (int k4 = 0; k4 < 4; ++k4) {          // hi and lo halves accumulate into the SAME 64 columns [S | G]
                     const uint32_t acc = (db > 0 || k4 > 0) ? 1u : 0u;
                     const uint32_t ko = (uint32_t)(db * 4 + k4) * 128u;
-                    mma_lo(acc_s, a + k4 * 2, qk0 + ko, IDESC_K_MN32, acc);
-                    mma_lo(acc_s, a + k4 * 2, qk0 + 4 + ko, IDESC_K_MN32, 1u);
-                    mma_lo(acc_g, a + k4 * 2, du0 + ko, IDESC_K_MN32, acc);
-                    mma_lo(acc_g, a + k4 * 2, du0 + 4 + ko, IDESC_K_MN32, 1u);
+                    mma_lo(acc_sg, a + k4 * 2, hi0 + ko, IDESC_K_MN64, acc);
+                    mma_lo(acc_sg, a + k4 * 2, lo0 + ko, IDESC_K_MN64, 1u);
                 }
             }
             __syncwarp();
@@ -107,8 +109,8 @@ __device__ __forceinline__ void softmax_bwd_tiles(const Ctx& c, const Dims& d, i
     constexpr float LOG2E = 1.4426950408889634f;
     long long ph_last = clock64();
     const int K = c.K;
-    const uint32_t scol = c.tb + c.tlane + TB_S0 + 32u * (uint32_t)c.wg;
-    const uint32_t gcol = c.tb + c.tlane + TB_G0 + 32u * (uint32_t)c.wg;
+    const uint32_t scol = c.tb + c.tlane + TB_S0 + 64u * (uint32_t)c.wg;
+    const uint32_t gcol = scol + 32u;
     const uint32_t sw = (uint32_t)(c.o & 7);
     for (int i = 0; i < ntile; ++i) {
         const uint32_t nseq = ts.nseq + (uint32_t)i;
@@ -540,8 +542,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) savi_bwd_umma_kernel(const __grid
                     issue_linear(ring, el, X0, tb + TB_HP, 1, 2, false);
                     issue_linear(ring, el, X1, tb + TB_HP, 1, 2, true);
                     issue_linear(ring, el, X3, tb + TB_HP, 1, 2, true); if (el) mma_commit(&bars[B_HP]);             // W_hh^T dgh (consumed at the end of the step)
-                    wait_opnd();                                                           // dUx in X0, qk in X1
-                    issue_token_pass_bwd(ring, el, bars, tb, ntile, ts, X1, X0, X2, X3);
+                    wait_opnd();                                                           // [qk | dUx] hi halves in X0, lo halves in X1
+                    issue_token_pass_bwd(ring, el, bars, tb, ntile, ts, X0, X1, X2, X3);
                     wait_opnd();                                                           // d qk in X0
                     issue_linear(ring, el, X0, tb + TB_B, 1, 2, false); if (el) mma_commit(&bars[B_ACC]);            // d s~ = wqk^T d qk  (folded: dq is never formed)
                 }
@@ -761,8 +763,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) savi_bwd_umma_kernel(const __grid
                     for (int kk = 0; kk < KH; ++kk) if (kk < c.nk) scr[(c.k0 + kk) * F + o] = dux[kk] * ux[kk];
                     mbar_wait(&bars[B_HP], hpcall & 1u);                                   // W_hh^T product done: X0, X1, X3 may be rewritten
                     ++hpcall;
-                    write_operand(c, xop(L, 0), dux);
-                    write_operand(c, xop(L, 1), qk);
+                    write_operand_halves(c, xop(L, 0), xop(L, 1), qk, dux);      // X0 = [qk_hi | dUx_hi], X1 = [qk_lo | dUx_lo]
                     bar_sync_compute();
 #pragma unroll 1
                     for (int k = c.warp; k < K; k += NCW) {

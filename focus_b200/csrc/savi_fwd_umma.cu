@@ -11,8 +11,12 @@ using namespace uc;
 // development aid: cycle counters of compute thread 0 of CTA 0 (tools/phase_times.py); no barriers added
 #define UPH(id) do { if (dbg) { const long long t_ = clock64(); dbg[id] += t_ - ph_last; ph_last = t_; } } while (0)
 
-// TMEM columns: fp32 accumulators, 64 columns each (32 slots x {X_hi, X_lo} partial products)
-enum { TC_A = 0, TC_B = 64, TC_R = 128, TC_Z = 192, TC_HN = 256, TC_IN = 320, TC_S0 = 384, TC_S1 = 448,
+// TMEM columns: fp32 accumulators, 64 columns each (32 slots x {X_hi, X_lo} partial products).  IN shares A's columns (A holds
+// NUMX during the token pass and the mlp.0 product after the GRU gates have been read: never live together with IN), which
+// leaves room for THREE 64-column logits buffers: one tcgen05.mma costs 45 / 51 cycles at N = 32 / 64 (tools/umma_rate.cu),
+// so S = xhat . [qk_hi | qk_lo] as ONE N = 64 MMA per k-step (the thread adds the halves) takes a tile's first product from
+// 720 to 408 cycles; the tiles' first products are issued back to back at the head of every step's chain.
+enum { TC_A = 0, TC_B = 64, TC_R = 128, TC_Z = 192, TC_HN = 256, TC_IN = TC_A, TC_S0 = 320 /* 3 x 64 logits buffers: tile n -> n % 3 */,
        TC_NUMX = TC_A, TC_SSUM = TC_B,        // live only during the token pass, when A and B are dead
        TC_F0 = TC_R,                          // predictor FFN hidden tiles (4 x 64): the GRU accumulators are dead there
        TC_COLS = 512 };
@@ -25,7 +29,7 @@ struct FwdUArgs {
 
 // ------------------------------------------------------------------------------------------------
 // issuer: attention step products of this CTA's token tiles
-//   P1(i): S[i&1]  = xhat_i . [qk_hi | qk_lo]       (A = token tile, K-major;  B = qk operand)
+//   P1(i): S[i%3]  = xhat_i . [qk_hi | qk_lo]       (A = token tile, K-major;  B = qk operand, N = 64)
 //   P2(i): NUMX   += xhat_i^T . [A_hi | A_lo]       (A = token tile, MN-major; B = attention-weight tile)
 //          SSUM   += 1 . [A_hi | A_lo]
 // ------------------------------------------------------------------------------------------------
@@ -65,10 +69,12 @@ __device__ __forceinline__ void issue_token_pass(Ring& r, bool el, unsigned char
     const uint32_t qk0 = dlo_mn(qk_op, BLK);
     for (int i = 0; i < ntile; ++i) {
         const uint32_t n = n0 + (uint32_t)i, w = n & 3u;
-        mbar_wait(&bars[B_SFREE4 + w], ((n >> 2) & 1u) ^ 1u);           // warpgroup w has drained its previous logits
-        fence_after_sync();
+        if (n >= 3u) {                                      // logits buffer n % 3: tile n - 3 (warpgroup (n - 3) & 3) has drained it
+            mbar_wait(&bars[B_SFREE4 + ((n - 3u) & 3u)], ((n - 3u) >> 2) & 1u);
+            fence_after_sync();
+        }
         ts0[w] = r.stage;                                   // the ring has an even number of stages: the pair never wraps
-        const uint32_t acc_s = tb + TC_S0 + 32u * w;
+        const uint32_t acc_s = tb + TC_S0 + 64u * (n % 3u);
 #pragma unroll
         for (int db = 0; db < 2; ++db) {
             mbar_wait(&r.full[r.stage], r.phase);
@@ -76,10 +82,8 @@ __device__ __forceinline__ void issue_token_pass(Ring& r, bool el, unsigned char
             const uint32_t a = dlo_k(rb + r.stage * BLK);
             if (el) {
 #pragma unroll
-                for (int k4 = 0; k4 < 4; ++k4) {          // hi and lo halves of qk accumulate into the SAME 32 columns (lo: 64 B into the swizzled row)
-                    mma_lo(acc_s, a + k4 * 2, qk0 + (db * 4 + k4) * 128, IDESC_K_MN32, (db > 0 || k4 > 0) ? 1u : 0u);
-                    mma_lo(acc_s, a + k4 * 2, qk0 + 4 + (db * 4 + k4) * 128, IDESC_K_MN32, 1u);
-                }
+                for (int k4 = 0; k4 < 4; ++k4)            // [S_hi | S_lo]: one N = 64 MMA per k-step
+                    mma_lo(acc_s, a + k4 * 2, qk0 + (db * 4 + k4) * 128, IDESC_K_MN64, (db > 0 || k4 > 0) ? 1u : 0u);
             }
             __syncwarp();
             r.advance();
@@ -102,7 +106,6 @@ __device__ __forceinline__ void softmax_tiles(const Ctx& c, const Dims& d, int n
     constexpr float LOG2E = 1.4426950408889634f;
     long long ph_last = clock64();
     const int K = c.K;
-    const uint32_t scol = c.tb + c.tlane + TC_S0 + 32u * (uint32_t)c.wg;
     const uint32_t sw = (uint32_t)(c.o & 7);
     for (int i = 0; i < ntile; ++i) {
         const uint32_t nseq = ts.nseq + (uint32_t)i;
@@ -113,9 +116,16 @@ __device__ __forceinline__ void softmax_tiles(const Ctx& c, const Dims& d, int n
         ++ts.own_s;
         fence_after_sync();
         UPH(50);
+        const uint32_t scol = c.tb + c.tlane + TC_S0 + 64u * (nseq % 3u);
         float l[KTOK];
-        tmem_ld16(scol, l); tmem_ld8(scol + 16, l + 16);
-        tmem_wait_ld();
+        {
+            float lo[KTOK];
+            tmem_ld16(scol, l); tmem_ld8(scol + 16, l + 16);
+            tmem_ld16(scol + 32, lo); tmem_ld8(scol + 48, lo + 16);
+            tmem_wait_ld();
+#pragma unroll
+            for (int s = 0; s < KTOK; ++s) l[s] += lo[s];
+        }
         fence_before_sync();
         __syncwarp();
         if (c.lane == 0) mbar_arrive(&c.bars[B_SFREE4 + c.wg]);
@@ -179,11 +189,11 @@ __device__ __forceinline__ void mha_core(const Ctx& c, int H, const float (&q)[K
     // rows of sQ / sK / sV are 16-byte aligned (ld % 4 == 0) and 4 banks apart: float4 reads along a head's features are
     // conflict-free across slots, column reads [k][o] across o.  Attention rows are padded to ka = 4-aligned K.
     const int K = c.K, ld = MHA_LD, ka = mha_ka(K), dh = F / H;
-    float* sQ = reinterpret_cast<float*>(c.sm + c.L.aw0);            // aw0 | aw1 | scratch are contiguous
+    float* sQ = reinterpret_cast<float*>(c.sm + c.L.aw0);            // q, k tiles in aw0 | aw1 (the LayerNorm scratch aliases aw1: idle here)
     float* sK = sQ + K * ld;
-    float* sV = sK + K * ld;
     float* sA = reinterpret_cast<float*>(c.sm + c.L.opB);            // [H*K][ka] logits -> probabilities (opB | opC are free here)
     float* sAT = sA + H * K * ka;                                    // [H][K key][ka query]: the transposed probabilities
+    float* sV = sAT + H * K * ka;                                    // v tile behind them, still inside opB | opC (savi_umma_mha_fits)
 #pragma unroll
     for (int kk = 0; kk < KH; ++kk) {
         const int k = c.k0 + kk;
@@ -454,7 +464,12 @@ __global__ void __launch_bounds__(NTHREADS, 1) savi_fwd_umma_kernel(const __grid
                 if (CN > 1) {                                                              // exchange the partial sums with the peer CTA
                     // inbox layout [feature o][KR8 slots] (+ [KR8] sums): a thread's 8 slot values are 32 contiguous bytes, two
                     // 16-byte remote stores instead of eight scalar ones
+#if SAVI_FWD_RING8
+                    const int buf = 0;                       // single inbox: the peer must have consumed what this CTA sent in the previous step
+                    if (step > 0) mbar_wait_cluster(&bars[B_INBOX + 1], (step - 1) & 1u);     // (it says so on OUR barrier)
+#else
                     const int buf = step & 1;
+#endif
                     const int KR8 = (K + 7) & ~7;
                     float* ib = reinterpret_cast<float*>(sm + L.inbox + buf * L.inbox_stride);
                     const uint32_t peer = rank ^ 1u;
@@ -471,7 +486,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) savi_fwd_umma_kernel(const __grid
                     __syncwarp();
                     if (lane == 0) mbar_arrive_remote(map_to_rank(&bars[B_INBOX + buf], peer));
                     UPH(8);
+#if SAVI_FWD_RING8
+                    mbar_wait_cluster(&bars[B_INBOX], step & 1u);
+#else
                     mbar_wait_cluster(&bars[B_INBOX + buf], (step >> 1) & 1u);
+#endif
                     UPH(9);
                     if (c.nk > 0) {
                         float pn[KH], pd[KH];
@@ -484,6 +503,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) savi_fwd_umma_kernel(const __grid
                             den[kk] = lead ? den[kk] + pd[kk] : pd[kk] + den[kk];
                         }
                     }
+#if SAVI_FWD_RING8
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive_remote(map_to_rank(&bars[B_INBOX + 1], peer));     // consumed: the peer may send again
+#endif
                 }
 #pragma unroll
                 for (int kk = 0; kk < KH; ++kk) y[kk] = (kk < c.nk) ? num[kk] * rcp_fast(den[kk]) : 0.f;      // Ux (:82-83)
@@ -641,9 +664,10 @@ int savi_umma_mha_fits(int K, int heads) {
     if (heads < 1 || F % heads || (F / heads) % 4) return 0;
     const int KR = (K + 3) & ~3, ka = mha_ka(K);
     const int win_bwd = 5 * OPB;                              // opA .. aw1
-    const int win_fwd = 2 * OPB + KR * F * 4;                 // aw0 .. scratch (q, k, v tiles); the attention matrices take opB | opC
+    (void)KR;
+    // forward: q, k tiles in aw0 | aw1; the two attention matrices and the v tile in opB | opC
     return heads * K * K <= 8 * NCT && mha_bwd_bytes(K, heads) <= win_bwd &&
-           3 * K * MHA_LD * 4 <= win_fwd && 2 * heads * K * ka * 4 <= 2 * OPB;
+           2 * K * MHA_LD * 4 <= 2 * OPB && (2 * heads * K * ka + K * MHA_LD) * 4 <= 2 * OPB;
 }
 
 int savi_fwd_umma_smem_bytes(const Dims& d) {

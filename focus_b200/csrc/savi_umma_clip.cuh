@@ -17,6 +17,9 @@
 // fp16 in the forward, where the activation operands are fp16 hi | lo too; bf16 in the backward): per 16-wide k-step a
 // product is ONE MMA,  W . [X_hi | X_lo]  (N = 64), and the epilogue adds accumulator columns s and 32 + s.
 #pragma once
+#ifndef SAVI_FWD_RING8
+#define SAVI_FWD_RING8 1          // forward shared-memory plan with 8 ring stages (0: round-1 plan, 6 stages; A/B builds)
+#endif
 #include <cuda_fp16.h>
 #include "savi_umma.cuh"
 #include "savi_dev.cuh"
@@ -111,13 +114,18 @@ __host__ __device__ inline Smem plan_smem(int K, int CN, bool bwd) {
     // tile).  The fp32 LayerNorm / c-vector scratch therefore lives in aw1 (not an operand buffer in the backward), the
     // float2 LayerNorm-backward scratch in opC | aw0 (idle at every call site: the products that read them have completed),
     // and the cluster inbox is single-buffered behind a "consumed" handshake.  (Measured in the forward: no gain, not done.)
-    if (bwd) s.scratch = s.aw1; else { s.scratch = p; p += KR * F * 4; }
+    // Round 2: the forward uses the same plan (8 ring stages = the token blocks of four tiles in flight).  With many tiles
+    // per CTA (N >= 4096) the forward token pass was starved by the ring: a tile's two blocks stay resident from their bulk copy
+    // until its second product completes (~4.5 us), so 6 stages delivered one tile per ~1.5 us while the compute warpgroups
+    // needed ~0.5 us (profiles/r02p_phase_n16k.txt: 70 % of the forward spent in "WAIT logits").
+    const bool alias = bwd || SAVI_FWD_RING8;
+    if (alias) s.scratch = s.aw1; else { s.scratch = p; p += KR * F * 4; }
     s.stats = p; p += 512;                         // float2 [32] LayerNorm statistics | float [64] c, 1/S (backward)
     p = (p + 1023) & ~1023;
     s.ones = p; p += bwd ? 0 : 4096;
     const int KR8 = (K + 7) & ~7;                 // inbox layout [128 features][KR8 slots] (+ [KR8] sums in the forward)
     s.inbox_stride = (KR8 * F * 4 + (bwd ? 0 : 32 * 4) + 127) & ~127;
-    s.inbox = p; p += (CN > 1) ? (bwd ? 1 : 2) * s.inbox_stride : 0;
+    s.inbox = p; p += (CN > 1) ? (alias ? 1 : 2) * s.inbox_stride : 0;
     s.aux = p;
     p = (p + 15) & ~15;
     s.bars = p; p += NBAR * 8 + 16 + 512;          // mbarriers, TMEM base, development counters
@@ -252,6 +260,25 @@ __device__ __forceinline__ void write_operand(const Ctx& c, int op_off, const fl
     }
     *reinterpret_cast<uint4*>(c.sm + op_off + c.row_hi) = make_uint4(h[0], h[1], h[2], h[3]);
     *reinterpret_cast<uint4*>(c.sm + op_off + c.row_lo) = make_uint4(l[0], l[1], l[2], l[3]);
+}
+// Two [K][128] tensors a, b that multiply the SAME A operand, packed by precision half: op_hi row = [a_hi 32 slots | b_hi 32 slots],
+// op_lo row = [a_lo | b_lo] (bf16).  One N = 64 MMA per half then yields [A . a | A . b] in one 64-column accumulator.
+__device__ __forceinline__ void write_operand_halves(const Ctx& c, int op_hi, int op_lo, const float (&a)[KH], const float (&b)[KH]) {
+    uint32_t ah[4], al[4], bh[4], bl[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const float a0 = (2 * j < c.nk) ? a[2 * j] : 0.f, a1 = (2 * j + 1 < c.nk) ? a[2 * j + 1] : 0.f;
+        const float b0 = (2 * j < c.nk) ? b[2 * j] : 0.f, b1 = (2 * j + 1 < c.nk) ? b[2 * j + 1] : 0.f;
+        const __nv_bfloat162 ha = __floats2bfloat162_rn(a0, a1), hb = __floats2bfloat162_rn(b0, b1);
+        const float2 fa = __bfloat1622float2(ha), fb = __bfloat1622float2(hb);
+        ah[j] = *reinterpret_cast<const uint32_t*>(&ha); bh[j] = *reinterpret_cast<const uint32_t*>(&hb);
+        al[j] = pack_bf16x2(a0 - fa.x, a1 - fa.y); bl[j] = pack_bf16x2(b0 - fb.x, b1 - fb.y);
+    }
+    // row_hi = this thread's chunk in the first 32 columns, row_lo = the same chunk in the second 32
+    *reinterpret_cast<uint4*>(c.sm + op_hi + c.row_hi) = make_uint4(ah[0], ah[1], ah[2], ah[3]);
+    *reinterpret_cast<uint4*>(c.sm + op_hi + c.row_lo) = make_uint4(bh[0], bh[1], bh[2], bh[3]);
+    *reinterpret_cast<uint4*>(c.sm + op_lo + c.row_hi) = make_uint4(al[0], al[1], al[2], al[3]);
+    *reinterpret_cast<uint4*>(c.sm + op_lo + c.row_lo) = make_uint4(bl[0], bl[1], bl[2], bl[3]);
 }
 // same as fp16 hi | lo (operands of the forward's slot-side linears, whose weight images are fp16).  The conversion
 // saturates: a slot state beyond fp16's range (65504) would otherwise turn into inf - inf = NaN in the lo half.

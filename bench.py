@@ -150,11 +150,18 @@ def time_cpu_reference(cfg, sample_clips, steps, warmup):
     c = cfg
     ref = _reference_module(c)
     x, noise, gs, ga = _ref_inputs(c, sample_clips)
-    if ref is None:
-        raise SystemExit("bench.py: neither /root/reference nor oracle/_ref is present; run `python oracle/make_ref.py` "
-                         "(or __graft_entry__.build()) in the build container")
-    kind, what = "reference", "the unmodified reference module slowfast/models/STEVE/steve.py:SlotAttentionVideo (oracle/_ref)"
-    run = lambda: _ref_step(ref, x, noise, gs, ga)
+    if ref is not None:
+        kind, what = "reference", "the unmodified reference module slowfast/models/STEVE/steve.py:SlotAttentionVideo (oracle/_ref)"
+        run = lambda: _ref_step(ref, x, noise, gs, ga)
+    else:
+        # the reference sources did not travel (oracle/make_ref.py / __graft_entry__.build() not run where /root/reference exists):
+        # time the oracle's torch port instead (same ATen operations in the reference's order) and SAY so
+        from oracle import savi_numpy as O
+        from oracle import savi_torch as OT
+        kind = "port"
+        what = "oracle/savi_torch.py (torch CPU ops in the reference's operation order; the reference sources were not found)"
+        P = {k: torch.from_numpy(v).float() for k, v in O.random_params(c["K"], c["D"], c["Ds"], c["M"], c["blocks"], seed=0).items()}
+        run = lambda: OT.forward_backward(P, x, noise, c["I"], c["heads"], gs, ga)
     times = []
     for i in range(warmup + steps):
         t0 = time.perf_counter()

@@ -492,7 +492,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) savi_bwd_umma_kernel(const __grid
                     if (it < d.I - 1) { prod_blocks(ring, Wi + wi.w2T, 2 * NBW); prod_blocks(ring, Wi + wi.w1T, 2 * NBW); }
                     prod_blocks(ring, Wi + wi.wgT, 6 * NBW);
                     prod_blocks(ring, Wi + wi.whhT, 6 * NBW);
-                    prod_blocks(ring, xf, 2 * ntile);
+                    prod_token_blocks(ring, xf, 2 * ntile, 16);
                     prod_blocks(ring, Wi + wi.wqkT, 2 * NBW);
                 }
             }

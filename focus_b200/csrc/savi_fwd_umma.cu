@@ -335,7 +335,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) savi_fwd_umma_kernel(const __grid
                 const unsigned char* xf = ximg + ((size_t)(b * d.T + t) * d.NTILE + tile0) * 2 * BLK;
                 for (int it = 0; it < d.I; ++it) {
                     prod_blocks(ring, W + wi.wqk, 2 * NBW);
-                    prod_blocks(ring, xf, 2 * ntile);
+                    prod_token_blocks(ring, xf, 2 * ntile, 16);
                     prod_blocks(ring, W + wi.whh, 6 * NBW);
                     prod_blocks(ring, W + wi.wg, 6 * NBW);
                     if (it < d.I - 1) { prod_blocks(ring, W + wi.w1, 2 * NBW); prod_blocks(ring, W + wi.w2, 2 * NBW); }

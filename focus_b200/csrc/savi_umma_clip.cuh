@@ -175,6 +175,21 @@ __device__ __forceinline__ void prod_blocks(Ring& r, const unsigned char* src, i
     }
 }
 
+// Token blocks: the same, plus an L2 prefetch `ahead` blocks in front of the shared-memory copy.  A block stays in the ring from its
+// bulk copy until the tile's second product completes, so with many tiles per CTA (N >= 4096) the ring turns over once per
+// HBM round trip; pulling the blocks into L2 a few tiles early makes that round trip an L2 hit.
+__device__ __forceinline__ void prod_token_blocks(Ring& r, const unsigned char* src, int nblk, int ahead) {
+    for (int i = 0; i < ahead && i < nblk; ++i) prefetch_l2(src + (size_t)i * BLK, BLK);
+#pragma unroll 1
+    for (int i = 0; i < nblk; ++i) {
+        if (i + ahead < nblk) prefetch_l2(src + (size_t)(i + ahead) * BLK, BLK);
+        mbar_wait(&r.empty[r.stage], r.phase ^ 1u);
+        mbar_expect_tx(&r.full[r.stage], BLK);
+        bulk_g2s(r.base + (size_t)r.stage * BLK, src + (size_t)i * BLK, BLK, &r.full[r.stage]);
+        r.advance();
+    }
+}
+
 // ---- issuer ------------------------------------------------------------------------------------
 // One linear layer, transposed: acc[rt] (+)= Wimg[rt] . X^T.  Weight blocks arrive through the ring in image
 // order (rt, cb, hi, lo).  xop: shared address of the activation operand; its rows [cb*64, cb*64 + 64) are the

@@ -29,7 +29,7 @@ class SaviShape(ctypes.Structure):
 class SaviSizes(ctypes.Structure):
     _fields_ = [(n, ctypes.c_int64) for n in
                 ("n_params", "param_floats", "packed_bytes", "saved_bytes", "fwd_ws_bytes", "bwd_ws_bytes")] + \
-               [("cluster", ctypes.c_int32), ("path", ctypes.c_int32)]
+               [("cluster", ctypes.c_int32), ("path", ctypes.c_int32), ("dropout_floats", ctypes.c_int64)]
 
 
 def _load():
@@ -48,9 +48,9 @@ def _load():
     lib.savi_param_layout.restype = ip
     lib.savi_pack_params.argtypes = [ctypes.POINTER(SaviShape), ctypes.POINTER(vp), vp, vp]
     lib.savi_pack_params.restype = ip
-    lib.savi_forward.argtypes = [ctypes.POINTER(SaviShape)] + [vp] * 8
+    lib.savi_forward.argtypes = [ctypes.POINTER(SaviShape)] + [vp] * 9
     lib.savi_forward.restype = ip
-    lib.savi_backward.argtypes = [ctypes.POINTER(SaviShape)] + [vp] * 11
+    lib.savi_backward.argtypes = [ctypes.POINTER(SaviShape)] + [vp] * 12
     lib.savi_backward.restype = ip
     lib.savi_profile_enable.argtypes = [ip]
     lib.savi_profile_enable.restype = ip

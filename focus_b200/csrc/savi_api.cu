@@ -227,6 +227,7 @@ extern "C" int savi_query(const SaviShape* shape, SaviSizes* sizes) {
     sizes->bwd_ws_bytes = bl.total_bytes;
     sizes->cluster = d.CN;
     sizes->path = d.umma ? SAVI_PATH_TCGEN05 : d.mma ? SAVI_PATH_MMA_SYNC : SAVI_PATH_SIMT;
+    sizes->dropout_floats = savi_dropout_layout(d).total;
     return SAVI_OK;
 }
 
@@ -436,7 +437,7 @@ extern "C" int savi_pack_params(const SaviShape* shape, const void* const* param
 }
 
 extern "C" int savi_forward(const SaviShape* shape, const void* packed, const void* inputs, const void* noise,
-                            void* slots_out, void* attn_out, void* saved, void* fwd_ws, void* stream) {
+                            void* slots_out, void* attn_out, void* saved, void* fwd_ws, const void* dropout_masks, void* stream) {
     FwdArgs a;
     int rc = validate(shape, a.d);
     if (rc) return rc;
@@ -453,6 +454,7 @@ extern "C" int savi_forward(const SaviShape* shape, const void* packed, const vo
     a.saved = reinterpret_cast<unsigned char*>(saved);
     a.ws = reinterpret_cast<float*>(fwd_ws);
     a.dbg = g_dbg;
+    a.drop = reinterpret_cast<const float*>(dropout_masks);
     g_launches = 0;
     cudaError_t e = savi_launch_forward(a, inputs, reinterpret_cast<cudaStream_t>(stream), &g_launches);
     if (e != cudaSuccess) return cuda_fail(e, "savi_forward launch");
@@ -461,7 +463,7 @@ extern "C" int savi_forward(const SaviShape* shape, const void* packed, const vo
 
 extern "C" int savi_backward(const SaviShape* shape, const void* packed, const void* inputs, const void* noise,
                              const void* saved, const void* grad_slots, const void* grad_attn, void* grad_inputs,
-                             void* grad_params, void* grad_noise, void* bwd_ws, void* stream) {
+                             void* grad_params, void* grad_noise, void* bwd_ws, const void* dropout_masks, void* stream) {
     BwdArgs a;
     int rc = validate(shape, a.d);
     if (rc) return rc;
@@ -481,6 +483,7 @@ extern "C" int savi_backward(const SaviShape* shape, const void* packed, const v
     a.grad_noise = reinterpret_cast<float*>(grad_noise);
     a.ws = reinterpret_cast<float*>(bwd_ws);
     a.dbg = g_dbg;
+    a.drop = reinterpret_cast<const float*>(dropout_masks);
     g_launches = 0;
     cudaError_t e = savi_launch_backward(a, inputs, grad_inputs, reinterpret_cast<cudaStream_t>(stream), &g_launches);
     if (e != cudaSuccess) return cuda_fail(e, "savi_backward launch");

@@ -19,6 +19,7 @@ struct FwdArgs {
     int op_bytes;         // bytes of ONE shared-memory operand buffer (two are carved before the arena; 0 = none)
     int op_width;         // the common contraction width those buffers serve (max(D, Ds)); 0 = pre-staging off
     long long* dbg;       // optional per-phase cycle counters (CTA 0), see savi_debug_set_phase_buffer
+    const float* drop;    // predictor dropout masks (training mode, p > 0), nullptr otherwise: savi_dropout_layout()
     int TN;               // tokens per shared-memory tile
     int arena_floats;     // floats of dynamic shared memory usable as the linear-layer staging arena
     int smem_bytes;
@@ -38,6 +39,7 @@ struct BwdArgs {
     float* grad_noise;          // nullable
     float* ws;
     long long* dbg;
+    const float* drop;          // predictor dropout masks of the forward (nullable)
     int stages;
     int op_bytes;
     int op_width;
@@ -45,6 +47,19 @@ struct BwdArgs {
     int arena_floats;
     int smem_bytes;
 };
+
+// Predictor dropout masks (reference transformer.py:12-13, 44, 48, 68): ONE flat fp32 buffer holding, for every predictor block
+// evaluation f = j * (T - 1) + t and clip b, the multiplicative masks (0 or 1 / (1 - p)) of the three dropout sites:
+//   att [Sp][B][H][K][K]   on the attention probabilities (attn_dropout)
+//   out [Sp][B][K][Ds]     on the proj_o output (output_dropout)
+//   ffn [Sp][B][K][Ds]     on the ffn.2 output (the nn.Dropout closing the FFN)
+struct DropLayout { int64_t att, out, ffn, total; };     // float offsets
+static SAVI_HD DropLayout savi_dropout_layout(const Dims& d) {
+    DropLayout L;
+    const int64_t n = (int64_t)d.Sp * d.B;
+    L.att = 0; L.out = n * d.heads * d.K * d.K; L.ffn = L.out + n * d.K * d.Ds; L.total = L.ffn + n * d.K * d.Ds;
+    return L;
+}
 
 // phase-timing macro shared by the clip kernels (active only when a.dbg != nullptr; CTA 0 reports)
 #define SAVI_PH(id) do { if (a.dbg && blockIdx.x == 0) { __syncthreads(); if (threadIdx.x == 0) { long long t_ = clock64(); \

@@ -161,8 +161,9 @@ __device__ __noinline__ void token_pass_bwd(const Dims& d, const TokT* __restric
 }
 
 // Backward of the predictor's attention core.  dQ is w.r.t. the UNSCALED projection.
+// m (nullable): the forward's dropout mask of the probabilities: O = (att . m) V, so dV uses att . m and d att = (dO V^T) . m.
 static __device__ __noinline__ void mha_core_bwd(const float* dO, const float* Q, const float* Kk, const float* V, const float* att,
-                             float* datt, float* dQ, float* dKk, float* dV, int K, int Ds, int H, float hscale) {
+                             float* datt, float* dQ, float* dKk, float* dV, int K, int Ds, int H, float hscale, const float* m) {
     const int dh = Ds / H, tid = threadIdx.x;
     for (int idx = tid; idx < H * K * K; idx += NT) {
         const int j = idx % K, i = (idx / K) % K, h = idx / (K * K);
@@ -170,7 +171,7 @@ static __device__ __noinline__ void mha_core_bwd(const float* dO, const float* Q
         const float* v = V + (size_t)j * Ds + h * dh;
         float s = 0.f;
         for (int c = 0; c < dh; ++c) s = fmaf(a[c], v[c], s);
-        datt[idx] = s;
+        datt[idx] = m ? s * m[idx] : s;
     }
     __syncthreads();
     for (int row = tid; row < H * K; row += NT) {
@@ -189,7 +190,7 @@ static __device__ __noinline__ void mha_core_bwd(const float* dO, const float* Q
         for (int j = 0; j < K; ++j) {
             sq = fmaf(dlg[(size_t)i * K + j], Kk[(size_t)j * Ds + c], sq);
             sk = fmaf(dlg[(size_t)j * K + i], Q[(size_t)j * Ds + c], sk);
-            sv = fmaf(at[(size_t)j * K + i], dO[(size_t)j * Ds + c], sv);
+            sv = fmaf(m ? at[(size_t)j * K + i] * m[(size_t)h * K * K + (size_t)j * K + i] : at[(size_t)j * K + i], dO[(size_t)j * Ds + c], sv);
         }
         dQ[idx] = sq * hscale; dKk[idx] = sk; dV[idx] = sv;
     }
@@ -198,7 +199,7 @@ static __device__ __noinline__ void mha_core_bwd(const float* dO, const float* Q
 
 // Shared-memory version of mha_core_bwd (all five operands staged, odd row strides).
 static __device__ __noinline__ void mha_core_bwd_smem(const float* dO, const float* Q, const float* Kk, const float* V, const float* att,
-                                                      float* dQ, float* dKk, float* dV, int K, int Ds, int H, float hscale, float* arena) {
+                                                      float* dQ, float* dKk, float* dV, int K, int Ds, int H, float hscale, float* arena, const float* m) {
     const int dh = Ds / H, tid = threadIdx.x, ld = Ds + 1, ka = K | 1;
     float* sO = arena; float* sQ = sO + (size_t)K * ld; float* sK = sQ + (size_t)K * ld; float* sV = sK + (size_t)K * ld;
     float* sA = sV + (size_t)K * ld; float* sD = sA + (size_t)H * K * ka;
@@ -220,7 +221,7 @@ static __device__ __noinline__ void mha_core_bwd_smem(const float* dO, const flo
         const float* v = sV + (size_t)j * ld + h * dh;
         float s = 0.f;
         for (int c = 0; c < dh; ++c) s = fmaf(a[c], v[c], s);
-        sD[(size_t)(h * K + i) * ka + j] = s;
+        sD[(size_t)(h * K + i) * ka + j] = m ? s * m[idx] : s;
     }
     __syncthreads();
     for (int row = tid; row < H * K; row += NT) {
@@ -231,6 +232,10 @@ static __device__ __noinline__ void mha_core_bwd_smem(const float* dO, const flo
         for (int j = 0; j < K; ++j) da[j] = a[j] * (da[j] - dot);
     }
     __syncthreads();
+    if (m) {                                                  // d V = (att . m)^T dO: the probabilities are not needed undropped any more
+        for (int idx = tid; idx < H * K * K; idx += NT) sA[(size_t)(idx / K) * ka + idx % K] *= m[idx];
+        __syncthreads();
+    }
     for (int idx = tid; idx < K * Ds; idx += NT) {
         const int c = idx % Ds, i = idx / Ds, h = c / dh;
         const float* dlg = sD + (size_t)h * K * ka;
@@ -318,22 +323,39 @@ __global__ void __launch_bounds__(NT, 1) savi_bwd_kernel(const __grid_constant__
                 float* s_dx2 = lead ? frow(W, a.wl.pdx2, f, b, B, K, Ds) : cs + a.wl.sh_pdx2;
                 float* s_df = lead ? frow(W, a.wl.pdf, f, b, B, K, 4 * Ds) : cs + a.wl.sh_pdf;
                 (void)p_y;
-                cta_copy(s_dx2, t0, K * Ds);
-                if (lead) cta_colsum_atomic(G + bo.f2b, t0, Ds, K, Ds);
-                LIN(s_df, 4 * Ds, t0, Ds, bo.f2, bt.f2_t, nullptr, 0, p_f, 4 * Ds, K, Ds, 4 * Ds, 1.0f);      // d relu-out, masked
+                // training-mode dropout masks of this block evaluation (nullptr otherwise): savi_args.h, DropLayout
+                const DropLayout dl = savi_dropout_layout(d);
+                const float* m_att = a.drop ? a.drop + dl.att + (f * B + b) * ((int64_t)d.heads * K * K) : nullptr;
+                const float* m_out = a.drop ? a.drop + dl.out + (f * B + b) * ((int64_t)K * Ds) : nullptr;
+                const float* m_ffn = a.drop ? a.drop + dl.ffn + (f * B + b) * ((int64_t)K * Ds) : nullptr;
+                // d(ffn.2 output) = d x2 . m_ffn: staged for d W2 / d b2 and pushed through ffn.2^T; the residual branch keeps d x2 (t0)
+                if (m_ffn) { for (int i = tid; i < K * Ds; i += NT) s_dx2[i] = t0[i] * m_ffn[i]; __syncthreads(); }
+                else cta_copy(s_dx2, t0, K * Ds);
+                const float* dff = m_ffn ? s_dx2 : t0;       // (without dropout: the CTA-local copy, already synchronised)
+                if (lead) cta_colsum_atomic(G + bo.f2b, dff, Ds, K, Ds);
+                LIN(s_df, 4 * Ds, dff, Ds, bo.f2, bt.f2_t, nullptr, 0, p_f, 4 * Ds, K, Ds, 4 * Ds, 1.0f);      // d relu-out, masked
                 if (lead) cta_colsum_atomic(G + bo.f1b, s_df, 4 * Ds, K, 4 * Ds);
                 LIN(t1, Ds, s_df, 4 * Ds, bo.f1, bt.f1_t, nullptr, 0, nullptr, 0, K, 4 * Ds, Ds, 1.0f);
                 cta_ln_bwd(s_dx1, Ds, t0, Ds, t1, Ds, p_x1, Ds, P + bo.ln2_w, G + bo.ln2_w, G + bo.ln2_b, K, Ds, d.ln_eps, lead);
+                // s_dx1 = d x1.  With output dropout the proj_o branch sees d x1 . m_out: THAT is staged (d W_o) and pushed through
+                // proj_o^T, while the residual branch below needs the undropped d x1: kept in the CTA scratch `dhg` (idle here)
+                const float* dx1_res = s_dx1;
+                if (m_out) {
+                    __syncthreads();
+                    for (int i = tid; i < K * Ds; i += NT) { const float v = s_dx1[i]; dhg[i] = v; s_dx1[i] = v * m_out[i]; }
+                    __syncthreads();
+                    dx1_res = dhg;
+                }
                 LIN(t1, Ds, s_dx1, Ds, bo.po, bt.po_t, nullptr, 0, nullptr, 0, K, Ds, Ds, 1.0f);                  // dO
                 SAVI_PH(31);
-                if (4 * K * (Ds + 1) + 2 * d.heads * K * (K | 1) <= AF) mha_core_bwd_smem(t1, p_q, p_k, p_v, p_att, s_dq, s_dk, s_dv, K, Ds, d.heads, hscale, arena);
-                else mha_core_bwd(t1, p_q, p_k, p_v, p_att, t2, s_dq, s_dk, s_dv, K, Ds, d.heads, hscale);
+                if (4 * K * (Ds + 1) + 2 * d.heads * K * (K | 1) <= AF) mha_core_bwd_smem(t1, p_q, p_k, p_v, p_att, s_dq, s_dk, s_dv, K, Ds, d.heads, hscale, arena, m_att);
+                else mha_core_bwd(t1, p_q, p_k, p_v, p_att, t2, s_dq, s_dk, s_dv, K, Ds, d.heads, hscale, m_att);
                 SAVI_PH(32);
-                LIN(t1, Ds, s_dq, Ds, bo.pq, bt.pq_t, (j == 0) ? s_dx1 : nullptr, Ds, nullptr, 0, K, Ds, Ds, 1.0f);
+                LIN(t1, Ds, s_dq, Ds, bo.pq, bt.pq_t, (j == 0) ? dx1_res : nullptr, Ds, nullptr, 0, K, Ds, Ds, 1.0f);
                 LIN(t1, Ds, s_dk, Ds, bo.pk, bt.pk_t, t1, Ds, nullptr, 0, K, Ds, Ds, 1.0f);
                 LIN(t1, Ds, s_dv, Ds, bo.pv, bt.pv_t, t1, Ds, nullptr, 0, K, Ds, Ds, 1.0f);                      // dy
                 const float* x_in = (j == 0) ? px0 : frow(fb, a.sl.px2, (int64_t)(j - 1) * (d.T - 1) + t, b, B, K, Ds);
-                cta_ln_bwd(t0, Ds, (j == 0) ? nullptr : s_dx1, Ds, t1, Ds, x_in, Ds, P + bo.ln1_w, G + bo.ln1_w, G + bo.ln1_b,
+                cta_ln_bwd(t0, Ds, (j == 0) ? nullptr : dx1_res, Ds, t1, Ds, x_in, Ds, P + bo.ln1_w, G + bo.ln1_w, G + bo.ln1_b,
                            K, Ds, d.ln_eps, lead);
             }
             cta_copy(dh, t0, K * Ds);

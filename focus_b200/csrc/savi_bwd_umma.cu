@@ -270,6 +270,7 @@ __device__ __forceinline__ void ln_bwd(const Ctx& c, const float (&dy)[KH], cons
 constexpr int ATT_PT = 8;     // attention-matrix elements per thread: heads * K * K <= 8 * 512
 __device__ __forceinline__ void mha_core_bwd(const Ctx& c, int H, float hscale, const float (&dO)[KH], const float (&Qv)[KH], const float (&Kv)[KH],
                                              const float (&Vv)[KH], const float (&attv)[ATT_PT], float (&dQ)[KH], float (&dK)[KH], float (&dV)[KH],
+                                             const float* matt /* nullable: the forward's dropout mask of the probabilities [H][K][K] */,
                                              long long* dbg, long long& ph_last) {
     // layout as in the forward core (savi_fwd_umma.cu: mha_core): 16-byte aligned rows, attention rows padded to ka
     const int K = c.K, ld = MHA_LD, ka = mha_ka(K), dh = F / H;
@@ -315,7 +316,8 @@ __device__ __forceinline__ void mha_core_bwd(const Ctx& c, int H, float hscale, 
             }
         }
 #pragma unroll
-        for (int jj = 0; jj < MHA_JP; ++jj) if (jj < JP && j0 + jj < K) sD[row * ka + j0 + jj] = acc[jj];
+        // O = (att . m) V: d att = (dO V^T) . m
+        for (int jj = 0; jj < MHA_JP; ++jj) if (jj < JP && j0 + jj < K) sD[row * ka + j0 + jj] = matt ? acc[jj] * matt[row * K + j0 + jj] : acc[jj];
     }
     bar_sync_compute();
     UPH(46);
@@ -341,6 +343,7 @@ __device__ __forceinline__ void mha_core_bwd(const Ctx& c, int H, float hscale, 
             if (row < H * K && c.lane < K) {
                 const float dl = av[r] * (dav[r] - dot[r]);
                 sD[row * ka + c.lane] = dl; sDT[((row / K) * K + c.lane) * ka + row % K] = dl;
+                if (matt) sA[row * ka + c.lane] = av[r] * matt[row * K + c.lane];     // from here on only d V = (att . m)^T dO reads the probabilities
             }
         }
     }
@@ -594,10 +597,25 @@ __global__ void __launch_bounds__(NTHREADS, 1) savi_bwd_umma_kernel(const __grid
                     const float* p_f = frow(fbw, a.sl.pf, f, b, B, K, 4 * F);
                     const float* p_att = fb + a.sl.patt + (f * B + b) * ((int64_t)d.heads * K * K);
                     UPH(37);
-                    // t0 = d x2
-                    if (svB) save_field(c, frow(W, a.wl.pdx2, f, b, B, K, F), F, o, t0);
-                    if (lead) atomicAdd(G + bo.f2b + o, sum8(c, t0));
-                    write_operand(c, xop(L, 0), t0);
+                    // training-mode dropout masks of this block evaluation (nullptr otherwise): savi_args.h, DropLayout
+                    const DropLayout dlay = savi_dropout_layout(d);
+                    const float* m_att = a.drop ? a.drop + dlay.att + (f * B + b) * ((int64_t)d.heads * K * K) : nullptr;
+                    const float* m_out = a.drop ? a.drop + dlay.out + (f * B + b) * ((int64_t)K * F) : nullptr;
+                    const float* m_ffn = a.drop ? a.drop + dlay.ffn + (f * B + b) * ((int64_t)K * F) : nullptr;
+                    // t0 = d x2; the FFN branch sees d x2 . m_ffn (staged for d W2 / d b2, pushed through ffn.2^T), the residual keeps t0
+                    float tm[KH];
+                    if (m_ffn) {
+                        float mf[KH];
+                        load_field(c, m_ffn, F, o, mf);
+#pragma unroll
+                        for (int kk = 0; kk < KH; ++kk) tm[kk] = t0[kk] * mf[kk];
+                    } else {
+#pragma unroll
+                        for (int kk = 0; kk < KH; ++kk) tm[kk] = t0[kk];
+                    }
+                    if (svB) save_field(c, frow(W, a.wl.pdx2, f, b, B, K, F), F, o, tm);
+                    if (lead) atomicAdd(G + bo.f2b + o, sum8(c, tm));
+                    write_operand(c, xop(L, 0), tm);
                     signal_operand(c);
                     // d f = (ffn.2^T d x2) masked by relu; chunks 1..3 go to X1..X3 at once, chunk 0 to X0 after all four tiles are done
                     float df0[KH];
@@ -634,8 +652,20 @@ __global__ void __launch_bounds__(NTHREADS, 1) savi_bwd_umma_kernel(const __grid
                     }
 #pragma unroll
                     for (int kk = 0; kk < KH; ++kk) dx1[kk] += t0[kk];
-                    if (svB) save_field(c, frow(W, a.wl.pdx1, f, b, B, K, F), F, o, dx1);
-                    write_operand(c, xop(L, 0), dx1);
+                    {   // the proj_o branch sees d x1 . m_out (staged for d W_o, pushed through proj_o^T); the residual below keeps d x1
+                        float dm[KH];
+                        if (m_out) {
+                            float mo[KH];
+                            load_field(c, m_out, F, o, mo);
+#pragma unroll
+                            for (int kk = 0; kk < KH; ++kk) dm[kk] = dx1[kk] * mo[kk];
+                        } else {
+#pragma unroll
+                            for (int kk = 0; kk < KH; ++kk) dm[kk] = dx1[kk];
+                        }
+                        if (svB) save_field(c, frow(W, a.wl.pdx1, f, b, B, K, F), F, o, dm);
+                        write_operand(c, xop(L, 0), dm);
+                    }
                     signal_operand(c);
                     UPH(40);
                     float dO[KH], dQ[KH], dK[KH], dV[KH];
@@ -646,7 +676,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) savi_bwd_umma_kernel(const __grid
                         for (int e = 0; e < ATT_PT; ++e) { const int idx = tid + e * NCT; attv[e] = (idx < d.heads * K * K) ? p_att[idx] : 0.f; }
                         wait_acc(c); load_acc(c, TB_B, dO);
                         UPH(41);
-                        mha_core_bwd(c, d.heads, hscale, dO, qv, kv, vv, attv, dQ, dK, dV, dbg, ph_last);
+                        mha_core_bwd(c, d.heads, hscale, dO, qv, kv, vv, attv, dQ, dK, dV, m_att, dbg, ph_last);
                         UPH(42);
                     }
                     if (svA) {

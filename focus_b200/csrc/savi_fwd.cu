@@ -230,8 +230,9 @@ __device__ __noinline__ void token_pass_fwd(const Dims& d, const TokT* __restric
 
 // Multi-head self-attention core of the predictor on one clip (transformer.py:34-47).
 // Q is already scaled by dh^-1/2.  att: [H][K][K] (global), O: [K][Ds].
+// m (nullable): training-mode dropout mask of the probabilities [H][K][K] (0 or 1/(1-p)); `att` keeps the UNDROPPED softmax.
 static __device__ __noinline__ void mha_core_fwd(const float* Q, const float* Kk, const float* V, float* att, float* O,
-                             int K, int Ds, int H) {
+                             int K, int Ds, int H, const float* m) {
     const int dh = Ds / H, tid = threadIdx.x;
     for (int idx = tid; idx < H * K * K; idx += NT) {
         const int j = idx % K, i = (idx / K) % K, h = idx / (K * K);
@@ -255,8 +256,9 @@ static __device__ __noinline__ void mha_core_fwd(const float* Q, const float* Kk
     for (int idx = tid; idx < K * Ds; idx += NT) {
         const int c = idx % Ds, i = idx / Ds, h = c / dh;
         const float* a = att + ((size_t)h * K + i) * K;
+        const float* mm = m ? m + ((size_t)h * K + i) * K : nullptr;
         float s = 0.f;
-        for (int j = 0; j < K; ++j) s = fmaf(a[j], V[(size_t)j * Ds + c], s);
+        for (int j = 0; j < K; ++j) s = fmaf(mm ? a[j] * mm[j] : a[j], V[(size_t)j * Ds + c], s);
         O[idx] = s;
     }
     __syncthreads();
@@ -265,7 +267,7 @@ static __device__ __noinline__ void mha_core_fwd(const float* Q, const float* Kk
 // Same computation with Q, K, V and the attention matrix staged in shared memory (rows padded to an
 // odd stride: conflict-free for both the per-key and the per-feature access patterns).
 static __device__ __noinline__ void mha_core_fwd_smem(const float* Q, const float* Kk, const float* V, float* att, float* O,
-                                                      int K, int Ds, int H, float* arena) {
+                                                      int K, int Ds, int H, float* arena, const float* m) {
     const int dh = Ds / H, tid = threadIdx.x, ld = Ds + 1, ka = K | 1;
     float* sQ = arena; float* sK = sQ + (size_t)K * ld; float* sV = sK + (size_t)K * ld; float* sA = sV + (size_t)K * ld;
     __syncthreads();
@@ -298,6 +300,11 @@ static __device__ __noinline__ void mha_core_fwd_smem(const float* Q, const floa
     }
     __syncthreads();
     for (int idx = tid; idx < H * K * K; idx += NT) att[idx] = sA[(size_t)(idx / K) * ka + idx % K];     // saved for backward
+    if (m) {                                                  // attn_dropout (transformer.py:44): the product below uses the dropped probabilities
+        __syncthreads();
+        for (int idx = tid; idx < H * K * K; idx += NT) sA[(size_t)(idx / K) * ka + idx % K] *= m[idx];
+        __syncthreads();
+    }
     for (int idx = tid; idx < K * Ds; idx += NT) {
         const int c = idx % Ds, i = idx / Ds, h = c / dh;
         const float* a = sA + (size_t)(h * K + i) * ka;
@@ -492,16 +499,34 @@ __global__ void __launch_bounds__(NT, 1) savi_fwd_kernel(const __grid_constant__
                 LINP(p_k, Ds, p_y, Ds, bt.pk_t, bo.pk, nullptr, nullptr, 0, K, Ds, Ds, 1.0f, 0, OP_IF(Ds, opA), nullptr);
                 LINP(p_v, Ds, p_y, Ds, bt.pv_t, bo.pv, nullptr, nullptr, 0, K, Ds, Ds, 1.0f, 0, OP_IF(Ds, opA), nullptr);
                 SAVI_PH(16);
-                if (3 * K * (Ds + 1) + d.heads * K * (K | 1) <= AF) mha_core_fwd_smem(p_q, p_k, p_v, p_att, p_o, K, Ds, d.heads, arena);
-                else mha_core_fwd(p_q, p_k, p_v, p_att, p_o, K, Ds, d.heads);
+                // training-mode dropout masks of this block evaluation (nullptr otherwise): savi_args.h, DropLayout
+                const DropLayout dl = savi_dropout_layout(d);
+                const float* m_att = a.drop ? a.drop + dl.att + (f * B + b) * ((int64_t)d.heads * K * K) : nullptr;
+                const float* m_out = a.drop ? a.drop + dl.out + (f * B + b) * ((int64_t)K * Ds) : nullptr;
+                const float* m_ffn = a.drop ? a.drop + dl.ffn + (f * B + b) * ((int64_t)K * Ds) : nullptr;
+                if (3 * K * (Ds + 1) + d.heads * K * (K | 1) <= AF) mha_core_fwd_smem(p_q, p_k, p_v, p_att, p_o, K, Ds, d.heads, arena, m_att);
+                else mha_core_fwd(p_q, p_k, p_v, p_att, p_o, K, Ds, d.heads, m_att);
                 SAVI_PH(17);
                 // first block adds the residual to the NORMALISED input (transformer.py:75-78)
-                LIN(p_x1, Ds, p_o, Ds, bt.po_t, bo.po, nullptr, (j == 0) ? p_y : x, Ds, K, Ds, Ds, 1.0f, 0);
+                const float* res1 = (j == 0) ? p_y : x;
+                if (m_out) {                                  // x1 = residual + output_dropout(proj_o(O))   (transformer.py:48)
+                    LIN(p_x1, Ds, p_o, Ds, bt.po_t, bo.po, nullptr, nullptr, 0, K, Ds, Ds, 1.0f, 0);
+                    __syncthreads();
+                    for (int i = tid; i < K * Ds; i += NT) p_x1[i] = res1[i] + m_out[i] * p_x1[i];
+                    __syncthreads();
+                } else
+                LIN(p_x1, Ds, p_o, Ds, bt.po_t, bo.po, nullptr, res1, Ds, K, Ds, Ds, 1.0f, 0);
                 SAVI_PH(18);
                 cta_ln(p_l2, Ds, p_x1, Ds, P + bo.ln2_w, P + bo.ln2_b, K, Ds, d.ln_eps);
                 SAVI_PH(19);
                 LINP(p_f, 4 * Ds, p_l2, Ds, bt.f1_t, bo.f1, P + bo.f1b, nullptr, 0, K, Ds, 4 * Ds, 1.0f, LIN_RELU, OP_IF(Ds, opA), nullptr);
                 SAVI_PH(20);
+                if (m_ffn) {                                  // x2 = x1 + Dropout(ffn.2(f) + b2)   (transformer.py:68)
+                    LIN(p_x2, Ds, p_f, 4 * Ds, bt.f2_t, bo.f2, P + bo.f2b, nullptr, 0, K, 4 * Ds, Ds, 1.0f, 0);
+                    __syncthreads();
+                    for (int i = tid; i < K * Ds; i += NT) p_x2[i] = p_x1[i] + m_ffn[i] * p_x2[i];
+                    __syncthreads();
+                } else
                 LIN(p_x2, Ds, p_f, 4 * Ds, bt.f2_t, bo.f2, P + bo.f2b, p_x1, Ds, K, 4 * Ds, Ds, 1.0f, 0);
                 x = p_x2;
             }

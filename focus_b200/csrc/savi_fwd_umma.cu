@@ -185,7 +185,8 @@ __device__ __forceinline__ void softmax_tiles(const Ctx& c, const Dims& d, int n
 // q (scaled), k, v columns.  Output: its column of O = softmax(q k^T) v per head.
 // ------------------------------------------------------------------------------------------------
 __device__ __forceinline__ void mha_core(const Ctx& c, int H, const float (&q)[KH], const float (&kx)[KH], const float (&v)[KH],
-                                         float (&out)[KH], float* att_g /* nullable: [H][K][K] saved */) {
+                                         float (&out)[KH], float* att_g /* nullable: [H][K][K] saved */,
+                                         const float* matt /* nullable: training-mode dropout mask of the probabilities [H][K][K] */) {
     // rows of sQ / sK / sV are 16-byte aligned (ld % 4 == 0) and 4 banks apart: float4 reads along a head's features are
     // conflict-free across slots, column reads [k][o] across o.  Attention rows are padded to ka = 4-aligned K.
     const int K = c.K, ld = MHA_LD, ka = mha_ka(K), dh = F / H;
@@ -251,7 +252,8 @@ __device__ __forceinline__ void mha_core(const Ctx& c, int H, const float (&q)[K
             const int row = row0 + r * NCW;
             if (row < H * K && c.lane < K) {
                 const float pr = e[r] * (1.0f / sm[r]);
-                sAT[((row / K) * K + c.lane) * ka + row % K] = pr;
+                // attn_dropout (transformer.py:44) acts on what multiplies V; the saved matrix stays the undropped softmax
+                sAT[((row / K) * K + c.lane) * ka + row % K] = matt ? pr * matt[row * K + c.lane] : pr;
                 if (att_g) att_g[row * K + c.lane] = pr;
             }
         }
@@ -608,12 +610,23 @@ __global__ void __launch_bounds__(NTHREADS, 1) savi_fwd_umma_kernel(const __grid
                     }
                     if (svB) save_field(c, frow(fb, a.sl.pk, f, b, B, K, F), F, o, kx);
                     float ov[KH];
-                    mha_core(c, d.heads, q, kx, v, ov, svB ? fb + a.sl.patt + (f * B + b) * ((int64_t)d.heads * K * K) : nullptr);
+                    // training-mode dropout masks of this block evaluation (nullptr otherwise): savi_args.h, DropLayout
+                    const DropLayout dl = savi_dropout_layout(d);
+                    const float* m_att = a.drop ? a.drop + dl.att + (f * B + b) * ((int64_t)d.heads * K * K) : nullptr;
+                    const float* m_out = a.drop ? a.drop + dl.out + (f * B + b) * ((int64_t)K * F) : nullptr;
+                    const float* m_ffn = a.drop ? a.drop + dl.ffn + (f * B + b) * ((int64_t)K * F) : nullptr;
+                    mha_core(c, d.heads, q, kx, v, ov, svB ? fb + a.sl.patt + (f * B + b) * ((int64_t)d.heads * K * K) : nullptr, m_att);
                     if (svA) save_field(c, frow(fb, a.sl.po, f, b, B, K, F), F, o, ov);
                     write_operand_f16(c, L.opB, ov);
                     signal_operand(c);
                     PPH(22);
                     wait_acc(c);  load_acc(c, TC_A, x1);
+                    if (m_out) {                                                           // output_dropout (transformer.py:48)
+                        float mo[KH];
+                        load_field(c, m_out, F, o, mo);
+#pragma unroll
+                        for (int kk = 0; kk < KH; ++kk) x1[kk] *= mo[kk];
+                    }
                     // the first block adds the residual to the NORMALISED input (transformer.py:75-78)
 #pragma unroll
                     for (int kk = 0; kk < KH; ++kk) x1[kk] += (j == 0) ? yv[kk] : x[kk];
@@ -638,8 +651,15 @@ __global__ void __launch_bounds__(NTHREADS, 1) savi_fwd_umma_kernel(const __grid
                     
                     wait_acc(c);  load_acc(c, TC_B, yv);
                     const float bb2 = P[bo.f2b + o];
+                    if (m_ffn) {                                                           // the Dropout closing the FFN (transformer.py:68)
+                        float mf[KH];
+                        load_field(c, m_ffn, F, o, mf);
 #pragma unroll
-                    for (int kk = 0; kk < KH; ++kk) x[kk] = x1[kk] + yv[kk] + bb2;
+                        for (int kk = 0; kk < KH; ++kk) x[kk] = x1[kk] + (yv[kk] + bb2) * mf[kk];
+                    } else {
+#pragma unroll
+                        for (int kk = 0; kk < KH; ++kk) x[kk] = x1[kk] + yv[kk] + bb2;
+                    }
                     if (svB) save_field(c, frow(fb, a.sl.px2, f, b, B, K, F), F, o, x);
                 }
                 layer_norm(c, x, h, P[po.lnf_w + o], P[po.lnf_b + o], d.ln_eps);

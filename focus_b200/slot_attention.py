@@ -82,7 +82,7 @@ class _SaviFunction(torch.autograd.Function):
     """autograd.Function over the C ABI: savi_pack_params + savi_forward / savi_backward."""
 
     @staticmethod
-    def forward(ctx, shape, grad_sync, inputs, noise, *params):
+    def forward(ctx, shape, grad_sync, drop, inputs, noise, *params):
         dev = inputs.device
         sizes = _lib.query(shape)
         stream = ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
@@ -99,12 +99,13 @@ class _SaviFunction(torch.autograd.Function):
         _lib.check(_lib.lib.savi_pack_params(ctypes.byref(shape), ptrs, _ptr(packed), stream), "savi_pack_params")
         launches = _lib.lib.savi_last_launch_count()
         _lib.check(_lib.lib.savi_forward(ctypes.byref(shape), _ptr(packed), _ptr(inputs), _ptr(noise), _ptr(slots),
-                                         _ptr(attn), _ptr(saved), _ptr(ws), stream), "savi_forward")
+                                         _ptr(attn), _ptr(saved), _ptr(ws), _ptr(drop), stream), "savi_forward")
         _SaviFunction.last_launches = launches + _lib.lib.savi_last_launch_count()
         ctx.shape = shape
         ctx.grad_sync = grad_sync
         ctx.sizes = sizes
         ctx.param_meta = [(p.shape, p.dtype) for p in params]
+        ctx.drop = drop
         ctx.save_for_backward(inputs, noise, packed, saved)
         ctx.set_materialize_grads(False)
         return (slots if inputs.dtype == torch.float32 else slots.to(inputs.dtype)), attn
@@ -123,10 +124,10 @@ class _SaviFunction(torch.autograd.Function):
         ws = torch.empty(max(sizes.bwd_ws_bytes, 16), dtype=torch.uint8, device=dev)
         g_in = torch.empty_like(inputs)
         g_par = torch.empty(sizes.param_floats, dtype=torch.float32, device=dev)
-        g_noise = torch.empty_like(noise) if ctx.needs_input_grad[3] else None
+        g_noise = torch.empty_like(noise) if ctx.needs_input_grad[4] else None
         _lib.check(_lib.lib.savi_backward(ctypes.byref(shape), _ptr(packed), _ptr(inputs), _ptr(noise), _ptr(saved),
                                           _ptr(g_slots), _ptr(g_attn), _ptr(g_in), _ptr(g_par), _ptr(g_noise),
-                                          _ptr(ws), stream), "savi_backward")
+                                          _ptr(ws), _ptr(ctx.drop), stream), "savi_backward")
         _SaviFunction.last_launches = _lib.lib.savi_last_launch_count()
         if ctx.grad_sync is not None:                # data parallel: ONE all-reduce of the flat buffer (focus_b200/distributed.py)
             ctx.grad_sync(g_par)
@@ -135,7 +136,7 @@ class _SaviFunction(torch.autograd.Function):
         for (shp, dt), o, n in zip(ctx.param_meta, off, num):
             g = g_par[o:o + n].view(shp)           # every parameter gets a tensor (zeros when unused): DDP-safe
             grads.append(g if dt == torch.float32 else g.to(dt))
-        return (None, None, g_in if ctx.needs_input_grad[2] else None, g_noise) + tuple(grads)
+        return (None, None, None, g_in if ctx.needs_input_grad[3] else None, g_noise) + tuple(grads)
 
 
 _SaviFunction.last_launches = 0
@@ -182,24 +183,41 @@ class SlotAttentionVideo(nn.Module):
         if num_predictor_blocks > 0:
             assert slot_size % num_predictor_heads == 0, "d_model must be divisible by num_heads"
         self.predictor = _Predictor(num_predictor_blocks, slot_size)
-        if self._dropout_active():
-            import warnings
-            warnings.warn("focus_b200.SlotAttentionVideo: predictor dropout=%g is accepted for evaluation only; .train() will raise "
-                          "(every FOCUS config sets SLOTS.PREDICTOR_DROPOUT = 0.0; construct with dropout=0.0 to train: the "
-                          "parameters and the state_dict do not depend on it)" % dropout, stacklevel=2)
 
     def _dropout_active(self):
-        return self.dropout > 0 and self.num_predictor_blocks > 0
+        return self.training and self.dropout > 0 and self.num_predictor_blocks > 0
 
-    def train(self, mode=True):
-        """Training-mode predictor dropout (reference transformer.py:12-13,44,48,68; constructor default 0.1, steve.py:16) is
-        not implemented by the CUDA kernels: fail when training is switched ON (the first thing a trainer does,
-        tools/steve_train_net.py:88), not in the middle of an epoch.  Evaluation (dropout is the identity) is unaffected."""
-        if mode and getattr(self, "predictor", None) is not None and self._dropout_active():
-            raise NotImplementedError(
-                "predictor dropout > 0 in training mode is not supported (every FOCUS config uses SLOTS.PREDICTOR_DROPOUT = 0.0); "
-                "construct with dropout=0.0 (same parameters / state_dict) or keep the module in .eval()")
-        return super().train(mode)
+    def _draw_dropout_masks(self, B, T, like, sizes):
+        """Training-mode predictor dropout (reference transformer.py:12-13, 44, 48, 68; constructor default 0.1, steve.py:16).
+        The kernels multiply by masks drawn HERE with the reference's own RNG consumption: the reference runs the predictor
+        after EVERY frame (the result after the last one is discarded, steve.py:100), and each block draws, in this order,
+        F.dropout on the attention probabilities [B,H,K,K], on the proj_o output [B,K,Ds] and on the FFN output [B,K,Ds].
+        Calling torch's own dropout on ones of those shapes and dtypes consumes the generator exactly as the reference does
+        (same kernel, same launch geometry), so with equal seeds the masks ARE the reference's
+        (tests/test_reference_integration.py).  Layout: include/focus_savi.h, savi_forward."""
+        import torch.nn.functional as Fn
+        p, H, K, Ds, nb = self.dropout, self.num_predictor_heads, self.num_slots, self.slot_size, self.num_predictor_blocks
+        amp = torch.is_autocast_enabled("cuda")
+        att_dt = torch.float32 if amp else like.dtype            # softmax output (autocast: an fp32 op)
+        lin_dt = torch.get_autocast_dtype("cuda") if amp else like.dtype     # nn.Linear outputs
+        Sp = (T - 1) * nb
+        dev = like.device
+        att = torch.empty(max(Sp, 1), B, H, K, K, dtype=torch.float32, device=dev)
+        out = torch.empty(max(Sp, 1), B, K, Ds, dtype=torch.float32, device=dev)
+        ffn = torch.empty(max(Sp, 1), B, K, Ds, dtype=torch.float32, device=dev)
+        one_att = torch.ones(B, H, K, K, dtype=att_dt, device=dev)
+        one_lin = torch.ones(B, K, Ds, dtype=lin_dt, device=dev)
+        for t in range(T):
+            for j in range(nb):
+                m_a, m_o, m_f = Fn.dropout(one_att, p, True), Fn.dropout(one_lin, p, True), Fn.dropout(one_lin, p, True)
+                if t < T - 1:                                   # the draw after the last frame only advances the generator
+                    f = j * (T - 1) + t
+                    att[f], out[f], ffn[f] = m_a, m_o, m_f
+        if Sp == 0:
+            return None
+        flat = torch.cat([att.reshape(-1), out.reshape(-1), ffn.reshape(-1)])
+        assert flat.numel() == sizes.dropout_floats
+        return flat
 
     def _ordered_params(self):
         """Parameters in the order of the flat buffer (include/focus_savi.h: savi_param_layout)."""
@@ -223,9 +241,11 @@ class SlotAttentionVideo(nn.Module):
                               dtype=_lib.SAVI_DTYPE_F32 if dtype == torch.float32 else _lib.SAVI_DTYPE_BF16,
                               cluster=self.cluster, eps=self.epsilon, ln_eps=1e-5)
 
-    def forward(self, inputs, noise=None):
+    def forward(self, inputs, noise=None, dropout_masks=None):
         """inputs [B,T,N,D] (fp32 or bf16, CUDA).  `noise` [B,K,Ds] optionally injects the
-        N(0,1) slot draw (tests); by default it is drawn exactly as the reference does (steve.py:56)."""
+        N(0,1) slot draw (tests); by default it is drawn exactly as the reference does (steve.py:56).
+        `dropout_masks` (tests) injects the flat predictor dropout-mask buffer of include/focus_savi.h; by default the masks
+        are drawn with the reference's RNG consumption when the module is in training mode with dropout > 0."""
         if inputs.dim() != 4 or inputs.shape[-1] != self.input_size:
             raise ValueError("inputs must be [B, T, num_inputs, %d], got %s" % (self.input_size, tuple(inputs.shape)))
         if not inputs.is_cuda:
@@ -238,18 +258,22 @@ class SlotAttentionVideo(nn.Module):
             raise TypeError("compute_dtype must be None, torch.float32 or torch.bfloat16, got %s" % cd)
         if inputs.dtype != cd:
             inputs = inputs.to(cd)                 # differentiable: the gradient comes back in the caller's dtype
-        if self.training and self._dropout_active():     # a freshly constructed module is in training mode: see train()
-            raise NotImplementedError(
-                "predictor dropout > 0 in training mode is not supported (every FOCUS config uses "
-                "SLOTS.PREDICTOR_DROPOUT = 0.0); construct with dropout=0.0 or call .eval()")
         B, T, N, _ = inputs.shape
         if noise is None:
             noise = inputs.new_empty(B, self.num_slots, self.slot_size).normal_()
         noise = noise.to(device=inputs.device, dtype=torch.float32).contiguous()
         inputs = inputs.contiguous()
         shape = self.make_shape(B, T, N, inputs.dtype)
+        drop = None
+        if dropout_masks is not None:
+            drop = dropout_masks.to(device=inputs.device, dtype=torch.float32).contiguous()
+            if drop.numel() != _lib.query(shape).dropout_floats:
+                raise ValueError("dropout_masks must hold %d floats" % _lib.query(shape).dropout_floats)
+        elif self._dropout_active():                  # after the slot-noise draw, as in the reference (steve.py:56 precedes :100)
+            with torch.cuda.device(inputs.device):
+                drop = self._draw_dropout_masks(B, T, inputs, _lib.query(shape))
         with torch.cuda.device(inputs.device), torch.autocast("cuda", enabled=False):
-            slots, attns = _SaviFunction.apply(shape, self.grad_sync if torch.is_grad_enabled() else None, inputs, noise,
+            slots, attns = _SaviFunction.apply(shape, self.grad_sync if torch.is_grad_enabled() else None, drop, inputs, noise,
                                                *self._ordered_params())
         if out_dtype != cd:
             slots, attns = slots.to(out_dtype), attns.to(out_dtype)

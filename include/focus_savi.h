@@ -36,7 +36,7 @@
 extern "C" {
 #endif
 
-#define SAVI_VERSION 1
+#define SAVI_VERSION 2   /* 2: savi_forward / savi_backward take the predictor dropout masks */
 #define SAVI_MAX_BLOCKS 4   /* predictor blocks (reference default 4: slowfast/config/defaults.py:41-62) */
 #define SAVI_MAX_SLOTS 64
 
@@ -82,6 +82,7 @@ typedef struct {
     int64_t bwd_ws_bytes;    /* backward scratch                                      */
     int32_t cluster;         /* cluster size that will be used                        */
     int32_t path;            /* SAVI_PATH_*: which kernel family this shape runs on   */
+    int64_t dropout_floats;  /* floats of the predictor dropout-mask buffer (below)   */
 } SaviSizes;
 
 int savi_version(void);
@@ -109,19 +110,24 @@ int savi_pack_params(const SaviShape* shape, const void* const* param_ptrs_host,
  *   inputs    [B,T,N,D]   token dtype, contiguous
  *   noise     [B,K,Ds]    fp32, the N(0,1) draw of steve.py:56
  *   slots_out [B,T,K,Ds]  fp32
- *   attn_out  [B,T,N,K]   token dtype (softmax over slots, pre-epsilon; steve.py:77,96) */
+ *   attn_out  [B,T,N,K]   token dtype (softmax over slots, pre-epsilon; steve.py:77,96)
+ *   dropout_masks  NULL (evaluation, or dropout = 0), or the predictor's dropout masks for a training-mode forward
+ *             (transformer.py:12-13,44,48,68): fp32 [sizes.dropout_floats] = att [Sp,B,heads,K,K] | out [Sp,B,K,Ds] |
+ *             ffn [Sp,B,K,Ds] with Sp = (T-1)*blocks, block evaluation index f = j*(T-1)+t; every entry 0 or 1/(1-p).
+ *             The caller draws them (the Python wrapper with the reference's own RNG consumption order). */
 int savi_forward(const SaviShape* shape, const void* packed, const void* inputs, const void* noise,
-                 void* slots_out, void* attn_out, void* saved, void* fwd_ws, void* stream);
+                 void* slots_out, void* attn_out, void* saved, void* fwd_ws, const void* dropout_masks, void* stream);
 
 /* Backward (the reference relies on autograd; steve.py has no explicit backward).
  *   grad_slots  [B,T,K,Ds] fp32
  *   grad_attn   [B,T,N,K]  token dtype, or NULL (the trainer's case: SURVEY.md §3.1)
  *   grad_inputs [B,T,N,D]  token dtype
  *   grad_params flat fp32 buffer of sizes.param_floats (fully overwritten)
- *   grad_noise  [B,K,Ds]   fp32 or NULL */
+ *   grad_noise  [B,K,Ds]   fp32 or NULL
+ *   dropout_masks  the buffer the forward was given (NULL if none) */
 int savi_backward(const SaviShape* shape, const void* packed, const void* inputs, const void* noise,
                   const void* saved, const void* grad_slots, const void* grad_attn,
-                  void* grad_inputs, void* grad_params, void* grad_noise, void* bwd_ws, void* stream);
+                  void* grad_inputs, void* grad_params, void* grad_noise, void* bwd_ws, const void* dropout_masks, void* stream);
 
 /* Number of kernel launches the last savi_forward / savi_backward call on this
  * thread enqueued (bench.py reports it as gpu_launches). */

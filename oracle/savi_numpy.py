@@ -128,9 +128,11 @@ def _acc(d, k, v):
 
 
 # ----------------------------------------------------------------------------
-# predictor (transformer.py:22-49, 70-86, 106-114); dropout is identity (p=0 / eval)
+# predictor (transformer.py:22-49, 70-86, 106-114).  Dropout is the identity in evaluation; in training mode it is three
+# multiplicative masks per block (attention probabilities :44, proj_o output :48, FFN output :68), which the caller passes
+# in (`drop` = (att [B,H,K,K], out [B,K,Ds], ffn [B,K,Ds]) per block, entries 0 or 1/(1-p)): the oracle has no RNG.
 # ----------------------------------------------------------------------------
-def _predictor_fwd(P, x, blocks, heads):
+def _predictor_fwd(P, x, blocks, heads, drop=None):
     B, K, Ds = x.shape
     dh = Ds // heads
     scale = x.dtype.type(dh ** -0.5)
@@ -142,13 +144,14 @@ def _predictor_fwd(P, x, blocks, heads):
         Kk = (y @ P[p + "attn.proj_k.weight"].T).reshape(B, K, heads, dh).transpose(0, 2, 1, 3)
         V = (y @ P[p + "attn.proj_v.weight"].T).reshape(B, K, heads, dh).transpose(0, 2, 1, 3)
         att = _softmax(Q @ Kk.transpose(0, 1, 3, 2))                       # [B,H,K,K]
-        O = (att @ V).transpose(0, 2, 1, 3).reshape(B, K, Ds)
-        mha = O @ P[p + "attn.proj_o.weight"].T
+        m_att, m_out, m_ffn = drop[j] if drop is not None else (1.0, 1.0, 1.0)
+        O = ((att * m_att) @ V).transpose(0, 2, 1, 3).reshape(B, K, Ds)
+        mha = (O @ P[p + "attn.proj_o.weight"].T) * m_out
         x1 = (y if j == 0 else x) + mha                                     # transformer.py:75-82
         l2, z2, r2 = _ln(x1, P[p + "ffn_layer_norm.weight"], P[p + "ffn_layer_norm.bias"])
         f = np.maximum(l2 @ P[p + "ffn.0.weight"].T + P[p + "ffn.0.bias"], 0)
-        x2 = x1 + f @ P[p + "ffn.2.weight"].T + P[p + "ffn.2.bias"]
-        sv.append(dict(y=y, z1=z1, r1=r1, Q=Q, Kk=Kk, V=V, att=att, O=O, l2=l2, z2=z2, r2=r2, f=f))
+        x2 = x1 + (f @ P[p + "ffn.2.weight"].T + P[p + "ffn.2.bias"]) * m_ffn
+        sv.append(dict(y=y, z1=z1, r1=r1, Q=Q, Kk=Kk, V=V, att=att, O=O, l2=l2, z2=z2, r2=r2, f=f, drop=(m_att, m_out, m_ffn)))
         x = x2
     out, zf, rf = _ln(x, P["predictor.layer_norm.weight"], P["predictor.layer_norm.bias"])
     return out, dict(blocks=sv, zf=zf, rf=rf)
@@ -164,10 +167,12 @@ def _predictor_bwd(P, sv, dout, blocks, heads, G):
     for j in reversed(range(blocks)):
         p = "predictor.blocks.%d." % j
         s = sv["blocks"][j]
+        m_att, m_out, m_ffn = s["drop"]
         dx2 = dx
-        _acc(G, p + "ffn.2.bias", dx2.sum((0, 1)))
-        _acc(G, p + "ffn.2.weight", np.einsum("bko,bkc->oc", dx2, s["f"]))
-        df = (dx2 @ P[p + "ffn.2.weight"]) * (s["f"] > 0)
+        dff = dx2 * m_ffn                                                  # gradient of the (dropped) FFN output
+        _acc(G, p + "ffn.2.bias", dff.sum((0, 1)))
+        _acc(G, p + "ffn.2.weight", np.einsum("bko,bkc->oc", dff, s["f"]))
+        df = (dff @ P[p + "ffn.2.weight"]) * (s["f"] > 0)
         _acc(G, p + "ffn.0.bias", df.sum((0, 1)))
         _acc(G, p + "ffn.0.weight", np.einsum("bko,bkc->oc", df, s["l2"]))
         dl2 = df @ P[p + "ffn.0.weight"]
@@ -176,10 +181,11 @@ def _predictor_bwd(P, sv, dout, blocks, heads, G):
         _acc(G, p + "ffn_layer_norm.bias", db)
         dx1 = dx2 + d
         # MHA backward
-        _acc(G, p + "attn.proj_o.weight", np.einsum("bko,bkc->oc", dx1, s["O"]))
-        dO = (dx1 @ P[p + "attn.proj_o.weight"]).reshape(B, K, heads, dh).transpose(0, 2, 1, 3)
-        datt = dO @ s["V"].transpose(0, 1, 3, 2)
-        dV = s["att"].transpose(0, 1, 3, 2) @ dO
+        dmo = dx1 * m_out                                                  # gradient of the (dropped) proj_o output
+        _acc(G, p + "attn.proj_o.weight", np.einsum("bko,bkc->oc", dmo, s["O"]))
+        dO = (dmo @ P[p + "attn.proj_o.weight"]).reshape(B, K, heads, dh).transpose(0, 2, 1, 3)
+        datt = (dO @ s["V"].transpose(0, 1, 3, 2)) * m_att
+        dV = (s["att"] * m_att).transpose(0, 1, 3, 2) @ dO
         dlog = s["att"] * (datt - (s["att"] * datt).sum(-1, keepdims=True))
         dQ = (dlog @ s["Kk"]) * scale
         dKk = dlog.transpose(0, 1, 3, 2) @ s["Q"]                            # Q already scaled
@@ -206,7 +212,8 @@ def round_f16(a):
     return np.asarray(a).astype(np.float16).astype(np.asarray(a).dtype)
 
 
-def forward(P, x, noise, num_iterations, heads, eps=1e-8, folded=True, keep=False, token_dtype=None, weight_dtype=None):
+def forward(P, x, noise, num_iterations, heads, eps=1e-8, folded=True, keep=False, token_dtype=None, weight_dtype=None,
+            drop_masks=None):
     """x [B,T,N,D], noise [B,K,Ds] -> slots [B,T,K,Ds], attn [B,T,N,K] (pre-eps softmax).
 
     dtype follows x (run float64 for the oracle, float32 to measure rounding).
@@ -220,6 +227,8 @@ def forward(P, x, noise, num_iterations, heads, eps=1e-8, folded=True, keep=Fals
     an fp16 image — the folded products wqk = Ds^-1/2 Wk^T Wq and wg = W_ih W_v (formed in
     full precision, then rounded), W_hh, the MLP and the predictor matrices; biases,
     LayerNorm affines and all activations stay full precision.  (folded form only.)
+    drop_masks=(att [Sp,B,H,K,K], out [Sp,B,K,Ds], ffn [Sp,B,K,Ds]) are the predictor's training-mode dropout masks, block
+    evaluation f = j*(T-1)+t (the layout of include/focus_savi.h); None = evaluation.
     """
     dt = x.dtype
     P = {k: np.asarray(v, dtype=dt) for k, v in P.items()}
@@ -295,7 +304,10 @@ def forward(P, x, noise, num_iterations, heads, eps=1e-8, folded=True, keep=Fals
         slots_out[:, t] = h                                                          # :96-97
         attn_out[:, t] = Pm
         if t < T - 1:     # the reference also runs it after the last frame and discards it (:100)
-            h, psv = _predictor_fwd(Ppred, h, blocks, heads)
+            drop = None
+            if drop_masks is not None:
+                drop = [tuple(np.asarray(m[j * (T - 1) + t], dt) for m in drop_masks) for j in range(blocks)]
+            h, psv = _predictor_fwd(Ppred, h, blocks, heads, drop)
             preds.append(psv)
     if not keep:
         return slots_out, attn_out

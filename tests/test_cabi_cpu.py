@@ -28,7 +28,7 @@ def test_library_exports_every_declared_symbol():
     for name in declared:
         assert hasattr(raw, name), name
     assert declared == set(L.EXPORTS)
-    assert L.lib.savi_version() == 1
+    assert L.lib.savi_version() == 2
 
 
 def test_query_sizes_and_validation():

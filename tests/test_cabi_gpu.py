@@ -36,9 +36,9 @@ def _enqueue(m, shape, b, stream):
     ptrs = (ctypes.c_void_p * len(params))(*[p.data_ptr() for p in params])
     _lib.check(_lib.lib.savi_pack_params(ctypes.byref(shape), ptrs, P(b["packed"]), st), "pack")
     _lib.check(_lib.lib.savi_forward(ctypes.byref(shape), P(b["packed"]), P(b["x"]), P(b["noise"]), P(b["slots"]), P(b["attn"]),
-                                     P(b["saved"]), P(b["fws"]), st), "forward")
+                                     P(b["saved"]), P(b["fws"]), ctypes.c_void_p(0), st), "forward")
     _lib.check(_lib.lib.savi_backward(ctypes.byref(shape), P(b["packed"]), P(b["x"]), P(b["noise"]), P(b["saved"]), P(b["gs"]), P(b["ga"]),
-                                      P(b["gx"]), P(b["gp"]), P(b["gn"]), P(b["bws"]), st), "backward")
+                                      P(b["gx"]), P(b["gp"]), P(b["gn"]), P(b["bws"]), ctypes.c_void_p(0), st), "backward")
 
 
 @pytest.mark.parametrize("cfg", [

@@ -311,16 +311,12 @@ def test_errors_are_loud():
     bad = SlotAttentionVideo(2, 4, 12, 16, 16, 1, 2, 0.0).cuda()   # D=12 is not a multiple of 8
     with pytest.raises(RuntimeError, match="input_size"):
         bad(torch.randn(1, 1, 8, 12, device="cuda"))
-    with pytest.warns(UserWarning, match="evaluation only"):
-        drop = SlotAttentionVideo(2, 4, 16, 16, 16, 1, 2, 0.1).cuda()
-    with pytest.raises(NotImplementedError):
-        drop.train()                                               # fails when training is switched on, not mid-epoch
-    with pytest.raises(NotImplementedError):
-        drop(torch.randn(1, 1, 8, 16, device="cuda"))              # (a fresh module is in training mode)
-    drop.eval()
-    s_, a_ = drop(torch.randn(1, 2, 8, 16, device="cuda"))         # evaluation with the reference's default dropout works
-    assert s_.shape == (1, 2, 4, 16)
-    SlotAttentionVideo(2, 4, 16, 16, 16, 0, 2, 0.1).train()        # no predictor blocks: dropout never acts
+    # the reference's constructor default (dropout = 0.1) trains and evaluates: tests/test_dropout.py
+    drop = SlotAttentionVideo(2, 4, 16, 16, 16, 1, 2, 0.1).cuda().train()
+    s_, a_ = drop(torch.randn(1, 2, 8, 16, device="cuda"))
+    assert s_.shape == (1, 2, 4, 16) and torch.isfinite(s_).all()
+    with pytest.raises(ValueError, match="dropout_masks"):
+        drop(torch.randn(1, 2, 8, 16, device="cuda"), dropout_masks=torch.ones(7))
 
 
 # ---- BASELINE.json configs at FULL size against the oracle ---------------------------------------

@@ -1,6 +1,6 @@
 """setup.py — builds the C-ABI CUDA library in-tree (focus_b200/libfocus_savi.so) with nvcc for sm_100a.
 
-    python setup.py build_ext --inplace        # = python -m focus_b200.build
+    python setup.py build_ext --inplace        # = python focus_b200/build.py
     pip install -e . --no-build-isolation      # development install; the library stays in the source tree
 
 The library has no Python / torch dependency (plain `extern "C"`, loaded with ctypes), so there is no
@@ -29,8 +29,11 @@ class BuildCudaLibrary(Command):
         pass
 
     def run(self):
-        sys.path.insert(0, ROOT)
-        from focus_b200 import build as b
+        # load the build script by path: importing the package would load (and symbol-check) a stale library first
+        import importlib.util
+        spec = importlib.util.spec_from_file_location("_focus_b200_build", os.path.join(ROOT, "focus_b200", "build.py"))
+        b = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(b)
         print("built", b.build(force=bool(self.force), verbose=False))
 
 

@@ -46,11 +46,11 @@ s, a = mm(xs, noise=nz)
 (s.float() * gsl).sum().backward()
 P = {k: v.detach().cpu().numpy() for k, v in mm.state_dict().items()}
 x64 = xs.detach().float().cpu().numpy().astype(np.float64)
-rs, ra, sv = O.forward(P, x64, nz.cpu().numpy().astype(np.float64), I, 4, keep=True, token_dtype="bf16")
-dx, G, _ = O.backward(P, sv, gsl.cpu().numpy().astype(np.float64), None)
+rs, ra, sv = O.forward(P, x64, nz.cpu().numpy().astype(np.float64), I, 4, keep=True, token_dtype="bf16", weight_dtype="f16")
+dx, G, _ = O.backward(P, sv, gsl.cpu().numpy().astype(np.float64), None, bwd_weight_dtype="bf16")
 es = O.max_norm_err(s.detach().float().cpu().numpy(), rs); ea = O.max_norm_err(a.detach().float().cpu().numpy(), ra)
 ed = O.max_norm_err(xs.grad.float().cpu().numpy(), dx)
 gmax = max(float(np.abs(v).max()) for v in G.values())
 eg = max(float(np.abs(p.grad.cpu().numpy() - G[n]).max()) / gmax for n, p in mm.named_parameters())
-print("N=16384 clip vs oracle (bf16 token quantisation point): slots %.2e attn %.2e d_inputs %.2e param grads %.2e (bar 2e-2)" % (es, ea, ed, eg))
+print("N=16384 clip vs oracle (at the quantisation points: bf16 tokens, fp16 / bf16 weight images): slots %.2e attn %.2e d_inputs %.2e param grads %.2e (bar 2e-2)" % (es, ea, ed, eg))
 assert max(es, ea, ed, eg) < 2e-2

@@ -21,16 +21,22 @@ def _round_bf16(a):
 
 def token_mlp(emb, ln_w, ln_b, w1, b1, w2, b2, eps=1e-5, operand_dtype=None):
     """emb [BT,C,H,W] -> emb_set [BT,H*W,C] = mlp(layer_norm(emb.permute(0,2,3,1).flatten(1,2)))  (steve.py:307-308), float64.
-    operand_dtype="bf16" models the CUDA kernel's tensor-core operands: the LayerNorm output, both weight matrices and the
-    hidden activations are rounded to bfloat16 before each product (accumulation and biases stay full precision)."""
-    r = _round_bf16 if operand_dtype == "bf16" else (lambda a: a)
+    operand_dtype="bf16" models the CUDA kernel's tensor-core operands: it folds the LayerNorm affine into the first Linear
+    (W1' = W1 diag(ln_w), b1' = b1 + W1 ln_b — the same function in exact arithmetic) and rounds the normalised token, W1', the
+    hidden activations and W2 to bfloat16 before each product (accumulation and biases stay full precision)."""
     x = np.asarray(emb, np.float64)
     BT, C, H, W = x.shape
     x = x.transpose(0, 2, 3, 1).reshape(BT, H * W, C)
     mu = x.mean(-1, keepdims=True)
     xc = x - mu
-    xn = xc / np.sqrt((xc * xc).mean(-1, keepdims=True) + eps) * np.asarray(ln_w, np.float64) + np.asarray(ln_b, np.float64)
-    h = np.maximum(r(xn) @ r(np.asarray(w1, np.float64)).T + np.asarray(b1, np.float64), 0.0)
+    xh = xc / np.sqrt((xc * xc).mean(-1, keepdims=True) + eps)
+    ln_w, ln_b, w1, b1 = (np.asarray(t, np.float64) for t in (ln_w, ln_b, w1, b1))
+    if operand_dtype == "bf16":
+        r = _round_bf16
+        h = np.maximum(r(xh) @ r(w1 * ln_w[None, :]).T + (b1 + w1 @ ln_b), 0.0)
+    else:
+        r = lambda a: a
+        h = np.maximum((xh * ln_w + ln_b) @ w1.T + b1, 0.0)
     return r(h) @ r(np.asarray(w2, np.float64)).T + np.asarray(b2, np.float64)
 
 

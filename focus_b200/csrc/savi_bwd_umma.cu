@@ -205,10 +205,11 @@ __device__ __forceinline__ void softmax_bwd_tiles(const Ctx& c, const Dims& d, i
         __syncwarp();
         if (c.lane == 0) mbar_arrive(&c.bars[B_AREADY + g]);
         UPH(58);
-        if (valid) {
+        {
             // coefficients of the d_inputs kernel: this token's row of the iteration's K-major operand block,
             // [128 tokens][32 dL | 32 W] bf16, SWIZZLE_128B (savi_dx_umma.cu fetches the block with one bulk copy);
-            // slots [24, 32) belong to nobody: written as zeros so the block stays finite
+            // slots [24, 32) belong to nobody and rows past N (ragged last tile) to no token: written as zeros, the d_inputs
+            // kernel also sums the block's columns over its rows on the tensor cores
             unsigned char* row = coef + (size_t)(tile0 + i) * d.I * 16384 + (size_t)c.o * 128;
 #pragma unroll
             for (int s = 0; s < KTOK; s += 8) {

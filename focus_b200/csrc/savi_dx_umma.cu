@@ -134,17 +134,29 @@ __global__ void __launch_bounds__(DX_THREADS, 1) dx_umma_kernel(const __grid_con
         mbar_expect_tx(&bars[BF], I * 16384); bulk_g2s(ct, coef_f, I * 16384, &bars[BF]);
     }
     // right-hand side rows: iteration i -> rows [64 i, 64 i + 64): qk_i (32 rows, zero beyond K) then dUx_i; MN-major, two 64-column blocks
-#pragma unroll 4
-    for (int idx = tid; idx < KT * 16; idx += DX_THREADS) {
-        const int k = idx >> 4, c8 = (idx & 15) * 8;            // row, first of 8 columns
-        const int i = k >> 6, which = (k >> 5) & 1, s = k & 31;
-        uint4 v = make_uint4(0u, 0u, 0u, 0u);
-        if (s < K) {
-            const float* src = (which == 0 ? a.qk : a.dux) + ((((size_t)t * I + i) * a.B + b) * K + s) * D128 + c8;
-            const float4 p = ld4(src), q = ld4(src + 4);
-            v.x = pack2(p.x, p.y); v.y = pack2(p.z, p.w); v.z = pack2(q.x, q.y); v.w = pack2(q.z, q.w);
+    // (all of a thread's loads are issued before the first is converted: one DRAM round trip instead of three)
+    {
+        constexpr int RH_IT = (64 * 3 * 16 + DX_THREADS - 1) / DX_THREADS;      // I <= 3
+        float4 p[RH_IT], q[RH_IT];
+#pragma unroll
+        for (int it = 0; it < RH_IT; ++it) {
+            const int idx = tid + it * DX_THREADS;
+            const int k = idx >> 4, c8 = (idx & 15) * 8;        // row, first of 8 columns
+            const int i = k >> 6, which = (k >> 5) & 1, s = k & 31;
+            p[it] = q[it] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (idx < KT * 16 && s < K) {
+                const float* src = (which == 0 ? a.qk : a.dux) + ((((size_t)t * I + i) * a.B + b) * K + s) * D128 + c8;
+                p[it] = ld4(src); q[it] = ld4(src + 4);
+            }
         }
-        *reinterpret_cast<uint4*>(rhs + (c8 >> 6) * (KT * 128) + k * 128 + ((((c8 & 63) >> 3) ^ (k & 7)) << 4)) = v;
+#pragma unroll
+        for (int it = 0; it < RH_IT; ++it) {
+            const int idx = tid + it * DX_THREADS;
+            const int k = idx >> 4, c8 = (idx & 15) * 8;
+            if (idx < KT * 16)
+                *reinterpret_cast<uint4*>(rhs + (c8 >> 6) * (KT * 128) + k * 128 + ((((c8 & 63) >> 3) ^ (k & 7)) << 4)) =
+                    make_uint4(pack2(p[it].x, p[it].y), pack2(p[it].z, p[it].w), pack2(q[it].x, q[it].y), pack2(q[it].z, q[it].w));
+        }
     }
     fence_async_smem();
     fence_before_sync();

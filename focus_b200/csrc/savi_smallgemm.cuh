@@ -11,8 +11,9 @@ struct SmallGemm {
     int sai, sak;            // A(i, k) = A[i * sai + k * sak]
     int sbk, sbj;            // B(k, j) = B[k * sbk + j * sbj]
     float alpha;
+    int accumulate;          // 0: C = alpha A B (plain store); 1: C += alpha A B (atomic: a split contraction into a zeroed C)
 };
-constexpr int SMALLGEMM_MAX = 4;
+constexpr int SMALLGEMM_MAX = 6;
 struct SmallGemmArgs { SmallGemm g[SMALLGEMM_MAX]; int count; };
 
 constexpr int SG_KC = 128;       // contraction chunk: 32 independent loads in flight per thread, 1-3 chunks per product
@@ -53,7 +54,10 @@ static __global__ void __launch_bounds__(256) small_gemm_kernel(const __grid_con
         }
     }
 #pragma unroll
-    for (int m = 0; m < 4; ++m) g.C[(size_t)(i0 + ty + 8 * m) * g.N + j0 + tx] = g.alpha * acc[m];
+    for (int m = 0; m < 4; ++m) {
+        float* dst = g.C + (size_t)(i0 + ty + 8 * m) * g.N + j0 + tx;
+        if (g.accumulate) atomicAdd(dst, g.alpha * acc[m]); else *dst = g.alpha * acc[m];
+    }
 }
 
 static inline cudaError_t launch_small_gemms(const SmallGemmArgs& ga, cudaStream_t st) {

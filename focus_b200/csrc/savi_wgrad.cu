@@ -74,11 +74,14 @@ __global__ void __launch_bounds__(256) wgrad_kernel(const __grid_constant__ Wgra
 // (project_q / project_k / project_v / gru.weight_ih receive no other contribution on this path: plain stores.)
 static cudaError_t launch_fold_grads(const float* P, const float* dwqk, const float* dwg, float* G, const ParamOff& po,
                                      int D, int Ds, float s, cudaStream_t st) {
-    SmallGemmArgs ga; ga.count = 4;
-    ga.g[0] = SmallGemm{P + po.wk, dwqk, G + po.wq, Ds, Ds, D, D, 1, Ds, 1, s};
-    ga.g[1] = SmallGemm{P + po.wq, dwqk, G + po.wk, Ds, D, Ds, Ds, 1, 1, Ds, s};
-    ga.g[2] = SmallGemm{dwg, P + po.wv, G + po.wih, 3 * Ds, Ds, D, D, 1, 1, D, 1.0f};
-    ga.g[3] = SmallGemm{P + po.wih, dwg, G + po.wv, Ds, D, 3 * Ds, 1, Ds, D, 1, 1.0f};
+    SmallGemmArgs ga; ga.count = 0;
+    ga.g[ga.count++] = SmallGemm{P + po.wk, dwqk, G + po.wq, Ds, Ds, D, D, 1, Ds, 1, s, 0};
+    ga.g[ga.count++] = SmallGemm{P + po.wq, dwqk, G + po.wk, Ds, D, Ds, Ds, 1, 1, Ds, s, 0};
+    ga.g[ga.count++] = SmallGemm{dwg, P + po.wv, G + po.wih, 3 * Ds, Ds, D, D, 1, 1, D, 1.0f, 0};
+    // dWv contracts over the 3 Ds gate rows: one product per gate block, accumulated into the (zeroed) gradient buffer, so that no
+    // CTA walks more than one 128-deep chunk
+    for (int gate = 0; gate < 3; ++gate)
+        ga.g[ga.count++] = SmallGemm{P + po.wih + (size_t)gate * Ds * Ds, dwg + (size_t)gate * Ds * D, G + po.wv, Ds, D, Ds, 1, Ds, D, 1, 1.0f, 1};
     return launch_small_gemms(ga, st);
 }
 

@@ -16,7 +16,7 @@ SAVI_MAX_SLOTS = 64
 PATH_NAMES = {0: "simt-fp32", 1: "mma.sync-bf16", 2: "tcgen05-bf16"}
 
 EXPORTS = ["savi_version", "savi_last_error", "savi_query", "savi_param_layout", "savi_pack_params",
-           "savi_forward", "savi_backward", "savi_last_launch_count", "savi_profile_enable", "savi_profile_read", "savi_debug_set_phase_buffer", "savi_set_option"]
+           "savi_forward", "savi_backward", "savi_last_launch_count", "savi_profile_enable", "savi_profile_read", "savi_debug_set_phase_buffer", "savi_set_option", "savi_allreduce_peers"]
 EXPORTS_STEVE = ["steve_attention_overlay", "steve_ari_tables", "steve_token_mlp", "steve_token_mlp_ws_bytes"]            # include/focus_steve.h
 
 
@@ -38,7 +38,7 @@ def _load():
             "focus_b200: %s is missing. Build it with `python -m focus_b200.build` (nvcc, sm_100a). "
             "There is no CPU or PyTorch fallback for this path." % LIB_PATH)
     lib = ctypes.CDLL(LIB_PATH)
-    vp, ip = ctypes.c_void_p, ctypes.c_int
+    vp, ip, i64 = ctypes.c_void_p, ctypes.c_int, ctypes.c_int64
     lib.savi_version.restype = ip
     lib.savi_last_error.restype = ctypes.c_char_p
     lib.savi_last_launch_count.restype = ip
@@ -60,7 +60,8 @@ def _load():
     lib.savi_debug_set_phase_buffer.restype = ip
     lib.savi_set_option.argtypes = [ctypes.c_char_p, ip]
     lib.savi_set_option.restype = ip
-    i64 = ctypes.c_int64
+    lib.savi_allreduce_peers.argtypes = [ctypes.POINTER(vp), ctypes.POINTER(vp), vp, ip, ip, vp, i64, ctypes.c_float, i64, vp]
+    lib.savi_allreduce_peers.restype = ip
     lib.steve_attention_overlay.argtypes = [vp, ip, vp, vp, vp, i64, ip, ip, ip, ip, ip, ip, vp]
     lib.steve_attention_overlay.restype = ip
     lib.steve_ari_tables.argtypes = [vp, vp, vp, ip, ip, ip, i64, vp]

@@ -15,6 +15,7 @@ UNITS = [("savi_api.cu", "savi_api.o", []),
          ("savi_bwd_umma.cu", "savi_bwd_umma.o", []),
          ("savi_dx_umma.cu", "savi_dx_umma.o", []),
          ("savi_wgrad_umma.cu", "savi_wgrad_umma.o", []),
+         ("savi_allreduce.cu", "savi_allreduce.o", []),
          ("steve_neighbors.cu", "steve_neighbors.o", []),
          ("steve_token_mlp.cu", "steve_token_mlp.o", []),
          ("savi_fwd.cu", "savi_fwd_f32.o", ["-DSAVI_TOK=float", "-DSAVI_SUFFIX=f32"]),

@@ -2,11 +2,18 @@
 
 The path shards by batch of clips only (every clip is independent in forward and backward; the
 reference does the same with DDP + DistributedSampler: slowfast/models/build.py:79-83,
-slowfast/datasets/loader.py:97).  The single exchange step is the parameter-gradient all-reduce.
-`FlatGradAllReduce` does it as ONE collective on one contiguous buffer (the module's gradients are
-only ~1.5-3.4 MB, so the cost is launch latency, not bandwidth) instead of DDP's per-bucket calls.
-Works with any torch.distributed backend (nccl on B200s, gloo in the CPU tests).
+slowfast/datasets/loader.py:97).  The single exchange step is the parameter-gradient all-reduce, on ONE
+contiguous buffer (the module's gradients are only ~1.5-3.4 MB, so the cost is latency, not bandwidth):
+  * `PeerGradSync` — the library's own kernel over NVLink / NVSwitch peer memory (csrc/savi_allreduce.cu,
+    include/focus_savi.h: savi_allreduce_peers): the CUDA backward writes its flat gradient buffer straight into
+    symmetric memory and one kernel per rank sums all peers' buffers (one `multimem.ld_reduce` through the switch where
+    the allocation has a multicast mapping).  One node, NCCL process group, <= 16 ranks;
+  * `GradSync` — one NCCL (or gloo, in the CPU tests) all-reduce of the same buffer: the fallback and the multi-node path.
 """
+import ctypes
+import os
+import warnings
+
 import torch
 import torch.distributed as dist
 
@@ -53,12 +60,97 @@ class GradSync:
         return all_reduce_flat_(flat, self.group, self.average)
 
 
-def attach_grad_sync(module, group=None, average=True, broadcast_parameters=True):
-    """Enable the fused flat-gradient all-reduce on `module`; rank 0's parameters are broadcast first (as DDP does)."""
+class PeerGradSync:
+    """The same exchange as `GradSync`, as ONE kernel of this library over peer memory instead of an NCCL call.
+
+    `buffer(n, device)` hands the backward a flat fp32 gradient buffer in symmetric memory (allocated and exchanged with the
+    peers on first use: a collective, so every rank must reach its first backward); `__call__(flat)` launches
+    savi_allreduce_peers on the current stream and returns a NEW local tensor with the rank-averaged (or summed) gradients —
+    the symmetric buffer itself is reused by the next step, autograd keeps views of the returned one."""
+
+    def __init__(self, group=None, average=True, multicast=True):
+        self.group = group if group is not None else dist.group.WORLD
+        self.average, self.multicast = average, multicast
+        self.buf = self.hdl = None
+
+    def buffer(self, n, device):
+        cap = (n + 3) // 4 * 4                              # the kernel moves 16-byte vectors
+        if self.buf is None or self.buf.numel() < cap or self.buf.device != device:
+            import torch.distributed._symmetric_memory as symm
+            self.buf = symm.empty(cap, dtype=torch.float32, device=device)
+            self.buf.zero_()
+            self.hdl = symm.rendezvous(self.buf, self.group)
+            w = self.hdl.world_size
+            vp = ctypes.c_void_p
+            self._bufs = (vp * w)(*[int(p) for p in self.hdl.buffer_ptrs])
+            self._pads = (vp * w)(*[int(p) for p in self.hdl.signal_pad_ptrs])
+            mc = int(getattr(self.hdl, "multicast_ptr", 0) or 0) if self.multicast else 0     # 0: no NVLS mapping for this allocation
+            self._mc = vp(mc if mc else None)
+            self._pad_bytes = int(symm.get_signal_pad_size())
+        return self.buf[:n]
+
+    @property
+    def uses_multicast(self):
+        return self.hdl is not None and bool(self._mc.value)
+
+    def __call__(self, flat):
+        from . import _lib
+        if self.hdl is None or flat.data_ptr() != self.buf.data_ptr():
+            raise RuntimeError("PeerGradSync: the gradient buffer must be the symmetric one returned by buffer()")
+        n, cap = flat.numel(), (flat.numel() + 3) // 4 * 4
+        out = torch.empty(cap, dtype=torch.float32, device=flat.device)     # ordinary device memory: autograd keeps views of it
+        stream = ctypes.c_void_p(torch.cuda.current_stream(flat.device).cuda_stream)
+        scale = 1.0 / self.hdl.world_size if self.average else 1.0
+        with torch.cuda.device(flat.device):
+            _lib.check(_lib.lib.savi_allreduce_peers(self._bufs, self._pads, self._mc, self.hdl.rank, self.hdl.world_size,
+                                                     ctypes.c_void_p(out.data_ptr()), cap, scale, self._pad_bytes, stream),
+                       "savi_allreduce_peers")
+        return out[:n]
+
+
+def _peer_sync_possible(module, group):
+    """One node, NCCL, CUDA parameters, <= 16 ranks: the conditions of the peer-memory kernel."""
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_backend(group) != "nccl":
+        return False
+    world = dist.get_world_size(group)
+    if world < 2 or world > 16 or world > torch.cuda.device_count():
+        return False
+    p = next(module.parameters(), None)
+    return p is not None and p.is_cuda
+
+
+def attach_grad_sync(module, group=None, average=True, broadcast_parameters=True, peer="auto"):
+    """Enable the fused flat-gradient all-reduce on `module`; rank 0's parameters are broadcast first (as DDP does).
+    peer = "auto": the library's peer-memory kernel when the group is one node of NVLink-connected GPUs under NCCL (all ranks
+    must take the same branch: the decision is agreed with one small all-reduce), else the NCCL / gloo all-reduce;
+    True: require the peer kernel; False (or FOCUS_SAVI_PEER_SYNC=0): always the collective library."""
     if broadcast_parameters and dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
         for t in list(module.parameters()) + list(module.buffers()):
             dist.broadcast(t.data, src=dist.get_global_rank(group, 0) if group is not None else 0, group=group)
-    module.grad_sync = GradSync(group, average)
+    if os.environ.get("FOCUS_SAVI_PEER_SYNC") == "0":
+        peer = False
+    sync = None
+    if peer and _peer_sync_possible(module, group):
+        dev = next(module.parameters()).device
+        ok = torch.ones(1, device=dev)
+        try:                                                # allocate + rendezvous now, so a failure is seen by every rank here
+            cand = PeerGradSync(group, average)
+            cand.buffer(sum(p.numel() for p in module.parameters()), dev)
+        except Exception as e:                              # no symmetric memory on this system: fall back, on all ranks
+            if peer is True:
+                raise
+            warnings.warn("focus_b200: peer-memory gradient sync unavailable (%s: %s); using the %s all-reduce"
+                          % (type(e).__name__, str(e)[:120], dist.get_backend(group)))
+            ok.zero_()
+            cand = None
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=group)
+        if ok.item() > 0:
+            sync = cand
+        elif peer is True:
+            raise RuntimeError("peer-memory gradient sync is not available on every rank")
+    elif peer is True:
+        raise RuntimeError("peer-memory gradient sync needs an NCCL group of 2-16 CUDA ranks on one node")
+    module.grad_sync = sync if sync is not None else GradSync(group, average)
     return module.grad_sync
 
 

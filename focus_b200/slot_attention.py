@@ -123,14 +123,17 @@ class _SaviFunction(torch.autograd.Function):
             g_attn = g_attn.to(inputs.dtype).contiguous()
         ws = torch.empty(max(sizes.bwd_ws_bytes, 16), dtype=torch.uint8, device=dev)
         g_in = torch.empty_like(inputs)
-        g_par = torch.empty(sizes.param_floats, dtype=torch.float32, device=dev)
+        if ctx.grad_sync is not None and hasattr(ctx.grad_sync, "buffer"):
+            g_par = ctx.grad_sync.buffer(sizes.param_floats, dev)        # symmetric memory: the peers read it directly
+        else:
+            g_par = torch.empty(sizes.param_floats, dtype=torch.float32, device=dev)
         g_noise = torch.empty_like(noise) if ctx.needs_input_grad[4] else None
         _lib.check(_lib.lib.savi_backward(ctypes.byref(shape), _ptr(packed), _ptr(inputs), _ptr(noise), _ptr(saved),
                                           _ptr(g_slots), _ptr(g_attn), _ptr(g_in), _ptr(g_par), _ptr(g_noise),
                                           _ptr(ws), _ptr(ctx.drop), stream), "savi_backward")
         _SaviFunction.last_launches = _lib.lib.savi_last_launch_count()
         if ctx.grad_sync is not None:                # data parallel: ONE all-reduce of the flat buffer (focus_b200/distributed.py)
-            ctx.grad_sync(g_par)
+            g_par = ctx.grad_sync(g_par)
         off, num = _lib.param_layout(shape, len(ctx.param_meta))
         grads = []
         for (shp, dt), o, n in zip(ctx.param_meta, off, num):

@@ -152,6 +152,21 @@ int savi_profile_read(float* ms_host, int n);
  * Returns SAVI_EINVAL for an unknown name.  Not thread-safe against concurrent forward / backward calls. */
 int savi_set_option(const char* name, int value);
 
+/* Data-parallel exchange step (replaces the gradient all-reduce DistributedDataParallel performs for the
+ * reference, slowfast/models/build.py:79-83): out = scale * sum over ranks of the flat gradient buffer, as ONE kernel over
+ * NVLink / NVSwitch peer memory.  Every rank calls it once per step on its own stream with
+ *   peer_bufs_host[r]    this process's mapping of rank r's gradient buffer (symmetric memory: same size on every rank;
+ *                        entry [rank] is the local buffer savi_backward wrote grad_params_flat into),
+ *   signal_pads_host[r]  this process's mapping of rank r's zero-initialised signal pad (signal_pad_bytes each; the kernel
+ *                        uses 2 * blocks * world 32-bit slots of it and leaves them zero),
+ *   multicast            multicast (NVLS) address of the buffer, or NULL to read the peers one by one,
+ *   out                  local result, n_floats fp32 (n_floats % 4 == 0); must not alias the gradient buffer.
+ * Both arrays are HOST arrays of `world` device pointers (world <= 16).  The kernel waits for all ranks to arrive (so each
+ * peer's backward, earlier on that peer's stream, is complete) and does not finish before every peer has read this rank's
+ * buffer, so the buffer may be overwritten by the next step.  No NCCL, no host synchronisation; capturable in a CUDA graph. */
+int savi_allreduce_peers(const void* const* peer_bufs_host, void* const* signal_pads_host, const void* multicast,
+                         int rank, int world, void* out, int64_t n_floats, float scale, int64_t signal_pad_bytes, void* stream);
+
 /* Development aid: when set to a device buffer of 64 int64 counters, CTA 0 of the clip kernels
  * accumulates the SM cycles spent in each phase of the recurrence (tools/phase_times.py).
  * Pass NULL to disable (default).  Adds barriers; never enable while benchmarking. */

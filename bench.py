@@ -232,7 +232,7 @@ def config_dict(args, cfg, n):
             "clips_per_gpu": cfg["B"], "global_clips": cfg["B"] * n, "T": cfg["T"], "N": cfg["N"], "D": cfg["D"],
             "Ds": cfg["Ds"], "M": cfg["M"], "K": cfg["K"], "iters": cfg["I"], "predictor": "%d block x %d heads" % (cfg["blocks"], cfg["heads"]),
             "token_dtype": cfg["dtype"], "grad_attn": "dense N(0,1)",
-            "parallelism": "dp%d" % n + ("" if n == 1 else " (torch DDP)" if args.ddp else " (one flat NCCL gradient all-reduce inside backward)"),
+            "parallelism": "dp%d" % n + ("" if n == 1 else " (torch DDP)" if args.ddp else " (gradient exchange inside backward: %s)" % getattr(args, "exchange", "one flat all-reduce")),
             "l2": "flushed between timed steps (256 MiB write outside the event brackets); step working set >> 126 MB L2"}
 
 
@@ -259,9 +259,11 @@ def run_ours(args, cfg, rank, world, local_rank):
     if world > 1 and args.ddp:       # stock DistributedDataParallel, what the reference wraps the model in (models/build.py:79-83)
         ddp = torch.nn.parallel.DistributedDataParallel(model, device_ids=[local_rank], output_device=local_rank,
                                                         gradient_as_bucket_view=True, bucket_cap_mb=64)
-    elif world > 1:                  # the path's own exchange step: ONE NCCL all-reduce of the flat gradient buffer inside backward
-        from focus_b200.distributed import attach_grad_sync
-        attach_grad_sync(model)
+    elif world > 1:                  # the path's own exchange step: ONE all-reduce of the flat gradient buffer inside backward
+        from focus_b200.distributed import PeerGradSync, attach_grad_sync
+        sync = attach_grad_sync(model, peer=False if args.nccl_sync else "auto")
+        args.exchange = ("library kernel over NVLink peer memory (savi_allreduce_peers%s)" % (", multimem.ld_reduce" if sync.uses_multicast else "")
+                         if isinstance(sync, PeerGradSync) else "one flat NCCL all-reduce")
     g = torch.Generator(device="cpu").manual_seed(1 + rank)
     B, T, N, D, K, Ds = c["B"], c["T"], c["N"], c["D"], c["K"], c["Ds"]
     x_host = torch.randn(B, T, N, D, generator=g).to(dt).pin_memory()
@@ -502,6 +504,7 @@ def main():
     ap.add_argument("--clips", type=int, default=0, help="override clips per GPU")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--ddp", action="store_true", help="N>1: wrap the module in torch DDP instead of the fused flat all-reduce")
+    ap.add_argument("--nccl-sync", action="store_true", help="N>1: NCCL all-reduce of the flat gradient buffer instead of the library's peer-memory kernel")
     ap.add_argument("--no-graph", action="store_true", help="do not try the CUDA-graph replay of the step")
     ap.add_argument("--gpu-eager", action="store_true", help="--impl reference only: also time the reference module through PyTorch eager on cuda:0")
     args = ap.parse_args()

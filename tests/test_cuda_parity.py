@@ -155,6 +155,12 @@ SHAPES = [
     (1, 2, 1, 8, 8, 4, 3, 2, 1, 1),              # N=1 (a single token), smallest dims
     (2, 2, 136, 128, 128, 128, 64, 3, 1, 4),     # K=64 with 3 iterations: mma.sync path, d_inputs kernel in iteration groups
     (2, 2, 264, 64, 64, 64, 40, 3, 1, 2),        # K=40 (3 slot m-tiles), D=64
+    # the tcgen05 family (D = Ds = M = 128, K <= 24) off its MOVi shape: ragged / odd / sub-tile token counts (TMA tensor tiles:
+    # rows past N zero-filled and clipped; coefficient rows past N zeroed for the tensor-core column sums), 1-3 iterations
+    (2, 2, 300, 128, 128, 128, 11, 3, 1, 4),     # N = 2 tiles + 44 tokens
+    (1, 2, 77, 128, 128, 128, 24, 2, 2, 4),      # N < one tile, 2 predictor blocks, 2 iterations
+    (3, 1, 129, 128, 128, 128, 5, 1, 1, 2),      # one token past a tile, I = 1, T = 1
+    (2, 3, 257, 128, 128, 128, 24, 3, 1, 4),     # odd N
 ]
 
 

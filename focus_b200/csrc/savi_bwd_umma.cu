@@ -396,7 +396,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) savi_bwd_umma_kernel(const __grid
     const ParamOff& po = a.po;
     unsigned char* sm = smem_raw;
     if ((smem_u32(sm) & 1023u) != 0u) __trap();                // SWIZZLE_128B operands need a 1024-byte aligned base
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    // (warp index through a lane-0 broadcast: ptxas then treats it, and every role branch on it, as warp-uniform)
+    const int tid = threadIdx.x, warp = __shfl_sync(0xffffffffu, tid >> 5, 0), lane = tid & 31;
     const int CN = d.CN, b = blockIdx.x / CN, rank = blockIdx.x % CN;
     const int K = d.K, B = d.B, KP = d.KP;
     const Smem L = plan_smem(K, CN, true);

@@ -253,7 +253,7 @@ struct Ctx {
 };
 
 __device__ __forceinline__ void ctx_init(Ctx& c, int tid, int K, unsigned char* sm, const Smem& L, uint32_t tb, uint64_t* bars) {
-    c.tid = tid; c.warp = tid >> 5; c.lane = tid & 31; c.wg = c.warp >> 2; c.o = (c.warp & 3) * 32 + c.lane; c.K = K;
+    c.tid = tid; c.warp = __shfl_sync(0xffffffffu, tid >> 5, 0); c.lane = tid & 31; c.wg = c.warp >> 2; c.o = (c.warp & 3) * 32 + c.lane; c.K = K;
     c.k0 = c.wg * KH;
     c.nk = min(max(K - c.k0, 0), KH);
     c.sm = sm; c.L = L; c.tb = tb; c.bars = bars; c.ph_acc = 0;

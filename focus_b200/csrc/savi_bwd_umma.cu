@@ -838,6 +838,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) savi_bwd_umma_kernel(const __grid
                         *reinterpret_cast<float4*>(pn) = ld4(ib + o * KR8 + c.k0); *reinterpret_cast<float4*>(pn + 4) = ld4(ib + o * KR8 + c.k0 + 4);
 #pragma unroll
                         for (int kk = 0; kk < KH; ++kk) dqk[kk] = lead ? dqk[kk] + pn[kk] : pn[kk] + dqk[kk];
+                        loaded_before_release(pn[0]); loaded_before_release(pn[4]);
                     }
                     __syncwarp();
                     if (lane == 0) mbar_arrive_remote(map_to_rank(&bars[B_INBOX + 1], peer));     // consumed: the peer may send again

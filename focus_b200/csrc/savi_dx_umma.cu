@@ -73,7 +73,7 @@ __device__ __forceinline__ void tma_store_3d(const CUtensorMap* tm, int c0, int 
 __global__ void __launch_bounds__(DX_THREADS, 1) dx_umma_kernel(const __grid_constant__ DxUArgs a) {
     extern __shared__ __align__(1024) unsigned char sm[];
     if ((smem_u32(sm) & 1023u) != 0u) __trap();
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int tid = threadIdx.x, warp = __shfl_sync(0xffffffffu, tid >> 5, 0), lane = tid & 31;      // (provably warp-uniform role index)
     const int I = a.I, K = a.K, N = a.N, KT = 64 * I;
     // frames in the order the backward clip kernel finishes them: t descending, all clips of a frame together
     const int t = a.T - 1 - (int)blockIdx.y / a.B, b = (int)blockIdx.y % a.B, f = b * a.T + t;

@@ -505,6 +505,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) savi_fwd_umma_kernel(const __grid
                             num[kk] = lead ? num[kk] + pn[kk] : pn[kk] + num[kk];
                             den[kk] = lead ? den[kk] + pd[kk] : pd[kk] + den[kk];
                         }
+                        loaded_before_release(pn[0]); loaded_before_release(pn[4]); loaded_before_release(pd[0]); loaded_before_release(pd[4]);
                     }
 #if SAVI_FWD_RING8
                     __syncwarp();

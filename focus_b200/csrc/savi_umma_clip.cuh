@@ -84,6 +84,10 @@ __device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity
     while (!mbar_try_wait_cluster(bar, parity)) { }
 #endif
 }
+// A buffer that other agents refill (peer stores, bulk copies) must only be released once the values read from it have ARRIVED:
+// an arrive that merely follows the loads in program order can be scheduled ahead of their data.  Naming a loaded value as the
+// input of an (empty) volatile asm pins the release behind the load's completion at no cost.
+__device__ __forceinline__ void loaded_before_release(float v) { asm volatile("" :: "f"(v) : "memory"); }
 __device__ __forceinline__ void mbar_arrive_remote(uint32_t cluster_addr) {
     asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];\n" :: "r"(cluster_addr) : "memory");
 }

@@ -54,7 +54,7 @@ __global__ void __launch_bounds__(WU_THREADS, 1) wgrad_umma_kernel(const __grid_
     extern __shared__ __align__(1024) unsigned char sm[];
     if ((smem_u32(sm) & 1023u) != 0u) __trap();
     const WgradArgs& wa = ua.wa;
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int tid = threadIdx.x, warp = __shfl_sync(0xffffffffu, tid >> 5, 0), lane = tid & 31;      // (provably warp-uniform role index)
     // ---- locate this CTA's work item: (job, output tile, row slice) ----
     int job = -1, tile = 0, slice = 0;
     {
@@ -117,8 +117,6 @@ __global__ void __launch_bounds__(WU_THREADS, 1) wgrad_umma_kernel(const __grid_
                 pa[i][0] = h ? y1 : y0; pa[i][1] = h ? y0 : y1;
                 pb[i][0] = h ? x1 : x0; pb[i][1] = h ? x0 : x1;
             }
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&bars[BRE + rs]);                   // the ring stage may be refilled
             mbar_wait(&bars[BOE + st], ((ch >> 1) & 1u) ^ 1u);             // the MMAs that read this operand stage two chunks ago are done
 #pragma unroll
             for (int i = 0; i < WU_LD; ++i) {
@@ -132,7 +130,13 @@ __global__ void __launch_bounds__(WU_THREADS, 1) wgrad_umma_kernel(const __grid_
             }
             fence_async_smem();
             __syncwarp();
-            if (lane == 0) mbar_arrive(&bars[BOF + st]);
+            if (lane == 0) {
+                // The ring stage is released only HERE, behind the stores that consumed its values: an arrive that merely follows
+                // the shared-memory loads in program order may be scheduled before their data has returned (it was, once the
+                // role branches became provably uniform), and the next tensor copy then overwrites what is still being read.
+                mbar_arrive(&bars[BRE + rs]);
+                mbar_arrive(&bars[BOF + st]);
+            }
         }
         // ---- epilogue (warps 0-3: thread = output row o) ----
         if (warp < 4 && nch > 0) {

@@ -564,7 +564,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) savi_bwd_umma_kernel(const __grid
         TokState ts = {0, 0, 0};
         long long* sdbg = reinterpret_cast<long long*>(sm + L.bars + NBAR * 8 + 16);
         if (a.dbg && blockIdx.x == 0 && tid == 0) for (int i = 0; i < 64; ++i) sdbg[i] = 0;
+#ifdef SAVI_PHASE_PROFILE
         long long* dbg = (a.dbg && blockIdx.x == 0 && tid == 0) ? sdbg : nullptr;
+#else
+        long long* const dbg = nullptr;      // production build: the ~30 UPH probes fold away (tools/phase_times.py builds its own library)
+#endif
         long long ph_last = clock64();
         const float g_s = P[po.ln_s_w + o], g_m = P[po.ln_m_w + o];
         const float hscale = 1.0f / sqrtf((float)(F / d.heads));

@@ -365,10 +365,16 @@ __global__ void __launch_bounds__(NTHREADS, 1) savi_fwd_umma_kernel(const __grid
             const uint32_t opA = smem_u32(sm + L.opA), opB = smem_u32(sm + L.opB), opC = smem_u32(sm + L.opC);
             const uint32_t aw0 = smem_u32(sm + L.aw0), aw1 = smem_u32(sm + L.aw1);
             // development counters of the issuer (CTA 0): [60] waiting for operands, [61] waiting for ring blocks, [62] token pass, [63] total
+#ifdef SAVI_PHASE_PROFILE
             long long* idbg = (a.dbg && blockIdx.x == 0 && el) ? reinterpret_cast<long long*>(sm + L.bars + NBAR * 8 + 16) : nullptr;
+#else
+            long long* const idbg = nullptr;
+#endif
             long long i_opnd = 0, i_ring = 0, i_tok = 0;
             const long long i_t0 = clock64();
+#ifdef SAVI_PHASE_PROFILE
             if (a.dbg && blockIdx.x == 0) ring.wait_cycles = &i_ring;
+#endif
             auto wait_opnd = [&]() {
                 const long long t0 = clock64();
                 mbar_wait(&bars[B_OPND], ph_opnd); ph_opnd ^= 1u; fence_after_sync();
@@ -435,7 +441,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) savi_fwd_umma_kernel(const __grid
         uint32_t step = 0, pcall = 0;
         long long* sdbg = reinterpret_cast<long long*>(sm + L.bars + NBAR * 8 + 16);
         if (a.dbg && blockIdx.x == 0 && tid == 0) for (int i = 0; i < 64; ++i) sdbg[i] = 0;
+#ifdef SAVI_PHASE_PROFILE
         long long* dbg = (a.dbg && blockIdx.x == 0 && tid == 0) ? sdbg : nullptr;      // counters in shared memory: a global RMW per probe would stall the warp
+#else
+        long long* const dbg = nullptr;      // production build: the ~25 UPH probes (a per-thread branch + a live 64-bit timestamp each) fold away
+#endif
         long long ph_last = clock64();
         for (int t = 0; t < d.T; ++t) {
             for (int it = 0; it < d.I; ++it, ++step) {

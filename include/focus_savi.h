@@ -169,7 +169,8 @@ int savi_allreduce_peers(const void* const* peer_bufs_host, void* const* signal_
 
 /* Development aid: when set to a device buffer of 64 int64 counters, CTA 0 of the clip kernels
  * accumulates the SM cycles spent in each phase of the recurrence (tools/phase_times.py).
- * Pass NULL to disable (default).  Adds barriers; never enable while benchmarking. */
+ * Pass NULL to disable (default).  Adds barriers; never enable while benchmarking.  The tcgen05 clip kernels carry their
+ * probes only in a library built with -DSAVI_PHASE_PROFILE (the tool builds one); in the production build they are compiled out. */
 int savi_debug_set_phase_buffer(void* dev_ptr);
 
 #ifdef __cplusplus

@@ -1,7 +1,16 @@
-"""Per-phase cycle breakdown of the clip kernels (CTA 0), via savi_debug_set_phase_buffer."""
-import os, sys
+"""Per-phase cycle breakdown of the clip kernels (CTA 0), via savi_debug_set_phase_buffer, on a -DSAVI_PHASE_PROFILE build of the
+library (tools/build/libfocus_savi_phases.so, built on first use: the production library has no probes in its tcgen05 kernels)."""
+import importlib.util, os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
+# the production library compiles the phase probes of the tcgen05 clip kernels out: build (once) a profiling variant and load THAT
+_spec = importlib.util.spec_from_file_location("_focus_b200_build", os.path.join(ROOT, "focus_b200", "build.py"))
+_b = importlib.util.module_from_spec(_spec); _spec.loader.exec_module(_b)
+_lib_path = os.path.join(ROOT, "tools", "build", "libfocus_savi_phases.so")
+if not os.path.exists(_lib_path) or os.path.getmtime(_lib_path) < _b._newest_source_mtime():
+    os.makedirs(os.path.dirname(_lib_path), exist_ok=True)
+    _b.build(force=True, verbose=False, out=_lib_path, extra_flags=["-DSAVI_PHASE_PROFILE"])
+os.environ["FOCUS_SAVI_LIB"] = _lib_path
 import torch, bench
 from focus_b200 import _lib
 NAMES = {0: "top/pred-tail", 1: "copy+LN", 2: "lin q", 3: "lin qk", 4: "token pass", 5: "cluster sync", 6: "combine", 7: "lin U",

@@ -389,6 +389,10 @@ __device__ __forceinline__ float sum8(const Ctx& c, const float (&v)[KH]) {
 // ------------------------------------------------------------------------------------------------
 // the kernel
 // ------------------------------------------------------------------------------------------------
+// KFIX / CNFIX / HFIX: slots, CTAs per clip and predictor heads when the launch site knows them at compile time (0: read them from
+// the shape).  The MOVi configurations get their own instances: with K fixed, the per-slot predicates of the token threads and
+// the row / K index arithmetic of the predictor fold away; everything else runs the generic <0, 0, 0> instance.
+template <int KFIX, int CNFIX, int HFIX>
 __global__ void __launch_bounds__(NTHREADS, 1) savi_bwd_umma_kernel(const __grid_constant__ BwdUArgs ua) {
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     const BwdArgs& a = ua.a;
@@ -398,8 +402,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) savi_bwd_umma_kernel(const __grid
     if ((smem_u32(sm) & 1023u) != 0u) __trap();                // SWIZZLE_128B operands need a 1024-byte aligned base
     // (warp index through a lane-0 broadcast: ptxas then treats it, and every role branch on it, as warp-uniform)
     const int tid = threadIdx.x, warp = __shfl_sync(0xffffffffu, tid >> 5, 0), lane = tid & 31;
-    const int CN = d.CN, b = blockIdx.x / CN, rank = blockIdx.x % CN;
-    const int K = d.K, B = d.B, KP = d.KP;
+    const int CN = CNFIX ? CNFIX : d.CN, b = blockIdx.x / CN, rank = blockIdx.x % CN;
+    const int K = KFIX ? KFIX : d.K, B = d.B, KP = KFIX ? ((KFIX + 3) & ~3) : d.KP;
+    const int HEADS = HFIX ? HFIX : d.heads;
     const Smem L = plan_smem(K, CN, true);
     uint64_t* bars = reinterpret_cast<uint64_t*>(sm + L.bars);
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + NBAR);
@@ -489,7 +494,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) savi_bwd_umma_kernel(const __grid
                                 prefetch_l2(frow(fbw, a.sl.px2, f, b, B, K, F), rowb); prefetch_l2(frow(fbw, a.sl.px1, f, b, B, K, F), rowb);
                                 prefetch_l2(frow(fbw, a.sl.pq, f, b, B, K, F), rowb); prefetch_l2(frow(fbw, a.sl.pk, f, b, B, K, F), rowb);
                                 prefetch_l2(frow(fbw, a.sl.pv, f, b, B, K, F), rowb); prefetch_l2(frow(fbw, a.sl.pf, f, b, B, K, 4 * F), 4 * rowb);
-                                const int natt = d.heads * K * K;                               // saved attention matrices of the block
+                                const int natt = HEADS * K * K;                               // saved attention matrices of the block
                                 if ((natt & 3) == 0) prefetch_l2(fb + a.sl.patt + (f * B + b) * (int64_t)natt, (uint32_t)natt * 4u);
                             }
                         }
@@ -571,7 +576,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) savi_bwd_umma_kernel(const __grid
 #endif
         long long ph_last = clock64();
         const float g_s = P[po.ln_s_w + o], g_m = P[po.ln_m_w + o];
-        const float hscale = 1.0f / sqrtf((float)(F / d.heads));
+        const float hscale = 1.0f / sqrtf((float)(F / HEADS));
         // per-feature parameter-gradient accumulators over all steps of this clip (added to the flat buffer at the end)
         float a_gs = 0.f, a_bs = 0.f, a_gm = 0.f, a_bm = 0.f, a_b1 = 0.f, a_b2 = 0.f;
         float a_dr = 0.f, a_dz = 0.f, a_dn = 0.f, a_dnr = 0.f;
@@ -601,11 +606,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) savi_bwd_umma_kernel(const __grid
                     const float* p_v = frow(fbw, a.sl.pv, f, b, B, K, F);
                     const float* p_x1 = frow(fbw, a.sl.px1, f, b, B, K, F);
                     const float* p_f = frow(fbw, a.sl.pf, f, b, B, K, 4 * F);
-                    const float* p_att = fb + a.sl.patt + (f * B + b) * ((int64_t)d.heads * K * K);
+                    const float* p_att = fb + a.sl.patt + (f * B + b) * ((int64_t)HEADS * K * K);
                     UPH(37);
                     // training-mode dropout masks of this block evaluation (nullptr otherwise): savi_args.h, DropLayout
                     const DropLayout dlay = savi_dropout_layout(d);
-                    const float* m_att = a.drop ? a.drop + dlay.att + (f * B + b) * ((int64_t)d.heads * K * K) : nullptr;
+                    const float* m_att = a.drop ? a.drop + dlay.att + (f * B + b) * ((int64_t)HEADS * K * K) : nullptr;
                     const float* m_out = a.drop ? a.drop + dlay.out + (f * B + b) * ((int64_t)K * F) : nullptr;
                     const float* m_ffn = a.drop ? a.drop + dlay.ffn + (f * B + b) * ((int64_t)K * F) : nullptr;
                     // t0 = d x2; the FFN branch sees d x2 . m_ffn (staged for d W2 / d b2, pushed through ffn.2^T), the residual keeps t0
@@ -679,10 +684,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) savi_bwd_umma_kernel(const __grid
                         float qv[KH], kv[KH], vv[KH], attv[ATT_PT];
                         load_field(c, p_q, F, o, qv); load_field(c, p_k, F, o, kv); load_field(c, p_v, F, o, vv);
 #pragma unroll
-                        for (int e = 0; e < ATT_PT; ++e) { const int idx = tid + e * NCT; attv[e] = (idx < d.heads * K * K) ? p_att[idx] : 0.f; }
+                        for (int e = 0; e < ATT_PT; ++e) { const int idx = tid + e * NCT; attv[e] = (idx < HEADS * K * K) ? p_att[idx] : 0.f; }
                         wait_acc(c); load_acc(c, TB_B, dO);
                         UPH(41);
-                        mha_core_bwd(c, d.heads, hscale, dO, qv, kv, vv, attv, dQ, dK, dV, m_att, dbg, ph_last);
+                        mha_core_bwd(c, HEADS, hscale, dO, qv, kv, vv, attv, dQ, dK, dV, m_att, dbg, ph_last);
                         UPH(42);
                     }
                     if (svA) {
@@ -920,7 +925,11 @@ cudaError_t savi_launch_bwd_umma(const BwdArgs& a, const unsigned char* wimg, co
     ua.trace = (a.dbg && savi_options().dx_trace) ? a.dbg + 64 + 3 * 4096 : nullptr;      // [0] = min start (preset to LLONG_MAX), [1] = max end
     if (ua.trace) ua.a.dbg = nullptr;                                                         // no phase counters in a trace run
     ua.a.smem_bytes = savi_bwd_umma_smem_bytes(a.d);
-    cudaError_t e = cudaFuncSetAttribute(savi_bwd_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ua.a.smem_bytes);
+    // instances: C2 (K = 24, 4 heads), C4 (K = 11), both as CTA pairs; generic otherwise
+    void (*kern)(BwdUArgs) = savi_bwd_umma_kernel<0, 0, 0>;
+    if (ua.a.d.CN == 2 && ua.a.d.heads == 4 && ua.a.d.K == 24) kern = savi_bwd_umma_kernel<24, 2, 4>;
+    else if (ua.a.d.CN == 2 && ua.a.d.heads == 4 && ua.a.d.K == 11) kern = savi_bwd_umma_kernel<11, 2, 4>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, ua.a.smem_bytes);
     if (e != cudaSuccess) return e;
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(a.d.B * a.d.CN);
@@ -931,5 +940,5 @@ cudaError_t savi_launch_bwd_umma(const BwdArgs& a, const unsigned char* wimg, co
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = a.d.CN; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr; cfg.numAttrs = 1;
-    return cudaLaunchKernelEx(&cfg, savi_bwd_umma_kernel, ua);
+    return cudaLaunchKernelEx(&cfg, kern, ua);
 }

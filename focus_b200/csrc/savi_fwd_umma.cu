@@ -277,6 +277,10 @@ __device__ __forceinline__ void mha_core(const Ctx& c, int H, const float (&q)[K
 // ------------------------------------------------------------------------------------------------
 // the kernel
 // ------------------------------------------------------------------------------------------------
+// KFIX / CNFIX / HFIX: slots, CTAs per clip and predictor heads when the launch site knows them at compile time (0: read them from
+// the shape).  The MOVi configurations get their own instances: with K fixed, the per-slot predicates of the token threads and
+// the row / K index arithmetic of the predictor fold away; everything else runs the generic <0, 0, 0> instance.
+template <int KFIX, int CNFIX, int HFIX>
 __global__ void __launch_bounds__(NTHREADS, 1) savi_fwd_umma_kernel(const __grid_constant__ FwdUArgs ua) {
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     const FwdArgs& a = ua.a;
@@ -286,8 +290,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) savi_fwd_umma_kernel(const __grid
     if ((smem_u32(sm) & 1023u) != 0u) __trap();                // SWIZZLE_128B operands need a 1024-byte aligned base
     // (warp index through a lane-0 broadcast: ptxas then treats it, and every role branch on it, as warp-uniform)
     const int tid = threadIdx.x, warp = __shfl_sync(0xffffffffu, tid >> 5, 0), lane = tid & 31;
-    const int CN = d.CN, b = blockIdx.x / CN, rank = blockIdx.x % CN;
-    const int K = d.K, B = d.B, KP = d.KP;
+    const int CN = CNFIX ? CNFIX : d.CN, b = blockIdx.x / CN, rank = blockIdx.x % CN;
+    const int K = KFIX ? KFIX : d.K, B = d.B, KP = KFIX ? ((KFIX + 3) & ~3) : d.KP;
+    const int HEADS = HFIX ? HFIX : d.heads;
     const Smem L = plan_smem(K, CN, false);
     uint64_t* bars = reinterpret_cast<uint64_t*>(sm + L.bars);
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + NBAR);
@@ -596,7 +601,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) savi_fwd_umma_kernel(const __grid
             if (t < d.T - 1) {
                 // ---- predictor (:100; transformer.py:106-114) ----
                 if (svA) save_field(c, fb + a.sl.px0 + ((size_t)t * B + b) * K * F, F, o, h);
-                const float hscale = 1.0f / sqrtf((float)(F / d.heads));
+                const float hscale = 1.0f / sqrtf((float)(F / HEADS));
                 float x[KH];
 #pragma unroll
                 for (int kk = 0; kk < KH; ++kk) x[kk] = h[kk];
@@ -624,10 +629,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) savi_fwd_umma_kernel(const __grid
                     float ov[KH];
                     // training-mode dropout masks of this block evaluation (nullptr otherwise): savi_args.h, DropLayout
                     const DropLayout dl = savi_dropout_layout(d);
-                    const float* m_att = a.drop ? a.drop + dl.att + (f * B + b) * ((int64_t)d.heads * K * K) : nullptr;
+                    const float* m_att = a.drop ? a.drop + dl.att + (f * B + b) * ((int64_t)HEADS * K * K) : nullptr;
                     const float* m_out = a.drop ? a.drop + dl.out + (f * B + b) * ((int64_t)K * F) : nullptr;
                     const float* m_ffn = a.drop ? a.drop + dl.ffn + (f * B + b) * ((int64_t)K * F) : nullptr;
-                    mha_core(c, d.heads, q, kx, v, ov, svB ? fb + a.sl.patt + (f * B + b) * ((int64_t)d.heads * K * K) : nullptr, m_att);
+                    mha_core(c, HEADS, q, kx, v, ov, svB ? fb + a.sl.patt + (f * B + b) * ((int64_t)HEADS * K * K) : nullptr, m_att);
                     if (svA) save_field(c, frow(fb, a.sl.po, f, b, B, K, F), F, o, ov);
                     write_operand_f16(c, L.opB, ov);
                     signal_operand(c);
@@ -710,7 +715,11 @@ cudaError_t savi_launch_fwd_umma(const FwdArgs& a, const unsigned char* wimg, co
     FwdUArgs ua;
     ua.a = a; ua.wimg = wimg; ua.wi = wi;
     ua.a.smem_bytes = savi_fwd_umma_smem_bytes(a.d);
-    cudaError_t e = cudaFuncSetAttribute(savi_fwd_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ua.a.smem_bytes);
+    // instances: C2 (K = 24, 4 heads), C4 (K = 11), both as CTA pairs; generic otherwise
+    void (*kern)(FwdUArgs) = savi_fwd_umma_kernel<0, 0, 0>;
+    if (ua.a.d.CN == 2 && ua.a.d.heads == 4 && ua.a.d.K == 24) kern = savi_fwd_umma_kernel<24, 2, 4>;
+    else if (ua.a.d.CN == 2 && ua.a.d.heads == 4 && ua.a.d.K == 11) kern = savi_fwd_umma_kernel<11, 2, 4>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, ua.a.smem_bytes);
     if (e != cudaSuccess) return e;
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(a.d.B * a.d.CN);
@@ -721,5 +730,5 @@ cudaError_t savi_launch_fwd_umma(const FwdArgs& a, const unsigned char* wimg, co
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = a.d.CN; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr; cfg.numAttrs = 1;
-    return cudaLaunchKernelEx(&cfg, savi_fwd_umma_kernel, ua);
+    return cudaLaunchKernelEx(&cfg, kern, ua);
 }

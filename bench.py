@@ -233,7 +233,7 @@ def config_dict(args, cfg, n):
             "Ds": cfg["Ds"], "M": cfg["M"], "K": cfg["K"], "iters": cfg["I"], "predictor": "%d block x %d heads" % (cfg["blocks"], cfg["heads"]),
             "token_dtype": cfg["dtype"], "grad_attn": "dense N(0,1)",
             "parallelism": "dp%d" % n + ("" if n == 1 else " (torch DDP)" if args.ddp else " (gradient exchange inside backward: %s)" % getattr(args, "exchange", "one flat all-reduce")),
-            "l2": "flushed between timed steps (256 MiB write outside the event brackets); step working set >> 126 MB L2"}
+            "l2": "flushed between timed steps (256 MiB write outside the event brackets%s); step working set >> 126 MB L2" % ("" if n == 1 else "; ranks re-aligned on the device after the flush, before each start event")}
 
 
 # ---------------------------------------------------------------------------------------------
@@ -296,9 +296,20 @@ def run_ours(args, cfg, rank, world, local_rank):
     sampler = ClockSampler(local_rank)
     sampler.start()
     evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    # N > 1: the L2 flush between timed steps (outside the event brackets) takes a different time on every rank, and a rank that
+    # starts its step early then spends the difference waiting inside the step's gradient exchange.  A training loop has no flush
+    # and stays in lock-step through the exchange, so the ranks are re-aligned ON THE DEVICE (a 4-byte all-reduce the stream
+    # waits for, no host synchronisation) between the flush and the start event; the bracket still holds exactly one step.
+    align = torch.zeros(1, device=dev) if world > 1 else None
+
+    def align_ranks():
+        if align is not None:
+            dist.all_reduce(align)
+
     sync_all()
     for i in range(args.steps):
         flush.fill_(i & 0xFF)
+        align_ranks()
         evs[i][0].record()
         step(x)
         evs[i][1].record()
@@ -331,6 +342,7 @@ def run_ours(args, cfg, rank, world, local_rank):
             gevs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
             for i in range(args.steps):
                 flush.fill_(i & 0xFF)
+                align_ranks()
                 gevs[i][0].record()
                 graph.replay()
                 gevs[i][1].record()

@@ -8,7 +8,7 @@
 // peer-mapped, with a zero-initialised "signal pad" per rank).  CTA b of a rank only ever talks to CTA b of its peers:
 //   barrier (channel 0): peer buffers are complete — each rank's kernel runs behind its own backward in stream order, so a peer
 //                        CTA that has arrived implies that peer's buffer is final
-//   out[chunk b] = scale * sum_r peer_r[chunk b]
+//   out[chunk b] = scale * sum_r peer_r[chunk b]        (chunk b: the float4 elements CTA b's threads stride over)
 //   barrier (channel 1): every peer has finished reading this rank's chunk b; when the kernel ends no rank reads the buffer any
 //                        more and the next step may overwrite it
 // A barrier is the signal-pad handshake torch's own symmetric-memory kernels use: put = CAS 0 -> 1 (release, system scope) on the
@@ -71,16 +71,22 @@ __device__ __forceinline__ float4 ld_reduce_mc(const float* p) {  // the NVSwitc
 __global__ void __launch_bounds__(AR_THREADS) allreduce_peers_kernel(const __grid_constant__ ArArgs a) {
     const int blk = blockIdx.x;
     peer_barrier(a, 0, blk);
-    const long long per = (a.n4 + a.nblk - 1) / a.nblk;
-    const long long lo = blk * per, hi = lo + per < a.n4 ? lo + per : a.n4;
+    // chunk b = float4 elements {b, b + nblk, ...} x 512 threads; the multicast path keeps four loads per thread in flight, the peer
+    // path one element (= `world` loads) at a time
+    const long long stride = (long long)a.nblk * AR_THREADS;
     if (a.mc) {
-        for (long long i = lo + threadIdx.x; i < hi; i += AR_THREADS) {
-            float4 s = ld_reduce_mc(a.mc + 4 * i);
-            s.x *= a.scale; s.y *= a.scale; s.z *= a.scale; s.w *= a.scale;
-            reinterpret_cast<float4*>(a.out)[i] = s;
+        for (long long i0 = (long long)blk * AR_THREADS + threadIdx.x; i0 < a.n4; i0 += 4 * stride) {
+            float4 s[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+                if (i0 + u * stride < a.n4) s[u] = ld_reduce_mc(a.mc + 4 * (i0 + u * stride));
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+                if (i0 + u * stride < a.n4)
+                    reinterpret_cast<float4*>(a.out)[i0 + u * stride] = make_float4(s[u].x * a.scale, s[u].y * a.scale, s[u].z * a.scale, s[u].w * a.scale);
         }
     } else {
-        for (long long i = lo + threadIdx.x; i < hi; i += AR_THREADS) {
+        for (long long i = (long long)blk * AR_THREADS + threadIdx.x; i < a.n4; i += stride) {
             float4 v[AR_MAX_WORLD];
 #pragma unroll
             for (int r = 0; r < AR_MAX_WORLD; ++r)               // all peers' loads in flight together; summed in rank order on every rank
@@ -89,8 +95,7 @@ __global__ void __launch_bounds__(AR_THREADS) allreduce_peers_kernel(const __gri
 #pragma unroll
             for (int r = 1; r < AR_MAX_WORLD; ++r)
                 if (r < a.world) { s.x += v[r].x; s.y += v[r].y; s.z += v[r].z; s.w += v[r].w; }
-            s.x *= a.scale; s.y *= a.scale; s.z *= a.scale; s.w *= a.scale;
-            reinterpret_cast<float4*>(a.out)[i] = s;
+            reinterpret_cast<float4*>(a.out)[i] = make_float4(s.x * a.scale, s.y * a.scale, s.z * a.scale, s.w * a.scale);
         }
     }
     peer_barrier(a, 1, blk);
@@ -113,11 +118,11 @@ extern "C" int savi_allreduce_peers(const void* const* peer_bufs, void* const* s
     a.mc = reinterpret_cast<const float*>(multicast);
     a.out = reinterpret_cast<float*>(out);
     a.n4 = n_floats / 4; a.scale = scale; a.rank = rank; a.world = world;
-    // one CTA per ~8 K floats, at most what the signal pad has slots for (2 channels x nblk x world words) and 64
-    long long nblk = (a.n4 + 2047) / 2048;
+    // one CTA per 2 K float4 elements (4 per thread), at most what the signal pad has slots for (2 channels x nblk x world words) and 128
+    long long nblk = (a.n4 + 4 * AR_THREADS - 1) / (4 * AR_THREADS);
     const long long cap = signal_pad_bytes / 4 / (2 * world);
     if (nblk > cap) nblk = cap;
-    if (nblk > 64) nblk = 64;
+    if (nblk > 128) nblk = 128;
     if (nblk < 1) return savi_set_error(SAVI_EINVAL, "savi_allreduce_peers: signal pad of %lld bytes is too small", (long long)signal_pad_bytes);
     a.nblk = (int)nblk;
     allreduce_peers_kernel<<<(unsigned)nblk, AR_THREADS, 0, reinterpret_cast<cudaStream_t>(stream)>>>(a);

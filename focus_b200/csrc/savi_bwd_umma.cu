@@ -925,10 +925,11 @@ cudaError_t savi_launch_bwd_umma(const BwdArgs& a, const unsigned char* wimg, co
     ua.trace = (a.dbg && savi_options().dx_trace) ? a.dbg + 64 + 3 * 4096 : nullptr;      // [0] = min start (preset to LLONG_MAX), [1] = max end
     if (ua.trace) ua.a.dbg = nullptr;                                                         // no phase counters in a trace run
     ua.a.smem_bytes = savi_bwd_umma_smem_bytes(a.d);
-    // instances: C2 (K = 24, 4 heads), C4 (K = 11), both as CTA pairs; generic otherwise
+    // instances: C2 (K = 24, 4 heads) and C4 (K = 11), as CTA pairs (B <= 74 clips per GPU) and as single CTAs; generic otherwise
     void (*kern)(BwdUArgs) = savi_bwd_umma_kernel<0, 0, 0>;
-    if (ua.a.d.CN == 2 && ua.a.d.heads == 4 && ua.a.d.K == 24) kern = savi_bwd_umma_kernel<24, 2, 4>;
-    else if (ua.a.d.CN == 2 && ua.a.d.heads == 4 && ua.a.d.K == 11) kern = savi_bwd_umma_kernel<11, 2, 4>;
+    const Dims& dd = ua.a.d;
+    if (dd.heads == 4 && dd.K == 24) kern = dd.CN == 2 ? savi_bwd_umma_kernel<24, 2, 4> : dd.CN == 1 ? savi_bwd_umma_kernel<24, 1, 4> : kern;
+    else if (dd.heads == 4 && dd.K == 11) kern = dd.CN == 2 ? savi_bwd_umma_kernel<11, 2, 4> : dd.CN == 1 ? savi_bwd_umma_kernel<11, 1, 4> : kern;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, ua.a.smem_bytes);
     if (e != cudaSuccess) return e;
     cudaLaunchConfig_t cfg = {};

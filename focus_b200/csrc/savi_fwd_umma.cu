@@ -715,10 +715,11 @@ cudaError_t savi_launch_fwd_umma(const FwdArgs& a, const unsigned char* wimg, co
     FwdUArgs ua;
     ua.a = a; ua.wimg = wimg; ua.wi = wi;
     ua.a.smem_bytes = savi_fwd_umma_smem_bytes(a.d);
-    // instances: C2 (K = 24, 4 heads), C4 (K = 11), both as CTA pairs; generic otherwise
+    // instances: C2 (K = 24, 4 heads) and C4 (K = 11), as CTA pairs (B <= 74 clips per GPU) and as single CTAs; generic otherwise
     void (*kern)(FwdUArgs) = savi_fwd_umma_kernel<0, 0, 0>;
-    if (ua.a.d.CN == 2 && ua.a.d.heads == 4 && ua.a.d.K == 24) kern = savi_fwd_umma_kernel<24, 2, 4>;
-    else if (ua.a.d.CN == 2 && ua.a.d.heads == 4 && ua.a.d.K == 11) kern = savi_fwd_umma_kernel<11, 2, 4>;
+    const Dims& dd = ua.a.d;
+    if (dd.heads == 4 && dd.K == 24) kern = dd.CN == 2 ? savi_fwd_umma_kernel<24, 2, 4> : dd.CN == 1 ? savi_fwd_umma_kernel<24, 1, 4> : kern;
+    else if (dd.heads == 4 && dd.K == 11) kern = dd.CN == 2 ? savi_fwd_umma_kernel<11, 2, 4> : dd.CN == 1 ? savi_fwd_umma_kernel<11, 1, 4> : kern;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, ua.a.smem_bytes);
     if (e != cudaSuccess) return e;
     cudaLaunchConfig_t cfg = {};

@@ -9,7 +9,7 @@ import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
 
-from focus_b200.distributed import FlatGradAllReduce, GradSync, shard_range
+from focus_b200.distributed import FlatGradAllReduce, GradSync, attach_grad_sync, shard_range
 
 
 def test_shard_range_partitions_every_clip_once():
@@ -53,6 +53,17 @@ def _worker(rank, world, port, out):
     GradSync(average=True)(flat)
     flat_ref = torch.cat([p.grad.reshape(-1) for p in params])
     assert float((flat - flat_ref).abs().max()) <= 1e-6 * float(flat_ref.abs().max())
+    # exchange selection: a gloo / CPU group cannot use the library's peer-memory kernel — "auto" falls back to the collective on
+    # every rank (and broadcasts rank 0's parameters), peer=True refuses
+    holder = torch.nn.Linear(3, 2)
+    with torch.no_grad():
+        holder.weight.fill_(float(rank + 1))
+    assert isinstance(attach_grad_sync(holder, peer="auto"), GradSync) and float(holder.weight[0, 0]) == 1.0
+    try:
+        attach_grad_sync(holder, peer=True)
+        raise AssertionError("peer=True must refuse a gloo group")
+    except RuntimeError:
+        pass
     if rank == 0:
         _, _, _, Gfull = OT.forward_backward(P, x, noise, I, heads, gs / Bg)
         worst = max(float((p.grad.double() - Gfull[k]).abs().max() / Gfull[k].abs().max().clamp_min(1e-30))

@@ -1,6 +1,6 @@
 // The data-parallel exchange step of the path as the library's own kernel: a one-shot all-reduce of the flat
 // parameter-gradient buffer over NVLink / NVSwitch peer memory (the reference gets it from DDP: slowfast/models/build.py:79-83).
-// The buffer is only ~1.6 MB, so an NCCL all-reduce costs its launch + protocol latency (60-80 us exposed at 8 GPUs);
+// The buffer is only ~1.6 MB, so the exchange is pure latency (NCCL: ~33 us per call at 8 GPUs, plus its host-side launch cost);
 // here every rank reads all peers' buffers directly (or ONE multimem.ld_reduce through the switch where the allocation has a
 // multicast mapping) and writes the scaled sum into its own output: ~11 MB of peer reads per rank at 8 GPUs.
 //
